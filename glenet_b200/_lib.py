@@ -1,0 +1,71 @@
+"""ctypes binding of ``libglenet_geom.so`` (the C ABI declared in ``include/glenet_geom.h``).
+
+There is no CPU or eager fallback: if the shared object is missing it is built with nvcc
+(``glenet_b200.build``); if that is impossible the import of the op fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+from . import build as _build
+
+_lock = threading.Lock()
+_lib = None
+
+c_float_p = ctypes.c_void_p  # raw device pointers travel as integers (tensor.data_ptr())
+
+_SIGNATURES = {
+    "glenet_abi_version": (ctypes.c_int, []),
+    "glenet_last_error": (ctypes.c_char_p, []),
+    "glenet_boxes_overlap_bev_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "glenet_boxes_iou_bev_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "glenet_boxes_iou3d_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "glenet_boxes_iou_aligned_gpu": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "glenet_boxes_iou_bev_cpu_dialect": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "glenet_host_trig4": (None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "glenet_host_trig2": (None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "glenet_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "glenet_nms_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "glenet_nms_normal_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "glenet_points_in_boxes_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "glenet_points_in_boxes_gpu": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "glenet_points_in_boxes_cpu_dialect": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+}
+
+EXPORTS = tuple(_SIGNATURES)
+ABI_VERSION = 1
+
+
+def lib_path() -> str:
+    return _build.LIBPATH
+
+
+def load() -> ctypes.CDLL:
+    """Load (building first if needed) the native library.  Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIBPATH
+        if not os.path.isfile(path):
+            _build.build_library()
+        lib = ctypes.CDLL(path)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the ABI does not export it
+            fn.restype = restype
+            fn.argtypes = argtypes
+        got = lib.glenet_abi_version()
+        if got != ABI_VERSION:
+            raise RuntimeError(f"libglenet_geom.so ABI {got} != expected {ABI_VERSION}: rebuild with `python -m glenet_b200.build --force`")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().glenet_last_error().decode(errors="replace")
+        raise RuntimeError(f"libglenet_geom {what} failed ({rc}): {msg}")

@@ -1,0 +1,266 @@
+// Rotated-rectangle geometry shared by the IoU, NMS and points-in-boxes kernels.
+//
+// The arithmetic of every rounding-sensitive expression is pinned with explicit
+// __f{add,sub,mul,maf}_rn intrinsics so that nvcc can neither contract nor
+// re-associate it.  The sequences reproduce, operation for operation, what the
+// reference computes:
+//
+//   FMA = true   "GPU dialect": the reference's CUDA kernels as nvcc 12.9 compiles
+//                them for sm_100a (fmad on) -- pcdet/ops/iou3d_nms/src/iou3d_nms_kernel.cu
+//                :35-234 (cross / check_rect_cross / check_in_box2d / intersection /
+//                rotate_around_center / point_cmp / box_overlap / iou_bev).  Which product
+//                of every a*b +- c*d is fused was read from the reference's SASS.
+//   FMA = false  "CPU dialect": the reference's host twin, pcdet/ops/iou3d_nms/src/
+//                iou3d_cpu.cpp:59-229, compiled by gcc for x86-64 (no FMA, every
+//                operation rounded separately).  Trigonometry then comes from the
+//                host's libm through the `trig` argument of the kernels.
+//
+// The structure is NOT the reference's: per-box work (trig, corners, margin
+// thresholds, areas) is hoisted into a BoxPre record computed once per box, the
+// polygon lives in shared memory (no local-memory stack), and the angular sort
+// evaluates one atan2f per vertex instead of two per comparison.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace glenet {
+
+// ---------------------------------------------------------------- pinned arithmetic
+template <bool FMA>
+__device__ __forceinline__ float mul_sub(float a, float b, float c, float d) {
+    // a*b - c*d ; GPU dialect: fma(a, b, -(c*d)) (second product rounded first)
+    if (FMA) return __fmaf_rn(a, b, -__fmul_rn(c, d));
+    return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d));
+}
+template <bool FMA>
+__device__ __forceinline__ float mul_add(float a, float b, float c, float d) {
+    // a*b + c*d ; GPU dialect: fma(a, b, (c*d))
+    if (FMA) return __fmaf_rn(a, b, __fmul_rn(c, d));
+    return __fadd_rn(__fmul_rn(a, b), __fmul_rn(c, d));
+}
+
+// ---------------------------------------------------------------- per-box record
+// Layout of one BoxPre record (floats).  Stride 21 keeps consecutive records on
+// different shared-memory banks.
+enum {
+    BP_CX = 0, BP_CY = 1,      // centre
+    BP_CN = 2, BP_SN = 3,      // cosf(-heading), sinf(-heading)   (check_in_box2d)
+    BP_THX = 4, BP_THY = 5,    // dx/2 + 0.01f, dy/2 + 0.01f        (MARGIN, iou3d_nms_kernel.cu:53)
+    BP_AREA = 6,               // dx*dy
+    BP_PX = 7,                 // 4 rotated corner x
+    BP_PY = 11,                // 4 rotated corner y
+    BP_ZMIN = 15, BP_ZMAX = 16, BP_VOL = 17,   // boxes_iou3d_gpu terms (iou3d_nms_utils.py:100-117)
+    BP_STRIDE = 21
+};
+
+// trig4 = {cos(h), sin(h), cos(-h), sin(-h)}
+template <bool FMA>
+__device__ __forceinline__ void box_prepare(const float* __restrict__ box, const float4 trig4,
+                                            float* __restrict__ o) {
+    const float cx = box[0], cy = box[1], z = box[2], dx = box[3], dy = box[4], dz = box[5];
+    // iou3d_nms_kernel.cu:109-113 : half extents are exact, so one rounding each
+    const float x1 = __fmaf_rn(dx, -0.5f, cx), x2 = __fmaf_rn(dx, 0.5f, cx);
+    const float y1 = __fmaf_rn(dy, -0.5f, cy), y2 = __fmaf_rn(dy, 0.5f, cy);
+    // rotate_around_center (:91-95) works on (p - centre)
+    const float ex1 = __fsub_rn(x1, cx), ex2 = __fsub_rn(x2, cx);
+    const float ey1 = __fsub_rn(y1, cy), ey2 = __fsub_rn(y2, cy);
+    const float c = trig4.x, s = trig4.y;
+    const float exs[4] = {ex1, ex2, ex2, ex1};
+    const float eys[4] = {ey1, ey1, ey2, ey2};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // new_x = ex*cos + ey*(-sin) + cx ; new_y = ex*sin + ey*cos + cy
+        o[BP_PX + k] = __fadd_rn(mul_sub<FMA>(c, exs[k], s, eys[k]), cx);
+        o[BP_PY + k] = __fadd_rn(mul_add<FMA>(s, exs[k], c, eys[k]), cy);
+    }
+    o[BP_CX] = cx;
+    o[BP_CY] = cy;
+    o[BP_CN] = trig4.z;
+    o[BP_SN] = trig4.w;
+    o[BP_THX] = __fmaf_rn(dx, 0.5f, 0.01f);   // == dx/2 + MARGIN, single rounding in both dialects
+    o[BP_THY] = __fmaf_rn(dy, 0.5f, 0.01f);
+    o[BP_AREA] = __fmul_rn(dx, dy);
+    const float hz = __fmul_rn(dz, 0.5f);
+    o[BP_ZMIN] = __fsub_rn(z, hz);
+    o[BP_ZMAX] = __fadd_rn(z, hz);
+    o[BP_VOL] = __fmul_rn(__fmul_rn(dx, dy), dz);
+}
+
+__device__ __forceinline__ float4 device_trig(float heading) {
+    // exactly the four libdevice calls the reference issues (cos(a), sin(a), cos(-a), sin(-a))
+    float4 t;
+    t.x = cosf(heading);
+    t.y = sinf(heading);
+    t.z = cosf(-heading);
+    t.w = sinf(-heading);
+    return t;
+}
+
+// Conservative cull radius: circumscribed circle of the box grown by the 0.01 margin
+// (a corner may be admitted up to MARGIN outside, in both axes) plus slack for the
+// rounding of absolute corner coordinates.  Two boxes whose centres are farther apart
+// than r_a + r_b produce no polygon vertex in the reference => overlap is exactly +0.
+__device__ __forceinline__ float cull_radius(const float* __restrict__ box) {
+    const float dx = box[3], dy = box[4];
+    const float r = 0.5f * sqrtf(dx * dx + dy * dy);
+    return r * 1.0001f + 0.03f + 2e-6f * (fabsf(box[0]) + fabsf(box[1]));
+}
+
+// ---------------------------------------------------------------- polygon scratch
+// Vertex k of thread t lives at vx[k * VSTRIDE + t] (column per thread => conflict free).
+constexpr int MAX_POLY = 16;
+struct PolyScratch {
+    float* vx;
+    float* vy;
+    float* key;
+    int stride;
+};
+
+// intersection() of iou3d_nms_kernel.cu:57-89 for edge p0->p1 of box a and q0->q1 of box b.
+template <bool FMA>
+__device__ __forceinline__ bool edge_intersection(float p0x, float p0y, float p1x, float p1y,
+                                                  float q0x, float q0y, float q1x, float q1y,
+                                                  float& ox, float& oy) {
+    // check_rect_cross (:43-48)
+    const bool rc = fminf(p0x, p1x) <= fmaxf(q0x, q1x) && fminf(q0x, q1x) <= fmaxf(p0x, p1x) &&
+                    fminf(p0y, p1y) <= fmaxf(q0y, q1y) && fminf(q0y, q1y) <= fmaxf(p0y, p1y);
+    if (!rc) return false;
+    const float pdx = __fsub_rn(p1x, p0x), pdy = __fsub_rn(p1y, p0y);   // p1 - p0
+    const float qdx = __fsub_rn(q1x, q0x), qdy = __fsub_rn(q1y, q0y);   // q1 - q0
+    // s1 = cross(q0, p1, p0)
+    const float s1 = mul_sub<FMA>(__fsub_rn(q0x, p0x), pdy, pdx, __fsub_rn(q0y, p0y));
+    // s2 = cross(p1, q1, p0) and s5 = cross(q1, p1, p0) share both products (each rounded)
+    const float m1 = __fmul_rn(pdx, __fsub_rn(q1y, p0y));
+    const float m2 = __fmul_rn(pdy, __fsub_rn(q1x, p0x));
+    const float s2 = __fsub_rn(m1, m2);
+    // s3 = cross(p0, q1, q0)
+    const float s3 = mul_sub<FMA>(__fsub_rn(p0x, q0x), qdy, __fsub_rn(p0y, q0y), qdx);
+    // s4 = cross(q1, p1, q0)
+    const float s4 = mul_sub<FMA>(qdx, __fsub_rn(p1y, q0y), qdy, __fsub_rn(p1x, q0x));
+    if (!(__fmul_rn(s1, s2) > 0.f && __fmul_rn(s3, s4) > 0.f)) return false;
+    const float s5 = __fsub_rn(m2, m1);
+    const float den = __fsub_rn(s5, s1);
+    if (fabsf(den) > 1e-8f) {
+        ox = __fdiv_rn(mul_sub<FMA>(q0x, s5, q1x, s1), den);
+        oy = __fdiv_rn(mul_sub<FMA>(q0y, s5, q1y, s1), den);
+    } else {
+        const float a0 = __fsub_rn(p0y, p1y), b0 = pdx, c0 = mul_sub<FMA>(p0x, p1y, p1x, p0y);
+        const float a1 = __fsub_rn(q0y, q1y), b1 = qdx, c1 = mul_sub<FMA>(q0x, q1y, q0y, q1x);
+        const float D = mul_sub<FMA>(b1, a0, b0, a1);
+        ox = __fdiv_rn(mul_sub<FMA>(b0, c1, b1, c0), D);
+        oy = __fdiv_rn(mul_sub<FMA>(c0, a1, a0, c1), D);
+    }
+    return true;
+}
+
+// check_in_box2d (:50-60) of point (px,py) against a prepared box.
+template <bool FMA>
+__device__ __forceinline__ bool corner_in_box(const float* __restrict__ b, float px, float py) {
+    const float dxp = __fsub_rn(px, b[BP_CX]), dyp = __fsub_rn(py, b[BP_CY]);
+    const float cn = b[BP_CN], sn = b[BP_SN];
+    const float rx = mul_sub<FMA>(cn, dxp, sn, dyp);   // dxp*cos + dyp*(-sin)
+    const float ry = mul_add<FMA>(cn, dyp, sn, dxp);   // dxp*sin + dyp*cos (dyp*cos is the fused product)
+    return fabsf(rx) < b[BP_THX] && fabsf(ry) < b[BP_THY];
+}
+
+// box_overlap (:104-225): overlap area of prepared boxes a (row) and b (column).
+template <bool FMA>
+__device__ float box_overlap(const float* __restrict__ a, const float* __restrict__ b,
+                             const PolyScratch& ps, int tid) {
+    float ax[4], ay[4], bx[4], by[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ax[k] = a[BP_PX + k]; ay[k] = a[BP_PY + k];
+        bx[k] = b[BP_PX + k]; by[k] = b[BP_PY + k];
+    }
+    float* vx = ps.vx + tid;
+    float* vy = ps.vy + tid;
+    const int S = ps.stride;
+    int cnt = 0;
+    float sx = 0.f, sy = 0.f;   // poly_center accumulator, in append order
+    // cross_points[16] (:155) is exactly large enough for every non-degenerate pair; the guard
+    // only keeps a pathological (NaN/degenerate) pair from writing outside its scratch column.
+    auto push = [&](float x, float y) {
+        if (cnt < MAX_POLY) {
+            sx = __fadd_rn(sx, x);
+            sy = __fadd_rn(sy, y);
+            vx[cnt * S] = x;
+            vy[cnt * S] = y;
+            ++cnt;
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float ox, oy;
+            if (edge_intersection<FMA>(ax[i], ay[i], ax[(i + 1) & 3], ay[(i + 1) & 3],
+                                       bx[j], by[j], bx[(j + 1) & 3], by[(j + 1) & 3], ox, oy)) {
+                push(ox, oy);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (corner_in_box<FMA>(a, bx[k], by[k])) {
+            push(bx[k], by[k]);
+        }
+        if (corner_in_box<FMA>(b, ax[k], ay[k])) {
+            push(ax[k], ay[k]);
+        }
+    }
+    if (cnt < 3) return 0.f;   // the fan of 0, 1 or 2 vertices has area exactly +0 in the reference too
+    const float fc = (float)cnt;
+    const float ccx = __fdiv_rn(sx, fc), ccy = __fdiv_rn(sy, fc);
+    // stable insertion sort by atan2f(y - cy, x - cx): same permutation as the reference's
+    // stable bubble sort with a strict '>' comparison (:201-209)
+    float* key = ps.key + tid;
+    for (int k = 0; k < cnt; ++k) {
+        const float x = vx[k * S], y = vy[k * S];
+        const float kk = atan2f(__fsub_rn(y, ccy), __fsub_rn(x, ccx));
+        int m = k;
+        while (m > 0 && key[(m - 1) * S] > kk) {
+            key[m * S] = key[(m - 1) * S];
+            vx[m * S] = vx[(m - 1) * S];
+            vy[m * S] = vy[(m - 1) * S];
+            --m;
+        }
+        key[m * S] = kk;
+        vx[m * S] = x;
+        vy[m * S] = y;
+    }
+    // fan from the first sorted vertex (:219-222)
+    const float x0 = vx[0], y0 = vy[0];
+    float area = 0.f;
+    float ux = 0.f, uy = 0.f;   // vertex 0 minus itself
+    for (int k = 1; k < cnt; ++k) {
+        const float wx = __fsub_rn(vx[k * S], x0), wy = __fsub_rn(vy[k * S], y0);
+        area = __fadd_rn(area, mul_sub<FMA>(ux, wy, uy, wx));
+        ux = wx;
+        uy = wy;
+    }
+    return __fmul_rn(fabsf(area), 0.5f);
+}
+
+// iou_bev (:227-234)
+__device__ __forceinline__ float iou_from_overlap(float sa, float sb, float ov) {
+    return __fdiv_rn(ov, fmaxf(__fsub_rn(__fadd_rn(sa, sb), ov), 1e-8f));
+}
+
+// torch.clamp(x, min=lo) propagates NaN (iou3d_nms_utils.py:112,119)
+__device__ __forceinline__ float clamp_min_nan(float v, float lo) { return (v != v) ? v : fmaxf(v, lo); }
+__device__ __forceinline__ float max_nan(float a, float b) { return (a != a || b != b) ? (a + b) : fmaxf(a, b); }
+__device__ __forceinline__ float min_nan(float a, float b) { return (a != a || b != b) ? (a + b) : fminf(a, b); }
+
+// boxes_iou3d_gpu (iou3d_nms_utils.py:100-119), every step separately rounded as torch does
+__device__ __forceinline__ float iou3d_from_overlap(const float* __restrict__ a, const float* __restrict__ b, float ov) {
+    const float max_of_min = max_nan(a[BP_ZMIN], b[BP_ZMIN]);
+    const float min_of_max = min_nan(a[BP_ZMAX], b[BP_ZMAX]);
+    const float oh = clamp_min_nan(__fsub_rn(min_of_max, max_of_min), 0.f);
+    const float o3 = __fmul_rn(ov, oh);
+    const float den = clamp_min_nan(__fsub_rn(__fadd_rn(a[BP_VOL], b[BP_VOL]), o3), 1e-6f);
+    return __fdiv_rn(o3, den);
+}
+
+}  // namespace glenet

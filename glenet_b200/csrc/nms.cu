@@ -1,0 +1,285 @@
+// Bitmask NMS (rotated and axis-aligned) entirely on the device, for sm_100a.
+//
+// Replaces nms_kernel / nms_normal_kernel (pcdet/ops/iou3d_nms/src/iou3d_nms_kernel.cu:267-372)
+// and the host side of nms_gpu / nms_normal_gpu (pcdet/ops/iou3d_nms/src/iou3d_nms.cpp:90-186):
+// cudaMalloc of the mask, blocking D2H copy of N*ceil(N/64) words, serial host sweep.
+//
+//   mask kernel : one CTA per 64x64 tile of the UPPER triangle only (the reference launches
+//                 the full square and never reads the lower half).  Pairs are circle-culled,
+//                 compacted into a shared queue, and the survivors go through the same
+//                 clipping code as boxes_iou_bev (row box = box_a, column box = box_b, as in
+//                 the reference) -> bit (i, j) = iou(i, j) > thresh, j > i.
+//   sweep kernel: one CTA per frame.  For every 64-box chunk, warp 0 resolves the diagonal
+//                 tile with a find-first-set loop over the not-yet-suppressed bits (only kept
+//                 boxes cost an iteration), then all warps OR the kept rows' mask words into
+//                 the running suppression words `remv`.  keep[] and the count stay on the device.
+#include "common.cuh"
+#include "geom.cuh"
+#include "../../include/glenet_geom.h"
+
+namespace glenet {
+
+constexpr int NMS_THREADS = 256;
+constexpr int NMS_TILE = 64;
+constexpr int SWEEP_THREADS = 512;
+
+struct NmsSmem {
+    float rcx[NMS_TILE], rcy[NMS_TILE], rrad[NMS_TILE];
+    float ccx[NMS_TILE], ccy[NMS_TILE], crad[NMS_TILE];
+    float rpre[NMS_TILE * BP_STRIDE];
+    float cpre[NMS_TILE * BP_STRIDE];
+    float vx[MAX_POLY * NMS_THREADS], vy[MAX_POLY * NMS_THREADS], key[MAX_POLY * NMS_THREADS];
+    unsigned long long bits[NMS_TILE];
+    unsigned short queue[NMS_TILE * NMS_TILE];
+    unsigned char rflag[NMS_TILE], cflag[NMS_TILE];
+    int qcount;
+};
+
+// iou_normal (iou3d_nms_kernel.cu:314-325) as compiled in nms_normal_kernel: a = row box, b = column box,
+// Sa + Sb is contracted to fma(b.dx, b.dy, Sa).
+__device__ __forceinline__ float iou_normal_pair(const float* __restrict__ a, const float* __restrict__ b) {
+    const float left = fmaxf(__fmaf_rn(a[3], -0.5f, a[0]), __fmaf_rn(b[3], -0.5f, b[0]));
+    const float right = fminf(__fmaf_rn(a[3], 0.5f, a[0]), __fmaf_rn(b[3], 0.5f, b[0]));
+    const float top = fmaxf(__fmaf_rn(a[4], -0.5f, a[1]), __fmaf_rn(b[4], -0.5f, b[1]));
+    const float bottom = fminf(__fmaf_rn(a[4], 0.5f, a[1]), __fmaf_rn(b[4], 0.5f, b[1]));
+    const float width = fmaxf(__fsub_rn(right, left), 0.f), height = fmaxf(__fsub_rn(bottom, top), 0.f);
+    const float inter = __fmul_rn(width, height);
+    const float sa = __fmul_rn(a[3], a[4]);
+    const float den = fmaxf(__fsub_rn(__fmaf_rn(b[3], b[4], sa), inter), 1e-8f);
+    return __fdiv_rn(inter, den);
+}
+
+// linear index over the upper triangle (row-major, cb >= rb) -> (rb, cb)
+__device__ __forceinline__ void tri_decode(int t, int nblk, int& rb, int& cb) {
+    // rows before rb hold sum_{k<rb} (nblk - k) = rb*nblk - rb*(rb-1)/2 tiles
+    const float fn = (float)nblk + 0.5f;
+    int r = (int)(fn - sqrtf(fmaxf(fn * fn - 2.f * (float)t, 0.f)));
+    r = max(0, min(r, nblk - 1));
+    while (r > 0 && r * nblk - r * (r - 1) / 2 > t) --r;
+    while ((r + 1) * nblk - (r + 1) * r / 2 <= t) ++r;
+    rb = r;
+    cb = r + (t - (r * nblk - r * (r - 1) / 2));
+}
+
+template <bool NORMAL>
+__global__ void __launch_bounds__(NMS_THREADS)
+nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsigned long long* __restrict__ mask_all,
+                int col_blocks, int tiles_per_frame) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NmsSmem& sm = *reinterpret_cast<NmsSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int frame = blockIdx.x / tiles_per_frame;
+    const int t = blockIdx.x - frame * tiles_per_frame;
+    const float* boxes = boxes_all + (size_t)frame * n * 7;
+    unsigned long long* mask = mask_all + (size_t)frame * n * col_blocks;
+    int rb, cb;
+    tri_decode(t, col_blocks, rb, cb);
+    const int r0 = rb * NMS_TILE, c0 = cb * NMS_TILE;
+    const int tr = min(NMS_TILE, n - r0), tc = min(NMS_TILE, n - c0);
+
+    if (NORMAL) {
+        // cheap pair function: no culling or queueing, every thread evaluates its pairs directly
+        float* rraw = sm.rpre;   // reuse: 64 x 7 raw floats each
+        float* craw = sm.cpre;
+        for (int i = tid; i < tr * 7; i += NMS_THREADS) rraw[i] = boxes[(size_t)r0 * 7 + i];
+        for (int i = tid; i < tc * 7; i += NMS_THREADS) craw[i] = boxes[(size_t)c0 * 7 + i];
+        if (tid < NMS_TILE) sm.bits[tid] = 0ull;
+        __syncthreads();
+        // thread -> (row = tid / 4, 16 columns starting at (tid % 4) * 16)
+        const int r = tid >> 2, cs = (tid & 3) * 16;
+        unsigned long long w = 0ull;
+        if (r < tr) {
+            for (int c = cs; c < min(cs + 16, tc); ++c) {
+                if (rb == cb && c <= r) continue;
+                if (iou_normal_pair(rraw + r * 7, craw + c * 7) > thresh) w |= 1ull << c;
+            }
+        }
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        if ((tid & 3) == 0 && r < tr) mask[(size_t)(r0 + r) * col_blocks + cb] = w;
+        return;
+    }
+
+    for (int i = tid; i < tr + tc; i += NMS_THREADS) {
+        const bool is_row = i < tr;
+        const int k = is_row ? i : i - tr;
+        const float* box = boxes + (size_t)((is_row ? r0 : c0) + k) * 7;
+        const float cx = box[0], cy = box[1], rad = cull_radius(box);
+        if (is_row) { sm.rcx[k] = cx; sm.rcy[k] = cy; sm.rrad[k] = rad; sm.rflag[k] = 0; }
+        else        { sm.ccx[k] = cx; sm.ccy[k] = cy; sm.crad[k] = rad; sm.cflag[k] = 0; }
+    }
+    if (tid < NMS_TILE) sm.bits[tid] = 0ull;
+    if (tid == 0) sm.qcount = 0;
+    __syncthreads();
+
+    // cull pass over the 64 x 64 pairs (only j > i on the diagonal tile, iou3d_nms_kernel.cu:300-302)
+    const bool diag = rb == cb;
+#pragma unroll 4
+    for (int k = 0; k < NMS_TILE * NMS_TILE / NMS_THREADS; ++k) {
+        const int p = k * NMS_THREADS + tid;
+        const int r = p >> 6, c = p & 63;
+        bool heavy = false;
+        if (r < tr && c < tc && !(diag && c <= r)) {
+            const float ddx = sm.rcx[r] - sm.ccx[c], ddy = sm.rcy[r] - sm.ccy[c];
+            const float rr = sm.rrad[r] + sm.crad[c];
+            heavy = !(ddx * ddx + ddy * ddy > rr * rr);
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, heavy);
+        if (m) {
+            int qb = 0;
+            if (lane == 0) qb = atomicAdd(&sm.qcount, __popc(m));
+            qb = __shfl_sync(0xffffffffu, qb, 0);
+            if (heavy) {
+                sm.queue[qb + __popc(m & ((1u << lane) - 1))] = (unsigned short)p;
+                if (sm.rflag[r] == 0) sm.rflag[r] = 1;
+                if (sm.cflag[c] == 0) sm.cflag[c] = 1;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < tr + tc; i += NMS_THREADS) {
+        const bool is_row = i < tr;
+        const int k = is_row ? i : i - tr;
+        if ((is_row ? sm.rflag[k] : sm.cflag[k]) == 1) {
+            const float* box = boxes + (size_t)((is_row ? r0 : c0) + k) * 7;
+            box_prepare<true>(box, device_trig(box[6]), (is_row ? sm.rpre : sm.cpre) + k * BP_STRIDE);
+        }
+    }
+    __syncthreads();
+    const int nq = sm.qcount;
+    PolyScratch ps{sm.vx, sm.vy, sm.key, NMS_THREADS};
+    for (int q = tid; q < nq; q += NMS_THREADS) {
+        const int p = sm.queue[q];
+        const int r = p >> 6, c = p & 63;
+        const float* a = sm.rpre + r * BP_STRIDE;
+        const float* b = sm.cpre + c * BP_STRIDE;
+        const float ov = box_overlap<true>(a, b, ps, tid);
+        if (iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) > thresh) atomicOr(&sm.bits[r], 1ull << c);
+    }
+    __syncthreads();
+    if (tid < tr) mask[(size_t)(r0 + tid) * col_blocks + cb] = sm.bits[tid];
+}
+
+// Greedy sweep of iou3d_nms.cpp:116-132 on the device.  One CTA per frame.
+__global__ void __launch_bounds__(SWEEP_THREADS)
+nms_sweep_kernel(const unsigned long long* __restrict__ mask_all, int n, int col_blocks,
+                 long long* __restrict__ keep_all, int* __restrict__ num_keep_all) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* remv = reinterpret_cast<unsigned long long*>(smem_raw);   // [col_blocks]
+    __shared__ unsigned long long s_diag[NMS_TILE];
+    __shared__ int s_rows[NMS_TILE];
+    __shared__ int s_nrows;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.x;
+    const unsigned long long* mask = mask_all + (size_t)frame * n * col_blocks;
+    long long* keep = keep_all + (size_t)frame * n;
+
+    for (int j = tid; j < col_blocks; j += SWEEP_THREADS) remv[j] = 0ull;
+    int num_keep = 0;   // tracked by warp 0
+    __syncthreads();
+
+    for (int c = 0; c < col_blocks; ++c) {
+        const int rows = min(NMS_TILE, n - c * NMS_TILE);
+        if (warp == 0) {
+            // diagonal tile: rows 64c..64c+63, column word c
+            for (int i = lane; i < NMS_TILE; i += 32)
+                s_diag[i] = (i < rows) ? mask[(size_t)(c * NMS_TILE + i) * col_blocks + c] : 0ull;
+            __syncwarp();
+            const unsigned long long valid = (rows == NMS_TILE) ? ~0ull : ((1ull << rows) - 1ull);
+            unsigned long long w = remv[c];
+            unsigned long long cand = ~w & valid, kept = 0ull;
+            while (cand) {
+                const int i = __ffsll((long long)cand) - 1;
+                kept |= 1ull << i;
+                w |= s_diag[i];
+                cand = ~w & valid & ~((2ull << i) - 1ull);
+            }
+            // emit kept indices in ascending order
+            for (int i = lane; i < NMS_TILE; i += 32) {
+                if ((kept >> i) & 1ull) {
+                    const int pos = __popcll(kept & ((1ull << i) - 1ull));
+                    keep[num_keep + pos] = (long long)(c * NMS_TILE + i);
+                    s_rows[pos] = c * NMS_TILE + i;
+                }
+            }
+            num_keep += __popcll(kept);
+            if (lane == 0) s_nrows = __popcll(kept);
+        }
+        __syncthreads();
+        // propagate the kept rows of this chunk to all later suppression words
+        const int nrem = col_blocks - (c + 1);
+        const int nrows = s_nrows;
+        const int items = nrows * nrem;
+        for (int it = tid; it < items; it += SWEEP_THREADS) {
+            const int ki = it / nrem, j = c + 1 + (it - ki * nrem);
+            const unsigned long long m = mask[(size_t)s_rows[ki] * col_blocks + j];
+            if (m) atomicOr(&remv[j], m);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) num_keep_all[frame] = num_keep;
+}
+
+static int launch_nms(bool normal, const float* boxes, int frames, int n, float thresh, int64_t* keep,
+                      int32_t* num_keep, void* ws, size_t ws_bytes, cudaStream_t stream, const char* what) {
+    if (frames < 0 || n < 0) return fail(GLENET_EINVAL, "%s: negative size", what);
+    if (frames == 0) return GLENET_OK;
+    if (!num_keep) return fail(GLENET_EINVAL, "%s: null num_keep", what);
+    if (n == 0) {
+        cudaError_t e = cudaMemsetAsync(num_keep, 0, sizeof(int32_t) * frames, stream);
+        return e == cudaSuccess ? GLENET_OK : fail(-(int)e, "%s: memset failed", what);
+    }
+    if (!boxes || !keep) return fail(GLENET_EINVAL, "%s: null pointer", what);
+    if (ws_bytes < glenet_nms_workspace_bytes(frames, n) || !ws) return fail(GLENET_EWORKSPACE, "%s: workspace too small", what);
+    if ((uintptr_t)ws & 15) return fail(GLENET_EALIGN, "%s: workspace must be 16-byte aligned", what);
+    const int col_blocks = (n + NMS_TILE - 1) / NMS_TILE;
+    const long tiles = (long)col_blocks * (col_blocks + 1) / 2;
+    if (tiles * frames > 0x7fffffffL) return fail(GLENET_EINVAL, "%s: too many tiles", what);
+    unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws);
+    static bool attr_done = false;
+    if (!attr_done) {
+        int rc = set_smem(nms_mask_kernel<false>, sizeof(NmsSmem), what);
+        if (rc) return rc;
+        rc = set_smem(nms_mask_kernel<true>, sizeof(NmsSmem), what);
+        if (rc) return rc;
+        attr_done = true;
+    }
+    const unsigned grid = (unsigned)(tiles * frames);
+    if (normal)
+        nms_mask_kernel<true><<<grid, NMS_THREADS, sizeof(NmsSmem), stream>>>(boxes, n, thresh, mask, col_blocks, (int)tiles);
+    else
+        nms_mask_kernel<false><<<grid, NMS_THREADS, sizeof(NmsSmem), stream>>>(boxes, n, thresh, mask, col_blocks, (int)tiles);
+    int rc = check_launch(what);
+    if (rc) return rc;
+    const size_t sweep_smem = sizeof(unsigned long long) * col_blocks;
+    if (sweep_smem > 200 * 1024) return fail(GLENET_EINVAL, "%s: n too large for the on-chip suppression words", what);
+    if (sweep_smem > 40 * 1024) {
+        rc = set_smem(nms_sweep_kernel, sweep_smem, what);
+        if (rc) return rc;
+    }
+    nms_sweep_kernel<<<frames, SWEEP_THREADS, sweep_smem, stream>>>(mask, n, col_blocks, reinterpret_cast<long long*>(keep), num_keep);
+    return check_launch(what);
+}
+
+}  // namespace glenet
+
+using namespace glenet;
+
+extern "C" {
+
+size_t glenet_nms_workspace_bytes(int frames, int n) {
+    if (frames <= 0 || n <= 0) return 16;
+    const size_t col_blocks = ((size_t)n + NMS_TILE - 1) / NMS_TILE;
+    return align_up((size_t)frames * n * col_blocks * sizeof(unsigned long long), 16);
+}
+
+int glenet_nms_gpu(const float* boxes, int frames, int n, float thresh, int64_t* keep, int32_t* num_keep, void* ws,
+                   size_t ws_bytes, glenet_stream_t s) {
+    return launch_nms(false, boxes, frames, n, thresh, keep, num_keep, ws, ws_bytes, (cudaStream_t)s, "glenet_nms_gpu");
+}
+int glenet_nms_normal_gpu(const float* boxes, int frames, int n, float thresh, int64_t* keep, int32_t* num_keep,
+                          void* ws, size_t ws_bytes, glenet_stream_t s) {
+    return launch_nms(true, boxes, frames, n, thresh, keep, num_keep, ws, ws_bytes, (cudaStream_t)s, "glenet_nms_normal_gpu");
+}
+
+}  // extern "C"

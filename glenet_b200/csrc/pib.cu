@@ -1,0 +1,381 @@
+// points_in_boxes for sm_100a.
+//
+// Replaces points_in_boxes_kernel (+ launcher) of
+// pcdet/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu:16-36,313-359 and, in the CPU
+// dialect, points_in_boxes_cpu of pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:121-168.
+//
+// The reference walks all N boxes for every point and re-evaluates cosf/sinf per
+// (point, box).  Exhaustively that is ~2000 instructions per point for N = 200 -- compute
+// bound at < 10 % of what HBM can stream (16 B / point).  Here:
+//
+//   build kernel (1 CTA / frame): per-box record {cx, cy, cz, cos(-h), sin(-h), tx, ty, tz}
+//       with the reference's FP64 comparisons folded into directed-rounded FP32 thresholds
+//       (exactly equivalent, see box_record()), plus a G x G uniform grid over the frame's
+//       boxes in CSR form: cell -> list of boxes whose (padded) footprint touches the cell.
+//   query kernel: points stream through coalesced; a point looks up its cell in a
+//       shared-memory copy of the CSR offsets and runs the exact reference predicate only
+//       against that cell's candidates, keeping the minimum index (= first hit of the
+//       reference's ascending loop with `break`).
+// Frames whose boxes cannot be binned (non-finite extents, list overflow) fall back, on the
+// device and per frame, to the exhaustive loop with the same predicate -- never to the host.
+#include "common.cuh"
+#include "../../include/glenet_geom.h"
+#include <float.h>
+#include <math.h>
+
+namespace glenet {
+
+constexpr int PIB_G = 64;                       // grid cells per axis
+constexpr int PIB_CELLS = PIB_G * PIB_G;
+constexpr int PIB_THREADS = 256;
+constexpr int PIB_PTS_PER_CTA = 8192;
+constexpr int PIB_BUILD_THREADS = 512;
+constexpr int PIB_SMEM_BOXES = 512;             // box records cached in shared memory by the query kernel
+
+struct PibFrame {          // 32 B header per frame
+    float gx0, gy0, inv_x, inv_y;
+    int exhaustive;        // 1 => query kernel loops over all boxes
+    int list_len;
+    int pad0, pad1;
+};
+
+__host__ __device__ inline size_t pib_list_cap(int n) { return (size_t)32 * n + 2 * PIB_CELLS; }
+
+struct PibWorkspace {
+    PibFrame* frames;      // [B]
+    float* rec;            // [B][N][8]
+    unsigned int* start;   // [B][PIB_CELLS + 1]
+    unsigned int* list;    // [B][cap]
+    size_t cap;
+    size_t bytes;
+};
+
+__host__ __device__ inline PibWorkspace pib_layout(void* base, int B, int N) {
+    PibWorkspace w;
+    size_t off = 0;
+    unsigned char* p = (unsigned char*)base;
+    w.frames = (PibFrame*)(p + off); off += ((size_t)B * sizeof(PibFrame) + 15) / 16 * 16;
+    w.rec = (float*)(p + off);       off += ((size_t)B * N * 8 * sizeof(float) + 15) / 16 * 16;
+    w.start = (unsigned int*)(p + off); off += ((size_t)B * (PIB_CELLS + 1) * sizeof(unsigned int) + 15) / 16 * 16;
+    w.cap = pib_list_cap(N);
+    w.list = (unsigned int*)(p + off);  off += ((size_t)B * w.cap * sizeof(unsigned int) + 15) / 16 * 16;
+    w.bytes = off;
+    return w;
+}
+
+// The reference predicate (check_pt_in_box3d, roiaware_pool3d_kernel.cu:23-36), as compiled:
+//   skip   if (double)|z - cz| >  (double)dz * 0.5
+//   inside if (double)|lx|     <  fma((double)dx, 0.5, (double)MARGIN)   (same for y)
+// For a float a and a double t:  a > t  <=>  a > round_down_to_float(t)
+//                                a < t  <=>  a < round_up_to_float(t)
+// so the three thresholds are rounded once per box and the per-point test is pure FP32,
+// bit-identical to the FP64 comparisons (NaN thresholds keep the same truth values).
+template <bool CPU_DIALECT>
+__device__ __forceinline__ void box_thresholds(float dx, float dy, float dz, float& tx, float& ty, float& tz) {
+    const double margin = CPU_DIALECT ? (double)1e-2f : (double)1e-5f;   // `const float MARGIN` promoted
+    tx = __double2float_ru(fma((double)dx, 0.5, margin));
+    ty = __double2float_ru(fma((double)dy, 0.5, margin));
+    tz = __double2float_rd((double)dz * 0.5);
+}
+
+// lidar_to_local_coords (:16-20) as compiled for the GPU: lx = fma(sx, c, -(sy*s)), ly = fma(sy, c, sx*s)
+__device__ __forceinline__ bool pt_in_box_gpu(float x, float y, float z, const float* __restrict__ r) {
+    if (fabsf(__fsub_rn(z, r[2])) > r[7]) return false;
+    const float sx = __fsub_rn(x, r[0]), sy = __fsub_rn(y, r[1]);
+    const float c = r[3], s = r[4];
+    const float lx = __fmaf_rn(sx, c, -__fmul_rn(sy, s));
+    const float ly = __fmaf_rn(sy, c, __fmul_rn(sx, s));
+    return (r[5] > fabsf(lx)) & (r[6] > fabsf(ly));
+}
+
+__global__ void __launch_bounds__(PIB_BUILD_THREADS)
+pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
+    __shared__ unsigned int cnt[PIB_CELLS];
+    __shared__ unsigned int scan_tmp[PIB_BUILD_THREADS];
+    __shared__ float red[4][PIB_BUILD_THREADS / 32];
+    __shared__ float s_bounds[4];
+    __shared__ int s_bad;
+    __shared__ unsigned int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.x;
+    const float* boxes = boxes_all + (size_t)f * N * 7;
+    float* rec = ws.rec + (size_t)f * N * 8;
+    unsigned int* start = ws.start + (size_t)f * (PIB_CELLS + 1);
+    unsigned int* list = ws.list + (size_t)f * ws.cap;
+
+    for (int i = tid; i < PIB_CELLS; i += PIB_BUILD_THREADS) cnt[i] = 0;
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+
+    // pass 1: records + frame bounds
+    float bx0 = FLT_MAX, by0 = FLT_MAX, bx1 = -FLT_MAX, by1 = -FLT_MAX;
+    bool bad = false;
+    for (int k = tid; k < N; k += PIB_BUILD_THREADS) {
+        const float* b = boxes + (size_t)k * 7;
+        const float cx = b[0], cy = b[1], cz = b[2], dx = b[3], dy = b[4], dz = b[5], rz = b[6];
+        const float c = cosf(-rz), s = sinf(-rz);
+        float tx, ty, tz;
+        box_thresholds<false>(dx, dy, dz, tx, ty, tz);
+        float* r = rec + (size_t)k * 8;
+        r[0] = cx; r[1] = cy; r[2] = cz; r[3] = c; r[4] = s; r[5] = tx; r[6] = ty; r[7] = tz;
+        // footprint: can this box ever contain a point, and where?
+        const bool never = !(tx > 0.f) || !(ty > 0.f) || (c != c) || (s != s) || !(fabsf(cx) <= FLT_MAX) || !(fabsf(cy) <= FLT_MAX);
+        if (never) continue;
+        const float hx = fabsf(c) * tx + fabsf(s) * ty, hy = fabsf(s) * tx + fabsf(c) * ty;
+        const float pad = 2e-3f + 1e-6f * (fabsf(cx) + fabsf(cy) + hx + hy);
+        const float x0 = cx - hx - pad, x1 = cx + hx + pad, y0 = cy - hy - pad, y1 = cy + hy + pad;
+        if (!(fabsf(x0) <= FLT_MAX) || !(fabsf(x1) <= FLT_MAX) || !(fabsf(y0) <= FLT_MAX) || !(fabsf(y1) <= FLT_MAX)) { bad = true; continue; }
+        bx0 = fminf(bx0, x0); bx1 = fmaxf(bx1, x1); by0 = fminf(by0, y0); by1 = fmaxf(by1, y1);
+    }
+    if (bad) s_bad = 1;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
+        by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+        bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+        by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+    }
+    if (lane == 0) { red[0][warp] = bx0; red[1][warp] = by0; red[2][warp] = bx1; red[3][warp] = by1; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < PIB_BUILD_THREADS / 32; ++w) {
+            bx0 = fminf(bx0, red[0][w]); by0 = fminf(by0, red[1][w]);
+            bx1 = fmaxf(bx1, red[2][w]); by1 = fmaxf(by1, red[3][w]);
+        }
+        s_bounds[0] = bx0; s_bounds[1] = by0; s_bounds[2] = bx1; s_bounds[3] = by1;
+    }
+    __syncthreads();
+    bx0 = s_bounds[0]; by0 = s_bounds[1]; bx1 = s_bounds[2]; by1 = s_bounds[3];
+    const bool empty = !(bx1 >= bx0);   // no box can contain anything
+    float inv_x = 0.f, inv_y = 0.f;
+    bool exhaustive = s_bad != 0;
+    if (!empty) {
+        const float ex = bx1 - bx0, ey = by1 - by0;
+        inv_x = ((float)PIB_G - 0.01f) / ex;
+        inv_y = ((float)PIB_G - 0.01f) / ey;
+        if (!(inv_x > 0.f) || !(inv_y > 0.f) || !(inv_x <= FLT_MAX) || !(inv_y <= FLT_MAX)) exhaustive = true;
+    }
+    if (N > 65535) exhaustive = true;
+
+    // pass 2: count, pass 3: fill (same traversal)
+    unsigned int total = 0;
+    if (!exhaustive && !empty) {
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int k = tid; k < N; k += PIB_BUILD_THREADS) {
+                const float* r = rec + (size_t)k * 8;
+                const float cx = r[0], cy = r[1], c = r[3], s = r[4], tx = r[5], ty = r[6];
+                const bool never = !(tx > 0.f) || !(ty > 0.f) || (c != c) || (s != s) || !(fabsf(cx) <= FLT_MAX) || !(fabsf(cy) <= FLT_MAX);
+                if (never) continue;
+                const float hx = fabsf(c) * tx + fabsf(s) * ty, hy = fabsf(s) * tx + fabsf(c) * ty;
+                const float pad = 2e-3f + 1e-6f * (fabsf(cx) + fabsf(cy) + hx + hy);
+                const float x0 = cx - hx - pad, x1 = cx + hx + pad, y0 = cy - hy - pad, y1 = cy + hy + pad;
+                // identical mapping to the query kernel => monotone => every x in [x0, x1] lands in [ix0, ix1]
+                const int ix0 = max(0, min(PIB_G - 1, (int)floorf((x0 - bx0) * inv_x)));
+                const int ix1 = max(0, min(PIB_G - 1, (int)floorf((x1 - bx0) * inv_x)));
+                const int iy0 = max(0, min(PIB_G - 1, (int)floorf((y0 - by0) * inv_y)));
+                const int iy1 = max(0, min(PIB_G - 1, (int)floorf((y1 - by0) * inv_y)));
+                // cell size in box-frame terms, for a separating-axis rejection of corner cells
+                const float cwx = 1.f / inv_x, cwy = 1.f / inv_y;
+                const float rx_ext = 0.5f * (fabsf(c) * cwx + fabsf(s) * cwy), ry_ext = 0.5f * (fabsf(s) * cwx + fabsf(c) * cwy);
+                for (int iy = iy0; iy <= iy1; ++iy) {
+                    for (int ix = ix0; ix <= ix1; ++ix) {
+                        // cell centre in the box frame; reject when the cell's projection misses the padded box
+                        const float mx = bx0 + ((float)ix + 0.5f) * cwx - cx, my = by0 + ((float)iy + 0.5f) * cwy - cy;
+                        const float lx = mx * c - my * s, ly = mx * s + my * c;
+                        const float slack = pad + 1e-3f * (cwx + cwy);
+                        if (fabsf(lx) > tx + rx_ext + slack || fabsf(ly) > ty + ry_ext + slack) continue;
+                        const int cell = iy * PIB_G + ix;
+                        if (pass == 0) atomicAdd(&cnt[cell], 1u);
+                        else {
+                            const unsigned int pos = atomicAdd(&cnt[cell], 1u);
+                            list[pos] = (unsigned int)k;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (pass == 0) {
+                // exclusive scan of cnt[PIB_CELLS] -> start[], cnt becomes the fill cursor
+                constexpr int PER = PIB_CELLS / PIB_BUILD_THREADS;
+                unsigned int local[PER], sum = 0;
+#pragma unroll
+                for (int i = 0; i < PER; ++i) { local[i] = cnt[tid * PER + i]; sum += local[i]; }
+                scan_tmp[tid] = sum;
+                __syncthreads();
+                for (int o = 1; o < PIB_BUILD_THREADS; o <<= 1) {
+                    unsigned int v = (tid >= o) ? scan_tmp[tid - o] : 0u;
+                    __syncthreads();
+                    scan_tmp[tid] += v;
+                    __syncthreads();
+                }
+                unsigned int run = scan_tmp[tid] - sum;
+                if (tid == PIB_BUILD_THREADS - 1) s_total = scan_tmp[tid];
+#pragma unroll
+                for (int i = 0; i < PER; ++i) {
+                    start[tid * PER + i] = run;
+                    cnt[tid * PER + i] = run;
+                    run += local[i];
+                }
+                __syncthreads();
+                total = s_total;
+                if (tid == 0) start[PIB_CELLS] = total;
+                if (total > ws.cap) { exhaustive = true; break; }   // uniform
+            }
+        }
+    }
+    if (tid == 0) {
+        PibFrame h;
+        h.gx0 = bx0; h.gy0 = by0; h.inv_x = inv_x; h.inv_y = inv_y;
+        h.exhaustive = exhaustive ? 1 : 0;
+        h.list_len = empty ? -1 : (int)total;   // -1: nothing can match in this frame
+        h.pad0 = h.pad1 = 0;
+        ws.frames[f] = h;
+    }
+}
+
+__global__ void __launch_bounds__(PIB_THREADS)
+pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace ws, int* __restrict__ out_all,
+                 int chunks_per_frame) {
+    __shared__ unsigned int s_start[PIB_CELLS + 1];
+    __shared__ __align__(16) float s_rec[PIB_SMEM_BOXES * 8];
+    const int tid = threadIdx.x;
+    const int f = blockIdx.x / chunks_per_frame;
+    const int chunk = blockIdx.x - f * chunks_per_frame;
+    const PibFrame h = ws.frames[f];
+    const float* rec_g = ws.rec + (size_t)f * N * 8;
+    const unsigned int* list = ws.list + (size_t)f * ws.cap;
+    const float* pts = pts_all + (size_t)f * M * 3;
+    int* out = out_all + (size_t)f * M;
+    const int p_begin = chunk * PIB_PTS_PER_CTA;
+    const int p_end = min(M, p_begin + PIB_PTS_PER_CTA);
+
+    if (h.list_len < 0) {   // no box of this frame can contain a point
+        for (int p = p_begin + tid; p < p_end; p += PIB_THREADS) out[p] = -1;
+        return;
+    }
+    const bool rec_in_smem = N <= PIB_SMEM_BOXES;
+    if (rec_in_smem) {
+        const float4* src = reinterpret_cast<const float4*>(rec_g);
+        float4* dst = reinterpret_cast<float4*>(s_rec);
+        for (int i = tid; i < N * 2; i += PIB_THREADS) dst[i] = src[i];
+    }
+    const float* rec = rec_in_smem ? s_rec : rec_g;
+
+    if (h.exhaustive) {
+        __syncthreads();
+        for (int p = p_begin + tid; p < p_end; p += PIB_THREADS) {
+            const float x = pts[(size_t)p * 3], y = pts[(size_t)p * 3 + 1], z = pts[(size_t)p * 3 + 2];
+            int res = -1;
+            for (int k = 0; k < N; ++k) {
+                if (pt_in_box_gpu(x, y, z, rec + (size_t)k * 8)) { res = k; break; }
+            }
+            out[p] = res;
+        }
+        return;
+    }
+
+    {
+        const unsigned int* st = ws.start + (size_t)f * (PIB_CELLS + 1);
+        for (int i = tid; i < PIB_CELLS + 1; i += PIB_THREADS) s_start[i] = st[i];
+    }
+    __syncthreads();
+
+    for (int p = p_begin + tid; p < p_end; p += PIB_THREADS) {
+        const float x = pts[(size_t)p * 3], y = pts[(size_t)p * 3 + 1], z = pts[(size_t)p * 3 + 2];
+        const float fx = (x - h.gx0) * h.inv_x, fy = (y - h.gy0) * h.inv_y;
+        int res = 0x7fffffff;
+        if (fx >= 0.f && fx < (float)PIB_G && fy >= 0.f && fy < (float)PIB_G) {
+            const int cell = (int)fy * PIB_G + (int)fx;
+            const unsigned int s = s_start[cell], e = s_start[cell + 1];
+            for (unsigned int i = s; i < e; ++i) {
+                const int k = (int)list[i];
+                if (k < res && pt_in_box_gpu(x, y, z, rec + (size_t)k * 8)) res = k;
+            }
+        }
+        out[p] = (res == 0x7fffffff) ? -1 : res;
+    }
+}
+
+// points_in_boxes_cpu semantics (roiaware_pool3d.cpp:128-165): out[i][j] = point j in box i, MARGIN 1e-2,
+// host libm cos/sin, no FMA:  lx = sx*c + sy*(-s) ; ly = sx*s + sy*c  (each product rounded).
+__global__ void __launch_bounds__(256)
+pib_mask_cpu_dialect_kernel(const float* __restrict__ boxes, const float* __restrict__ trig, int N,
+                            const float* __restrict__ pts, int M, int* __restrict__ out) {
+    __shared__ float s_rec[8];
+    const int i = blockIdx.y;
+    if (threadIdx.x == 0) {
+        const float* b = boxes + (size_t)i * 7;
+        float tx, ty, tz;
+        box_thresholds<true>(b[3], b[4], b[5], tx, ty, tz);
+        s_rec[0] = b[0]; s_rec[1] = b[1]; s_rec[2] = b[2];
+        s_rec[3] = trig[2 * i]; s_rec[4] = trig[2 * i + 1];
+        s_rec[5] = tx; s_rec[6] = ty; s_rec[7] = tz;
+    }
+    __syncthreads();
+    const float cx = s_rec[0], cy = s_rec[1], cz = s_rec[2], c = s_rec[3], s = s_rec[4];
+    const float tx = s_rec[5], ty = s_rec[6], tz = s_rec[7];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
+        const float x = pts[(size_t)j * 3], y = pts[(size_t)j * 3 + 1], z = pts[(size_t)j * 3 + 2];
+        int in = 0;
+        if (!(fabsf(__fsub_rn(z, cz)) > tz)) {
+            const float sx = __fsub_rn(x, cx), sy = __fsub_rn(y, cy);
+            const float lx = __fsub_rn(__fmul_rn(sx, c), __fmul_rn(sy, s));
+            const float ly = __fadd_rn(__fmul_rn(sx, s), __fmul_rn(sy, c));
+            in = (tx > fabsf(lx)) & (ty > fabsf(ly));
+        }
+        out[(size_t)i * M + j] = in;
+    }
+}
+
+}  // namespace glenet
+
+using namespace glenet;
+
+extern "C" {
+
+size_t glenet_points_in_boxes_workspace_bytes(int batch, int boxes_num) {
+    if (batch <= 0 || boxes_num <= 0) return 16;
+    return pib_layout(nullptr, batch, boxes_num).bytes;
+}
+
+int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int N, int M, int32_t* out, void* ws,
+                               size_t ws_bytes, glenet_stream_t s) {
+    const char* what = "glenet_points_in_boxes_gpu";
+    cudaStream_t st = (cudaStream_t)s;
+    if (B < 0 || N < 0 || M < 0) return fail(GLENET_EINVAL, "%s: negative size", what);
+    if (B == 0 || M == 0) return GLENET_OK;
+    if (!pts || !out) return fail(GLENET_EINVAL, "%s: null pointer", what);
+    if (N == 0) {   // the reference's wrapper pre-fills -1 and the kernel loop never runs
+        cudaError_t e = cudaMemsetAsync(out, 0xff, sizeof(int32_t) * (size_t)B * M, st);
+        return e == cudaSuccess ? GLENET_OK : fail(-(int)e, "%s: memset failed", what);
+    }
+    if (!boxes) return fail(GLENET_EINVAL, "%s: null pointer", what);
+    if (!ws || ws_bytes < glenet_points_in_boxes_workspace_bytes(B, N)) return fail(GLENET_EWORKSPACE, "%s: workspace too small", what);
+    if ((uintptr_t)ws & 15) return fail(GLENET_EALIGN, "%s: workspace must be 16-byte aligned", what);
+    PibWorkspace w = pib_layout(ws, B, N);
+    pib_build_kernel<<<B, PIB_BUILD_THREADS, 0, st>>>(boxes, N, w);
+    int rc = check_launch(what);
+    if (rc) return rc;
+    const int chunks = (M + PIB_PTS_PER_CTA - 1) / PIB_PTS_PER_CTA;
+    if ((long)chunks * B > 0x7fffffffL) return fail(GLENET_EINVAL, "%s: too many chunks", what);
+    pib_query_kernel<<<(unsigned)(chunks * B), PIB_THREADS, 0, st>>>(pts, N, M, w, out, chunks);
+    return check_launch(what);
+}
+
+int glenet_points_in_boxes_cpu_dialect(const float* boxes, const float* trig, int N, const float* pts, int M,
+                                       int32_t* out, glenet_stream_t s) {
+    const char* what = "glenet_points_in_boxes_cpu_dialect";
+    if (N < 0 || M < 0) return fail(GLENET_EINVAL, "%s: negative size", what);
+    if (N == 0 || M == 0) return GLENET_OK;
+    if (!boxes || !trig || !pts || !out) return fail(GLENET_EINVAL, "%s: null pointer", what);
+    if (N > 65535) return fail(GLENET_EINVAL, "%s: more than 65535 boxes", what);
+    const int bx = (M + 255) / 256;
+    dim3 grid((unsigned)(bx < 1024 ? bx : 1024), (unsigned)N);
+    pib_mask_cpu_dialect_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(boxes, trig, N, pts, M, out);
+    return check_launch(what);
+}
+
+int glenet_abi_version(void) { return 1; }
+const char* glenet_last_error(void) { return last_error_buf(); }
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+"""Drop-in for ``pcdet.ops.iou3d_nms.iou3d_nms_utils`` backed by ``libglenet_geom.so``.
+
+Same function names, argument meaning, return types and assertion behaviour as
+``pcdet/ops/iou3d_nms/iou3d_nms_utils.py`` (reference lines cited per function).  Every
+function executes hand-written sm_100a kernels through the C ABI of
+``include/glenet_geom.h``; there is no CPU or eager fallback.
+
+Differences that are deliberate and invisible to the reference's callers:
+
+* outputs are allocated on the *inputs'* device and work is enqueued on torch's current
+  stream of that device (the reference always uses the current device and the legacy
+  default stream, ``iou3d_nms_utils.py:81,106`` / ``iou3d_nms_kernel.cu:383``);
+* ``nms_gpu`` keeps the suppression mask and the greedy sweep on the device; the only
+  host synchronisation is the read of the keep count that the variable-length return
+  value requires (the reference does cudaMalloc/cudaFree, a blocking D2H copy of the whole
+  mask and an H2D copy of ``keep``, ``iou3d_nms.cpp:103-114`` / ``iou3d_nms_utils.py:195-197``);
+* N == 0 returns empty results instead of printing a CUDA launch error.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = [
+    "boxes_bev_iou_cpu", "boxes_iou_bev", "boxes_iou3d_gpu", "boxes_overlap_bev",
+    "boxes_iou_bev_aligned", "boxes_iou3d_aligned",
+    "nms_gpu", "nms_normal_gpu", "nms_gpu_batch", "nms_normal_gpu_batch",
+]
+
+
+# ---------------------------------------------------------------- helpers
+def check_numpy_to_torch(x):
+    """pcdet/utils/common_utils.py:15-18."""
+    if isinstance(x, np.ndarray):
+        return torch.from_numpy(x).float(), True
+    return x, False
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _check_cuda_f32(t: torch.Tensor, name: str) -> None:
+    # the reference's CHECK_INPUT exits the process on a CPU tensor (iou3d_nms.cpp:14-26) and
+    # .data<float>() throws on another dtype; raise instead
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+
+
+def _pairwise(fn_name: str, boxes_a: torch.Tensor, boxes_b: torch.Tensor) -> torch.Tensor:
+    _check_cuda_f32(boxes_a, "boxes_a")
+    _check_cuda_f32(boxes_b, "boxes_b")
+    if boxes_a.device != boxes_b.device:
+        raise RuntimeError("boxes_a and boxes_b must be on the same device")
+    a = boxes_a.contiguous()
+    b = boxes_b.contiguous()
+    na, nb = a.shape[0], b.shape[0]
+    out = torch.empty((na, nb), dtype=torch.float32, device=a.device)
+    if na and nb:
+        lib = _lib.load()
+        with torch.cuda.device(a.device):
+            rc = getattr(lib, fn_name)(a.data_ptr(), na, b.data_ptr(), nb, out.data_ptr(), _stream(a.device))
+        _lib.check(rc, fn_name)
+    return out
+
+
+# ---------------------------------------------------------------- IoU
+def boxes_bev_iou_cpu(boxes_a, boxes_b):
+    """
+    Args:
+        boxes_a: (N, 7) [x, y, z, dx, dy, dz, heading]
+        boxes_b: (M, 7) [x, y, z, dx, dy, dz, heading]
+
+    Returns:
+        ans_iou: (N, M)
+
+    Reference: iou3d_nms_utils.py:52-68 -> boxes_iou_bev_cpu (iou3d_cpu.cpp:232-252), a
+    single-threaded host loop.  Same signature (CPU tensors or numpy in, same kind out; the
+    numpy flag follows ``boxes_b`` as in the reference), but the N x M clipping runs on the
+    GPU in the CPU dialect: host-libm trig per box, no FMA contraction.
+    """
+    boxes_a, is_numpy = check_numpy_to_torch(boxes_a)
+    boxes_b, is_numpy = check_numpy_to_torch(boxes_b)
+    assert not (boxes_a.is_cuda or boxes_b.is_cuda), 'Only support CPU tensors'
+    assert boxes_a.shape[1] == 7 and boxes_b.shape[1] == 7
+    if boxes_a.dtype != torch.float32 or boxes_b.dtype != torch.float32:
+        raise RuntimeError("boxes must be float32")   # reference: .data<float>() throws
+    a = boxes_a.contiguous()
+    b = boxes_b.contiguous()
+    na, nb = a.shape[0], b.shape[0]
+    ans_iou = boxes_a.new_zeros(torch.Size((na, nb)))
+    if na and nb:
+        lib = _lib.load()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        # one host buffer: [boxes_a | boxes_b | trig_a | trig_b] -> one H2D copy
+        host = torch.empty(na * 7 + nb * 7 + na * 4 + nb * 4, dtype=torch.float32).pin_memory()
+        o_b, o_ta, o_tb = na * 7, na * 7 + nb * 7, na * 7 + nb * 7 + na * 4
+        host[:o_b].copy_(a.view(-1))
+        host[o_b:o_ta].copy_(b.view(-1))
+        base = host.data_ptr()
+        lib.glenet_host_trig4(a.data_ptr(), na, base + 4 * o_ta)
+        lib.glenet_host_trig4(b.data_ptr(), nb, base + 4 * o_tb)
+        d = host.to(dev, non_blocking=True)
+        out = torch.empty((na, nb), dtype=torch.float32, device=dev)
+        p = d.data_ptr()
+        with torch.cuda.device(dev):
+            rc = lib.glenet_boxes_iou_bev_cpu_dialect(p, p + 4 * o_ta, na, p + 4 * o_b, p + 4 * o_tb, nb,
+                                                      out.data_ptr(), _stream(dev))
+        _lib.check(rc, "glenet_boxes_iou_bev_cpu_dialect")
+        ans_iou.copy_(out)   # D2H, synchronising
+    return ans_iou.numpy() if is_numpy else ans_iou
+
+
+def boxes_iou_bev(boxes_a, boxes_b):
+    """
+    Args:
+        boxes_a: (N, 7) [x, y, z, dx, dy, dz, heading]
+        boxes_b: (M, 7) [x, y, z, dx, dy, dz, heading]
+
+    Returns:
+        ans_iou: (N, M)
+
+    Reference: iou3d_nms_utils.py:71-85 -> boxes_iou_bev_gpu (iou3d_nms.cpp:70-88).
+    """
+    assert boxes_a.shape[1] == boxes_b.shape[1] == 7
+    return _pairwise("glenet_boxes_iou_bev_gpu", boxes_a, boxes_b)
+
+
+def boxes_overlap_bev(boxes_a, boxes_b):
+    """BEV overlap area (N, M): the native call inside the reference's boxes_iou3d_gpu
+    (iou3d_nms_utils.py:106-107 -> boxes_overlap_bev_gpu, iou3d_nms.cpp:49-68)."""
+    assert boxes_a.shape[1] == boxes_b.shape[1] == 7
+    return _pairwise("glenet_boxes_overlap_bev_gpu", boxes_a, boxes_b)
+
+
+def boxes_iou3d_gpu(boxes_a, boxes_b):
+    """
+    Args:
+        boxes_a: (N, 7) [x, y, z, dx, dy, dz, heading]
+        boxes_b: (M, 7) [x, y, z, dx, dy, dz, heading]
+
+    Returns:
+        ans_iou: (N, M)
+
+    Reference: iou3d_nms_utils.py:88-121 (one custom kernel + ~10 torch elementwise kernels,
+    each separately rounded).  Here: one fused kernel with the same rounding steps.
+    """
+    assert boxes_a.shape[1] == boxes_b.shape[1] == 7
+    return _pairwise("glenet_boxes_iou3d_gpu", boxes_a, boxes_b)
+
+
+def _aligned(mode: int, boxes_a: torch.Tensor, boxes_b: torch.Tensor, group: int) -> torch.Tensor:
+    assert boxes_a.shape[1] == boxes_b.shape[1] == 7
+    _check_cuda_f32(boxes_a, "boxes_a")
+    _check_cuda_f32(boxes_b, "boxes_b")
+    a, b = boxes_a.contiguous(), boxes_b.contiguous()
+    na = a.shape[0]
+    assert group >= 1 and b.shape[0] * group >= na, "boxes_b must hold ceil(N / group) rows"
+    out = torch.empty((na,), dtype=torch.float32, device=a.device)
+    if na:
+        lib = _lib.load()
+        with torch.cuda.device(a.device):
+            rc = lib.glenet_boxes_iou_aligned_gpu(mode, a.data_ptr(), na, b.data_ptr(), group, out.data_ptr(), _stream(a.device))
+        _lib.check(rc, "glenet_boxes_iou_aligned_gpu")
+    return out
+
+
+def boxes_iou_bev_aligned(boxes_a, boxes_b, group=1):
+    """out[i] = BEV IoU(boxes_a[i], boxes_b[i // group]).  Additive API: the block-diagonal of
+    boxes_iou_bev for the CVAE label-uncertainty workload (``group`` sampled boxes per GT)."""
+    return _aligned(1, boxes_a, boxes_b, group)
+
+
+def boxes_iou3d_aligned(boxes_a, boxes_b, group=1):
+    """out[i] = 3D IoU(boxes_a[i], boxes_b[i // group]); same arithmetic as boxes_iou3d_gpu."""
+    return _aligned(2, boxes_a, boxes_b, group)
+
+
+# ---------------------------------------------------------------- NMS
+def _nms_sorted(fn_name: str, boxes_sorted: torch.Tensor, thresh: float):
+    """boxes_sorted: (F, n, 7) contiguous CUDA float32.  Returns (keep (F, n) int64, num (F,) int32), on device."""
+    frames, n = boxes_sorted.shape[0], boxes_sorted.shape[1]
+    dev = boxes_sorted.device
+    keep = torch.empty((frames, n), dtype=torch.int64, device=dev)
+    num = torch.zeros((frames,), dtype=torch.int32, device=dev)
+    if frames and n:
+        lib = _lib.load()
+        ws_bytes = lib.glenet_nms_workspace_bytes(frames, n)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = getattr(lib, fn_name)(boxes_sorted.data_ptr(), frames, n, float(thresh), keep.data_ptr(),
+                                       num.data_ptr(), ws.data_ptr(), ws_bytes, _stream(dev))
+        _lib.check(rc, fn_name)
+    return keep, num
+
+
+def _nms(fn_name: str, boxes, scores, thresh, pre_maxsize=None):
+    assert boxes.shape[1] == 7
+    _check_cuda_f32(boxes, "boxes")
+    order = scores.sort(0, descending=True)[1]
+    if pre_maxsize is not None:
+        order = order[:pre_maxsize]
+    boxes = boxes[order].contiguous()
+    keep, num = _nms_sorted(fn_name, boxes.unsqueeze(0), thresh)
+    num_out = int(num.item())   # the one unavoidable sync: the result length
+    return order[keep[0, :num_out]].contiguous(), None
+
+
+def nms_gpu(boxes, scores, thresh, pre_maxsize=None, **kwargs):
+    """
+    :param boxes: (N, 7) [x, y, z, dx, dy, dz, heading]
+    :param scores: (N)
+    :param thresh:
+    :return: (indices into ``boxes`` of the kept boxes, by descending score; None)
+
+    Reference: iou3d_nms_utils.py:182-197 -> nms_gpu (iou3d_nms.cpp:90-136).  ``**kwargs``
+    swallows the NMS_CONFIG dict that model_nms_utils.py:50-52 splats into the call.
+    """
+    return _nms("glenet_nms_gpu", boxes, scores, thresh, pre_maxsize)
+
+
+def nms_normal_gpu(boxes, scores, thresh, **kwargs):
+    """
+    :param boxes: (N, 7) [x, y, z, dx, dy, dz, heading]
+    :param scores: (N)
+    :param thresh:
+    :return:
+
+    Reference: iou3d_nms_utils.py:276-290 -> nms_normal_gpu (iou3d_nms.cpp:139-186).
+    """
+    return _nms("glenet_nms_normal_gpu", boxes, scores, thresh)
+
+
+def _nms_batch(fn_name: str, boxes, scores, thresh):
+    assert boxes.dim() == 3 and boxes.shape[2] == 7 and scores.shape == boxes.shape[:2]
+    _check_cuda_f32(boxes, "boxes")
+    order = scores.sort(1, descending=True)[1]
+    sorted_boxes = torch.gather(boxes, 1, order.unsqueeze(-1).expand(-1, -1, 7)).contiguous()
+    keep, num = _nms_sorted(fn_name, sorted_boxes, thresh)
+    # map sorted positions back to indices of the caller's tensors; rows are valid up to num[f]
+    return torch.gather(order, 1, keep.clamp_(0, max(boxes.shape[1] - 1, 0))), num
+
+
+def nms_gpu_batch(boxes, scores, thresh):
+    """Additive API: NMS of F independent frames in one launch pair, no host synchronisation.
+    boxes (F, N, 7), scores (F, N) -> (keep (F, N) int64, num_keep (F,) int32); row f is valid
+    up to num_keep[f] and equals nms_gpu(boxes[f], scores[f], thresh)[0]."""
+    return _nms_batch("glenet_nms_gpu", boxes, scores, thresh)
+
+
+def nms_normal_gpu_batch(boxes, scores, thresh):
+    """Batched nms_normal_gpu, see nms_gpu_batch."""
+    return _nms_batch("glenet_nms_normal_gpu", boxes, scores, thresh)

@@ -1,0 +1,118 @@
+/*
+ * glenet_geom.h -- C ABI of libglenet_geom.so: the B200-native (sm_100a) rotated-box
+ * geometry hot path of GLENet / OpenPCDet (pairwise rotated BEV / 3D IoU, bitmask NMS,
+ * points-in-boxes).
+ *
+ * Every entry point replaces one function of the reference's two pybind11 FFI modules
+ * (`iou3d_nms_cuda`, `roiaware_pool3d_cuda`); the reference interface each one stands in
+ * for is cited as file:line relative to the reference tree.  Conventions:
+ *
+ *   - boxes are float32 rows [x, y, z, dx, dy, dz, heading], row-major, contiguous;
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller owns inputs, outputs and workspaces; the library never allocates,
+ *     frees or synchronises (all work is enqueued on `stream`);
+ *   - return value: 0 on success, a negative code on failure (-(cudaError_t) for CUDA
+ *     errors, <= -1000 for argument errors); glenet_last_error() gives the text;
+ *   - n == 0 is legal everywhere and launches nothing (the reference prints a launch
+ *     error instead, callers guard: pcdet/models/model_utils/model_nms_utils.py:26).
+ *
+ * The reference reports errors with fprintf + exit(-1) (iou3d_nms.cpp:14-38); this
+ * library returns codes instead so that the host wrapper can raise.
+ */
+#ifndef GLENET_GEOM_H
+#define GLENET_GEOM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* glenet_stream_t; /* == cudaStream_t */
+
+/* ABI version (bumped on any signature change) and last error text of this thread. */
+int glenet_abi_version(void);
+const char* glenet_last_error(void);
+
+/* ---------------------------------------------------------------- rotated IoU
+ * boxes_overlap_bev_gpu(boxes_a, boxes_b, ans_overlap)   pcdet/ops/iou3d_nms/src/iou3d_nms.cpp:49-68
+ * boxes_iou_bev_gpu(boxes_a, boxes_b, ans_iou)           pcdet/ops/iou3d_nms/src/iou3d_nms.cpp:70-88
+ * out is (na, nb) float32; every element is written (no pre-zeroing needed).
+ * GPU dialect: libdevice trig + the reference kernels' FMA contraction. */
+int glenet_boxes_overlap_bev_gpu(const float* boxes_a, int na, const float* boxes_b, int nb,
+                                 float* ans_overlap, glenet_stream_t stream);
+int glenet_boxes_iou_bev_gpu(const float* boxes_a, int na, const float* boxes_b, int nb,
+                             float* ans_iou, glenet_stream_t stream);
+
+/* boxes_iou3d_gpu(boxes_a, boxes_b): the reference composes it in Python from
+ * boxes_overlap_bev_gpu plus ~10 elementwise torch kernels
+ * (pcdet/ops/iou3d_nms/iou3d_nms_utils.py:88-121); here it is one fused kernel with the
+ * same per-step rounding. */
+int glenet_boxes_iou3d_gpu(const float* boxes_a, int na, const float* boxes_b, int nb,
+                           float* ans_iou3d, glenet_stream_t stream);
+
+/* Row-aligned variants: out[i] = f(boxes_a[i], boxes_b[i / group]) for i < na, where boxes_b
+ * holds ceil(na / group) rows.  Additive API for the CVAE label-uncertainty workload
+ * (30 sampled boxes per GT object); mode 0 = overlap, 1 = BEV IoU, 2 = 3D IoU.
+ * Same arithmetic as the pairwise entry points. */
+int glenet_boxes_iou_aligned_gpu(int mode, const float* boxes_a, int na, const float* boxes_b,
+                                 int group, float* out, glenet_stream_t stream);
+
+/* boxes_iou_bev_cpu(boxes_a, boxes_b, ans_iou)           pcdet/ops/iou3d_nms/src/iou3d_cpu.cpp:232-252
+ * The reference runs this single-threaded on the host.  Here it executes on the GPU in the
+ * "CPU dialect" (no FMA contraction; cos/sin supplied by the host's libm so that the
+ * 0.01 m margin predicate of check_in_box2d, iou3d_cpu.cpp:74-84, is decided bit-identically).
+ * trig_a / trig_b: (n, 4) float32 rows {cosf(h), sinf(h), cosf(-h), sinf(-h)}, device pointers. */
+int glenet_boxes_iou_bev_cpu_dialect(const float* boxes_a, const float* trig_a, int na,
+                                     const float* boxes_b, const float* trig_b, int nb,
+                                     float* ans_iou, glenet_stream_t stream);
+
+/* ---------------------------------------------------------------- NMS
+ * nms_gpu(boxes, keep, thresh)        pcdet/ops/iou3d_nms/src/iou3d_nms.cpp:90-136  (rotated)
+ * nms_normal_gpu(boxes, keep, thresh) pcdet/ops/iou3d_nms/src/iou3d_nms.cpp:139-186 (axis aligned)
+ *
+ * boxes: (frames, n, 7) already sorted by descending score within each frame.
+ * keep:  (frames, n) int64, device (the reference's is a host tensor); the first
+ *        num_keep[f] entries of row f are the kept indices in ascending order.
+ * num_keep: (frames) int32, device.
+ * The 64-bit suppression mask and the greedy sweep both stay on the device: no cudaMalloc,
+ * no D2H copy of the mask, no host loop.  workspace must hold
+ * glenet_nms_workspace_bytes(frames, n) bytes, 16-byte aligned. */
+size_t glenet_nms_workspace_bytes(int frames, int n);
+int glenet_nms_gpu(const float* boxes, int frames, int n, float nms_overlap_thresh,
+                   int64_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes,
+                   glenet_stream_t stream);
+int glenet_nms_normal_gpu(const float* boxes, int frames, int n, float nms_overlap_thresh,
+                          int64_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes,
+                          glenet_stream_t stream);
+
+/* ---------------------------------------------------------------- points in boxes
+ * points_in_boxes_gpu(boxes, pts, box_idx_of_points)  pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:98-118
+ * boxes (B, N, 7), pts (B, M, 3), box_idx_of_points (B, M) int32: index of the first box
+ * containing the point, -1 if none.  Every element is written (no pre-fill needed).
+ * workspace: glenet_points_in_boxes_workspace_bytes(B, N) bytes, 16-byte aligned. */
+size_t glenet_points_in_boxes_workspace_bytes(int batch, int boxes_num);
+int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int batch, int boxes_num,
+                               int pts_num, int32_t* box_idx_of_points, void* workspace,
+                               size_t workspace_bytes, glenet_stream_t stream);
+
+/* points_in_boxes_cpu(boxes, pts, pts_indices)        pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:143-168
+ * boxes (N, 7), pts (M, 3), pts_indices (N, M) int32 0/1 (MARGIN = 1e-2, no early exit).
+ * Executed on the GPU in the CPU dialect; trig: (N, 2) float32 rows {cosf(-h), sinf(-h)}
+ * evaluated by the host's libm. */
+int glenet_points_in_boxes_cpu_dialect(const float* boxes, const float* trig, int boxes_num,
+                                       const float* pts, int pts_num, int32_t* pts_indices,
+                                       glenet_stream_t stream);
+
+/* ---------------------------------------------------------------- host helpers (CPU dialect)
+ * Per-box trigonometry evaluated by the HOST's libm, exactly the calls the reference's CPU
+ * code makes (iou3d_cpu.cpp:74-84,146-151; roiaware_pool3d.cpp:121-125).  boxes_host: (n, 7)
+ * host floats.  trig4 rows: {cosf(h), sinf(h), cosf(-h), sinf(-h)}; trig2 rows: {cosf(-h), sinf(-h)}. */
+void glenet_host_trig4(const float* boxes_host, int n, float* out_host);
+void glenet_host_trig2(const float* boxes_host, int n, float* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLENET_GEOM_H */

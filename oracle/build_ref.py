@@ -1,0 +1,86 @@
+"""Build recipe for ``oracle/_ref`` -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Compiles the *unmodified* reference sources where they lie under
+``/root/reference`` into two torch extension modules:
+
+* ``oracle/_ref/iou3d_nms_cuda.so``       <- pcdet/ops/iou3d_nms/src/{iou3d_cpu.cpp,
+                                              iou3d_nms_api.cpp, iou3d_nms.cpp, iou3d_nms_kernel.cu}
+* ``oracle/_ref/roiaware_pool3d_cuda.so`` <- pcdet/ops/roiaware_pool3d/src/{roiaware_pool3d.cpp,
+                                              roiaware_pool3d_kernel.cu}
+
+(the same source lists as the reference's ``setup.py:58-76``).  Nothing is copied
+into the repository: only build products land in ``oracle/_ref`` which is
+git-ignored (but travels to the GPU box with ``gpurun``).
+
+Host code MUST be compiled with ``-O2``: ``iou3d_nms_kernel.cu:43`` declares
+``check_rect_cross`` as a non-inline ``__device__`` function, for which nvcc emits
+a strong host stub that calls ``exit(1)``; at ``-O0`` the CPU path in
+``iou3d_cpu.cpp:67`` binds to that stub and the process dies silently.
+
+The device code is generated for sm_100a so that, on the B200 box, the very
+same reference kernels act as the GPU-dialect oracle.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+REF = os.environ.get("GLENET_REFERENCE", "/root/reference")
+
+EXTS = {
+    "iou3d_nms_cuda": [
+        "pcdet/ops/iou3d_nms/src/iou3d_cpu.cpp",
+        "pcdet/ops/iou3d_nms/src/iou3d_nms_api.cpp",
+        "pcdet/ops/iou3d_nms/src/iou3d_nms.cpp",
+        "pcdet/ops/iou3d_nms/src/iou3d_nms_kernel.cu",
+    ],
+    "roiaware_pool3d_cuda": [
+        "pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp",
+        "pcdet/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu",
+    ],
+}
+
+
+def have_reference() -> bool:
+    return all(os.path.isfile(os.path.join(REF, s)) for srcs in EXTS.values() for s in srcs)
+
+
+def built() -> bool:
+    return all(os.path.isfile(os.path.join(OUT, n + ".so")) for n in EXTS)
+
+
+def build(force: bool = False, verbose: bool = False) -> bool:
+    """Build both extensions into oracle/_ref.  Returns True when they exist afterwards."""
+    if built() and not force:
+        return True
+    if not have_reference():
+        return built()
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    os.environ.setdefault("MAX_JOBS", "8")
+    from torch.utils.cpp_extension import load
+
+    os.makedirs(OUT, exist_ok=True)
+    for name, srcs in EXTS.items():
+        bdir = os.path.join(OUT, "build_" + name)
+        os.makedirs(bdir, exist_ok=True)
+        load(
+            name=name,
+            sources=[os.path.join(REF, s) for s in srcs],
+            extra_cflags=["-O2"],
+            extra_cuda_cflags=["-O3"],  # nvcc default device opt level; fmad on, no fast-math
+            build_directory=bdir,
+            is_python_module=False,
+            verbose=verbose,
+        )
+        shutil.copy2(os.path.join(bdir, name + ".so"), os.path.join(OUT, name + ".so"))
+        shutil.rmtree(bdir, ignore_errors=True)
+    return built()
+
+
+if __name__ == "__main__":
+    ok = build(force="--force" in sys.argv, verbose=True)
+    print("oracle/_ref built:", ok)
+    sys.exit(0 if ok else 1)

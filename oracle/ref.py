@@ -1,0 +1,151 @@
+"""Loader for the compiled reference (``oracle/_ref``) -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import this module.  The product package
+(``glenet_b200``) never does.
+
+``oracle/_ref/*.so`` are the reference's own pybind11 modules, built unmodified
+by ``oracle/build_ref.py``.  The thin Python functions below restate what the
+reference's wrapper modules do around those native calls so that the oracle is
+called with exactly the reference's argument preparation:
+
+* ``pcdet/ops/iou3d_nms/iou3d_nms_utils.py:52-121,182-197,276-290``
+* ``pcdet/ops/roiaware_pool3d/roiaware_pool3d_utils.py:9-41``
+* ``pcdet/utils/common_utils.py:15-18`` (``check_numpy_to_torch``)
+
+(``tests/test_oracle_ref.py`` checks these restatements against the reference's
+wrapper files imported verbatim, when ``/root/reference`` is present.)
+"""
+from __future__ import annotations
+
+import importlib.machinery
+import importlib.util
+import os
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+_mods = {}
+
+
+def available() -> bool:
+    return all(os.path.isfile(os.path.join(REF_DIR, n + ".so")) for n in ("iou3d_nms_cuda", "roiaware_pool3d_cuda"))
+
+
+def _load(name: str):
+    if name not in _mods:
+        path = os.path.join(REF_DIR, name + ".so")
+        if not os.path.isfile(path):
+            raise FileNotFoundError(f"{path} missing: run `python oracle/build_ref.py` where /root/reference exists")
+        loader = importlib.machinery.ExtensionFileLoader(name, path)
+        spec = importlib.util.spec_from_loader(name, loader)
+        mod = importlib.util.module_from_spec(spec)
+        loader.exec_module(mod)
+        _mods[name] = mod
+    return _mods[name]
+
+
+def iou3d_nms_cuda():
+    return _load("iou3d_nms_cuda")
+
+
+def roiaware_pool3d_cuda():
+    return _load("roiaware_pool3d_cuda")
+
+
+def _np2t(x):
+    # common_utils.py:15-18
+    if isinstance(x, np.ndarray):
+        return torch.from_numpy(x).float(), True
+    return x, False
+
+
+# ---------------------------------------------------------------- CPU dialect
+def boxes_bev_iou_cpu(boxes_a, boxes_b):
+    """iou3d_nms_utils.py:52-68."""
+    boxes_a, is_numpy = _np2t(boxes_a)
+    boxes_b, is_numpy = _np2t(boxes_b)
+    assert not (boxes_a.is_cuda or boxes_b.is_cuda)
+    assert boxes_a.shape[1] == 7 and boxes_b.shape[1] == 7
+    ans = boxes_a.new_zeros(torch.Size((boxes_a.shape[0], boxes_b.shape[0])))
+    iou3d_nms_cuda().boxes_iou_bev_cpu(boxes_a.contiguous(), boxes_b.contiguous(), ans)
+    return ans.numpy() if is_numpy else ans
+
+
+def points_in_boxes_cpu(points, boxes):
+    """roiaware_pool3d_utils.py:9-25."""
+    assert boxes.shape[1] == 7 and points.shape[1] == 3
+    points, is_numpy = _np2t(points)
+    boxes, is_numpy = _np2t(boxes)
+    out = points.new_zeros((boxes.shape[0], points.shape[0]), dtype=torch.int)
+    roiaware_pool3d_cuda().points_in_boxes_cpu(boxes.float().contiguous(), points.float().contiguous(), out)
+    return out.numpy() if is_numpy else out
+
+
+# ---------------------------------------------------------------- GPU dialect (needs a GPU)
+def boxes_iou_bev(boxes_a, boxes_b):
+    """iou3d_nms_utils.py:71-85."""
+    assert boxes_a.shape[1] == boxes_b.shape[1] == 7
+    ans = torch.zeros((boxes_a.shape[0], boxes_b.shape[0]), dtype=torch.float32, device=boxes_a.device)
+    if ans.numel():
+        iou3d_nms_cuda().boxes_iou_bev_gpu(boxes_a.contiguous(), boxes_b.contiguous(), ans)
+    return ans
+
+
+def boxes_overlap_bev(boxes_a, boxes_b):
+    ans = torch.zeros((boxes_a.shape[0], boxes_b.shape[0]), dtype=torch.float32, device=boxes_a.device)
+    if ans.numel():
+        iou3d_nms_cuda().boxes_overlap_bev_gpu(boxes_a.contiguous(), boxes_b.contiguous(), ans)
+    return ans
+
+
+def boxes_iou3d_gpu(boxes_a, boxes_b):
+    """iou3d_nms_utils.py:88-121 (each elementwise step separately rounded, as torch does)."""
+    assert boxes_a.shape[1] == boxes_b.shape[1] == 7
+    a_hmax = (boxes_a[:, 2] + boxes_a[:, 5] / 2).view(-1, 1)
+    a_hmin = (boxes_a[:, 2] - boxes_a[:, 5] / 2).view(-1, 1)
+    b_hmax = (boxes_b[:, 2] + boxes_b[:, 5] / 2).view(1, -1)
+    b_hmin = (boxes_b[:, 2] - boxes_b[:, 5] / 2).view(1, -1)
+    overlaps_bev = boxes_overlap_bev(boxes_a, boxes_b)
+    max_of_min = torch.max(a_hmin, b_hmin)
+    min_of_max = torch.min(a_hmax, b_hmax)
+    overlaps_h = torch.clamp(min_of_max - max_of_min, min=0)
+    overlaps_3d = overlaps_bev * overlaps_h
+    vol_a = (boxes_a[:, 3] * boxes_a[:, 4] * boxes_a[:, 5]).view(-1, 1)
+    vol_b = (boxes_b[:, 3] * boxes_b[:, 4] * boxes_b[:, 5]).view(1, -1)
+    return overlaps_3d / torch.clamp(vol_a + vol_b - overlaps_3d, min=1e-6)
+
+
+def _nms(fn, boxes, scores, thresh, pre_maxsize=None):
+    assert boxes.shape[1] == 7
+    order = scores.sort(0, descending=True)[1]
+    if pre_maxsize is not None:
+        order = order[:pre_maxsize]
+    boxes = boxes[order].contiguous()
+    keep = torch.zeros(boxes.size(0), dtype=torch.int64)
+    num_out = fn(boxes, keep, thresh) if boxes.size(0) else 0
+    return order[keep[:num_out].to(boxes.device)].contiguous(), None
+
+
+def nms_gpu(boxes, scores, thresh, pre_maxsize=None, **kwargs):
+    """iou3d_nms_utils.py:182-197."""
+    return _nms(iou3d_nms_cuda().nms_gpu, boxes, scores, thresh, pre_maxsize)
+
+
+def nms_normal_gpu(boxes, scores, thresh, **kwargs):
+    """iou3d_nms_utils.py:276-290."""
+    return _nms(iou3d_nms_cuda().nms_normal_gpu, boxes, scores, thresh)
+
+
+def points_in_boxes_gpu(points, boxes):
+    """roiaware_pool3d_utils.py:28-41."""
+    assert boxes.shape[0] == points.shape[0]
+    assert boxes.shape[2] == 7 and points.shape[2] == 3
+    b, m, _ = points.shape
+    out = points.new_zeros((b, m), dtype=torch.int).fill_(-1)
+    if out.numel() and boxes.shape[1]:
+        roiaware_pool3d_cuda().points_in_boxes_gpu(boxes.contiguous(), points.contiguous(), out)
+    return out
