@@ -1,0 +1,362 @@
+"""Benchmark of the rotated-box geometry hot path (BASELINE.json metric) -- one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Headline workload (named in ``config.workload``): BASELINE config 4, the anchor target-assignment
+sweep -- per GPU and step, 16 frames x boxes_iou_bev(211 200 KITTI 3-class anchors, 100 GT boxes)
+= 3.38e8 rotated-IoU pairs, 1.35 GB of float32 results.  One process per GPU; the sweep is row/frame
+sharded with no data-path collective ("scaling": "weak": every rank owns a 16-frame batch, as the
+reference's DDP ranks do); when N > 1 the ranks exchange only the per-column max/argmax reductions
+the assigner consumes (NCCL all_reduce, a few KB).
+
+``value``  rotated-IoU pairs/s, whole job, inputs resident in HBM, CUDA events, max over ranks.
+``e2e``    same metric through the public drop-in API with HOST buffers: per frame the boxes are
+           copied H2D from pinned memory and the full (211200, 100) IoU matrix is copied D2H into
+           pinned memory, all inside the timed region.
+``roofline`` dominant kernel iou_tile_kernel: HBM-write bound, 4 B per pair.
+``cpu_baseline`` the reference's own CPU implementation (oracle/_ref, boxes_iou_bev_cpu) on the
+           host cores of this box, rows split over processes; bounded sample, rank 0, N = 1 only.
+``extra``  the other configs of the path (points_in_boxes pts/s, NMS frames/s, dense IoU) measured
+           the same way in short side runs, each with its own roofline fraction.
+``--impl reference`` times only the reference CPU implementation on the same config/metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES = 16
+N_ANCHORS, N_GT = 211200, 100
+PAIRS_PER_FRAME = N_ANCHORS * N_GT
+BYTES_PER_PAIR = 4.0           # the culled sweep is bound by the float32 result write
+WORKLOAD = "cfg4 anchor sweep: 16 frames x boxes_iou_bev(211200 KITTI anchors x 100 GT) per GPU"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4, derived; not in MEASURED_PEAKS.json
+
+
+# ------------------------------------------------------------------ CPU reference arm / baseline
+_G = {}   # inherited by the forked CPU workers (no per-job pickling of the 5.9 MB anchor table)
+
+
+def _cpu_rows_worker(args):
+    f, lo, hi = args
+    import torch
+    a_np, b_np = _G["anchors"], _G["gts"][f]
+    if _G["kind"] == "reference":
+        out = torch.zeros((hi - lo, b_np.shape[0]), dtype=torch.float32)
+        _G["ext"].boxes_iou_bev_cpu(torch.from_numpy(a_np[lo:hi]), torch.from_numpy(b_np), out)
+        return float(out.sum())
+    from oracle import capi
+    return float(capi.boxes_iou_bev(a_np[lo:hi], b_np, dialect=capi.CPU).sum())
+
+
+class CpuArm:
+    """The reference's CPU implementation of the path on all host cores (rows split over processes)."""
+
+    def __init__(self):
+        import multiprocessing as mp
+        import numpy as np
+        import torch
+        from oracle import capi, ref
+        from glenet_b200 import synth
+        torch.set_num_threads(1)
+        self.kind = "reference" if ref.available() else "port"
+        self.cores = os.cpu_count() or 1
+        _G["kind"] = self.kind
+        _G["anchors"] = np.ascontiguousarray(synth.anchors_kitti3().numpy())
+        _G["gts"] = [np.ascontiguousarray(synth.kitti_boxes(N_GT, 100 + f).numpy()) for f in range(FRAMES)]
+        if self.kind == "reference":
+            _G["ext"] = ref.iou3d_nms_cuda()      # the unmodified reference extension (oracle/_ref)
+        else:
+            capi.load()
+        self.pool = mp.get_context("fork").Pool(self.cores)     # forked BEFORE any CUDA initialisation
+
+    def run_frames(self, frames):
+        """IoU of `frames` frames; returns seconds."""
+        t0 = time.perf_counter()
+        n = _G["anchors"].shape[0]
+        chunks = self.cores * 4
+        step = (n + chunks - 1) // chunks
+        for f in frames:
+            self.pool.map(_cpu_rows_worker, [(f % FRAMES, lo, min(n, lo + step)) for lo in range(0, n, step)], chunksize=1)
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    arm = CpuArm()
+    arm.run_frames([0])                          # one warm-up frame is enough for a CPU loop
+    t = arm.run_frames(list(range(args.steps)))  # a "step" of this arm = one frame (bounded sample of the 16-frame step)
+    arm.close()
+    value = args.steps * PAIRS_PER_FRAME / t
+    line = {
+        "impl": "reference", "metric": "rotated_iou_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": "each step = 1 of the 16 frames (211200 x 100 pairs)"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": arm.cores, "kind": arm.kind,
+                         "sample": f"{args.steps} frames of 211200x100 pairs, rows split over {arm.cores} processes"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            p = [x.strip() for x in s.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0])); mx = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args, rank, world, local_rank):
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        arm = CpuArm()                       # fork the CPU workers before CUDA is touched
+        arm.run_frames([0])
+        nfr = 4
+        t = arm.run_frames(list(range(nfr)))
+        arm.close()
+        cpu_base = {"value": nfr * PAIRS_PER_FRAME / t, "unit": "pairs/s", "cores": arm.cores, "kind": arm.kind,
+                    "sample": f"{nfr} of the 16 frames (211200x100 pairs each), reference boxes_iou_bev_cpu, rows split over {arm.cores} processes"}
+
+    import torch
+    import torch.distributed as dist
+    from glenet_b200 import iou3d_nms_utils as I, roiaware_pool3d_utils as R, synth
+    import glenet_b200
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = glenet_b200.load()
+    hbm_gbs, peak_src = measured_peaks()
+
+    anchors_h = synth.anchors_kitti3().pin_memory()
+    gts_h = torch.stack([synth.kitti_boxes(N_GT, 100 + f + 1000 * rank) for f in range(FRAMES)]).pin_memory()
+    anchors, gts = anchors_h.to(dev), gts_h.to(dev)
+    launches = [0]
+
+    def step_resident():
+        col_max = []
+        for f in range(FRAMES):
+            iou = I.boxes_iou_bev(anchors, gts[f])       # 1 kernel launch
+            launches[0] += 1
+            if world > 1:
+                col_max.append(iou.max(dim=0)[0])
+        if world > 1:                                     # the only exchange: assigner reductions (a few KB)
+            cm = torch.stack(col_max)
+            dist.all_reduce(cm, op=dist.ReduceOp.MAX)
+            return cm
+        return None
+
+    out_h = torch.empty((N_ANCHORS, N_GT), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        for f in range(FRAMES):
+            a_d = anchors_h.to(dev, non_blocking=True)
+            g_d = gts_h[f].to(dev, non_blocking=True)
+            iou = I.boxes_iou_bev(a_d, g_d)
+            out_h.copy_(iou, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches[0] = 0
+    ms = timed(step_resident, args.steps, args.warmup)
+    timed_launches = FRAMES * args.steps
+    clk = clocks.stop() if rank == 0 else None
+    pairs_step = FRAMES * PAIRS_PER_FRAME
+    value = world * pairs_step * args.steps / (ms * 1e-3)
+
+    e2e_steps = max(1, min(args.steps, 3))
+    ms_e2e = timed(step_e2e, e2e_steps, 1)
+    e2e_value = world * pairs_step * e2e_steps / (ms_e2e * 1e-3)
+
+    # dominant kernel: average launch duration over the timed region (events on the launching stream)
+    kernel_ms = ms / timed_launches
+    achieved = PAIRS_PER_FRAME * BYTES_PER_PAIR / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "iou_tile_kernel<IOU_BEV>", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
+                "frac": achieved / hbm_gbs, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": PAIRS_PER_FRAME * BYTES_PER_PAIR, "avg_launch_ms": kernel_ms}
+
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        extra = side_runs(torch, I, R, synth, dev, hbm_gbs)
+
+    if rank == 0:
+        line = {
+            "metric": "rotated_iou_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": pairs_step, "frames": FRAMES,
+                       "l2": "each step writes 1.35 GB of results per GPU (> 126 MB L2), so successive launches stream through L2",
+                       "exchange": "none" if world == 1 else "all_reduce(MAX) of the (16,100) column maxima per step"},
+            "clocks": clk, "gpu_launches": timed_launches,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": FRAMES * (N_ANCHORS + N_GT) * 28,
+                    "d2h_bytes_per_step": FRAMES * PAIRS_PER_FRAME * 4, "ms_per_step": ms_e2e / e2e_steps,
+                    "api": "glenet_b200.iou3d_nms_utils.boxes_iou_bev, pinned host boxes in, pinned host (211200,100) matrix out"},
+            "roofline": roofline,
+            "cpu_baseline": cpu_base,
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def side_runs(torch, I, R, synth, dev, hbm_gbs):
+    """Short device-timed runs of the other configs of the path (not the headline value)."""
+    out = {}
+
+    def ev(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / iters
+
+    # cfg2: points_in_boxes, 128 frames x 180k points x 200 boxes (276 MB of points > L2)
+    B, M, N = 128, 180000, 200
+    boxes = torch.stack([synth.waymo_boxes(N, 100 + f) for f in range(B)]).to(dev)
+    base = synth.points(M, boxes[0].cpu(), synth.WAYMO_RANGE, 0.05, seed=5).to(dev)
+    pts = (base.unsqueeze(0).repeat(B, 1, 1) + torch.randn(B, M, 3, device=dev) * 0.01).contiguous()
+    ms = ev(lambda: R.points_in_boxes_gpu(pts, boxes), 10)
+    gbs = B * M * 16 / (ms * 1e-3) / 1e9
+    out["points_in_boxes"] = {"workload": "cfg2: 128 frames x 180000 points x 200 boxes", "value": B * M / (ms * 1e-3), "unit": "points/s",
+                              "ms": ms, "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs,
+                                                     "algorithmic_bytes_per_point": 16}}
+    del pts, boxes
+    # cfg1: NMS 4096 -> keep, thresh 0.7, batch 8 (batched launch pair and the per-frame drop-in loop)
+    fb, fs = [], []
+    for f in range(8):
+        b, s = synth.proposals(4096, 20, 20 + f)
+        fb.append(b); fs.append(s)
+    fb, fs = torch.stack(fb).to(dev), torch.stack(fs).to(dev)
+    ms_b = ev(lambda: I.nms_gpu_batch(fb, fs, 0.7), 10)
+    ms_l = ev(lambda: [I.nms_gpu(fb[f], fs[f], 0.7)[0][:500] for f in range(8)], 5)
+    out["nms"] = {"workload": "cfg1: 8 frames x nms_gpu(4096 proposals, thresh 0.7)", "frames_per_s_batched": 8 / (ms_b * 1e-3),
+                  "frames_per_s_dropin_loop": 8 / (ms_l * 1e-3), "ms_batched": ms_b, "ms_dropin_loop": ms_l}
+    # cfg3: CVAE 30 samples x 20k GT, 3D IoU (dense: every pair takes the clipping path)
+    smp, gt = synth.cvae_samples(20000, 30, 0)
+    smp, gt = smp.to(dev), gt.to(dev)
+    ms = ev(lambda: I.boxes_iou3d_aligned(smp, gt, 30), 10)
+    out["iou3d_cvae"] = {"workload": "cfg3: 600000 aligned pairs (30 samples x 20000 GT), all overlapping", "value": 600000 / (ms * 1e-3),
+                         "unit": "pairs/s", "ms": ms,
+                         "roofline": {"bound": "fp32", "algorithmic_flop_per_pair": 790, "achieved": 600000 * 790 / (ms * 1e-3) / 1e12,
+                                      "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": 600000 * 790 / (ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
+                                      "peak_source": "derived 148 SM x 128 lanes x 2 x 1.965 GHz"}}
+    # cfg2: boxes_iou3d_gpu 4096 x 200
+    g2 = synth.waymo_boxes(200, 2)
+    pr, _ = synth.proposals(4096, seed=3, base=g2)
+    pr, g2 = pr.to(dev), g2.to(dev)
+    ms = ev(lambda: I.boxes_iou3d_gpu(pr, g2), 20)
+    out["iou3d_4096x200"] = {"workload": "cfg2: boxes_iou3d_gpu 4096 x 200", "value": 4096 * 200 / (ms * 1e-3), "unit": "pairs/s", "ms": ms}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -17,7 +17,7 @@
 //
 // The structure is NOT the reference's: per-box work (trig, corners, margin
 // thresholds, areas) is hoisted into a BoxPre record computed once per box, the
-// polygon lives in shared memory (no local-memory stack), and the angular sort
+// polygon is the only per-thread array left, and the angular sort
 // evaluates one atan2f per vertex instead of two per comparison.
 #pragma once
 #include <cuda_runtime.h>
@@ -107,15 +107,9 @@ __device__ __forceinline__ float cull_radius(const float* __restrict__ box) {
     return r * 1.0001f + 0.03f + 2e-6f * (fabsf(box[0]) + fabsf(box[1]));
 }
 
-// ---------------------------------------------------------------- polygon scratch
-// Vertex k of thread t lives at vx[k * VSTRIDE + t] (column per thread => conflict free).
+// ---------------------------------------------------------------- polygon
+// cross_points[16] of the reference (:155)
 constexpr int MAX_POLY = 16;
-struct PolyScratch {
-    float* vx;
-    float* vy;
-    float* key;
-    int stride;
-};
 
 // intersection() of iou3d_nms_kernel.cu:57-89 for edge p0->p1 of box a and q0->q1 of box b.
 template <bool FMA>
@@ -164,29 +158,38 @@ __device__ __forceinline__ bool corner_in_box(const float* __restrict__ b, float
     return fabsf(rx) < b[BP_THX] && fabsf(ry) < b[BP_THY];
 }
 
+// Monotone stand-in for atan2f(dy, dx) on (-pi, pi]: same ordering of the polygon vertices about the
+// centroid as point_cmp (:97-99) except between directions that differ by a few ulps, where the fan
+// area is insensitive to the order.  ~8 instructions instead of ~50.
+__device__ __forceinline__ float pseudo_angle(float dy, float dx) {
+    const float den = fabsf(dx) + fabsf(dy);
+    const float q = (den > 0.f) ? __fdividef(dx, den) : 1.f;   // in [-1, 1]
+    return copysignf(1.f - q, dy);                             // [0, 2] for dy >= +0, [-2, -0] for dy <= -0
+}
+
 // box_overlap (:104-225): overlap area of prepared boxes a (row) and b (column).
+// The polygon (<= 16 vertices, dynamically indexed) lives in per-thread local memory, which the
+// hardware interleaves across lanes and serves from L1 -- it costs no shared memory, so the
+// kernels that call this keep a high CTA count per SM.
 template <bool FMA>
-__device__ float box_overlap(const float* __restrict__ a, const float* __restrict__ b,
-                             const PolyScratch& ps, int tid) {
+__device__ float box_overlap(const float* __restrict__ a, const float* __restrict__ b) {
     float ax[4], ay[4], bx[4], by[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         ax[k] = a[BP_PX + k]; ay[k] = a[BP_PY + k];
         bx[k] = b[BP_PX + k]; by[k] = b[BP_PY + k];
     }
-    float* vx = ps.vx + tid;
-    float* vy = ps.vy + tid;
-    const int S = ps.stride;
+    float vx[MAX_POLY], vy[MAX_POLY], key[MAX_POLY];
     int cnt = 0;
     float sx = 0.f, sy = 0.f;   // poly_center accumulator, in append order
     // cross_points[16] (:155) is exactly large enough for every non-degenerate pair; the guard
-    // only keeps a pathological (NaN/degenerate) pair from writing outside its scratch column.
+    // only keeps a pathological (NaN/degenerate) pair from writing outside its array.
     auto push = [&](float x, float y) {
         if (cnt < MAX_POLY) {
             sx = __fadd_rn(sx, x);
             sy = __fadd_rn(sy, y);
-            vx[cnt * S] = x;
-            vy[cnt * S] = y;
+            vx[cnt] = x;
+            vy[cnt] = y;
             ++cnt;
         }
     };
@@ -203,42 +206,75 @@ __device__ float box_overlap(const float* __restrict__ a, const float* __restric
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (corner_in_box<FMA>(a, bx[k], by[k])) {
-            push(bx[k], by[k]);
-        }
-        if (corner_in_box<FMA>(b, ax[k], ay[k])) {
-            push(ax[k], ay[k]);
-        }
+        if (corner_in_box<FMA>(a, bx[k], by[k])) push(bx[k], by[k]);
+        if (corner_in_box<FMA>(b, ax[k], ay[k])) push(ax[k], ay[k]);
     }
     if (cnt < 3) return 0.f;   // the fan of 0, 1 or 2 vertices has area exactly +0 in the reference too
-    const float fc = (float)cnt;
-    const float ccx = __fdiv_rn(sx, fc), ccy = __fdiv_rn(sy, fc);
-    // stable insertion sort by atan2f(y - cy, x - cx): same permutation as the reference's
-    // stable bubble sort with a strict '>' comparison (:201-209)
-    float* key = ps.key + tid;
-    for (int k = 0; k < cnt; ++k) {
-        const float x = vx[k * S], y = vy[k * S];
-        const float kk = atan2f(__fsub_rn(y, ccy), __fsub_rn(x, ccx));
-        int m = k;
-        while (m > 0 && key[(m - 1) * S] > kk) {
-            key[m * S] = key[(m - 1) * S];
-            vx[m * S] = vx[(m - 1) * S];
-            vy[m * S] = vy[(m - 1) * S];
-            --m;
-        }
-        key[m * S] = kk;
-        vx[m * S] = x;
-        vy[m * S] = y;
-    }
-    // fan from the first sorted vertex (:219-222)
-    const float x0 = vx[0], y0 = vy[0];
+    // The centroid only feeds the angular ordering (not the area), so an approximate reciprocal is enough.
+    const float inv_cnt = __frcp_rn((float)cnt);
+    const float ccx = sx * inv_cnt, ccy = sy * inv_cnt;
     float area = 0.f;
-    float ux = 0.f, uy = 0.f;   // vertex 0 minus itself
-    for (int k = 1; k < cnt; ++k) {
-        const float wx = __fsub_rn(vx[k * S], x0), wy = __fsub_rn(vy[k * S], y0);
-        area = __fadd_rn(area, mul_sub<FMA>(ux, wy, uy, wx));
-        ux = wx;
-        uy = wy;
+    if (cnt <= 8) {
+        // common case: the polygon goes into 8 register slots, is ordered by a branch-free 19-comparator
+        // sorting network on a monotone pseudo-angle, and the fan runs predicated -- no divergence
+        // between lanes whose polygons have different vertex counts.
+        float X[8], Y[8], K[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool v = k < cnt;
+            X[k] = v ? vx[k] : 0.f;
+            Y[k] = v ? vy[k] : 0.f;
+            K[k] = v ? pseudo_angle(__fsub_rn(Y[k], ccy), __fsub_rn(X[k], ccx)) : 3.0e38f;
+        }
+#define GLENET_CE(i, j)                                                       \
+        {                                                                     \
+            const bool sw = K[i] > K[j];                                      \
+            const float tk = sw ? K[j] : K[i], tx = sw ? X[j] : X[i], ty = sw ? Y[j] : Y[i]; \
+            K[j] = sw ? K[i] : K[j]; X[j] = sw ? X[i] : X[j]; Y[j] = sw ? Y[i] : Y[j];       \
+            K[i] = tk; X[i] = tx; Y[i] = ty;                                  \
+        }
+        GLENET_CE(0, 1) GLENET_CE(2, 3) GLENET_CE(4, 5) GLENET_CE(6, 7)
+        GLENET_CE(0, 2) GLENET_CE(1, 3) GLENET_CE(4, 6) GLENET_CE(5, 7)
+        GLENET_CE(1, 2) GLENET_CE(5, 6) GLENET_CE(0, 4) GLENET_CE(3, 7)
+        GLENET_CE(1, 5) GLENET_CE(2, 6)
+        GLENET_CE(1, 4) GLENET_CE(3, 6)
+        GLENET_CE(2, 4) GLENET_CE(3, 5)
+        GLENET_CE(3, 4)
+#undef GLENET_CE
+        // fan from the first sorted vertex (:219-222); term k = cross(v[k-1] - v0, v[k] - v0)
+        float ux = 0.f, uy = 0.f;
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            const float wx = __fsub_rn(X[k], X[0]), wy = __fsub_rn(Y[k], Y[0]);
+            const float term = mul_sub<FMA>(ux, wy, uy, wx);
+            if (k < cnt) area = __fadd_rn(area, term);
+            ux = wx;
+            uy = wy;
+        }
+    } else {
+        // rare: 9..16 vertices (degenerate / nearly coincident boxes) -- stable insertion sort in local memory
+        for (int k = 0; k < cnt; ++k) {
+            const float x = vx[k], y = vy[k];
+            const float kk = pseudo_angle(__fsub_rn(y, ccy), __fsub_rn(x, ccx));
+            int m = k;
+            while (m > 0 && key[m - 1] > kk) {
+                key[m] = key[m - 1];
+                vx[m] = vx[m - 1];
+                vy[m] = vy[m - 1];
+                --m;
+            }
+            key[m] = kk;
+            vx[m] = x;
+            vy[m] = y;
+        }
+        const float x0 = vx[0], y0 = vy[0];
+        float ux = 0.f, uy = 0.f;
+        for (int k = 1; k < cnt; ++k) {
+            const float wx = __fsub_rn(vx[k], x0), wy = __fsub_rn(vy[k], y0);
+            area = __fadd_rn(area, mul_sub<FMA>(ux, wy, uy, wx));
+            ux = wx;
+            uy = wy;
+        }
     }
     return __fmul_rn(fabsf(area), 0.5f);
 }

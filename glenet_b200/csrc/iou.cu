@@ -5,21 +5,25 @@
 // elementwise kernels of boxes_iou3d_gpu (pcdet/ops/iou3d_nms/iou3d_nms_utils.py:88-121).
 //
 // Design (one CTA = one TR x TC tile of the (na, nb) matrix):
-//   1. cull pass   : every pair is tested with an exact-conservative circle test on box
-//                    tiles staged in shared memory (SoA, conflict free).  Culled pairs
-//                    (> 99 % of an anchor sweep) store +0.0 with fully coalesced writes
-//                    -- this regime is HBM-write bound (4 B / pair).
+//   1. cull pass   : two-level exact-conservative circle test on box tiles staged in shared
+//                    memory.  First one test per COLUMN against the bounding box of the tile's
+//                    row centres (an anchor tile sees ~4 of 100 GT boxes), then one test per
+//                    (row, active column).  The tile itself is zero-filled with 16-byte streaming
+//                    stores -- > 99 % of an anchor sweep is exactly +0.0 and this regime is
+//                    HBM-write bound (4 B / pair).
 //   2. compaction  : surviving pairs are appended to a shared-memory queue with one
 //                    warp-aggregated atomic per warp, and their boxes are flagged.
 //   3. lazy prepare: only flagged boxes get their BoxPre record (4 trig calls, corners,
 //                    margin thresholds) -- once per box per tile, never per pair.
 //   4. clip pass   : the queue is drained with all lanes busy (no divergence between
-//                    "far" and "near" pairs); the polygon lives in shared memory.
+//                    "far" and "near" pairs).
 // The reference instead runs the full clipping code, incl. 20 sinf/cosf evaluations, for
 // every pair in a 16x16 thread block with 208 B of local-memory stack per thread.
 #include "common.cuh"
 #include "geom.cuh"
 #include "../../include/glenet_geom.h"
+#include <float.h>
+#include <math_constants.h>
 
 namespace glenet {
 
@@ -27,19 +31,19 @@ constexpr int IOU_THREADS = 256;
 constexpr int IOU_TR_MAX = 256;            // tile rows (boxes_a)
 constexpr int IOU_TC_MAX = 128;            // tile cols (boxes_b)
 constexpr int IOU_STEP = 8 * IOU_THREADS;  // pairs examined between two queue checks
-constexpr int IOU_QCAP = 3 * IOU_STEP;     // queue capacity; drained when > QCAP - STEP
+constexpr int IOU_QCAP = 2 * IOU_STEP;     // queue capacity; drained when it could overflow in the next step
 
 enum { MODE_OVERLAP = 0, MODE_IOU_BEV = 1, MODE_IOU3D = 2 };
 
-struct IouSmem {
-    float rcx[IOU_TR_MAX], rcy[IOU_TR_MAX], rrad[IOU_TR_MAX];
-    float ccx[IOU_TC_MAX], ccy[IOU_TC_MAX], crad[IOU_TC_MAX];
+struct __align__(16) IouSmem {
+    float4 row[IOU_TR_MAX];                // {cx, cy, cull radius, -}
+    float ccx[IOU_TC_MAX], ccy[IOU_TC_MAX], crad[IOU_TC_MAX];   // SoA so that 4 consecutive columns are one LDS.128
     float rpre[IOU_TR_MAX * BP_STRIDE];
     float cpre[IOU_TC_MAX * BP_STRIDE];
-    float vx[MAX_POLY * IOU_THREADS], vy[MAX_POLY * IOU_THREADS], key[MAX_POLY * IOU_THREADS];
     unsigned int queue[IOU_QCAP];
-    unsigned char rflag[IOU_TR_MAX], cflag[IOU_TC_MAX];
-    int qcount;
+    float red[IOU_THREADS / 32][5];
+    unsigned char rflag[IOU_TR_MAX], cflag[IOU_TC_MAX], act[IOU_TC_MAX];
+    int qcount, nact;
 };
 
 template <int MODE>
@@ -70,13 +74,12 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
         }
     }
     __syncthreads();
-    PolyScratch ps{sm.vx, sm.vy, sm.key, IOU_THREADS};
     for (int q = tid; q < n; q += IOU_THREADS) {
         const unsigned int e = sm.queue[q];
         const int r = e >> 8, c = e & 255;
         const float* a = sm.rpre + r * BP_STRIDE;
         const float* b = sm.cpre + c * BP_STRIDE;
-        const float ov = box_overlap<FMA>(a, b, ps, tid);
+        const float ov = box_overlap<FMA>(a, b);
         out[(size_t)(r0 + r) * nb + (c0 + c)] = finish_pair<MODE>(a, b, ov);
     }
     __syncthreads();
@@ -84,64 +87,123 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
     __syncthreads();
 }
 
+// append the lanes' surviving pairs with one atomic per warp
+__device__ __forceinline__ void enqueue_heavy(IouSmem& sm, unsigned int heavy, int r, int c, int lane) {
+    const unsigned int m = __ballot_sync(0xffffffffu, heavy != 0);
+    if (!m) return;
+    int qb = 0;
+    if (lane == 0) qb = atomicAdd(&sm.qcount, __popc(m));
+    qb = __shfl_sync(0xffffffffu, qb, 0);
+    if (heavy) {
+        sm.queue[qb + __popc(m & ((1u << lane) - 1))] = ((unsigned)r << 8) | (unsigned)c;
+        if (sm.rflag[r] == 0) sm.rflag[r] = 1;   // 0 = unused, 1 = wanted, 2 = prepared
+        if (sm.cflag[c] == 0) sm.cflag[c] = 1;
+    }
+}
+
 template <int MODE, bool FMA>
-__global__ void __launch_bounds__(IOU_THREADS)
+__global__ void __launch_bounds__(IOU_THREADS, 4)
 iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int nb,
                 const float4* __restrict__ trigA, const float4* __restrict__ trigB,
                 float* __restrict__ out, int TR, int TC, int col_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     IouSmem& sm = *reinterpret_cast<IouSmem*>(smem_raw);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_r = blockIdx.x / col_tiles, tile_c = blockIdx.x - tile_r * col_tiles;
     const int r0 = tile_r * TR, c0 = tile_c * TC;
     const int tr = min(TR, na - r0), tc = min(TC, nb - c0);
 
+    // ---- stage the tile's boxes (centre + cull radius) and the bounding box of the row centres
+    float minx = FLT_MAX, maxx = -FLT_MAX, miny = FLT_MAX, maxy = -FLT_MAX, maxr = 0.f;
     for (int i = tid; i < tr + tc; i += IOU_THREADS) {
         const bool is_row = i < tr;
         const int k = is_row ? i : i - tr;
         const float* box = (is_row ? A + (size_t)(r0 + k) * 7 : B + (size_t)(c0 + k) * 7);
         const float cx = box[0], cy = box[1], rad = cull_radius(box);
-        if (is_row) { sm.rcx[k] = cx; sm.rcy[k] = cy; sm.rrad[k] = rad; sm.rflag[k] = 0; }
-        else        { sm.ccx[k] = cx; sm.ccy[k] = cy; sm.crad[k] = rad; sm.cflag[k] = 0; }
+        if (is_row) {
+            sm.row[k] = make_float4(cx, cy, rad, 0.f); sm.rflag[k] = 0;
+            minx = fminf(minx, cx); maxx = fmaxf(maxx, cx); miny = fminf(miny, cy); maxy = fmaxf(maxy, cy);
+            maxr = (rad != rad) ? CUDART_INF_F : fmaxf(maxr, rad);   // a NaN radius must not be dropped by fmaxf
+        } else { sm.ccx[k] = cx; sm.ccy[k] = cy; sm.crad[k] = rad; sm.cflag[k] = 0; }
     }
-    if (tid == 0) sm.qcount = 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        minx = fminf(minx, __shfl_xor_sync(0xffffffffu, minx, o)); maxx = fmaxf(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+        miny = fminf(miny, __shfl_xor_sync(0xffffffffu, miny, o)); maxy = fmaxf(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+        maxr = fmaxf(maxr, __shfl_xor_sync(0xffffffffu, maxr, o));
+    }
+    if (lane == 0) { sm.red[warp][0] = minx; sm.red[warp][1] = maxx; sm.red[warp][2] = miny; sm.red[warp][3] = maxy; sm.red[warp][4] = maxr; }
+    if (tid == 0) { sm.qcount = 0; sm.nact = 0; }
     __syncthreads();
+    minx = sm.red[0][0]; maxx = sm.red[0][1]; miny = sm.red[0][2]; maxy = sm.red[0][3]; maxr = sm.red[0][4];
+#pragma unroll
+    for (int w = 1; w < IOU_THREADS / 32; ++w) {
+        minx = fminf(minx, sm.red[w][0]); maxx = fmaxf(maxx, sm.red[w][1]);
+        miny = fminf(miny, sm.red[w][2]); maxy = fmaxf(maxy, sm.red[w][3]); maxr = fmaxf(maxr, sm.red[w][4]);
+    }
 
-    const int npairs = tr * tc;
-    const int lane = tid & 31;
+    // ---- active columns: a column whose circle cannot reach the rows' bounding box is culled for the
+    //      whole tile with ONE test (rows with a NaN centre produce no polygon vertex in the reference
+    //      either, so leaving them out of the bounding box is exact).  NaN in the column => stays active.
+    for (int c = tid; c < tc; c += IOU_THREADS) {
+        const float cx = sm.ccx[c], cy = sm.ccy[c];
+        const float ddx = fmaxf(fmaxf(minx - cx, cx - maxx), 0.f), ddy = fmaxf(fmaxf(miny - cy, cy - maxy), 0.f);
+        const float rr = maxr + sm.crad[c];
+        const bool far = (cx == cx) && (cy == cy) && (ddx * ddx + ddy * ddy > rr * rr);
+        if (!far) sm.act[atomicAdd(&sm.nact, 1)] = (unsigned char)c;
+    }
+
+    // ---- zero fill of the whole tile: pure streaming stores (this is the HBM-write-bound part)
     float* out_tile = out + (size_t)r0 * nb + c0;
-    for (int base = 0; base < npairs; base += IOU_STEP) {
+    const bool vec = ((nb & 3) == 0) && ((c0 & 3) == 0) && ((tc & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
+    if (vec) {
+        const int nq = tc >> 2, nquads = tr * nq;
+        if (nq * 4 == nb) {   // the tile is one contiguous span of the output
+            float4* dst = reinterpret_cast<float4*>(out_tile);
+#pragma unroll 4
+            for (int q = tid; q < nquads; q += IOU_THREADS) dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            const int dr = IOU_THREADS / nq, dc = IOU_THREADS - dr * nq;
+            int r = tid / nq, cq = tid - r * nq;
+            for (int q = tid; q < nquads; q += IOU_THREADS) {
+                *reinterpret_cast<float4*>(out_tile + (size_t)r * nb + cq * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                r += dr; cq += dc;
+                if (cq >= nq) { cq -= nq; r += 1; }
+            }
+        }
+    } else {
+        const int npairs = tr * tc;
+        const int dr = IOU_THREADS / tc, dc = IOU_THREADS - dr * tc;
+        int r = tid / tc, c = tid - r * tc;
+        for (int p = tid; p < npairs; p += IOU_THREADS) {
+            out_tile[(size_t)r * nb + c] = 0.f;
+            r += dr; c += dc;
+            if (c >= tc) { c -= tc; r += 1; }
+        }
+    }
+    __syncthreads();   // act[] / nact complete; zero fill ordered before the clip pass's stores
+
+    // ---- per-pair circle test on the active columns only; survivors go to the queue
+    const int nact = sm.nact;
+    const int ntests = tr * nact;
+    for (int base = 0; base < ntests; base += IOU_STEP) {
         if (sm.qcount > IOU_QCAP - IOU_STEP) {   // uniform: qcount is stable between barriers
             drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out);
         }
-        int p = base + tid;
-        int r = p / tc, c = p - r * tc;
-        const int dr = IOU_THREADS / tc, dc = IOU_THREADS - dr * tc;
-#pragma unroll 4
+#pragma unroll 2
         for (int k = 0; k < IOU_STEP / IOU_THREADS; ++k) {
-            const bool valid = p < npairs;
-            bool heavy = false;
-            if (valid) {
-                const float ddx = sm.rcx[r] - sm.ccx[c], ddy = sm.rcy[r] - sm.ccy[c];
-                const float rr = sm.rrad[r] + sm.crad[c];
-                // NaN anywhere => not culled => the clip pass decides, like the reference
-                heavy = !(ddx * ddx + ddy * ddy > rr * rr);
-                if (!heavy) out_tile[(size_t)r * nb + c] = 0.f;
+            const int p = base + k * IOU_THREADS + tid;
+            unsigned int heavy = 0;
+            int r = 0, c = 0;
+            if (p < ntests) {
+                r = p / nact;
+                c = sm.act[p - r * nact];
+                const float4 rw = sm.row[r];
+                const float dx = rw.x - sm.ccx[c], dy = rw.y - sm.ccy[c], rr = rw.z + sm.crad[c];
+                // NaN anywhere => the comparison is false => not culled => the clip pass decides, like the reference
+                heavy = (!(dx * dx + dy * dy > rr * rr)) ? 1u : 0u;
             }
-            const unsigned int m = __ballot_sync(0xffffffffu, heavy);
-            if (m) {
-                int qb = 0;
-                if (lane == 0) qb = atomicAdd(&sm.qcount, __popc(m));
-                qb = __shfl_sync(0xffffffffu, qb, 0);
-                if (heavy) {
-                    sm.queue[qb + __popc(m & ((1u << lane) - 1))] = ((unsigned)r << 8) | (unsigned)c;
-                    if (sm.rflag[r] == 0) sm.rflag[r] = 1;   // 0 = unused, 1 = wanted, 2 = prepared
-                    if (sm.cflag[c] == 0) sm.cflag[c] = 1;
-                }
-            }
-            p += IOU_THREADS;
-            r += dr; c += dc;
-            if (c >= tc) { c -= tc; r += 1; }
+            enqueue_heavy(sm, heavy, r, c, lane);
         }
         __syncthreads();
     }
@@ -154,7 +216,6 @@ template <int MODE, bool FMA>
 __global__ void __launch_bounds__(ALIGNED_THREADS)
 iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int group,
                    float* __restrict__ out) {
-    __shared__ float vx[MAX_POLY * ALIGNED_THREADS], vy[MAX_POLY * ALIGNED_THREADS], key[MAX_POLY * ALIGNED_THREADS];
     const int tid = threadIdx.x;
     const int i = blockIdx.x * ALIGNED_THREADS + tid;
     if (i >= na) return;
@@ -167,8 +228,7 @@ iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict_
     if (!(ddx * ddx + ddy * ddy > rr * rr)) {
         box_prepare<FMA>(ba, device_trig(ba[6]), a);
         box_prepare<FMA>(bb, device_trig(bb[6]), b);
-        PolyScratch ps{vx, vy, key, ALIGNED_THREADS};
-        const float ov = box_overlap<FMA>(a, b, ps, tid);
+        const float ov = box_overlap<FMA>(a, b);
         out_v = finish_pair<MODE>(a, b, ov);
     }
     out[i] = out_v;
@@ -176,7 +236,7 @@ iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict_
 
 static void pick_tiles(int na, int nb, int& TR, int& TC, int& row_tiles, int& col_tiles) {
     col_tiles = (nb + IOU_TC_MAX - 1) / IOU_TC_MAX;
-    TC = (nb + col_tiles - 1) / col_tiles;
+    TC = ((nb + col_tiles - 1) / col_tiles + 3) / 4 * 4;   // multiple of 4 keeps every tile on the 16-byte store path
     // aim for >= 4 CTAs per SM (148 SMs) before growing the row tile
     long want = 4L * 148;
     long tr = ((long)na * col_tiles + want - 1) / want;

@@ -28,7 +28,6 @@ struct NmsSmem {
     float ccx[NMS_TILE], ccy[NMS_TILE], crad[NMS_TILE];
     float rpre[NMS_TILE * BP_STRIDE];
     float cpre[NMS_TILE * BP_STRIDE];
-    float vx[MAX_POLY * NMS_THREADS], vy[MAX_POLY * NMS_THREADS], key[MAX_POLY * NMS_THREADS];
     unsigned long long bits[NMS_TILE];
     unsigned short queue[NMS_TILE * NMS_TILE];
     unsigned char rflag[NMS_TILE], cflag[NMS_TILE];
@@ -147,13 +146,12 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
     }
     __syncthreads();
     const int nq = sm.qcount;
-    PolyScratch ps{sm.vx, sm.vy, sm.key, NMS_THREADS};
     for (int q = tid; q < nq; q += NMS_THREADS) {
         const int p = sm.queue[q];
         const int r = p >> 6, c = p & 63;
         const float* a = sm.rpre + r * BP_STRIDE;
         const float* b = sm.cpre + c * BP_STRIDE;
-        const float ov = box_overlap<true>(a, b, ps, tid);
+        const float ov = box_overlap<true>(a, b);
         if (iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) > thresh) atomicOr(&sm.bits[r], 1ull << c);
     }
     __syncthreads();

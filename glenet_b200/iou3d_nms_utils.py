@@ -97,10 +97,13 @@ def boxes_bev_iou_cpu(boxes_a, boxes_b):
         lib = _lib.load()
         dev = torch.device("cuda", torch.cuda.current_device())
         # one host buffer: [boxes_a | boxes_b | trig_a | trig_b] -> one H2D copy
-        host = torch.empty(na * 7 + nb * 7 + na * 4 + nb * 4, dtype=torch.float32).pin_memory()
-        o_b, o_ta, o_tb = na * 7, na * 7 + nb * 7, na * 7 + nb * 7 + na * 4
+        # (the trig tables are read as float4 => their offsets are padded to 16 bytes)
+        o_b = na * 7
+        o_ta = (o_b + nb * 7 + 3) // 4 * 4
+        o_tb = o_ta + na * 4
+        host = torch.empty(o_tb + nb * 4, dtype=torch.float32).pin_memory()
         host[:o_b].copy_(a.view(-1))
-        host[o_b:o_ta].copy_(b.view(-1))
+        host[o_b:o_b + nb * 7].copy_(b.view(-1))
         base = host.data_ptr()
         lib.glenet_host_trig4(a.data_ptr(), na, base + 4 * o_ta)
         lib.glenet_host_trig4(b.data_ptr(), nb, base + 4 * o_tb)

@@ -42,6 +42,7 @@ def load():
         lib = ctypes.CDLL(LIB)
         fp, ip, i64p = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p
         lib.oracle_boxes_iou_bev.argtypes = [ctypes.c_int, fp, ctypes.c_int, fp, ctypes.c_int, fp, ctypes.POINTER(IouStats)]
+        lib.oracle_boxes_iou_bev_flagged.argtypes = [ctypes.c_int, fp, ctypes.c_int, fp, ctypes.c_int, fp, ctypes.c_void_p]
         lib.oracle_boxes_iou_bev_rows.argtypes = [ctypes.c_int, fp, ctypes.c_int, ctypes.c_int, fp, ctypes.c_int, fp]
         lib.oracle_boxes_overlap_bev.argtypes = [ctypes.c_int, fp, ctypes.c_int, fp, ctypes.c_int, fp]
         lib.oracle_boxes_iou3d.argtypes = [ctypes.c_int, fp, ctypes.c_int, fp, ctypes.c_int, fp]
@@ -69,6 +70,15 @@ def boxes_iou_bev(a, b, dialect=CPU, stats=False):
     st = IouStats()
     load().oracle_boxes_iou_bev(dialect, a.ctypes.data, a.shape[0], b.ctypes.data, b.shape[0], out.ctypes.data, ctypes.byref(st))
     return (out, st) if stats else out
+
+
+def boxes_iou_bev_flagged(a, b, dialect=GPU):
+    """Returns (iou, near) where near marks pairs whose margin predicate is within 1e-4 m of flipping."""
+    a, b = _f32(a), _f32(b)
+    out = np.zeros((a.shape[0], b.shape[0]), dtype=np.float32)
+    near = np.zeros((a.shape[0], b.shape[0]), dtype=np.uint8)
+    load().oracle_boxes_iou_bev_flagged(dialect, a.ctypes.data, a.shape[0], b.ctypes.data, b.shape[0], out.ctypes.data, near.ctypes.data)
+    return out, near.astype(bool)
 
 
 def boxes_overlap_bev(a, b, dialect=GPU):

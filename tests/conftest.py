@@ -1,0 +1,52 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `pytest -m gpu`)")
+
+
+@pytest.fixture(scope="session")
+def cpu_golden():
+    return dict(np.load(os.path.join(GOLDEN_DIR, "cpu_golden.npz")))
+
+
+@pytest.fixture(scope="session")
+def gpu_golden():
+    path = os.path.join(GOLDEN_DIR, "gpu_golden.npz")
+    if not os.path.isfile(path):
+        pytest.skip("tests/golden/gpu_golden.npz missing (generate with make_golden.py gpu on a B200)")
+    return dict(np.load(path))
+
+
+@pytest.fixture(scope="session")
+def capi():
+    from oracle import capi as c
+    c.load()
+    return c
+
+
+@pytest.fixture(scope="session")
+def ref_so():
+    """The unmodified reference compiled into oracle/_ref (skips when it was not built/shipped)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference; run python oracle/build_ref.py)")
+    return ref
+
+
+@pytest.fixture(scope="session")
+def cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")

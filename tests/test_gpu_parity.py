@@ -1,0 +1,310 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).
+
+Every test calls the product through its public drop-in API (which goes through the C ABI of
+libglenet_geom.so) and checks it against
+  (1) the golden vectors recorded from the reference's own CUDA kernels (tests/golden/gpu_golden.npz),
+  (2) the C oracle (oracle/geom_oracle.c) on seeded inputs it finishes in seconds,
+  (3) the unmodified reference compiled into oracle/_ref, when that travelled to the box,
+  (4) size-independent properties at BASELINE.json's full sizes.
+Bars (BASELINE.json north_star): points-in-boxes and NMS keep indices bit-exact; IoU within
+IOU_TOL = 1e-5 absolute and exactly 0.0 wherever the reference is 0.0.
+"""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from glenet_b200 import iou3d_nms_utils as I
+from glenet_b200 import roiaware_pool3d_utils as R
+from glenet_b200 import synth
+
+pytestmark = pytest.mark.gpu
+IOU_TOL = 1e-5
+
+
+def t(x, dev):
+    return torch.as_tensor(np.asarray(x)).to(dev)
+
+
+def check_iou(got, want, exact_frac=0.99):
+    got, want = np.asarray(got.detach().cpu()) if torch.is_tensor(got) else got, np.asarray(want)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= IOU_TOL
+    np.testing.assert_array_equal(got == 0, want == 0)          # callers test `== 0` (database_sampler.py:250)
+    assert (got == want).mean() >= exact_frac                    # in practice bit-identical
+
+
+# ------------------------------------------------------------------ (1) goldens from the reference's GPU kernels
+@pytest.mark.parametrize("name,a,b", [("sparse", "sparse_a", "sparse_b"), ("dense", "dense", "dense"),
+                                      ("adv", "adv", "adv"), ("waymo", "waymo_p", "waymo_gt")])
+def test_iou_family_vs_gpu_golden(cuda, cpu_golden, gpu_golden, name, a, b):
+    A, B = t(cpu_golden[a], cuda), t(cpu_golden[b], cuda)
+    check_iou(I.boxes_iou_bev(A, B), gpu_golden[f"gpu_iou_bev_{name}"])
+    check_iou(I.boxes_overlap_bev(A, B), gpu_golden[f"gpu_overlap_{name}"])
+    check_iou(I.boxes_iou3d_gpu(A, B), gpu_golden[f"gpu_iou3d_{name}"])
+
+
+@pytest.mark.parametrize("thr", [0.7, 0.1, 0.01])
+def test_nms_vs_gpu_golden(cuda, cpu_golden, gpu_golden, thr):
+    boxes, scores = t(cpu_golden["nms_boxes"], cuda), t(cpu_golden["nms_scores"], cuda)
+    keep, none = I.nms_gpu(boxes, scores, thr)
+    assert none is None and keep.dtype == torch.int64 and keep.is_cuda
+    np.testing.assert_array_equal(keep.cpu().numpy(), gpu_golden[f"gpu_nms_{thr}"])
+    keep_n, _ = I.nms_normal_gpu(boxes, scores, thr)
+    np.testing.assert_array_equal(keep_n.cpu().numpy(), gpu_golden[f"gpu_nms_normal_{thr}"])
+
+
+def test_nms_pre_maxsize_and_kwargs_vs_gpu_golden(cuda, cpu_golden, gpu_golden):
+    boxes, scores = t(cpu_golden["nms_boxes"], cuda), t(cpu_golden["nms_scores"], cuda)
+    # model_nms_utils.py:50-52 splats the whole NMS_CONFIG into the call
+    keep, _ = I.nms_gpu(boxes, scores, 0.7, pre_maxsize=100, NMS_TYPE="nms_gpu", NMS_PRE_MAXSIZE=4096, NMS_POST_MAXSIZE=500)
+    np.testing.assert_array_equal(keep.cpu().numpy(), gpu_golden["gpu_nms_pre100_0.7"])
+
+
+def test_points_in_boxes_vs_gpu_golden(cuda, cpu_golden, gpu_golden):
+    pts, boxes = t(cpu_golden["pib_points"], cuda), t(cpu_golden["pib_boxes"], cuda)
+    got = R.points_in_boxes_gpu(pts, boxes)
+    assert got.dtype == torch.int32 and got.shape == pts.shape[:2]
+    np.testing.assert_array_equal(got.cpu().numpy(), gpu_golden["gpu_pib_index"])
+    # frame by frame (callers pass B = 1) gives the same answer
+    for f in range(pts.shape[0]):
+        one = R.points_in_boxes_gpu(pts[f:f + 1], boxes[f:f + 1])
+        np.testing.assert_array_equal(one.cpu().numpy()[0], gpu_golden["gpu_pib_index"][f])
+
+
+# ------------------------------------------------------------------ (2) against the C oracle
+@pytest.mark.parametrize("seed", [0, 1])
+def test_iou_vs_c_oracle(cuda, capi, seed):
+    p, _ = synth.proposals(700, 16, seed)
+    q = synth.kitti_boxes(90, seed + 5)
+    b = torch.cat([p[:200], q])
+    want, near = capi.boxes_iou_bev_flagged(p, b, dialect=capi.GPU)
+    got = I.boxes_iou_bev(p.to(cuda), b.to(cuda)).cpu().numpy()
+    ok = ~near     # pairs whose 0.01 m margin predicate sits within 1e-4 m of flipping depend on trig ulps
+    assert ok.mean() > 0.99
+    assert np.abs(got - want)[ok].max() <= IOU_TOL
+    np.testing.assert_array_equal((got == 0)[ok], (want == 0)[ok])
+    want3 = capi.boxes_iou3d(p, b, dialect=capi.GPU)
+    got3 = I.boxes_iou3d_gpu(p.to(cuda), b.to(cuda)).cpu().numpy()
+    assert np.abs(got3 - want3)[ok].max() <= IOU_TOL
+
+
+def test_cpu_signature_functions_vs_c_oracle(cuda, capi, cpu_golden):
+    """boxes_bev_iou_cpu / points_in_boxes_cpu keep the reference's CPU signatures and CPU-dialect results."""
+    a, b = synth.kitti_boxes(200, 0), synth.kitti_boxes(50, 1)      # BASELINE config 0
+    got = I.boxes_bev_iou_cpu(a, b)
+    assert isinstance(got, torch.Tensor) and not got.is_cuda
+    check_iou(got, capi.boxes_iou_bev(a, b, dialect=capi.CPU))
+    check_iou(I.boxes_bev_iou_cpu(cpu_golden["dense"], cpu_golden["dense"]), cpu_golden["cpu_iou_dense"])
+    check_iou(I.boxes_bev_iou_cpu(cpu_golden["adv"], cpu_golden["adv"]), cpu_golden["cpu_iou_adv"], exact_frac=0.98)
+    assert isinstance(I.boxes_bev_iou_cpu(a.numpy(), b.numpy()), np.ndarray)
+    assert isinstance(I.boxes_bev_iou_cpu(a.numpy(), b), torch.Tensor)      # flag follows boxes_b (iou3d_nms_utils.py:61-62)
+    boxes = synth.kitti_boxes(20, 3)
+    pts = synth.points(120000, boxes, synth.KITTI_RANGE, 0.05, seed=3)        # BASELINE config 0
+    got = R.points_in_boxes_cpu(pts, boxes)
+    assert got.dtype == torch.int32 and got.shape == (20, 120000) and not got.is_cuda
+    np.testing.assert_array_equal(got.numpy(), capi.points_in_boxes_mask(pts, boxes, dialect=capi.CPU))
+    for f in range(2):
+        want = np.unpackbits(cpu_golden[f"cpu_pib_mask_{f}"], axis=1)[:, :6000].astype(np.int32)
+        got = R.points_in_boxes_cpu(cpu_golden["pib_points"][f], cpu_golden["pib_boxes"][f])
+        assert isinstance(got, np.ndarray)
+        np.testing.assert_array_equal(got, want)
+
+
+def test_points_in_boxes_vs_c_oracle(cuda, capi):
+    boxes = torch.stack([synth.waymo_boxes(60, s) for s in range(2)])
+    pts = torch.stack([synth.points(40000, boxes[s], synth.WAYMO_RANGE, 0.2, seed=s) for s in range(2)])
+    want = capi.points_in_boxes_index(pts, boxes, dialect=capi.GPU)
+    got = R.points_in_boxes_gpu(pts.to(cuda), boxes.to(cuda)).cpu().numpy()
+    assert (got != want).mean() < 1e-4      # the restatement uses glibc trig; exact parity is tested against the reference below
+    assert (want >= 0).sum() > 5000
+
+
+# ------------------------------------------------------------------ (3) against the reference itself (oracle/_ref)
+def test_everything_bit_exact_vs_reference_kernels(cuda, ref_so):
+    g = torch.Generator().manual_seed(5)
+    gt = synth.waymo_boxes(200, 2)
+    pr, _ = synth.proposals(4096, seed=3, base=gt)                         # BASELINE config 2: 4096 x 200
+    for a, b in ((pr, gt), (synth.kitti_boxes(1500, 0), synth.kitti_boxes(333, 1)), (synth.anchors_kitti3()[:40000], synth.kitti_boxes(100, 4))):
+        a, b = a.to(cuda), b.to(cuda)
+        assert torch.equal(I.boxes_iou_bev(a, b), ref_so.boxes_iou_bev(a, b))
+        assert torch.equal(I.boxes_overlap_bev(a, b), ref_so.boxes_overlap_bev(a, b))
+        assert torch.equal(I.boxes_iou3d_gpu(a, b), ref_so.boxes_iou3d_gpu(a, b))
+    boxes, scores = synth.proposals(4096, 20, 7)                            # BASELINE config 1
+    boxes, scores = boxes.to(cuda), scores.to(cuda)
+    for thr in (0.7, 0.1, 0.01):
+        assert torch.equal(I.nms_gpu(boxes, scores, thr)[0], ref_so.nms_gpu(boxes, scores, thr)[0])
+        assert torch.equal(I.nms_normal_gpu(boxes, scores, thr)[0], ref_so.nms_normal_gpu(boxes, scores, thr)[0])
+    bx = torch.stack([synth.waymo_boxes(200, 30 + f) for f in range(2)])
+    pts = torch.stack([synth.points(180000, bx[f], synth.WAYMO_RANGE, 0.05, seed=f) for f in range(2)]).to(cuda)   # config 2
+    bx = bx.to(cuda)
+    assert torch.equal(R.points_in_boxes_gpu(pts, bx), ref_so.points_in_boxes_gpu(pts, bx))
+    many, _ = synth.proposals(3000, 20, 9)                                   # heavily overlapping boxes: first-hit order
+    p2 = synth.points(60000, many[:20], synth.KITTI_RANGE, 0.5, seed=9)[None].to(cuda)
+    assert torch.equal(R.points_in_boxes_gpu(p2, many[None].to(cuda)), ref_so.points_in_boxes_gpu(p2, many[None].to(cuda)))
+    del g
+
+
+# ------------------------------------------------------------------ (4) properties at full size
+def test_anchor_sweep_properties_full_size(cuda):
+    """BASELINE config 4: 211 200 anchors x 100 GT."""
+    anchors, gt = synth.anchors_kitti3().to(cuda), synth.kitti_boxes(100, 4).to(cuda)
+    iou = I.boxes_iou_bev(anchors, gt)
+    assert iou.shape == (211200, 100)
+    assert float(iou.min()) >= 0.0 and float(iou.max()) <= 1.0 + 1e-5 and not torch.isnan(iou).any()
+    frac = float((iou > 0).float().mean())
+    assert 0.002 < frac < 0.006
+    # symmetry: IoU(a, b) == IoU(b, a)^T within tolerance
+    sub = anchors[::37]
+    assert float((I.boxes_iou_bev(sub, gt) - I.boxes_iou_bev(gt, sub).t()).abs().max()) <= IOU_TOL
+    # rows are independent: a row-sharded evaluation reproduces the matrix bit for bit
+    parts = [I.boxes_iou_bev(anchors[s:s + 52800], gt) for s in range(0, 211200, 52800)]
+    assert torch.equal(torch.cat(parts), iou)
+    # far boxes are exactly zero, identical boxes give 1
+    assert torch.equal(I.boxes_iou_bev(gt, gt).diagonal(), torch.ones(100, device=cuda)) or \
+        float((I.boxes_iou_bev(gt, gt).diagonal() - 1).abs().max()) <= IOU_TOL
+    # 3D IoU <= BEV IoU where both are positive, and zero patterns nest
+    i3 = I.boxes_iou3d_gpu(anchors[:50000], gt)
+    assert bool(((i3 > 0) <= (iou[:50000] > 0)).all())
+
+
+def test_nms_is_greedy_full_size(cuda):
+    """BASELINE config 1: 4096 proposals, thresh 0.7 -- verify the greedy fixed point from the IoU matrix."""
+    boxes, scores = synth.proposals(4096, 20, 11)
+    boxes, scores = boxes.to(cuda), scores.to(cuda)
+    thr = 0.7
+    keep, _ = I.nms_gpu(boxes, scores, thr)
+    order = scores.sort(0, descending=True)[1]
+    sb = boxes[order]
+    iou = I.boxes_iou_bev(sb, sb).cpu().numpy()
+    sup = np.triu(iou > np.float32(thr), k=1)
+    alive, kept = np.ones(4096, dtype=bool), []
+    for i in range(4096):
+        if alive[i]:
+            kept.append(i)
+            alive &= ~sup[i]
+    np.testing.assert_array_equal(order.cpu().numpy()[kept], keep.cpu().numpy())
+    # batch API == per-frame API, without a host sync inside
+    fb = torch.stack([boxes, boxes.flip(0)])
+    fs = torch.stack([scores, scores.flip(0)])
+    kb, nb = I.nms_gpu_batch(fb, fs, thr)
+    assert torch.equal(kb[0, :int(nb[0])], keep)
+    assert torch.equal(kb[1, :int(nb[1])], I.nms_gpu(fb[1], fs[1], thr)[0])
+
+
+def test_points_in_boxes_properties_full_size(cuda):
+    """BASELINE config 2 shape: 180 000 points x 200 boxes."""
+    boxes = synth.waymo_boxes(200, 3)
+    g = torch.Generator().manual_seed(0)
+    # points strictly inside box k (well away from faces) must be assigned an index <= k
+    k = torch.randint(0, 200, (50000,), generator=g)
+    loc = (torch.rand((50000, 3), generator=g) - 0.5) * boxes[k, 3:6] * 0.9
+    c, s = torch.cos(boxes[k, 6]), torch.sin(boxes[k, 6])
+    inside = torch.stack([loc[:, 0] * c - loc[:, 1] * s + boxes[k, 0], loc[:, 0] * s + loc[:, 1] * c + boxes[k, 1], loc[:, 2] + boxes[k, 2]], 1)
+    far = torch.rand((130000, 3), generator=g) * 10 + torch.tensor([500.0, 500.0, 0.0])
+    pts = torch.cat([inside, far])[None].contiguous().to(cuda)
+    out = R.points_in_boxes_gpu(pts, boxes[None].to(cuda))[0].cpu()
+    assert bool(((out[:50000] >= 0) & (out[:50000] <= k)).all())
+    assert bool((out[50000:] == -1).all())
+    # permuting the points permutes the answer; NaN points are background
+    perm = torch.randperm(180000, generator=g)
+    out_p = R.points_in_boxes_gpu(pts[:, perm.to(cuda)].contiguous(), boxes[None].to(cuda))[0].cpu()
+    assert torch.equal(out_p, out[perm])
+    pts_nan = pts.clone(); pts_nan[0, :7] = float("nan")
+    assert bool((R.points_in_boxes_gpu(pts_nan, boxes[None].to(cuda))[0, :7] == -1).all())
+
+
+# ------------------------------------------------------------------ edge cases and error behaviour
+def test_empty_and_ragged_inputs(cuda, capi):
+    e7 = torch.zeros((0, 7), device=cuda)
+    b = synth.kitti_boxes(5, 0).to(cuda)
+    assert I.boxes_iou_bev(e7, b).shape == (0, 5) and I.boxes_iou_bev(b, e7).shape == (5, 0)
+    assert I.boxes_iou3d_gpu(e7, e7).shape == (0, 0)
+    k, _ = I.nms_gpu(e7, torch.zeros(0, device=cuda), 0.5)
+    assert k.numel() == 0 and k.dtype == torch.int64
+    assert R.points_in_boxes_gpu(torch.zeros((2, 0, 3), device=cuda), torch.zeros((2, 4, 7), device=cuda)).shape == (2, 0)
+    out = R.points_in_boxes_gpu(torch.rand((2, 100, 3), device=cuda), torch.zeros((2, 0, 7), device=cuda))
+    assert bool((out == -1).all())
+    assert I.boxes_bev_iou_cpu(np.zeros((0, 7), np.float32), np.zeros((3, 7), np.float32)).shape == (0, 3)
+    assert R.points_in_boxes_cpu(np.zeros((0, 3), np.float32), np.zeros((2, 7), np.float32)).shape == (2, 0)
+    # sizes that are not multiples of any tile: 1, 63, 65, 129, 257 boxes; odd column counts
+    for na, nb in ((1, 1), (63, 65), (129, 3), (257, 131), (5, 1001)):
+        a, bb = synth.kitti_boxes(na, na), synth.kitti_boxes(nb, nb + 1)
+        a[:, :2] = a[:, :2] * 0.2 + 20          # squeeze them together so that many pairs overlap
+        bb[:, :2] = bb[:, :2] * 0.2 + 20
+        want, near = capi.boxes_iou_bev_flagged(a, bb, dialect=capi.GPU)
+        got = I.boxes_iou_bev(a.to(cuda), bb.to(cuda)).cpu().numpy()
+        assert np.abs(got - want)[~near].max() <= IOU_TOL
+    for n in (1, 2, 63, 64, 65, 130):
+        boxes, scores = synth.proposals(n, 3, n)
+        order = np.argsort(-scores.numpy(), kind="stable")
+        want, near = capi.nms(boxes.numpy()[order], 0.3, dialect=capi.GPU)
+        got = I.nms_gpu(boxes.to(cuda), scores.to(cuda), 0.3)[0].cpu().numpy()
+        if near == 0:
+            np.testing.assert_array_equal(got, order[want])
+    # points: M not a multiple of 4 and unaligned views
+    boxes = synth.kitti_boxes(7, 1)[None]
+    pts = synth.points(1003, boxes[0], synth.KITTI_RANGE, 0.5, seed=1)[None]
+    want = capi.points_in_boxes_index(pts, boxes, dialect=capi.GPU)
+    got = R.points_in_boxes_gpu(pts.to(cuda), boxes.to(cuda)).cpu().numpy()
+    assert (got != want).sum() <= 1
+    big = torch.cat([pts, pts], 1).to(cuda)
+    view = big[:, 1:1004]                       # non-contiguous start offset (12 B, not 16 B aligned)
+    got_v = R.points_in_boxes_gpu(view, boxes.to(cuda)).cpu().numpy()
+    np.testing.assert_array_equal(got_v[0, :1002], got[0, 1:1003])
+
+
+def test_non_contiguous_and_slices(cuda):
+    """Callers pass cur_gt[:, 0:7] of an (M, 8) tensor (axis_aligned_target_assigner.py:141)."""
+    gt8 = torch.cat([synth.kitti_boxes(40, 0), torch.ones(40, 1)], 1).to(cuda)
+    a = synth.kitti_boxes(300, 1).to(cuda)
+    assert torch.equal(I.boxes_iou3d_gpu(a, gt8[:, 0:7]), I.boxes_iou3d_gpu(a, gt8[:, 0:7].contiguous()))
+    assert torch.equal(I.boxes_iou_bev(a[::2], gt8[:, :7]), I.boxes_iou_bev(a[::2].contiguous(), gt8[:, :7].contiguous()))
+
+
+def test_error_behaviour(cuda):
+    a = synth.kitti_boxes(4, 0)
+    with pytest.raises(AssertionError):
+        I.boxes_iou_bev(a.to(cuda)[:, :6], a.to(cuda))
+    with pytest.raises(AssertionError):
+        I.boxes_bev_iou_cpu(a.to(cuda), a)                       # 'Only support CPU tensors'
+    with pytest.raises(RuntimeError):
+        I.boxes_iou_bev(a, a.to(cuda))                           # CPU tensor into a GPU entry point
+    with pytest.raises(RuntimeError):
+        I.boxes_iou_bev(a.double().to(cuda), a.double().to(cuda))
+    with pytest.raises(AssertionError):
+        R.points_in_boxes_gpu(torch.zeros((1, 5, 3), device=cuda), torch.zeros((2, 5, 7), device=cuda))
+    with pytest.raises(AssertionError):
+        I.nms_gpu(a.to(cuda)[:, :5], torch.zeros(4, device=cuda), 0.5)
+
+
+def test_c_abi_direct_calls_and_error_codes(cuda):
+    import glenet_b200
+    lib = glenet_b200.load()
+    a = synth.kitti_boxes(10, 0).to(cuda)
+    out = torch.empty((10, 10), device=cuda)
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.glenet_boxes_iou_bev_gpu(a.data_ptr(), 10, a.data_ptr(), 10, out.data_ptr(), st) == 0
+    torch.cuda.synchronize()
+    assert float((out.diagonal() - 1).abs().max()) <= IOU_TOL
+    assert lib.glenet_boxes_iou_bev_gpu(None, 10, a.data_ptr(), 10, out.data_ptr(), st) == -1000
+    assert b"null pointer" in lib.glenet_last_error()
+    keep = torch.empty(10, dtype=torch.int64, device=cuda)
+    num = torch.empty(1, dtype=torch.int32, device=cuda)
+    assert lib.glenet_nms_gpu(a.data_ptr(), 1, 10, ctypes.c_float(0.5), keep.data_ptr(), num.data_ptr(), None, 0, st) == -1001
+    assert lib.glenet_boxes_iou_bev_gpu(a.data_ptr(), 0, a.data_ptr(), 10, out.data_ptr(), st) == 0     # n == 0 launches nothing
+
+
+def test_streams_and_async(cuda):
+    """Work is enqueued on torch's current stream; results are correct when consumed on that stream."""
+    a, b = synth.kitti_boxes(5000, 0).to(cuda), synth.kitti_boxes(64, 1).to(cuda)
+    want = I.boxes_iou_bev(a, b)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        got = I.boxes_iou_bev(a, b)
+        total = got.sum()
+    s.synchronize()
+    assert torch.equal(got, want) and math.isfinite(float(total))

@@ -1,0 +1,110 @@
+"""Pin the C oracle (oracle/geom_oracle.c): against the golden vectors produced by running the
+reference (tests/golden), and -- where oracle/_ref exists -- bit-for-bit against the reference's
+own compiled CPU functions on fresh seeded inputs.  No GPU needed."""
+import numpy as np
+import pytest
+import torch
+
+from glenet_b200 import synth
+
+
+def unpack(mask_packed, m):
+    return np.unpackbits(mask_packed, axis=1)[:, :m].astype(np.int32)
+
+
+# ------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("name,a,b", [("sparse", "sparse_a", "sparse_b"), ("dense", "dense", "dense"),
+                                      ("adv", "adv", "adv"), ("waymo", "waymo_p", "waymo_gt")])
+def test_iou_cpu_dialect_matches_reference_golden(cpu_golden, capi, name, a, b):
+    got = capi.boxes_iou_bev(cpu_golden[a], cpu_golden[b], dialect=capi.CPU)
+    want = cpu_golden[f"cpu_iou_{name}"]
+    assert got.shape == want.shape
+    np.testing.assert_array_equal(got, want)   # bit-exact: same libm, same rounding sequence
+
+
+def test_pib_cpu_dialect_matches_reference_golden(cpu_golden, capi):
+    for f in range(2):
+        pts, boxes = cpu_golden["pib_points"][f], cpu_golden["pib_boxes"][f]
+        want = unpack(cpu_golden[f"cpu_pib_mask_{f}"], pts.shape[0])
+        got = capi.points_in_boxes_mask(pts, boxes, dialect=capi.CPU)
+        np.testing.assert_array_equal(got, want)
+        assert want.sum() > 100   # the fixture really has points inside boxes
+
+
+def test_gpu_dialect_restatement_close_to_gpu_golden(gpu_golden, cpu_golden, capi):
+    """The fma-pattern restatement differs from the real GPU only by libdevice-vs-glibc trig ulps."""
+    for name, a, b in (("sparse", "sparse_a", "sparse_b"), ("dense", "dense", "dense"), ("waymo", "waymo_p", "waymo_gt")):
+        got = capi.boxes_iou_bev(cpu_golden[a], cpu_golden[b], dialect=capi.GPU)
+        want = gpu_golden[f"gpu_iou_bev_{name}"]
+        assert np.abs(got - want).max() <= 1e-5
+        np.testing.assert_array_equal(got == 0, want == 0)
+        got3 = capi.boxes_iou3d(cpu_golden[a], cpu_golden[b], dialect=capi.GPU)
+        assert np.abs(got3 - gpu_golden[f"gpu_iou3d_{name}"]).max() <= 1e-5
+    idx = capi.points_in_boxes_index(cpu_golden["pib_points"], cpu_golden["pib_boxes"], dialect=capi.GPU)
+    assert (idx != gpu_golden["gpu_pib_index"]).mean() < 1e-4
+    for thr in (0.7, 0.1, 0.01):
+        order = np.argsort(-cpu_golden["nms_scores"], kind="stable")
+        keep, near = capi.nms(cpu_golden["nms_boxes"][order], thr, normal=False, dialect=capi.GPU)
+        if near == 0:
+            np.testing.assert_array_equal(order[keep], gpu_golden[f"gpu_nms_{thr}"])
+        keep, near = capi.nms(cpu_golden["nms_boxes"][order], thr, normal=True, dialect=capi.GPU)
+        if near == 0:
+            np.testing.assert_array_equal(order[keep], gpu_golden[f"gpu_nms_normal_{thr}"])
+
+
+# ------------------------------------------------------------------ against the compiled reference
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_oracle_bitexact_vs_reference_cpu_iou(ref_so, capi, seed):
+    a, b = synth.kitti_boxes(200, seed), synth.kitti_boxes(50, seed + 10)     # BASELINE config 0
+    np.testing.assert_array_equal(capi.boxes_iou_bev(a, b), ref_so.boxes_bev_iou_cpu(a, b).numpy())
+    p, _ = synth.proposals(300, 12, seed)
+    want = ref_so.boxes_bev_iou_cpu(p, p).numpy()
+    np.testing.assert_array_equal(capi.boxes_iou_bev(p, p), want)
+    assert (want > 0).mean() > 0.03
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_oracle_bitexact_vs_reference_cpu_pib(ref_so, capi, seed):
+    boxes = synth.kitti_boxes(20, seed)
+    pts = synth.points(30000, boxes, synth.KITTI_RANGE, 0.2, seed=seed)
+    want = ref_so.points_in_boxes_cpu(pts, boxes).numpy()
+    np.testing.assert_array_equal(capi.points_in_boxes_mask(pts, boxes), want)
+    assert want.sum() > 1000
+
+
+def test_reference_wrapper_quirks(ref_so):
+    """numpy-in/numpy-out follows the LAST converted argument (iou3d_nms_utils.py:61-62,68)."""
+    a, b = synth.kitti_boxes(4, 0), synth.kitti_boxes(3, 1)
+    assert isinstance(ref_so.boxes_bev_iou_cpu(a.numpy(), b.numpy()), np.ndarray)
+    assert isinstance(ref_so.boxes_bev_iou_cpu(a.numpy(), b), torch.Tensor)
+    assert isinstance(ref_so.boxes_bev_iou_cpu(a, b.numpy()), np.ndarray)
+
+
+# ------------------------------------------------------------------ oracle self-consistency
+def test_oracle_properties(capi):
+    a = synth.kitti_boxes(64, 3)
+    iou = capi.boxes_iou_bev(a, a)
+    assert np.allclose(np.diag(iou), 1.0, atol=1e-5)
+    assert np.abs(iou - iou.T).max() < 1e-5
+    # first-hit index == argmax of the mask's first set row
+    boxes = synth.kitti_boxes(12, 5)
+    pts = synth.points(5000, boxes, synth.KITTI_RANGE, 0.4, seed=5)
+    mask = capi.points_in_boxes_mask(pts, boxes, dialect=capi.GPU)
+    idx = capi.points_in_boxes_index(pts[None], boxes[None], dialect=capi.GPU)[0]
+    first = np.where(mask.any(0), mask.argmax(0), -1)
+    np.testing.assert_array_equal(idx, first)
+    # NMS keeps are sorted, start with 0 and are idempotent
+    p, s = synth.proposals(300, 10, 1)
+    order = np.argsort(-s.numpy(), kind="stable")
+    keep, _ = capi.nms(p.numpy()[order], 0.5)
+    assert keep[0] == 0 and np.all(np.diff(keep) > 0)
+    keep2, _ = capi.nms(p.numpy()[order][keep], 0.5)
+    np.testing.assert_array_equal(keep2, np.arange(len(keep)))
+
+
+def test_flop_model_counts(capi):
+    p, _ = synth.proposals(100, 5, 0)
+    _, st = capi.boxes_iou_bev(p, p, dialect=capi.GPU, stats=True)
+    assert st.pairs == 100 * 100
+    assert sum(st.cnt_hist) == st.pairs
+    assert st.flops() > 151 * st.pairs
