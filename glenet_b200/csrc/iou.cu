@@ -30,20 +30,31 @@ namespace glenet {
 constexpr int IOU_THREADS = 256;
 constexpr int IOU_TR_MAX = 256;            // tile rows (boxes_a)
 constexpr int IOU_TC_MAX = 128;            // tile cols (boxes_b)
-constexpr int IOU_STEP = 8 * IOU_THREADS;  // pairs examined between two queue checks
-constexpr int IOU_QCAP = 2 * IOU_STEP;     // queue capacity; drained when it could overflow in the next step
+constexpr int IOU_STEP = 4 * IOU_THREADS;  // pair tests between two queue checks
+constexpr int IOU_QCAP = 8 * IOU_THREADS;  // queue capacity (<= 8 clipped pairs per thread and drain)
+constexpr int IOU_ZCHUNK = 4 * 32;         // float4 stores per warp and zero-fill chunk
 
 enum { MODE_OVERLAP = 0, MODE_IOU_BEV = 1, MODE_IOU3D = 2 };
+
+#ifdef GLENET_PHASE_TIMING   // developer instrumentation: accumulated clock64() per phase, thread 0 of every CTA
+__device__ unsigned long long g_phase_cycles[8];
+#define PHASE_MARK(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_phase_cycles[k], (unsigned long long)(now_ - t_phase_)); t_phase_ = now_; } } while (0)
+#define PHASE_INIT long long t_phase_ = clock64()
+#else
+#define PHASE_MARK(k) do { } while (0)
+#define PHASE_INIT do { } while (0)
+#endif
 
 struct __align__(16) IouSmem {
     float4 row[IOU_TR_MAX];                // {cx, cy, cull radius, -}
     float ccx[IOU_TC_MAX], ccy[IOU_TC_MAX], crad[IOU_TC_MAX];   // SoA so that 4 consecutive columns are one LDS.128
     float rpre[IOU_TR_MAX * BP_STRIDE];
     float cpre[IOU_TC_MAX * BP_STRIDE];
-    unsigned int queue[IOU_QCAP];
+    float qres[IOU_QCAP];                  // clipped results, parked until the tile's zero fill is complete
+    unsigned short queue[IOU_QCAP];        // (row << 7) | col
     float red[IOU_THREADS / 32][5];
     unsigned char rflag[IOU_TR_MAX], cflag[IOU_TC_MAX], act[IOU_TC_MAX];
-    int qcount, nact;
+    int qcount, nact, zchunk;
 };
 
 template <int MODE>
@@ -53,12 +64,57 @@ __device__ __forceinline__ float finish_pair(const float* a, const float* b, flo
     return iou3d_from_overlap(a, b, ov);
 }
 
+// Zero-fill of the tile, chunked so that any warp can take part whenever it has nothing else to do:
+// the stores are fire-and-forget, which is what lets them overlap the clip pass of the other warps.
+__device__ __forceinline__ void zero_fill_tile(IouSmem& sm, float* __restrict__ out_tile, int tr, int tc, int nb, bool vec) {
+    const int lane = threadIdx.x & 31;
+    if (vec) {
+        const int nq = tc >> 2, nquads = tr * nq;
+        const int nchunks = (nquads + IOU_ZCHUNK - 1) / IOU_ZCHUNK;
+        const bool contiguous = (nq * 4 == nb);
+        for (;;) {
+            int ch = 0;
+            if (lane == 0) ch = atomicAdd(&sm.zchunk, 1);
+            ch = __shfl_sync(0xffffffffu, ch, 0);
+            if (ch >= nchunks) break;
+#pragma unroll
+            for (int k = 0; k < IOU_ZCHUNK / 32; ++k) {
+                const int q = ch * IOU_ZCHUNK + k * 32 + lane;
+                if (q < nquads) {
+                    float4* dst;
+                    if (contiguous) dst = reinterpret_cast<float4*>(out_tile) + q;
+                    else { const int r = q / nq; dst = reinterpret_cast<float4*>(out_tile + (size_t)r * nb) + (q - r * nq); }
+                    *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    } else {
+        const int npairs = tr * tc;
+        const int nchunks = (npairs + IOU_ZCHUNK - 1) / IOU_ZCHUNK;
+        for (;;) {
+            int ch = 0;
+            if (lane == 0) ch = atomicAdd(&sm.zchunk, 1);
+            ch = __shfl_sync(0xffffffffu, ch, 0);
+            if (ch >= nchunks) break;
+#pragma unroll
+            for (int k = 0; k < IOU_ZCHUNK / 32; ++k) {
+                const int p = ch * IOU_ZCHUNK + k * 32 + lane;
+                if (p < npairs) { const int r = p / tc; out_tile[(size_t)r * nb + (p - r * tc)] = 0.f; }
+            }
+        }
+    }
+}
+
+// Clip the queued pairs.  Results are parked until the tile's zero fill is complete (barrier),
+// then overwrite the zeros (parked in shared memory meanwhile).  Warps without queued pairs go straight to zero filling, the others join
+// when their pairs are done -- streaming stores and clipping overlap inside the CTA.
 template <int MODE, bool FMA>
 __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict__ A, const float* __restrict__ B,
                                             const float4* __restrict__ trigA, const float4* __restrict__ trigB,
-                                            int r0, int c0, int tr, int tc, int nb, float* __restrict__ out) {
+                                            int r0, int c0, int tr, int tc, int nb, float* __restrict__ out, bool vec) {
     const int tid = threadIdx.x;
     const int n = sm.qcount;
+    PHASE_INIT;
     // lazy per-box preparation of the boxes that take part in at least one queued pair
     for (int i = tid; i < tr + tc; i += IOU_THREADS) {
         const bool is_row = i < tr;
@@ -74,17 +130,25 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
         }
     }
     __syncthreads();
+    PHASE_MARK(3);
     for (int q = tid; q < n; q += IOU_THREADS) {
         const unsigned int e = sm.queue[q];
-        const int r = e >> 8, c = e & 255;
-        const float* a = sm.rpre + r * BP_STRIDE;
-        const float* b = sm.cpre + c * BP_STRIDE;
-        const float ov = box_overlap<FMA>(a, b);
-        out[(size_t)(r0 + r) * nb + (c0 + c)] = finish_pair<MODE>(a, b, ov);
+        const float* a = sm.rpre + (e >> 7) * BP_STRIDE;
+        const float* b = sm.cpre + (e & 127) * BP_STRIDE;
+        sm.qres[q] = finish_pair<MODE>(a, b, box_overlap<FMA>(a, b));
+    }
+    PHASE_MARK(7);
+    zero_fill_tile(sm, out + (size_t)r0 * nb + c0, tr, tc, nb, vec);   // no-op once every chunk has been taken
+    __syncthreads();
+    PHASE_MARK(4);
+    for (int q = tid; q < n; q += IOU_THREADS) {
+        const unsigned int e = sm.queue[q];
+        out[(size_t)(r0 + (e >> 7)) * nb + (c0 + (e & 127))] = sm.qres[q];
     }
     __syncthreads();
     if (tid == 0) sm.qcount = 0;
     __syncthreads();
+    PHASE_MARK(5);
 }
 
 // append the lanes' surviving pairs with one atomic per warp
@@ -95,7 +159,7 @@ __device__ __forceinline__ void enqueue_heavy(IouSmem& sm, unsigned int heavy, i
     if (lane == 0) qb = atomicAdd(&sm.qcount, __popc(m));
     qb = __shfl_sync(0xffffffffu, qb, 0);
     if (heavy) {
-        sm.queue[qb + __popc(m & ((1u << lane) - 1))] = ((unsigned)r << 8) | (unsigned)c;
+        sm.queue[qb + __popc(m & ((1u << lane) - 1))] = (unsigned short)((r << 7) | c);
         if (sm.rflag[r] == 0) sm.rflag[r] = 1;   // 0 = unused, 1 = wanted, 2 = prepared
         if (sm.cflag[c] == 0) sm.cflag[c] = 1;
     }
@@ -112,6 +176,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     const int tile_r = blockIdx.x / col_tiles, tile_c = blockIdx.x - tile_r * col_tiles;
     const int r0 = tile_r * TR, c0 = tile_c * TC;
     const int tr = min(TR, na - r0), tc = min(TC, nb - c0);
+    PHASE_INIT;
 
     // ---- stage the tile's boxes (centre + cull radius) and the bounding box of the row centres
     float minx = FLT_MAX, maxx = -FLT_MAX, miny = FLT_MAX, maxy = -FLT_MAX, maxr = 0.f;
@@ -133,8 +198,9 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
         maxr = fmaxf(maxr, __shfl_xor_sync(0xffffffffu, maxr, o));
     }
     if (lane == 0) { sm.red[warp][0] = minx; sm.red[warp][1] = maxx; sm.red[warp][2] = miny; sm.red[warp][3] = maxy; sm.red[warp][4] = maxr; }
-    if (tid == 0) { sm.qcount = 0; sm.nact = 0; }
+    if (tid == 0) { sm.qcount = 0; sm.nact = 0; sm.zchunk = 0; }
     __syncthreads();
+    PHASE_MARK(0);
     minx = sm.red[0][0]; maxx = sm.red[0][1]; miny = sm.red[0][2]; maxy = sm.red[0][3]; maxr = sm.red[0][4];
 #pragma unroll
     for (int w = 1; w < IOU_THREADS / 32; ++w) {
@@ -153,42 +219,18 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
         if (!far) sm.act[atomicAdd(&sm.nact, 1)] = (unsigned char)c;
     }
 
-    // ---- zero fill of the whole tile: pure streaming stores (this is the HBM-write-bound part)
     float* out_tile = out + (size_t)r0 * nb + c0;
+    (void)out_tile;
     const bool vec = ((nb & 3) == 0) && ((c0 & 3) == 0) && ((tc & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
-    if (vec) {
-        const int nq = tc >> 2, nquads = tr * nq;
-        if (nq * 4 == nb) {   // the tile is one contiguous span of the output
-            float4* dst = reinterpret_cast<float4*>(out_tile);
-#pragma unroll 4
-            for (int q = tid; q < nquads; q += IOU_THREADS) dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            const int dr = IOU_THREADS / nq, dc = IOU_THREADS - dr * nq;
-            int r = tid / nq, cq = tid - r * nq;
-            for (int q = tid; q < nquads; q += IOU_THREADS) {
-                *reinterpret_cast<float4*>(out_tile + (size_t)r * nb + cq * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-                r += dr; cq += dc;
-                if (cq >= nq) { cq -= nq; r += 1; }
-            }
-        }
-    } else {
-        const int npairs = tr * tc;
-        const int dr = IOU_THREADS / tc, dc = IOU_THREADS - dr * tc;
-        int r = tid / tc, c = tid - r * tc;
-        for (int p = tid; p < npairs; p += IOU_THREADS) {
-            out_tile[(size_t)r * nb + c] = 0.f;
-            r += dr; c += dc;
-            if (c >= tc) { c -= tc; r += 1; }
-        }
-    }
-    __syncthreads();   // act[] / nact complete; zero fill ordered before the clip pass's stores
+    __syncthreads();   // act[] / nact complete
+    PHASE_MARK(1);
 
     // ---- per-pair circle test on the active columns only; survivors go to the queue
     const int nact = sm.nact;
     const int ntests = tr * nact;
     for (int base = 0; base < ntests; base += IOU_STEP) {
-        if (sm.qcount > IOU_QCAP - IOU_STEP) {   // uniform: qcount is stable between barriers
-            drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out);
+        if (sm.qcount > IOU_QCAP - IOU_STEP) {   // uniform: qcount is stable between barriers (dense tiles only)
+            drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, vec);
         }
 #pragma unroll 2
         for (int k = 0; k < IOU_STEP / IOU_THREADS; ++k) {
@@ -207,7 +249,9 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
         }
         __syncthreads();
     }
-    drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out);
+    PHASE_MARK(2);
+    drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, vec);
+    PHASE_MARK(6);
 }
 
 // out[i] = f(a[i], b[i / group]) -- every pair is "heavy" by construction (CVAE samples vs their GT)
@@ -276,6 +320,17 @@ static int launch_iou(const float* A, const float* trigA, int na, const float* B
 using namespace glenet;
 
 extern "C" {
+
+#ifdef GLENET_PHASE_TIMING
+// developer-only: read and reset the per-phase cycle accumulators of iou_tile_kernel
+int glenet_debug_iou_phase_cycles(unsigned long long* host_out8) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host_out8, g_phase_cycles, sizeof(unsigned long long) * 8);
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+    return 0;
+}
+#endif
 
 int glenet_boxes_overlap_bev_gpu(const float* a, int na, const float* b, int nb, float* out, glenet_stream_t s) {
     return launch_iou<MODE_OVERLAP, true>(a, nullptr, na, b, nullptr, nb, out, (cudaStream_t)s, "glenet_boxes_overlap_bev_gpu");

@@ -29,9 +29,13 @@ constexpr int PIB_G = 64;                       // coarse grid (CSR candidate li
 constexpr int PIB_CELLS = PIB_G * PIB_G;
 constexpr int PIB_FG = 256;                     // fine occupancy bitmap, cells per axis (1 bit per cell)
 constexpr int PIB_FWORDS = PIB_FG * PIB_FG / 32;
-constexpr int PIB_ROUND = 4 * 256;              // points per CTA round (4 per thread)
+constexpr int PIB_ROUND = 4 * 256;              // points per CTA round of the direct kernel (4 per thread)
+constexpr int PIB_WBATCH = 128;                 // points per warp batch (4 per lane)
+constexpr int PIB_CHUNK = 4096;                 // points per work item of the query kernel
 constexpr int PIB_THREADS = 256;
-constexpr int PIB_PTS_PER_CTA = 8192;
+constexpr int PIB_DIRECT_BOXES = 32;            // at most this many boxes => single-launch direct kernel for small calls
+constexpr int PIB_DIRECT_PTS = 4096;            // points per CTA of the direct kernel
+constexpr long PIB_DIRECT_MAX_POINTS = 1 << 20; // ... when the whole call has at most this many points
 constexpr int PIB_BUILD_THREADS = 512;
 constexpr int PIB_SMEM_BOXES = 512;             // box records cached in shared memory by the query kernel
 
@@ -110,11 +114,12 @@ __device__ __forceinline__ Footprint footprint(const float* __restrict__ r) {
     return f;
 }
 
-// Visit every cell of a G x G grid (origin gx0/gy0, 1/cell = inv) that the footprint may touch.  The
-// cell range uses the very mapping of the query kernel (monotone => every point of [x0, x1] lands in
-// [ix0, ix1]); a separating-axis test in the box frame then drops the corner cells of rotated boxes.
+// Visit every cell of a G x G grid (origin gx0/gy0, 1/cell = inv) that the footprint may touch; the 32
+// lanes of the calling warp split the cell range.  The range uses the very mapping of the query kernel
+// (monotone => every point of [x0, x1] lands in [ix0, ix1]); a separating-axis test in the box frame
+// then drops the corner cells of rotated boxes.
 template <int G, typename F>
-__device__ __forceinline__ void for_cells(const Footprint& f, float gx0, float gy0, float inv_x, float inv_y, F visit) {
+__device__ __forceinline__ void for_cells_warp(const Footprint& f, float gx0, float gy0, float inv_x, float inv_y, int lane, F visit) {
     const int ix0 = max(0, min(G - 1, (int)floorf((f.x0 - gx0) * inv_x)));
     const int ix1 = max(0, min(G - 1, (int)floorf((f.x1 - gx0) * inv_x)));
     const int iy0 = max(0, min(G - 1, (int)floorf((f.y0 - gy0) * inv_y)));
@@ -122,13 +127,13 @@ __device__ __forceinline__ void for_cells(const Footprint& f, float gx0, float g
     const float cwx = 1.f / inv_x, cwy = 1.f / inv_y;
     const float rx_ext = 0.5f * (fabsf(f.c) * cwx + fabsf(f.s) * cwy), ry_ext = 0.5f * (fabsf(f.s) * cwx + fabsf(f.c) * cwy);
     const float slack = f.pad + 1e-3f * (cwx + cwy);
-    for (int iy = iy0; iy <= iy1; ++iy) {
-        for (int ix = ix0; ix <= ix1; ++ix) {
-            const float mx = gx0 + ((float)ix + 0.5f) * cwx - f.cx, my = gy0 + ((float)iy + 0.5f) * cwy - f.cy;
-            const float lx = mx * f.c - my * f.s, ly = mx * f.s + my * f.c;
-            if (fabsf(lx) > f.tx + rx_ext + slack || fabsf(ly) > f.ty + ry_ext + slack) continue;
-            visit(iy * G + ix);
-        }
+    const int nx = ix1 - ix0 + 1, ncell = nx * (iy1 - iy0 + 1);
+    for (int i = lane; i < ncell; i += 32) {
+        const int iy = iy0 + i / nx, ix = ix0 + (i - (i / nx) * nx);
+        const float mx = gx0 + ((float)ix + 0.5f) * cwx - f.cx, my = gy0 + ((float)iy + 0.5f) * cwy - f.cy;
+        const float lx = mx * f.c - my * f.s, ly = mx * f.s + my * f.c;
+        if (fabsf(lx) > f.tx + rx_ext + slack || fabsf(ly) > f.ty + ry_ext + slack) continue;
+        visit(iy * G + ix);
     }
 }
 
@@ -201,18 +206,18 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
 
     unsigned int total = 0;
     if (!exhaustive && !empty) {
-        // fine occupancy bitmap
-        for (int k = tid; k < N; k += PIB_BUILD_THREADS) {
+        // fine occupancy bitmap (one warp per box, lanes split the box's cells)
+        for (int k = warp; k < N; k += PIB_BUILD_THREADS / 32) {
             const Footprint fp = footprint(rec + (size_t)k * 8);
             if (fp.never) continue;
-            for_cells<PIB_FG>(fp, bx0, by0, finv_x, finv_y, [&](int cell) { atomicOr(&s_bits[cell >> 5], 1u << (cell & 31)); });
+            for_cells_warp<PIB_FG>(fp, bx0, by0, finv_x, finv_y, lane, [&](int cell) { atomicOr(&s_bits[cell >> 5], 1u << (cell & 31)); });
         }
         // coarse CSR: count, scan, fill (same traversal twice)
         for (int pass = 0; pass < 2; ++pass) {
-            for (int k = tid; k < N; k += PIB_BUILD_THREADS) {
+            for (int k = warp; k < N; k += PIB_BUILD_THREADS / 32) {
                 const Footprint fp = footprint(rec + (size_t)k * 8);
                 if (fp.never) continue;
-                for_cells<PIB_G>(fp, bx0, by0, inv_x, inv_y, [&](int cell) {
+                for_cells_warp<PIB_G>(fp, bx0, by0, inv_x, inv_y, lane, [&](int cell) {
                     const unsigned int pos = atomicAdd(&cnt[cell], 1u);
                     if (pass == 1) list[pos] = (unsigned int)k;
                 });
@@ -258,129 +263,191 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
     }
 }
 
-// Query: 256 threads x 4 consecutive points per round.
-//   phase A  every thread loads its 4 points (three float4 when aligned), maps them to the fine
-//            bitmap (shared memory, 8 KB) and stores -1 for all four with one int4.  Points whose
-//            fine cell is occupied (~13 % on a Waymo-shaped frame) are appended to a shared queue.
-//   phase B  the queue is drained with all lanes busy: coarse cell -> candidate list -> exact
-//            predicate -> minimum index, written over the provisional -1.
-__global__ void __launch_bounds__(PIB_THREADS, 4)
-pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace ws, int* __restrict__ out_all,
-                 int chunks_per_frame) {
-    __shared__ unsigned int s_bits[PIB_FWORDS];
-    __shared__ __align__(16) float s_rec[PIB_SMEM_BOXES * 8];
-    __shared__ __align__(16) float4 s_q[PIB_ROUND];
-    __shared__ int s_qn;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int f = blockIdx.x / chunks_per_frame;
-    const int chunk = blockIdx.x - f * chunks_per_frame;
-    const PibFrame h = ws.frames[f];
-    const float* rec_g = ws.rec + (size_t)f * N * 8;
-    const unsigned int* list = ws.list + (size_t)f * ws.cap;
-    const unsigned int* start = ws.start + (size_t)f * (PIB_CELLS + 1);
-    const float* pts = pts_all + (size_t)f * M * 3;
-    int* out = out_all + (size_t)f * M;
-    const int p_begin = chunk * PIB_PTS_PER_CTA;
-    const int p_end = min(M, p_begin + PIB_PTS_PER_CTA);
-
-    if (h.list_len < 0) {   // no box of this frame can contain a point
-        for (int p = p_begin + tid; p < p_end; p += PIB_THREADS) out[p] = -1;
-        return;
-    }
-    const bool rec_in_smem = N <= PIB_SMEM_BOXES;
-    if (rec_in_smem) {
-        const float4* src = reinterpret_cast<const float4*>(rec_g);
-        float4* dst = reinterpret_cast<float4*>(s_rec);
-        for (int i = tid; i < N * 2; i += PIB_THREADS) dst[i] = src[i];
-    }
-    const float* rec = rec_in_smem ? s_rec : rec_g;
-
-    if (h.exhaustive) {
-        __syncthreads();
-        for (int p = p_begin + tid; p < p_end; p += PIB_THREADS) {
-            const float x = pts[(size_t)p * 3], y = pts[(size_t)p * 3 + 1], z = pts[(size_t)p * 3 + 2];
-            int res = -1;
-            for (int k = 0; k < N; ++k) {
-                if (pt_in_box_gpu(x, y, z, rec + (size_t)k * 8)) { res = k; break; }
-            }
-            out[p] = res;
-        }
-        return;
-    }
-
-    {
-        const unsigned int* b = ws.bits + (size_t)f * PIB_FWORDS;
-        for (int i = tid; i < PIB_FWORDS; i += PIB_THREADS) s_bits[i] = b[i];
-    }
-    if (tid == 0) s_qn = 0;
-    __syncthreads();
-
-    // 16-byte alignment of this frame's point / output rows decides the vector path
-    const bool vec = ((((uintptr_t)pts) & 15) == 0) && ((((uintptr_t)out) & 15) == 0) && ((p_begin & 3) == 0);
-    int q_base = 0;
-    for (int base = p_begin; base < p_end; base += PIB_ROUND) {
-        const int p0 = base + tid * 4;
-        float px[4], py[4], pz[4];
-        const int nvalid = max(0, min(4, p_end - p0));
-        if (vec && nvalid == 4) {
-            const float4* src = reinterpret_cast<const float4*>(pts + (size_t)p0 * 3);
-            const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-            px[0] = a.x; py[0] = a.y; pz[0] = a.z; px[1] = a.w; py[1] = b.x; pz[1] = b.y;
-            px[2] = b.z; py[2] = b.w; pz[2] = c.x; px[3] = c.y; py[3] = c.z; pz[3] = c.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (i < nvalid) {
-                    px[i] = pts[(size_t)(p0 + i) * 3]; py[i] = pts[(size_t)(p0 + i) * 3 + 1]; pz[i] = pts[(size_t)(p0 + i) * 3 + 2];
-                } else { px[i] = py[i] = pz[i] = __int_as_float(0x7fc00000); }
-            }
-        }
-        unsigned int hot = 0;
+// 4 consecutive points of one thread (three float4 loads when the frame's rows are 16-byte aligned)
+struct Pts4 { float x[4], y[4], z[4]; };
+__device__ __forceinline__ void load_pts4(const float* __restrict__ pts, int p0, int p_end, bool vec, Pts4& o) {
+    const int nvalid = p_end - p0;
+    if (vec && nvalid >= 4) {
+        const float4* src = reinterpret_cast<const float4*>(pts + (size_t)p0 * 3);
+        const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        o.x[0] = a.x; o.y[0] = a.y; o.z[0] = a.z; o.x[1] = a.w; o.y[1] = b.x; o.z[1] = b.y;
+        o.x[2] = b.z; o.y[2] = b.w; o.z[2] = c.x; o.x[3] = c.y; o.y[3] = c.z; o.z[3] = c.w;
+    } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float fx = (px[i] - h.gx0) * h.finv_x, fy = (py[i] - h.gy0) * h.finv_y;
-            // NaN and out-of-grid coordinates fail the range test => cold (-1); inside the grid trunc == floor
-            if (i < nvalid && fx >= 0.f && fx < (float)PIB_FG && fy >= 0.f && fy < (float)PIB_FG) {
-                const int cell = (int)fy * PIB_FG + (int)fx;
-                hot |= ((s_bits[cell >> 5] >> (cell & 31)) & 1u) << i;
-            }
+            if (i < nvalid) {
+                o.x[i] = __ldg(pts + (size_t)(p0 + i) * 3); o.y[i] = __ldg(pts + (size_t)(p0 + i) * 3 + 1); o.z[i] = __ldg(pts + (size_t)(p0 + i) * 3 + 2);
+            } else { o.x[i] = o.y[i] = o.z[i] = __int_as_float(0x7fc00000); }   // NaN => never inside
         }
-        if (vec && nvalid == 4) *reinterpret_cast<int4*>(out + p0) = make_int4(-1, -1, -1, -1);
+    }
+}
+
+// Query kernel.  Persistent CTAs walk a contiguous range of (frame, chunk) work items and re-stage
+// the frame tables (fine bitmap 8 KB, coarse CSR offsets 16 KB, box records) only when the frame
+// changes.  Inside a chunk every WARP is autonomous -- no CTA barrier on the streaming path:
+//   1. 4 consecutive points per lane (three float4 loads, next batch prefetched into registers);
+//   2. fine-bitmap lookup in shared memory, provisional -1 for all four points with one int4 store;
+//   3. the ~13 % of points whose fine cell is occupied go to the warp's private queue
+//      (warp prefix sum, no atomics), and the warp drains it at once: coarse cell -> candidate
+//      list -> exact predicate -> minimum index over the provisional -1.
+__global__ void __launch_bounds__(PIB_THREADS, 4)
+pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace ws, int* __restrict__ out_all,
+                 int chunks_per_frame, int total_chunks) {
+    extern __shared__ __align__(16) unsigned char pib_smem[];
+    unsigned int* s_bits = reinterpret_cast<unsigned int*>(pib_smem);                       // [PIB_FWORDS]
+    unsigned int* s_start = s_bits + PIB_FWORDS;                                              // [PIB_CELLS + 4]
+    float4* s_q = reinterpret_cast<float4*>(s_start + PIB_CELLS + 4);                         // [warps][PIB_WBATCH]
+    float* s_rec = reinterpret_cast<float*>(s_q + (PIB_THREADS / 32) * PIB_WBATCH);           // [min(N, PIB_SMEM_BOXES) * 8]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float4* wq = s_q + warp * PIB_WBATCH;
+    const int c_begin = (int)((long)blockIdx.x * total_chunks / gridDim.x);
+    const int c_end = (int)((long)(blockIdx.x + 1) * total_chunks / gridDim.x);
+    const bool rec_in_smem = N <= PIB_SMEM_BOXES;
+    int cur_frame = -1;
+    PibFrame h;
+    h.list_len = -1; h.exhaustive = 0; h.gx0 = h.gy0 = h.inv_x = h.inv_y = h.finv_x = h.finv_y = 0.f;
+
+    for (int c = c_begin; c < c_end; ++c) {
+        const int f = c / chunks_per_frame;
+        const int chunk = c - f * chunks_per_frame;
+        const float* pts = pts_all + (size_t)f * M * 3;
+        int* out = out_all + (size_t)f * M;
+        const float* rec_g = ws.rec + (size_t)f * N * 8;
+        const unsigned int* list = ws.list + (size_t)f * ws.cap;
+        const float* rec = rec_in_smem ? s_rec : rec_g;
+        const int p_begin = chunk * PIB_CHUNK;
+        const int p_end = min(M, p_begin + PIB_CHUNK);
+        const bool vec = ((((uintptr_t)pts) & 15) == 0) && ((((uintptr_t)out) & 15) == 0);
+        if (f != cur_frame) {                                 // uniform over the CTA
+            __syncthreads();                                  // everyone is done with the previous frame's tables
+            h = ws.frames[f];
+            if (h.list_len >= 0) {
+                if (rec_in_smem) {
+                    const float4* src = reinterpret_cast<const float4*>(rec_g);
+                    float4* dst = reinterpret_cast<float4*>(s_rec);
+                    for (int i = tid; i < N * 2; i += PIB_THREADS) dst[i] = __ldg(src + i);
+                }
+                if (!h.exhaustive) {
+                    const uint4* b = reinterpret_cast<const uint4*>(ws.bits + (size_t)f * PIB_FWORDS);
+                    for (int i = tid; i < PIB_FWORDS / 4; i += PIB_THREADS) reinterpret_cast<uint4*>(s_bits)[i] = __ldg(b + i);
+                    const unsigned int* st = ws.start + (size_t)f * (PIB_CELLS + 1);
+                    for (int i = tid; i < PIB_CELLS + 1; i += PIB_THREADS) s_start[i] = __ldg(st + i);
+                }
+            }
+            __syncthreads();
+            cur_frame = f;
+        }
+        if (h.list_len < 0) {   // no box of this frame can contain a point
+            for (int p = p_begin + tid; p < p_end; p += PIB_THREADS) out[p] = -1;
+            continue;
+        }
+        if (h.exhaustive) {
+            for (int p = p_begin + tid; p < p_end; p += PIB_THREADS) {
+                const float x = pts[(size_t)p * 3], y = pts[(size_t)p * 3 + 1], z = pts[(size_t)p * 3 + 2];
+                int res = -1;
+                for (int k = 0; k < N; ++k) {
+                    if (pt_in_box_gpu(x, y, z, rec + (size_t)k * 8)) { res = k; break; }
+                }
+                out[p] = res;
+            }
+            continue;
+        }
+
+        // ---- warp-autonomous streaming over this chunk: batch j of warp w covers 128 points
+        constexpr int NB = PIB_CHUNK / (PIB_THREADS * 4);     // batches per warp and chunk
+        Pts4 cur;
+        load_pts4(pts, p_begin + warp * PIB_WBATCH + lane * 4, p_end, vec, cur);
+#pragma unroll 1
+        for (int j = 0; j < NB; ++j) {
+            const int p0 = p_begin + (j * (PIB_THREADS / 32) + warp) * PIB_WBATCH + lane * 4;
+            const int nvalid = max(0, min(4, p_end - p0));
+            Pts4 nxt;
+            if (j + 1 < NB) load_pts4(pts, p0 + (PIB_THREADS / 32) * PIB_WBATCH, p_end, vec, nxt);
+            unsigned int hot = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float fx = (cur.x[i] - h.gx0) * h.finv_x, fy = (cur.y[i] - h.gy0) * h.finv_y;
+                // NaN and out-of-grid coordinates fail the range test => cold (-1); inside the grid trunc == floor
+                if (i < nvalid && fx >= 0.f && fx < (float)PIB_FG && fy >= 0.f && fy < (float)PIB_FG) {
+                    const int cell = (int)fy * PIB_FG + (int)fx;
+                    hot |= ((s_bits[cell >> 5] >> (cell & 31)) & 1u) << i;
+                }
+            }
+            if (vec && nvalid == 4) *reinterpret_cast<int4*>(out + p0) = make_int4(-1, -1, -1, -1);
+            else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (i < nvalid) out[p0 + i] = -1;
+            }
+            if (__any_sync(0xffffffffu, hot != 0)) {
+                const int nh = __popc(hot);
+                int pre = nh;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+                const int total = __shfl_sync(0xffffffffu, pre, 31);
+                int qb = pre - nh;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if ((hot >> i) & 1u) wq[qb++] = make_float4(cur.x[i], cur.y[i], cur.z[i], __int_as_float(p0 + i));
+                __syncwarp();   // queue visible; also orders the provisional -1 stores before the results
+                for (int q = lane; q < total; q += 32) {
+                    const float4 e = wq[q];
+                    const int cx = (int)((e.x - h.gx0) * h.inv_x), cy = (int)((e.y - h.gy0) * h.inv_y);
+                    const int cell = min(cy, PIB_G - 1) * PIB_G + min(cx, PIB_G - 1);
+                    const unsigned int s = s_start[cell], t = s_start[cell + 1];
+                    int res = 0x7fffffff;
+                    for (unsigned int i = s; i < t; ++i) {
+                        const int k = (int)__ldg(list + i);
+                        if (k < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k * 8)) res = k;
+                    }
+                    if (res != 0x7fffffff) out[__float_as_int(e.w)] = res;
+                }
+                __syncwarp();   // the queue may be overwritten by the next batch
+            }
+            if (j + 1 < NB) cur = nxt;
+        }
+    }
+}
+
+// Small problems (N <= PIB_DIRECT_BOXES, few points): one launch, no grid.  Every CTA rebuilds the
+// N box records in shared memory and runs the reference's ascending loop with early exit.
+__global__ void __launch_bounds__(PIB_THREADS)
+pib_direct_kernel(const float* __restrict__ boxes_all, const float* __restrict__ pts_all, int N, int M,
+                  int* __restrict__ out_all, int chunks_per_frame) {
+    __shared__ __align__(16) float s_rec[PIB_DIRECT_BOXES * 8];
+    const int tid = threadIdx.x;
+    const int f = blockIdx.x / chunks_per_frame;
+    const int chunk = blockIdx.x - f * chunks_per_frame;
+    const float* pts = pts_all + (size_t)f * M * 3;
+    int* out = out_all + (size_t)f * M;
+    if (tid < N) {
+        const float* b = boxes_all + ((size_t)f * N + tid) * 7;
+        float tx, ty, tz;
+        box_thresholds<false>(b[3], b[4], b[5], tx, ty, tz);
+        float* r = s_rec + tid * 8;
+        r[0] = b[0]; r[1] = b[1]; r[2] = b[2]; r[3] = cosf(-b[6]); r[4] = sinf(-b[6]); r[5] = tx; r[6] = ty; r[7] = tz;
+    }
+    const int p_begin = chunk * PIB_DIRECT_PTS, p_end = min(M, p_begin + PIB_DIRECT_PTS);
+    const bool vec = ((((uintptr_t)pts) & 15) == 0) && ((((uintptr_t)out) & 15) == 0);
+    Pts4 cur;
+    load_pts4(pts, p_begin + tid * 4, p_end, vec, cur);
+    __syncthreads();
+    for (int base = p_begin; base < p_end; base += PIB_ROUND) {
+        const int p0 = base + tid * 4;
+        const int nvalid = max(0, min(4, p_end - p0));
+        Pts4 nxt;
+        load_pts4(pts, p0 + PIB_ROUND, p_end, vec, nxt);
+        int res[4] = {-1, -1, -1, -1};
+        for (int k = N - 1; k >= 0; --k) {      // descending + overwrite == first hit of the ascending loop
+            const float* r = s_rec + k * 8;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (pt_in_box_gpu(cur.x[i], cur.y[i], cur.z[i], r)) res[i] = k;
+        }
+        if (vec && nvalid == 4) *reinterpret_cast<int4*>(out + p0) = make_int4(res[0], res[1], res[2], res[3]);
         else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) if (i < nvalid) out[p0 + i] = -1;
+            for (int i = 0; i < 4; ++i) if (i < nvalid) out[p0 + i] = res[i];
         }
-        // warp-aggregated append of the hot points
-        const int nh = __popc(hot);
-        int pre = nh;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
-        const int wtotal = __shfl_sync(0xffffffffu, pre, 31);
-        if (wtotal) {
-            int qb = 0;
-            if (lane == 31) qb = atomicAdd(&s_qn, wtotal);
-            qb = __shfl_sync(0xffffffffu, qb, 31) - q_base + pre - nh;   // s_qn only grows; q_base = its value at round start
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if ((hot >> i) & 1u) s_q[qb++] = make_float4(px[i], py[i], pz[i], __int_as_float(p0 + i));
-        }
-        __syncthreads();
-        const int q_total = s_qn;
-        const int qn = q_total - q_base;
-        q_base = q_total;
-        for (int q = tid; q < qn; q += PIB_THREADS) {
-            const float4 e = s_q[q];
-            const int cx = (int)((e.x - h.gx0) * h.inv_x), cy = (int)((e.y - h.gy0) * h.inv_y);
-            const int cell = min(cy, PIB_G - 1) * PIB_G + min(cx, PIB_G - 1);
-            const unsigned int s = __ldg(start + cell), t = __ldg(start + cell + 1);
-            int res = 0x7fffffff;
-            for (unsigned int i = s; i < t; ++i) {
-                const int k = (int)__ldg(list + i);
-                if (k < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k * 8)) res = k;
-            }
-            if (res != 0x7fffffff) out[__float_as_int(e.w)] = res;
-        }
-        __syncthreads();   // the queue buffer is free again
+        cur = nxt;
     }
 }
 
@@ -440,13 +507,29 @@ int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int 
     if (!boxes) return fail(GLENET_EINVAL, "%s: null pointer", what);
     if (!ws || ws_bytes < glenet_points_in_boxes_workspace_bytes(B, N)) return fail(GLENET_EWORKSPACE, "%s: workspace too small", what);
     if ((uintptr_t)ws & 15) return fail(GLENET_EALIGN, "%s: workspace must be 16-byte aligned", what);
+    if (N <= PIB_DIRECT_BOXES && (long)B * M <= PIB_DIRECT_MAX_POINTS) {
+        const int chunks = (M + PIB_DIRECT_PTS - 1) / PIB_DIRECT_PTS;
+        pib_direct_kernel<<<(unsigned)(chunks * B), PIB_THREADS, 0, st>>>(boxes, pts, N, M, out, chunks);
+        return check_launch(what);
+    }
     PibWorkspace w = pib_layout(ws, B, N);
     pib_build_kernel<<<B, PIB_BUILD_THREADS, 0, st>>>(boxes, N, w);
     int rc = check_launch(what);
     if (rc) return rc;
-    const int chunks = (M + PIB_PTS_PER_CTA - 1) / PIB_PTS_PER_CTA;
-    if ((long)chunks * B > 0x7fffffffL) return fail(GLENET_EINVAL, "%s: too many chunks", what);
-    pib_query_kernel<<<(unsigned)(chunks * B), PIB_THREADS, 0, st>>>(pts, N, M, w, out, chunks);
+    const int chunks = (M + PIB_CHUNK - 1) / PIB_CHUNK;
+    const long total = (long)chunks * B;
+    if (total > 0x7fffffffL) return fail(GLENET_EINVAL, "%s: too many chunks", what);
+    const size_t smem_fixed = sizeof(unsigned int) * (PIB_FWORDS + PIB_CELLS + 4) + sizeof(float4) * (PIB_THREADS / 32) * PIB_WBATCH;
+    const size_t smem = smem_fixed + sizeof(float) * 8 * (size_t)(N <= PIB_SMEM_BOXES ? N : 0);
+    static bool attr_done = false;
+    if (!attr_done) {
+        rc = set_smem(pib_query_kernel, smem_fixed + sizeof(float) * 8 * PIB_SMEM_BOXES, what);
+        if (rc) return rc;
+        attr_done = true;
+    }
+    const long resident = 4L * 148;   // persistent: 4 CTAs per SM
+    const unsigned grid = (unsigned)(total < resident ? total : resident);
+    pib_query_kernel<<<grid, PIB_THREADS, smem, st>>>(pts, N, M, w, out, chunks, (int)total);
     return check_launch(what);
 }
 
