@@ -111,7 +111,12 @@ __device__ __forceinline__ float cull_radius(const float* __restrict__ box) {
 // cross_points[16] of the reference (:155)
 constexpr int MAX_POLY = 16;
 
-// intersection() of iou3d_nms_kernel.cu:57-89 for edge p0->p1 of box a and q0->q1 of box b.
+// intersection() of iou3d_nms_kernel.cu:57-89 for edge p0->p1 of box a and q0->q1 of box b, evaluated
+// BRANCH-FREE: in a warp of 32 different pairs some lane passes every test of every edge pair, so the
+// reference's early exits only add divergence overhead.  Everything (4 cross products, both divisions)
+// is computed unconditionally -- 16 independent straight-line blocks per pair that the scheduler can
+// overlap -- and only the result is predicated.  The values that ARE used are computed by exactly the
+// reference's operation sequence.  Returns true when the reference would have appended (ox, oy).
 template <bool FMA>
 __device__ __forceinline__ bool edge_intersection(float p0x, float p0y, float p1x, float p1y,
                                                   float q0x, float q0y, float q1x, float q1y,
@@ -119,7 +124,6 @@ __device__ __forceinline__ bool edge_intersection(float p0x, float p0y, float p1
     // check_rect_cross (:43-48)
     const bool rc = fminf(p0x, p1x) <= fmaxf(q0x, q1x) && fminf(q0x, q1x) <= fmaxf(p0x, p1x) &&
                     fminf(p0y, p1y) <= fmaxf(q0y, q1y) && fminf(q0y, q1y) <= fmaxf(p0y, p1y);
-    if (!rc) return false;
     const float pdx = __fsub_rn(p1x, p0x), pdy = __fsub_rn(p1y, p0y);   // p1 - p0
     const float qdx = __fsub_rn(q1x, q0x), qdy = __fsub_rn(q1y, q0y);   // q1 - q0
     // s1 = cross(q0, p1, p0)
@@ -132,20 +136,19 @@ __device__ __forceinline__ bool edge_intersection(float p0x, float p0y, float p1
     const float s3 = mul_sub<FMA>(__fsub_rn(p0x, q0x), qdy, __fsub_rn(p0y, q0y), qdx);
     // s4 = cross(q1, p1, q0)
     const float s4 = mul_sub<FMA>(qdx, __fsub_rn(p1y, q0y), qdy, __fsub_rn(p1x, q0x));
-    if (!(__fmul_rn(s1, s2) > 0.f && __fmul_rn(s3, s4) > 0.f)) return false;
+    const bool hit = rc && (__fmul_rn(s1, s2) > 0.f) && (__fmul_rn(s3, s4) > 0.f);
     const float s5 = __fsub_rn(m2, m1);
     const float den = __fsub_rn(s5, s1);
-    if (fabsf(den) > 1e-8f) {
-        ox = __fdiv_rn(mul_sub<FMA>(q0x, s5, q1x, s1), den);
-        oy = __fdiv_rn(mul_sub<FMA>(q0y, s5, q1y, s1), den);
-    } else {
+    ox = __fdiv_rn(mul_sub<FMA>(q0x, s5, q1x, s1), den);
+    oy = __fdiv_rn(mul_sub<FMA>(q0y, s5, q1y, s1), den);
+    if (hit && !(fabsf(den) > 1e-8f)) {   // (:77-89) practically never taken
         const float a0 = __fsub_rn(p0y, p1y), b0 = pdx, c0 = mul_sub<FMA>(p0x, p1y, p1x, p0y);
         const float a1 = __fsub_rn(q0y, q1y), b1 = qdx, c1 = mul_sub<FMA>(q0x, q1y, q0y, q1x);
         const float D = mul_sub<FMA>(b1, a0, b0, a1);
         ox = __fdiv_rn(mul_sub<FMA>(b0, c1, b1, c0), D);
         oy = __fdiv_rn(mul_sub<FMA>(c0, a1, a0, c1), D);
     }
-    return true;
+    return hit;
 }
 
 // check_in_box2d (:50-60) of point (px,py) against a prepared box.
@@ -167,65 +170,33 @@ __device__ __forceinline__ float pseudo_angle(float dy, float dx) {
     return copysignf(1.f - q, dy);                             // [0, 2] for dy >= +0, [-2, -0] for dy <= -0
 }
 
-// box_overlap (:104-225): overlap area of prepared boxes a (row) and b (column).
-// The polygon (<= 16 vertices, dynamically indexed) lives in per-thread local memory, which the
-// hardware interleaves across lanes and serves from L1 -- it costs no shared memory, so the
-// kernels that call this keep a high CTA count per SM.
-template <bool FMA>
-__device__ float box_overlap(const float* __restrict__ a, const float* __restrict__ b) {
-    float ax[4], ay[4], bx[4], by[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        ax[k] = a[BP_PX + k]; ay[k] = a[BP_PY + k];
-        bx[k] = b[BP_PX + k]; by[k] = b[BP_PY + k];
-    }
-    float vx[MAX_POLY], vy[MAX_POLY], key[MAX_POLY];
-    int cnt = 0;
-    float sx = 0.f, sy = 0.f;   // poly_center accumulator, in append order
-    // cross_points[16] (:155) is exactly large enough for every non-degenerate pair; the guard
-    // only keeps a pathological (NaN/degenerate) pair from writing outside its array.
-    auto push = [&](float x, float y) {
-        if (cnt < MAX_POLY) {
-            sx = __fadd_rn(sx, x);
-            sy = __fadd_rn(sy, y);
-            vx[cnt] = x;
-            vy[cnt] = y;
-            ++cnt;
-        }
-    };
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float ox, oy;
-            if (edge_intersection<FMA>(ax[i], ay[i], ax[(i + 1) & 3], ay[(i + 1) & 3],
-                                       bx[j], by[j], bx[(j + 1) & 3], by[(j + 1) & 3], ox, oy)) {
-                push(ox, oy);
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (corner_in_box<FMA>(a, bx[k], by[k])) push(bx[k], by[k]);
-        if (corner_in_box<FMA>(b, ax[k], ay[k])) push(ax[k], ay[k]);
-    }
+// Area of the polygon spanned by `cnt` vertices (any order): angular ordering about the centroid, then
+// the reference's fan from the first sorted vertex (:196-225).  Vertices are read through `V(k)`.
+//   cnt <= 8 (>98 % of pairs): 8 register slots, branch-free 19-comparator sorting network on a monotone
+//            pseudo-angle, predicated fan -- no divergence between lanes with different vertex counts.
+//   cnt  > 8 (degenerate / nearly coincident boxes): stable insertion sort in per-thread local memory.
+// The centroid only feeds the ordering (not the area), so its summation order and an approximate
+// reciprocal do not matter; the fan terms and their summation order are the reference's.
+template <bool FMA, typename VertexFn>
+__device__ __forceinline__ float polygon_area(int cnt, VertexFn V) {
     if (cnt < 3) return 0.f;   // the fan of 0, 1 or 2 vertices has area exactly +0 in the reference too
-    // The centroid only feeds the angular ordering (not the area), so an approximate reciprocal is enough.
-    const float inv_cnt = __frcp_rn((float)cnt);
-    const float ccx = sx * inv_cnt, ccy = sy * inv_cnt;
+    if (cnt > MAX_POLY) cnt = MAX_POLY;
     float area = 0.f;
     if (cnt <= 8) {
-        // common case: the polygon goes into 8 register slots, is ordered by a branch-free 19-comparator
-        // sorting network on a monotone pseudo-angle, and the fan runs predicated -- no divergence
-        // between lanes whose polygons have different vertex counts.
         float X[8], Y[8], K[8];
+        float sx = 0.f, sy = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const bool v = k < cnt;
-            X[k] = v ? vx[k] : 0.f;
-            Y[k] = v ? vy[k] : 0.f;
-            K[k] = v ? pseudo_angle(__fsub_rn(Y[k], ccy), __fsub_rn(X[k], ccx)) : 3.0e38f;
+            const float2 p = v ? V(k) : make_float2(0.f, 0.f);
+            X[k] = p.x; Y[k] = p.y;
+            sx += p.x; sy += p.y;
         }
+        const float inv_cnt = __frcp_rn((float)cnt);
+        const float ccx = sx * inv_cnt, ccy = sy * inv_cnt;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            K[k] = (k < cnt) ? pseudo_angle(__fsub_rn(Y[k], ccy), __fsub_rn(X[k], ccx)) : 3.0e38f;
 #define GLENET_CE(i, j)                                                       \
         {                                                                     \
             const bool sw = K[i] > K[j];                                      \
@@ -252,7 +223,11 @@ __device__ float box_overlap(const float* __restrict__ a, const float* __restric
             uy = wy;
         }
     } else {
-        // rare: 9..16 vertices (degenerate / nearly coincident boxes) -- stable insertion sort in local memory
+        float vx[MAX_POLY], vy[MAX_POLY], key[MAX_POLY];
+        float sx = 0.f, sy = 0.f;
+        for (int k = 0; k < cnt; ++k) { const float2 p = V(k); vx[k] = p.x; vy[k] = p.y; sx += p.x; sy += p.y; }
+        const float inv_cnt = __frcp_rn((float)cnt);
+        const float ccx = sx * inv_cnt, ccy = sy * inv_cnt;
         for (int k = 0; k < cnt; ++k) {
             const float x = vx[k], y = vy[k];
             const float kk = pseudo_angle(__fsub_rn(y, ccy), __fsub_rn(x, ccx));
@@ -277,6 +252,37 @@ __device__ float box_overlap(const float* __restrict__ a, const float* __restric
         }
     }
     return __fmul_rn(fabsf(area), 0.5f);
+}
+
+// box_overlap (:104-225): overlap area of prepared boxes a (row) and b (column), one thread per pair.
+// 16 edge-pair blocks + 8 corner tests, all straight-line and independent; only the append to the
+// vertex list (per-thread local memory, <= 16 entries) is predicated.
+template <bool FMA>
+__device__ __forceinline__ float box_overlap(const float* __restrict__ a, const float* __restrict__ b) {
+    float ax[4], ay[4], bx[4], by[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ax[k] = a[BP_PX + k]; ay[k] = a[BP_PY + k];
+        bx[k] = b[BP_PX + k]; by[k] = b[BP_PY + k];
+    }
+    float2 v[MAX_POLY];
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float ox, oy;
+            const bool hit = edge_intersection<FMA>(ax[i], ay[i], ax[(i + 1) & 3], ay[(i + 1) & 3],
+                                                    bx[j], by[j], bx[(j + 1) & 3], by[(j + 1) & 3], ox, oy);
+            if (hit && cnt < MAX_POLY) v[cnt++] = make_float2(ox, oy);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (corner_in_box<FMA>(a, bx[k], by[k]) && cnt < MAX_POLY) v[cnt++] = make_float2(bx[k], by[k]);
+        if (corner_in_box<FMA>(b, ax[k], ay[k]) && cnt < MAX_POLY) v[cnt++] = make_float2(ax[k], ay[k]);
+    }
+    return polygon_area<FMA>(cnt, [&](int k) { return v[k]; });
 }
 
 // iou_bev (:227-234)

@@ -30,8 +30,7 @@ namespace glenet {
 constexpr int IOU_THREADS = 256;
 constexpr int IOU_TR_MAX = 256;            // tile rows (boxes_a)
 constexpr int IOU_TC_MAX = 128;            // tile cols (boxes_b)
-constexpr int IOU_STEP = 4 * IOU_THREADS;  // pair tests between two queue checks
-constexpr int IOU_QCAP = 8 * IOU_THREADS;  // queue capacity (<= 8 clipped pairs per thread and drain)
+constexpr int IOU_QCAP = 6 * IOU_THREADS;  // queue capacity; drained when 4 more column steps could overflow it
 constexpr int IOU_ZCHUNK = 4 * 32;         // float4 stores per warp and zero-fill chunk
 
 enum { MODE_OVERLAP = 0, MODE_IOU_BEV = 1, MODE_IOU3D = 2 };
@@ -51,7 +50,7 @@ struct __align__(16) IouSmem {
     float rpre[IOU_TR_MAX * BP_STRIDE];
     float cpre[IOU_TC_MAX * BP_STRIDE];
     float qres[IOU_QCAP];                  // clipped results, parked until the tile's zero fill is complete
-    unsigned short queue[IOU_QCAP];        // (row << 7) | col
+    unsigned short queue[IOU_QCAP];        // (row << 8) | col  (row < 256, col < 128)
     float red[IOU_THREADS / 32][5];
     unsigned char rflag[IOU_TR_MAX], cflag[IOU_TC_MAX], act[IOU_TC_MAX];
     int qcount, nact, zchunk;
@@ -133,8 +132,8 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
     PHASE_MARK(3);
     for (int q = tid; q < n; q += IOU_THREADS) {
         const unsigned int e = sm.queue[q];
-        const float* a = sm.rpre + (e >> 7) * BP_STRIDE;
-        const float* b = sm.cpre + (e & 127) * BP_STRIDE;
+        const float* a = sm.rpre + (e >> 8) * BP_STRIDE;
+        const float* b = sm.cpre + (e & 255) * BP_STRIDE;
         sm.qres[q] = finish_pair<MODE>(a, b, box_overlap<FMA>(a, b));
     }
     PHASE_MARK(7);
@@ -143,7 +142,7 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
     PHASE_MARK(4);
     for (int q = tid; q < n; q += IOU_THREADS) {
         const unsigned int e = sm.queue[q];
-        out[(size_t)(r0 + (e >> 7)) * nb + (c0 + (e & 127))] = sm.qres[q];
+        out[(size_t)(r0 + (e >> 8)) * nb + (c0 + (e & 255))] = sm.qres[q];
     }
     __syncthreads();
     if (tid == 0) sm.qcount = 0;
@@ -159,7 +158,7 @@ __device__ __forceinline__ void enqueue_heavy(IouSmem& sm, unsigned int heavy, i
     if (lane == 0) qb = atomicAdd(&sm.qcount, __popc(m));
     qb = __shfl_sync(0xffffffffu, qb, 0);
     if (heavy) {
-        sm.queue[qb + __popc(m & ((1u << lane) - 1))] = (unsigned short)((r << 7) | c);
+        sm.queue[qb + __popc(m & ((1u << lane) - 1))] = (unsigned short)((r << 8) | c);
         if (sm.rflag[r] == 0) sm.rflag[r] = 1;   // 0 = unused, 1 = wanted, 2 = prepared
         if (sm.cflag[c] == 0) sm.cflag[c] = 1;
     }
@@ -225,29 +224,36 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     __syncthreads();   // act[] / nact complete
     PHASE_MARK(1);
 
-    // ---- per-pair circle test on the active columns only; survivors go to the queue
+    // ---- per-pair circle test on the active columns only; survivors go to the queue.
+    //      One row per thread (TR <= 256 = block size), uniform loop over the active columns whose
+    //      data is a shared-memory broadcast; the queue is checked every 4 columns (<= 1024 appends).
     const int nact = sm.nact;
-    const int ntests = tr * nact;
-    for (int base = 0; base < ntests; base += IOU_STEP) {
-        if (sm.qcount > IOU_QCAP - IOU_STEP) {   // uniform: qcount is stable between barriers (dense tiles only)
-            drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, vec);
-        }
-#pragma unroll 2
-        for (int k = 0; k < IOU_STEP / IOU_THREADS; ++k) {
-            const int p = base + k * IOU_THREADS + tid;
-            unsigned int heavy = 0;
-            int r = 0, c = 0;
-            if (p < ntests) {
-                r = p / nact;
-                c = sm.act[p - r * nact];
-                const float4 rw = sm.row[r];
+    {
+        // thread -> (row, column group): rows padded to a power of two so that small tiles still use all threads
+        int trp = 32;
+        while (trp < tr) trp <<= 1;
+        const int groups = IOU_THREADS / trp, row = tid & (trp - 1), grp = tid / trp;
+        const bool has_row = row < tr;
+        const float4 rw = has_row ? sm.row[row] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int iters = (nact + groups - 1) / groups;
+        for (int it0 = 0; it0 < iters; it0 += 4) {
+            const int qc = sm.qcount;
+            __syncthreads();   // everyone has read the count before anyone appends again => the branch is uniform
+            if (qc > IOU_QCAP - 4 * IOU_THREADS) {   // dense tiles only
+                drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, vec);
+            }
+            const int it1 = min(iters, it0 + 4);
+            for (int it = it0; it < it1; ++it) {
+                const int k = it * groups + grp;
+                const bool valid = has_row && k < nact;
+                const int c = valid ? sm.act[k] : 0;
                 const float dx = rw.x - sm.ccx[c], dy = rw.y - sm.ccy[c], rr = rw.z + sm.crad[c];
                 // NaN anywhere => the comparison is false => not culled => the clip pass decides, like the reference
-                heavy = (!(dx * dx + dy * dy > rr * rr)) ? 1u : 0u;
+                const unsigned int heavy = (valid && !(dx * dx + dy * dy > rr * rr)) ? 1u : 0u;
+                enqueue_heavy(sm, heavy, row, c, lane);
             }
-            enqueue_heavy(sm, heavy, r, c, lane);
+            __syncthreads();
         }
-        __syncthreads();
     }
     PHASE_MARK(2);
     drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, vec);
@@ -263,7 +269,9 @@ iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict_
     const int tid = threadIdx.x;
     const int i = blockIdx.x * ALIGNED_THREADS + tid;
     if (i >= na) return;
-    float a[BP_STRIDE], b[BP_STRIDE];   // statically indexed => registers
+    __shared__ float s_pre[2 * ALIGNED_THREADS * BP_STRIDE];
+    float* a = s_pre + tid * BP_STRIDE;
+    float* b = s_pre + (ALIGNED_THREADS + tid) * BP_STRIDE;
     const float* ba = A + (size_t)i * 7;
     const float* bb = B + (size_t)(i / group) * 7;
     float out_v = 0.f;

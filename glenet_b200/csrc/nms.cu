@@ -148,11 +148,10 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
     const int nq = sm.qcount;
     for (int q = tid; q < nq; q += NMS_THREADS) {
         const int p = sm.queue[q];
-        const int r = p >> 6, c = p & 63;
-        const float* a = sm.rpre + r * BP_STRIDE;
-        const float* b = sm.cpre + c * BP_STRIDE;
+        const float* a = sm.rpre + (p >> 6) * BP_STRIDE;
+        const float* b = sm.cpre + (p & 63) * BP_STRIDE;
         const float ov = box_overlap<true>(a, b);
-        if (iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) > thresh) atomicOr(&sm.bits[r], 1ull << c);
+        if (iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) > thresh) atomicOr(&sm.bits[p >> 6], 1ull << (p & 63));
     }
     __syncthreads();
     if (tid < tr) mask[(size_t)(r0 + tid) * col_blocks + cb] = sm.bits[tid];
