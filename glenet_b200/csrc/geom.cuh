@@ -111,12 +111,9 @@ __device__ __forceinline__ float cull_radius(const float* __restrict__ box) {
 // cross_points[16] of the reference (:155)
 constexpr int MAX_POLY = 16;
 
-// intersection() of iou3d_nms_kernel.cu:57-89 for edge p0->p1 of box a and q0->q1 of box b, evaluated
-// BRANCH-FREE: in a warp of 32 different pairs some lane passes every test of every edge pair, so the
-// reference's early exits only add divergence overhead.  Everything (4 cross products, both divisions)
-// is computed unconditionally -- 16 independent straight-line blocks per pair that the scheduler can
-// overlap -- and only the result is predicated.  The values that ARE used are computed by exactly the
-// reference's operation sequence.  Returns true when the reference would have appended (ox, oy).
+// intersection() of iou3d_nms_kernel.cu:57-89 for edge p0->p1 of box a and q0->q1 of box b.
+// (A branch-free variant that evaluates all 16 edge pairs unconditionally was measured and lost: the
+// straight-line code is 135 KB of SASS and stalls on instruction fetch; see DESIGN.md.)
 template <bool FMA>
 __device__ __forceinline__ bool edge_intersection(float p0x, float p0y, float p1x, float p1y,
                                                   float q0x, float q0y, float q1x, float q1y,
@@ -124,6 +121,7 @@ __device__ __forceinline__ bool edge_intersection(float p0x, float p0y, float p1
     // check_rect_cross (:43-48)
     const bool rc = fminf(p0x, p1x) <= fmaxf(q0x, q1x) && fminf(q0x, q1x) <= fmaxf(p0x, p1x) &&
                     fminf(p0y, p1y) <= fmaxf(q0y, q1y) && fminf(q0y, q1y) <= fmaxf(p0y, p1y);
+    if (!rc) return false;
     const float pdx = __fsub_rn(p1x, p0x), pdy = __fsub_rn(p1y, p0y);   // p1 - p0
     const float qdx = __fsub_rn(q1x, q0x), qdy = __fsub_rn(q1y, q0y);   // q1 - q0
     // s1 = cross(q0, p1, p0)
@@ -132,23 +130,25 @@ __device__ __forceinline__ bool edge_intersection(float p0x, float p0y, float p1
     const float m1 = __fmul_rn(pdx, __fsub_rn(q1y, p0y));
     const float m2 = __fmul_rn(pdy, __fsub_rn(q1x, p0x));
     const float s2 = __fsub_rn(m1, m2);
+    if (!(__fmul_rn(s1, s2) > 0.f)) return false;
     // s3 = cross(p0, q1, q0)
     const float s3 = mul_sub<FMA>(__fsub_rn(p0x, q0x), qdy, __fsub_rn(p0y, q0y), qdx);
     // s4 = cross(q1, p1, q0)
     const float s4 = mul_sub<FMA>(qdx, __fsub_rn(p1y, q0y), qdy, __fsub_rn(p1x, q0x));
-    const bool hit = rc && (__fmul_rn(s1, s2) > 0.f) && (__fmul_rn(s3, s4) > 0.f);
+    if (!(__fmul_rn(s3, s4) > 0.f)) return false;
     const float s5 = __fsub_rn(m2, m1);
     const float den = __fsub_rn(s5, s1);
-    ox = __fdiv_rn(mul_sub<FMA>(q0x, s5, q1x, s1), den);
-    oy = __fdiv_rn(mul_sub<FMA>(q0y, s5, q1y, s1), den);
-    if (hit && !(fabsf(den) > 1e-8f)) {   // (:77-89) practically never taken
+    if (fabsf(den) > 1e-8f) {
+        ox = __fdiv_rn(mul_sub<FMA>(q0x, s5, q1x, s1), den);
+        oy = __fdiv_rn(mul_sub<FMA>(q0y, s5, q1y, s1), den);
+    } else {
         const float a0 = __fsub_rn(p0y, p1y), b0 = pdx, c0 = mul_sub<FMA>(p0x, p1y, p1x, p0y);
         const float a1 = __fsub_rn(q0y, q1y), b1 = qdx, c1 = mul_sub<FMA>(q0x, q1y, q0y, q1x);
         const float D = mul_sub<FMA>(b1, a0, b0, a1);
         ox = __fdiv_rn(mul_sub<FMA>(b0, c1, b1, c0), D);
         oy = __fdiv_rn(mul_sub<FMA>(c0, a1, a0, c1), D);
     }
-    return hit;
+    return true;
 }
 
 // check_in_box2d (:50-60) of point (px,py) against a prepared box.
@@ -255,32 +255,29 @@ __device__ __forceinline__ float polygon_area(int cnt, VertexFn V) {
 }
 
 // box_overlap (:104-225): overlap area of prepared boxes a (row) and b (column), one thread per pair.
-// 16 edge-pair blocks + 8 corner tests, all straight-line and independent; only the append to the
-// vertex list (per-thread local memory, <= 16 entries) is predicated.
+// The vertex list (<= 16 entries, dynamically indexed) lives in per-thread local memory.  The 4 x 4 edge
+// loops are kept ROLLED (corners re-read from the BoxPre records in shared memory): the unrolled form is
+// ~6000 SASS instructions and thrashes the instruction cache when warps diverge.
 template <bool FMA>
-__device__ __forceinline__ float box_overlap(const float* __restrict__ a, const float* __restrict__ b) {
-    float ax[4], ay[4], bx[4], by[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        ax[k] = a[BP_PX + k]; ay[k] = a[BP_PY + k];
-        bx[k] = b[BP_PX + k]; by[k] = b[BP_PY + k];
-    }
+__device__ __noinline__ float box_overlap(const float* __restrict__ a, const float* __restrict__ b) {
     float2 v[MAX_POLY];
     int cnt = 0;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 4; ++i) {
-#pragma unroll
+        const float p0x = a[BP_PX + i], p0y = a[BP_PY + i], p1x = a[BP_PX + ((i + 1) & 3)], p1y = a[BP_PY + ((i + 1) & 3)];
+#pragma unroll 1
         for (int j = 0; j < 4; ++j) {
             float ox, oy;
-            const bool hit = edge_intersection<FMA>(ax[i], ay[i], ax[(i + 1) & 3], ay[(i + 1) & 3],
-                                                    bx[j], by[j], bx[(j + 1) & 3], by[(j + 1) & 3], ox, oy);
-            if (hit && cnt < MAX_POLY) v[cnt++] = make_float2(ox, oy);
+            if (edge_intersection<FMA>(p0x, p0y, p1x, p1y, b[BP_PX + j], b[BP_PY + j], b[BP_PX + ((j + 1) & 3)], b[BP_PY + ((j + 1) & 3)], ox, oy)) {
+                if (cnt < MAX_POLY) v[cnt++] = make_float2(ox, oy);
+            }
         }
     }
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 4; ++k) {
-        if (corner_in_box<FMA>(a, bx[k], by[k]) && cnt < MAX_POLY) v[cnt++] = make_float2(bx[k], by[k]);
-        if (corner_in_box<FMA>(b, ax[k], ay[k]) && cnt < MAX_POLY) v[cnt++] = make_float2(ax[k], ay[k]);
+        const float bxk = b[BP_PX + k], byk = b[BP_PY + k], axk = a[BP_PX + k], ayk = a[BP_PY + k];
+        if (corner_in_box<FMA>(a, bxk, byk) && cnt < MAX_POLY) v[cnt++] = make_float2(bxk, byk);
+        if (corner_in_box<FMA>(b, axk, ayk) && cnt < MAX_POLY) v[cnt++] = make_float2(axk, ayk);
     }
     return polygon_area<FMA>(cnt, [&](int k) { return v[k]; });
 }
