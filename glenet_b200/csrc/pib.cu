@@ -31,6 +31,7 @@ constexpr int PIB_FG = 256;                     // fine occupancy bitmap, cells 
 constexpr int PIB_FWORDS = PIB_FG * PIB_FG / 32;
 constexpr int PIB_ROUND = 4 * 256;              // points per CTA round of the direct kernel (4 per thread)
 constexpr int PIB_WBATCH = 128;                 // points per warp batch (4 per lane)
+constexpr int PIB_WQ = PIB_WBATCH + 32;         // warp queue: one batch of hot points + a remainder of < 32
 constexpr int PIB_CHUNK = 4096;                 // points per work item of the query kernel
 constexpr int PIB_THREADS = 256;
 constexpr int PIB_DIRECT_BOXES = 32;            // at most this many boxes => single-launch direct kernel for small calls
@@ -54,6 +55,7 @@ struct PibWorkspace {
     unsigned int* start;   // [B][PIB_CELLS + 1]
     unsigned int* list;    // [B][cap]
     unsigned int* bits;    // [B][PIB_FWORDS] fine occupancy bitmap
+    unsigned long long* cells;   // [B][PIB_CELLS] packed coarse cell: id0:16 | id1:16 | list start:24 | count:8
     size_t cap;
     size_t bytes;
 };
@@ -68,6 +70,7 @@ __host__ __device__ inline PibWorkspace pib_layout(void* base, int B, int N) {
     w.cap = pib_list_cap(N);
     w.list = (unsigned int*)(p + off);  off += ((size_t)B * w.cap * sizeof(unsigned int) + 15) / 16 * 16;
     w.bits = (unsigned int*)(p + off);  off += ((size_t)B * PIB_FWORDS * sizeof(unsigned int) + 15) / 16 * 16;
+    w.cells = (unsigned long long*)(p + off);  off += ((size_t)B * PIB_CELLS * sizeof(unsigned long long) + 15) / 16 * 16;
     w.bytes = off;
     return w;
 }
@@ -114,12 +117,61 @@ __device__ __forceinline__ Footprint footprint(const float* __restrict__ r) {
     return f;
 }
 
-// Visit every cell of a G x G grid (origin gx0/gy0, 1/cell = inv) that the footprint may touch; the 32
-// lanes of the calling warp split the cell range.  The range uses the very mapping of the query kernel
+// Visit every cell of a G x G grid (origin gx0/gy0, 1/cell = inv) that the footprint may touch.
+// The range uses the very mapping of the query kernel
 // (monotone => every point of [x0, x1] lands in [ix0, ix1]); a separating-axis test in the box frame
 // then drops the corner cells of rotated boxes.
+// Fine-bitmap rasterisation of one footprint, row by row: the x-extent of (padded rotated
+// rectangle) n (horizontal strip of the row) comes from clipping the rectangle's four edges to the strip
+// -- O(rows) instead of O(cells) work -- and the row's bits are set word-wise.  Everything is padded
+// outwards (strip and span), so the bitmap is a superset of the cells any inside point can map to.
+__device__ __forceinline__ void raster_fine_rows(const Footprint& f, float gx0, float gy0, float finv_x, float finv_y,
+                                                 unsigned int* __restrict__ s_bits) {
+    const int iy0 = max(0, min(PIB_FG - 1, (int)floorf((f.y0 - gy0) * finv_y)));
+    const int iy1 = max(0, min(PIB_FG - 1, (int)floorf((f.y1 - gy0) * finv_y)));
+    const float ch = 1.f / finv_y, cw = 1.f / finv_x;
+    const float eps_y = f.pad + 2e-3f * ch, eps_x = f.pad + 2e-3f * cw;
+    // corners relative to the centre: local (sx*hx, sy*hy) -> world (lx*c + ly*s, -lx*s + ly*c)
+    const float hx = f.tx + f.pad, hy = f.ty + f.pad;
+    float px[4], py[4];
+    const float sxs[4] = {1.f, -1.f, -1.f, 1.f}, sys[4] = {1.f, 1.f, -1.f, -1.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float lx = sxs[k] * hx, ly = sys[k] * hy;
+        px[k] = lx * f.c + ly * f.s;
+        py[k] = -lx * f.s + ly * f.c;
+    }
+    for (int iy = iy0; iy <= iy1; ++iy) {
+        const float ylo = gy0 + (float)iy * ch - f.cy - eps_y, yhi = gy0 + (float)(iy + 1) * ch - f.cy + eps_y;
+        float xmin = FLT_MAX, xmax = -FLT_MAX;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float ax = px[k], ay = py[k], bx = px[(k + 1) & 3], by = py[(k + 1) & 3];
+            if ((ay < ylo && by < ylo) || (ay > yhi && by > yhi)) continue;
+            float xa = ax, xb = bx;
+            const float dy = by - ay;
+            if (dy != 0.f) {
+                const float inv = 1.f / dy;
+                const float t0 = fminf(fmaxf((ylo - ay) * inv, 0.f), 1.f), t1 = fminf(fmaxf((yhi - ay) * inv, 0.f), 1.f);
+                xa = ax + t0 * (bx - ax);
+                xb = ax + t1 * (bx - ax);
+            }
+            xmin = fminf(xmin, fminf(xa, xb));
+            xmax = fmaxf(xmax, fmaxf(xa, xb));
+        }
+        if (!(xmax >= xmin)) continue;
+        const int ix0 = max(0, min(PIB_FG - 1, (int)floorf((f.cx + xmin - eps_x - gx0) * finv_x)));
+        const int ix1 = max(0, min(PIB_FG - 1, (int)floorf((f.cx + xmax + eps_x - gx0) * finv_x)));
+        for (int w = ix0 >> 5; w <= (ix1 >> 5); ++w) {
+            const int lo = max(ix0 - (w << 5), 0), hi = min(ix1 - (w << 5), 31);
+            const unsigned int mask = (hi >= 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+            atomicOr(&s_bits[iy * (PIB_FG / 32) + w], mask);
+        }
+    }
+}
+
 template <int G, typename F>
-__device__ __forceinline__ void for_cells_warp(const Footprint& f, float gx0, float gy0, float inv_x, float inv_y, int lane, F visit) {
+__device__ __forceinline__ void for_cells(const Footprint& f, float gx0, float gy0, float inv_x, float inv_y, F visit) {
     const int ix0 = max(0, min(G - 1, (int)floorf((f.x0 - gx0) * inv_x)));
     const int ix1 = max(0, min(G - 1, (int)floorf((f.x1 - gx0) * inv_x)));
     const int iy0 = max(0, min(G - 1, (int)floorf((f.y0 - gy0) * inv_y)));
@@ -128,8 +180,9 @@ __device__ __forceinline__ void for_cells_warp(const Footprint& f, float gx0, fl
     const float rx_ext = 0.5f * (fabsf(f.c) * cwx + fabsf(f.s) * cwy), ry_ext = 0.5f * (fabsf(f.s) * cwx + fabsf(f.c) * cwy);
     const float slack = f.pad + 1e-3f * (cwx + cwy);
     const int nx = ix1 - ix0 + 1, ncell = nx * (iy1 - iy0 + 1);
-    for (int i = lane; i < ncell; i += 32) {
-        const int iy = iy0 + i / nx, ix = ix0 + (i - (i / nx) * nx);
+    (void)ncell;
+    for (int iy = iy0; iy <= iy1; ++iy)
+    for (int ix = ix0; ix <= ix1; ++ix) {
         const float mx = gx0 + ((float)ix + 0.5f) * cwx - f.cx, my = gy0 + ((float)iy + 0.5f) * cwy - f.cy;
         const float lx = mx * f.c - my * f.s, ly = mx * f.s + my * f.c;
         if (fabsf(lx) > f.tx + rx_ext + slack || fabsf(ly) > f.ty + ry_ext + slack) continue;
@@ -206,18 +259,15 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
 
     unsigned int total = 0;
     if (!exhaustive && !empty) {
-        // fine occupancy bitmap (one warp per box, lanes split the box's cells)
-        for (int k = warp; k < N; k += PIB_BUILD_THREADS / 32) {
-            const Footprint fp = footprint(rec + (size_t)k * 8);
-            if (fp.never) continue;
-            for_cells_warp<PIB_FG>(fp, bx0, by0, finv_x, finv_y, lane, [&](int cell) { atomicOr(&s_bits[cell >> 5], 1u << (cell & 31)); });
-        }
-        // coarse CSR: count, scan, fill (same traversal twice)
+        // One box per thread (N <= 512 boxes is one round): with a few hundred boxes per frame, box-level
+        // parallelism beats splitting one box's ~15 rows / ~15 cells over a warp (measured both ways).
+        //   pass 0: fine occupancy bitmap + coarse counts      pass 1: coarse fill (after the scan)
         for (int pass = 0; pass < 2; ++pass) {
-            for (int k = warp; k < N; k += PIB_BUILD_THREADS / 32) {
+            for (int k = tid; k < N; k += PIB_BUILD_THREADS) {
                 const Footprint fp = footprint(rec + (size_t)k * 8);
                 if (fp.never) continue;
-                for_cells_warp<PIB_G>(fp, bx0, by0, inv_x, inv_y, lane, [&](int cell) {
+                if (pass == 0) raster_fine_rows(fp, bx0, by0, finv_x, finv_y, s_bits);
+                for_cells<PIB_G>(fp, bx0, by0, inv_x, inv_y, [&](int cell) {
                     const unsigned int pos = atomicAdd(&cnt[cell], 1u);
                     if (pass == 1) list[pos] = (unsigned int)k;
                 });
@@ -252,6 +302,20 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
             }
         }
         for (int i = tid; i < PIB_FWORDS; i += PIB_BUILD_THREADS) bits[i] = s_bits[i];
+        if (!exhaustive) {
+            // packed coarse cells: the first two candidates inline (most cells hold <= 2), the rest via the list
+            unsigned long long* cells = ws.cells + (size_t)f * PIB_CELLS;
+            bool too_many = false;
+            for (int c = tid; c < PIB_CELLS; c += PIB_BUILD_THREADS) {
+                const unsigned int s0 = start[c], n = start[c + 1] - s0;
+                const unsigned long long id0 = n > 0 ? list[s0] : 0xffffull, id1 = n > 1 ? list[s0 + 1] : 0xffffull;
+                too_many |= n > 255u;
+                cells[c] = id0 | (id1 << 16) | ((unsigned long long)(s0 & 0xffffffu) << 32) | ((unsigned long long)min(n, 255u) << 56);
+            }
+            if (too_many || total > 0xffffffu) s_bad = 2;
+            __syncthreads();
+            if (s_bad == 2) exhaustive = true;
+        }
     }
     if (tid == 0) {
         PibFrame h;
@@ -294,12 +358,12 @@ __global__ void __launch_bounds__(PIB_THREADS, 4)
 pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace ws, int* __restrict__ out_all,
                  int chunks_per_frame, int total_chunks) {
     extern __shared__ __align__(16) unsigned char pib_smem[];
-    unsigned int* s_bits = reinterpret_cast<unsigned int*>(pib_smem);                       // [PIB_FWORDS]
-    unsigned int* s_start = s_bits + PIB_FWORDS;                                              // [PIB_CELLS + 4]
-    float4* s_q = reinterpret_cast<float4*>(s_start + PIB_CELLS + 4);                         // [warps][PIB_WBATCH]
-    float* s_rec = reinterpret_cast<float*>(s_q + (PIB_THREADS / 32) * PIB_WBATCH);           // [min(N, PIB_SMEM_BOXES) * 8]
+    float4* s_q = reinterpret_cast<float4*>(pib_smem);                                        // [warps][PIB_WQ] {x, y, z, index}
+    unsigned int* s_cells = reinterpret_cast<unsigned int*>(s_q + (PIB_THREADS / 32) * PIB_WQ); // [PIB_CELLS] id0:16 | id1:16
+    unsigned int* s_bits = s_cells + PIB_CELLS;                                               // [PIB_FWORDS]
+    float* s_rec = reinterpret_cast<float*>(s_bits + PIB_FWORDS);                             // [min(N, PIB_SMEM_BOXES) * 8]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float4* wq = s_q + warp * PIB_WBATCH;
+    float4* wq = s_q + warp * PIB_WQ;
     const int c_begin = (int)((long)blockIdx.x * total_chunks / gridDim.x);
     const int c_end = (int)((long)(blockIdx.x + 1) * total_chunks / gridDim.x);
     const bool rec_in_smem = N <= PIB_SMEM_BOXES;
@@ -330,8 +394,14 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
                 if (!h.exhaustive) {
                     const uint4* b = reinterpret_cast<const uint4*>(ws.bits + (size_t)f * PIB_FWORDS);
                     for (int i = tid; i < PIB_FWORDS / 4; i += PIB_THREADS) reinterpret_cast<uint4*>(s_bits)[i] = __ldg(b + i);
-                    const unsigned int* st = ws.start + (size_t)f * (PIB_CELLS + 1);
-                    for (int i = tid; i < PIB_CELLS + 1; i += PIB_THREADS) s_start[i] = __ldg(st + i);
+                    // shared copy keeps the two inline candidates; id1 = 0xFFFE flags "more in the list"
+                    const unsigned long long* cl = ws.cells + (size_t)f * PIB_CELLS;
+                    for (int i = tid; i < PIB_CELLS; i += PIB_THREADS) {
+                        const unsigned long long c64 = __ldg(cl + i);
+                        unsigned int c32 = (unsigned int)c64;
+                        if ((unsigned int)(c64 >> 56) > 2u) c32 = (c32 & 0xffffu) | 0xfffe0000u;
+                        s_cells[i] = c32;
+                    }
                 }
             }
             __syncthreads();
@@ -355,6 +425,29 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
 
         // ---- warp-autonomous streaming over this chunk: batch j of warp w covers 128 points
         constexpr int NB = PIB_CHUNK / (PIB_THREADS * 4);     // batches per warp and chunk
+        // candidate test of one queued point: coarse cell (two inline candidates in shared memory, longer
+        // lists through global memory) -> exact predicate -> minimum index
+        const unsigned long long* cells64 = ws.cells + (size_t)f * PIB_CELLS;
+        auto resolve = [&](const float4 e) {
+            const int cx = (int)((e.x - h.gx0) * h.inv_x), cy = (int)((e.y - h.gy0) * h.inv_y);
+            const int ci = min(cy, PIB_G - 1) * PIB_G + min(cx, PIB_G - 1);
+            const unsigned int cell = s_cells[ci];
+            const int k0 = (int)(cell & 0xffffu), k1 = (int)(cell >> 16);
+            int res = 0x7fffffff;
+            if (k1 == 0xfffe) {          // > 2 candidates: walk the whole list
+                const unsigned long long c64 = __ldg(cells64 + ci);
+                const unsigned int s0 = (unsigned int)(c64 >> 32) & 0xffffffu, n = (unsigned int)(c64 >> 56);
+                for (unsigned int i = 0; i < n; ++i) {
+                    const int k = (int)__ldg(list + s0 + i);
+                    if (k < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k * 8)) res = k;
+                }
+            } else {
+                if (k0 != 0xffff && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k0 * 8)) res = k0;
+                if (k1 != 0xffff && k1 < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k1 * 8)) res = k1;
+            }
+            if (res != 0x7fffffff) out[__float_as_int(e.w)] = res;
+        };
+        int qn = 0;                                           // warp-uniform fill of the warp's queue
         Pts4 cur;
         load_pts4(pts, p_begin + warp * PIB_WBATCH + lane * 4, p_end, vec, cur);
 #pragma unroll 1
@@ -363,16 +456,17 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
             const int nvalid = max(0, min(4, p_end - p0));
             Pts4 nxt;
             if (j + 1 < NB) load_pts4(pts, p0 + (PIB_THREADS / 32) * PIB_WBATCH, p_end, vec, nxt);
+            // branch-free fine-bitmap lookup: floor -> one unsigned range test for both axes -> one LDS.
+            // NaN maps to cell 0 (harmless: the exact predicate rejects it), out-of-grid to "cold".
             unsigned int hot = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float fx = (cur.x[i] - h.gx0) * h.finv_x, fy = (cur.y[i] - h.gy0) * h.finv_y;
-                // NaN and out-of-grid coordinates fail the range test => cold (-1); inside the grid trunc == floor
-                if (i < nvalid && fx >= 0.f && fx < (float)PIB_FG && fy >= 0.f && fy < (float)PIB_FG) {
-                    const int cell = (int)fy * PIB_FG + (int)fx;
-                    hot |= ((s_bits[cell >> 5] >> (cell & 31)) & 1u) << i;
-                }
+                const int ix = __float2int_rd((cur.x[i] - h.gx0) * h.finv_x), iy = __float2int_rd((cur.y[i] - h.gy0) * h.finv_y);
+                const unsigned int word = s_bits[((iy << 3) + (ix >> 5)) & (PIB_FWORDS - 1)];
+                const unsigned int in_grid = ((unsigned int)(ix | iy) < (unsigned int)PIB_FG) ? 1u : 0u;
+                hot |= ((word >> (ix & 31)) & in_grid) << i;
             }
+            hot &= (1u << nvalid) - 1u;                        // never queue a point beyond the chunk
             if (vec && nvalid == 4) *reinterpret_cast<int4*>(out + p0) = make_int4(-1, -1, -1, -1);
             else {
 #pragma unroll
@@ -384,26 +478,32 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
                 const int total = __shfl_sync(0xffffffffu, pre, 31);
-                int qb = pre - nh;
+                if (hot) {
+                    int qb = qn + pre - nh;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if ((hot >> i) & 1u) wq[qb++] = make_float4(cur.x[i], cur.y[i], cur.z[i], __int_as_float(p0 + i));
-                __syncwarp();   // queue visible; also orders the provisional -1 stores before the results
-                for (int q = lane; q < total; q += 32) {
-                    const float4 e = wq[q];
-                    const int cx = (int)((e.x - h.gx0) * h.inv_x), cy = (int)((e.y - h.gy0) * h.inv_y);
-                    const int cell = min(cy, PIB_G - 1) * PIB_G + min(cx, PIB_G - 1);
-                    const unsigned int s = s_start[cell], t = s_start[cell + 1];
-                    int res = 0x7fffffff;
-                    for (unsigned int i = s; i < t; ++i) {
-                        const int k = (int)__ldg(list + i);
-                        if (k < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k * 8)) res = k;
-                    }
-                    if (res != 0x7fffffff) out[__float_as_int(e.w)] = res;
+                    for (int i = 0; i < 4; ++i)
+                        if ((hot >> i) & 1u) wq[qb++] = make_float4(cur.x[i], cur.y[i], cur.z[i], __int_as_float(p0 + i));
                 }
-                __syncwarp();   // the queue may be overwritten by the next batch
+                qn += total;
+                __syncwarp();   // queue visible; also orders the provisional -1 stores before the results
+                // drain whole warps only; the remainder (< 32 entries) waits for the next batch
+                int head = 0;
+                for (; head + 32 <= qn; head += 32) resolve(wq[head + lane]);
+                if (head) {
+                    const int rest = qn - head;
+                    float4 keep = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (lane < rest) keep = wq[head + lane];
+                    __syncwarp();
+                    if (lane < rest) wq[lane] = keep;
+                    qn = rest;
+                    __syncwarp();
+                }
             }
             if (j + 1 < NB) cur = nxt;
+        }
+        if (qn) {                                              // leftovers of the chunk
+            if (lane < qn) resolve(wq[lane]);
+            __syncwarp();
         }
     }
 }
@@ -519,7 +619,7 @@ int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int 
     const int chunks = (M + PIB_CHUNK - 1) / PIB_CHUNK;
     const long total = (long)chunks * B;
     if (total > 0x7fffffffL) return fail(GLENET_EINVAL, "%s: too many chunks", what);
-    const size_t smem_fixed = sizeof(unsigned int) * (PIB_FWORDS + PIB_CELLS + 4) + sizeof(float4) * (PIB_THREADS / 32) * PIB_WBATCH;
+    const size_t smem_fixed = sizeof(float4) * (PIB_THREADS / 32) * PIB_WQ + sizeof(unsigned int) * (PIB_CELLS + PIB_FWORDS);
     const size_t smem = smem_fixed + sizeof(float) * 8 * (size_t)(N <= PIB_SMEM_BOXES ? N : 0);
     static bool attr_done = false;
     if (!attr_done) {
