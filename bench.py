@@ -256,7 +256,7 @@ def run_ours(args, rank, world, local_rank):
     kernel_ms = ms / timed_launches
     achieved = PAIRS_PER_FRAME * BYTES_PER_PAIR / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "iou_tile_kernel<IOU_BEV>", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
-                "frac": achieved / hbm_gbs, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_gbs, "traffic": 43.7e6, "traffic_note": "ncu dram read+write of one launch (profiles/r01_iou_sparse_summary.txt); below the algorithmic bytes because one launch's 84.5 MB result fits in L2 and is written back after the kernel ends", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": PAIRS_PER_FRAME * BYTES_PER_PAIR, "avg_launch_ms": kernel_ms}
 
     extra = {}

@@ -11,8 +11,10 @@
 //                 the reference) -> bit (i, j) = iou(i, j) > thresh, j > i.
 //   sweep kernel: one CTA per frame.  For every 64-box chunk, warp 0 resolves the diagonal
 //                 tile with a find-first-set loop over the not-yet-suppressed bits (only kept
-//                 boxes cost an iteration), then all warps OR the kept rows' mask words into
-//                 the running suppression words `remv`.  keep[] and the count stay on the device.
+//                 boxes cost an iteration) from shared-memory copies of the diagonal and
+//                 super-diagonal words; the other warps OR the kept rows' remaining mask words
+//                 into the running suppression words one step later.  keep[] and the count stay
+//                 on the device.
 #include "common.cuh"
 #include "geom.cuh"
 #include "../../include/glenet_geom.h"
@@ -157,60 +159,89 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
     if (tid < tr) mask[(size_t)(r0 + tid) * col_blocks + cb] = sm.bits[tid];
 }
 
-// Greedy sweep of iou3d_nms.cpp:116-132 on the device.  One CTA per frame.
+// Greedy sweep of iou3d_nms.cpp:116-132 on the device.  One CTA per frame, one barrier per 64-box chunk.
+// The serial dependency (chunk c+1 needs the kept set of chunk c) is kept off the memory system:
+//   * the diagonal words mask[r][r/64] and the super-diagonal words mask[r][r/64 + 1] of ALL rows are
+//     staged in shared memory up front (PRE = true; 16 bytes per box), so resolving a chunk and folding
+//     its kept rows into the next chunk's suppression word touches shared memory only;
+//   * the kept rows' words for chunks >= c+2 are ORed in by the other warps ONE STEP LATER (they are not
+//     needed before), overlapping their L2 latency with warp 0's next resolve.
+// For very large n (PRE = false) the two words are read from global memory instead.
+// (A barrier-free variant with 3 staged super-diagonals and flag-synchronised job warps was measured and
+//  lost to this one: the spinning warps cost more than the barrier.)
+template <bool PRE>
 __global__ void __launch_bounds__(SWEEP_THREADS)
 nms_sweep_kernel(const unsigned long long* __restrict__ mask_all, int n, int col_blocks,
                  long long* __restrict__ keep_all, int* __restrict__ num_keep_all) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* remv = reinterpret_cast<unsigned long long*>(smem_raw);   // [col_blocks]
-    __shared__ unsigned long long s_diag[NMS_TILE];
-    __shared__ int s_rows[NMS_TILE];
-    __shared__ int s_nrows;
+    unsigned long long* s_diag = remv + col_blocks;                                 // [n]  (PRE)
+    unsigned long long* s_sup = s_diag + (PRE ? n : 0);                             // [n]  (PRE)
+    __shared__ int s_rows[2][NMS_TILE];
+    __shared__ int s_nrows[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.x;
     const unsigned long long* mask = mask_all + (size_t)frame * n * col_blocks;
     long long* keep = keep_all + (size_t)frame * n;
 
     for (int j = tid; j < col_blocks; j += SWEEP_THREADS) remv[j] = 0ull;
+    if (PRE) {
+        for (int r = tid; r < n; r += SWEEP_THREADS) {
+            const int c = r >> 6;
+            s_diag[r] = mask[(size_t)r * col_blocks + c];
+            s_sup[r] = (c + 1 < col_blocks) ? mask[(size_t)r * col_blocks + c + 1] : 0ull;
+        }
+    }
+    if (tid < 2) s_nrows[tid] = 0;
     int num_keep = 0;   // tracked by warp 0
     __syncthreads();
 
     for (int c = 0; c < col_blocks; ++c) {
         const int rows = min(NMS_TILE, n - c * NMS_TILE);
         if (warp == 0) {
-            // diagonal tile: rows 64c..64c+63, column word c
-            for (int i = lane; i < NMS_TILE; i += 32)
-                s_diag[i] = (i < rows) ? mask[(size_t)(c * NMS_TILE + i) * col_blocks + c] : 0ull;
-            __syncwarp();
+            // resolve the diagonal tile: one iteration per KEPT box (find-first-set over the unsuppressed bits)
+            const int r_lo = c * NMS_TILE + lane, r_hi = r_lo + 32;
+            const unsigned long long d_lo = (lane < rows) ? (PRE ? s_diag[r_lo] : mask[(size_t)r_lo * col_blocks + c]) : 0ull;
+            const unsigned long long d_hi = (lane + 32 < rows) ? (PRE ? s_diag[r_hi] : mask[(size_t)r_hi * col_blocks + c]) : 0ull;
+            const bool has_next = c + 1 < col_blocks;
+            const unsigned long long u_lo = (has_next && lane < rows) ? (PRE ? s_sup[r_lo] : mask[(size_t)r_lo * col_blocks + c + 1]) : 0ull;
+            const unsigned long long u_hi = (has_next && lane + 32 < rows) ? (PRE ? s_sup[r_hi] : mask[(size_t)r_hi * col_blocks + c + 1]) : 0ull;
             const unsigned long long valid = (rows == NMS_TILE) ? ~0ull : ((1ull << rows) - 1ull);
             unsigned long long w = remv[c];
             unsigned long long cand = ~w & valid, kept = 0ull;
             while (cand) {
                 const int i = __ffsll((long long)cand) - 1;
                 kept |= 1ull << i;
-                w |= s_diag[i];
+                const unsigned long long lo = __shfl_sync(0xffffffffu, d_lo, i & 31), hi = __shfl_sync(0xffffffffu, d_hi, i & 31);
+                w |= (i < 32) ? lo : hi;
                 cand = ~w & valid & ~((2ull << i) - 1ull);
             }
-            // emit kept indices in ascending order
+            // kept rows of this chunk -> next chunk's suppression word, straight from registers
+            unsigned long long nx = (((kept >> lane) & 1ull) ? u_lo : 0ull) | (((kept >> (lane + 32)) & 1ull) ? u_hi : 0ull);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) nx |= __shfl_xor_sync(0xffffffffu, nx, o);
+            if (lane == 0 && has_next && nx) atomicOr(&remv[c + 1], nx);
+            // emit kept indices in ascending order; remember the rows for the lagging propagation
+            const int slot = c & 1;
             for (int i = lane; i < NMS_TILE; i += 32) {
                 if ((kept >> i) & 1ull) {
                     const int pos = __popcll(kept & ((1ull << i) - 1ull));
                     keep[num_keep + pos] = (long long)(c * NMS_TILE + i);
-                    s_rows[pos] = c * NMS_TILE + i;
+                    s_rows[slot][pos] = c * NMS_TILE + i;
                 }
             }
             num_keep += __popcll(kept);
-            if (lane == 0) s_nrows = __popcll(kept);
-        }
-        __syncthreads();
-        // propagate the kept rows of this chunk to all later suppression words
-        const int nrem = col_blocks - (c + 1);
-        const int nrows = s_nrows;
-        const int items = nrows * nrem;
-        for (int it = tid; it < items; it += SWEEP_THREADS) {
-            const int ki = it / nrem, j = c + 1 + (it - ki * nrem);
-            const unsigned long long m = mask[(size_t)s_rows[ki] * col_blocks + j];
-            if (m) atomicOr(&remv[j], m);
+            if (lane == 0) s_nrows[slot] = __popcll(kept);
+        } else if (c > 0) {
+            // lagging propagation: rows kept in chunk c-1 -> suppression words of chunks >= c+1
+            const int slot = (c - 1) & 1;
+            const int first = c + 1, nrem = col_blocks - first;
+            const int items = s_nrows[slot] * nrem;
+            for (int it = tid - 32; it < items; it += SWEEP_THREADS - 32) {
+                const int ki = it / nrem, j = first + (it - ki * nrem);
+                const unsigned long long m = mask[(size_t)s_rows[slot][ki] * col_blocks + j];
+                if (m) atomicOr(&remv[j], m);
+            }
         }
         __syncthreads();
     }
@@ -248,13 +279,21 @@ static int launch_nms(bool normal, const float* boxes, int frames, int n, float 
         nms_mask_kernel<false><<<grid, NMS_THREADS, sizeof(NmsSmem), stream>>>(boxes, n, thresh, mask, col_blocks, (int)tiles);
     int rc = check_launch(what);
     if (rc) return rc;
-    const size_t sweep_smem = sizeof(unsigned long long) * col_blocks;
-    if (sweep_smem > 200 * 1024) return fail(GLENET_EINVAL, "%s: n too large for the on-chip suppression words", what);
-    if (sweep_smem > 40 * 1024) {
-        rc = set_smem(nms_sweep_kernel, sweep_smem, what);
+    const size_t remv_bytes = sizeof(unsigned long long) * col_blocks;
+    const size_t pre_bytes = remv_bytes + 2 * sizeof(unsigned long long) * (size_t)n;
+    if (remv_bytes > 200 * 1024) return fail(GLENET_EINVAL, "%s: n too large for the on-chip suppression words", what);
+    const bool pre = pre_bytes <= 200 * 1024;   // n <= ~12 700 boxes
+    const size_t sweep_smem = pre ? pre_bytes : remv_bytes;
+    static bool sweep_attr[2] = {false, false};
+    if (!sweep_attr[pre]) {
+        rc = pre ? set_smem(nms_sweep_kernel<true>, 200 * 1024, what) : set_smem(nms_sweep_kernel<false>, 200 * 1024, what);
         if (rc) return rc;
+        sweep_attr[pre] = true;
     }
-    nms_sweep_kernel<<<frames, SWEEP_THREADS, sweep_smem, stream>>>(mask, n, col_blocks, reinterpret_cast<long long*>(keep), num_keep);
+    if (pre)
+        nms_sweep_kernel<true><<<frames, SWEEP_THREADS, sweep_smem, stream>>>(mask, n, col_blocks, reinterpret_cast<long long*>(keep), num_keep);
+    else
+        nms_sweep_kernel<false><<<frames, SWEEP_THREADS, sweep_smem, stream>>>(mask, n, col_blocks, reinterpret_cast<long long*>(keep), num_keep);
     return check_launch(what);
 }
 
