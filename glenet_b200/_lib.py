@@ -19,12 +19,11 @@ c_float_p = ctypes.c_void_p  # raw device pointers travel as integers (tensor.da
 _SIGNATURES = {
     "glenet_abi_version": (ctypes.c_int, []),
     "glenet_last_error": (ctypes.c_char_p, []),
-    "glenet_boxes_iou_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
-    "glenet_boxes_overlap_bev_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
-    "glenet_boxes_iou_bev_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
-    "glenet_boxes_iou3d_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "glenet_boxes_overlap_bev_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "glenet_boxes_iou_bev_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "glenet_boxes_iou3d_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "glenet_boxes_iou_aligned_gpu": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
-    "glenet_boxes_iou_bev_cpu_dialect": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "glenet_boxes_iou_bev_cpu_dialect": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "glenet_host_trig4": (None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "glenet_host_trig2": (None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "glenet_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),

@@ -37,6 +37,7 @@ enum { MODE_OVERLAP = 0, MODE_IOU_BEV = 1, MODE_IOU3D = 2 };
 
 #ifdef GLENET_PHASE_TIMING   // developer instrumentation: accumulated clock64() per phase, thread 0 of every CTA
 __device__ unsigned long long g_phase_cycles[8];
+__device__ int g_dbg_flags;   // bit 0: skip the clip pass, bit 1: skip the zero fill (timing experiments only)
 #define PHASE_MARK(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_phase_cycles[k], (unsigned long long)(now_ - t_phase_)); t_phase_ = now_; } } while (0)
 #define PHASE_INIT long long t_phase_ = clock64()
 #else
@@ -130,14 +131,19 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
     }
     __syncthreads();
     PHASE_MARK(3);
-    for (int q = tid; q < n; q += IOU_THREADS) {
+#ifdef GLENET_PHASE_TIMING
+    const int dbg = g_dbg_flags;
+#else
+    const int dbg = 0;
+#endif
+    for (int q = tid; q < ((dbg & 1) ? 0 : n); q += IOU_THREADS) {
         const unsigned int e = sm.queue[q];
         const float* a = sm.rpre + (e >> 8) * BP_STRIDE;
         const float* b = sm.cpre + (e & 255) * BP_STRIDE;
         sm.qres[q] = finish_pair<MODE>(a, b, box_overlap<FMA>(a, b));
     }
     PHASE_MARK(7);
-    zero_fill_tile(sm, out + (size_t)r0 * nb + c0, tr, tc, nb, vec);   // no-op once every chunk has been taken
+    if (!(dbg & 2)) zero_fill_tile(sm, out + (size_t)r0 * nb + c0, tr, tc, nb, vec);   // no-op once every chunk has been taken
     __syncthreads();
     PHASE_MARK(4);
     for (int q = tid; q < n; q += IOU_THREADS) {
@@ -260,256 +266,6 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     PHASE_MARK(6);
 }
 
-// ================================================================ persistent producer / consumer kernel
-// For large matrices the tile kernel above loses time twice: a tile's clip pass is one long dependent
-// chain that the rest of its CTA waits for, and tiles/CTA-slots quantise into waves.  Here streaming and
-// clipping are decoupled through a global queue (in the caller's workspace):
-//   produce : a CTA takes the next tile (atomic counter), zero-fills it with 16-byte streaming stores,
-//             runs the two-level cull and appends the surviving (row, col) pairs to the global queue --
-//             slots are reserved with one atomicAdd per tile and each pair is published by a single
-//             8-byte store behind a __threadfence(), so whoever sees a pair also sees the zeros of its tile
-//             (a memset node presets the queue to 0xFF.. = "not written yet" before the launch);
-//   consume : between two tiles the CTA claims up to 256 reserved pairs (one CAS on the queue head),
-//             prepares the two boxes of each on the fly and clips them with all lanes busy, whatever
-//             tile they came from.  The tile's stores drain in the background while the CTA clips.
-// No producer ever waits; a consumer only waits for a slot whose producer has already reserved it and is
-// past all of its barriers, so the scheme cannot deadlock whatever the residency.
-struct StreamCtl {
-    unsigned int tile_next, tiles_done, reserve, head, pad[4];
-};
-constexpr int STREAM_LQ = 2048;                  // per-tile local queue (drained to the global one when 3/4 full)
-constexpr int STREAM_WARPS = IOU_THREADS / 32;
-
-struct __align__(16) StreamSmem {
-    float4 row[IOU_TR_MAX];
-    float ccx[IOU_TC_MAX], ccy[IOU_TC_MAX], crad[IOU_TC_MAX];
-    float pre[STREAM_WARPS][32][2 * BP_STRIDE];  // on-the-fly BoxPre records of the pair each lane is clipping
-    float red[STREAM_WARPS][5];
-    unsigned short lq[STREAM_LQ];
-    unsigned char act[IOU_TC_MAX];
-    int lqcount, nact, tile, ccount;
-    unsigned int qstart, cstart;
-};
-
-__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
-
-template <int MODE, bool FMA>
-__device__ __forceinline__ void clip_one_pair(const float* __restrict__ A, const float* __restrict__ B,
-                                              const float4* __restrict__ trigA, const float4* __restrict__ trigB,
-                                              int row, int col, int nb, float* __restrict__ out, float* __restrict__ scratch) {
-    float* a = scratch;
-    float* b = scratch + BP_STRIDE;
-    const float* ba = A + (size_t)row * 7;
-    const float* bb = B + (size_t)col * 7;
-    box_prepare<FMA>(ba, trigA ? trigA[row] : device_trig(ba[6]), a);
-    box_prepare<FMA>(bb, trigB ? trigB[col] : device_trig(bb[6]), b);
-    out[(size_t)row * nb + col] = finish_pair<MODE>(a, b, box_overlap<FMA>(a, b));
-}
-
-// append this tile's local queue to the global one (all threads; contains barriers)
-template <int MODE, bool FMA>
-__device__ __forceinline__ void stream_publish(StreamSmem& sm, StreamCtl* ctl, uint2* __restrict__ queue, unsigned int qcap,
-                                               const float* __restrict__ A, const float* __restrict__ B,
-                                               const float4* __restrict__ trigA, const float4* __restrict__ trigB,
-                                               int r0, int c0, int nb, float* __restrict__ out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __threadfence();                       // this thread's zero-fill stores are visible device-wide ...
-    __syncthreads();                       // ... and so are everybody's, before any pair of the tile is published
-    const int n = sm.lqcount;
-    if (n == 0) return;                    // uniform
-    if (tid == 0) sm.qstart = atomicAdd(&ctl->reserve, (unsigned int)n);
-    __syncthreads();
-    const unsigned int start = sm.qstart;
-    const int n_fit = (start >= qcap) ? 0 : (int)min((unsigned int)n, qcap - start);
-    for (int i = tid; i < n_fit; i += IOU_THREADS) {
-        const unsigned int e = sm.lq[i];
-        // one 8-byte store publishes the pair: the slot held 0xFF..FF ("not written yet") until now
-        *reinterpret_cast<volatile unsigned long long*>(queue + start + i) =
-            ((unsigned long long)(unsigned)(c0 + (e & 255)) << 32) | (unsigned long long)(unsigned)(r0 + (e >> 8));
-    }
-    __threadfence();                       // entries visible before this tile is counted as done
-    // queue full: the part that did not fit is clipped right here (same code as the consumers)
-    for (int i = n_fit + tid; i < n; i += IOU_THREADS) {
-        const unsigned int e = sm.lq[i];
-        clip_one_pair<MODE, FMA>(A, B, trigA, trigB, r0 + (int)(e >> 8), c0 + (int)(e & 255), nb, out, sm.pre[warp][lane]);
-    }
-    __syncthreads();
-    if (tid == 0) sm.lqcount = 0;
-    __syncthreads();
-}
-
-// The CTA claims up to 256 reserved pairs (one thread, one CAS -- per-warp claiming turns into a retry
-// storm with 3500 contenders) and every thread clips one of them.  Contains barriers; returns the number
-// of pairs claimed (CTA-uniform).
-template <int MODE, bool FMA>
-__device__ __forceinline__ int stream_consume(StreamSmem& sm, StreamCtl* ctl, const uint2* __restrict__ queue, unsigned int qcap,
-                                              unsigned int ntiles, const float* __restrict__ A, const float* __restrict__ B,
-                                              const float4* __restrict__ trigA, const float4* __restrict__ trigB,
-                                              int nb, float* __restrict__ out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        unsigned int claimed = 0, h = 0;
-        const bool all_done = ld_volatile_u32(&ctl->tiles_done) == ntiles;   // read first: then `reserve` is final
-        const unsigned int c = ld_volatile_u32(&ctl->reserve);
-        h = ld_volatile_u32(&ctl->head);
-        for (int attempt = 0; attempt < 4 && h < c; ++attempt) {
-            unsigned int want = min((unsigned int)IOU_THREADS, c - h);
-            if (!all_done) want &= ~31u;                 // whole warps only while tiles are still coming
-            if (want == 0) break;
-            const unsigned int old = atomicCAS(&ctl->head, h, h + want);
-            if (old == h) { claimed = want; break; }
-            h = old;
-        }
-        sm.cstart = h;
-        sm.ccount = (int)claimed;
-    }
-    __syncthreads();
-    const int n = sm.ccount;
-    const unsigned int idx = sm.cstart + (unsigned int)tid;
-    if (tid < n && idx < qcap) {
-        // the slot was reserved by a producer that is about to write it (or already has)
-        const volatile unsigned long long* slot = reinterpret_cast<const volatile unsigned long long*>(queue + idx);
-        unsigned long long e = *slot;
-        while ((unsigned int)e == 0xffffffffu) e = *slot;
-        __threadfence();                                 // acquire: the zeros of the pair's tile are visible
-        clip_one_pair<MODE, FMA>(A, B, trigA, trigB, (int)(unsigned int)e, (int)(e >> 32), nb, out, sm.pre[warp][lane]);
-    }
-    __syncthreads();                                     // sm.cstart / sm.ccount may be rewritten
-    return n;
-}
-
-template <int MODE, bool FMA>
-__global__ void __launch_bounds__(IOU_THREADS, 3)
-iou_stream_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int nb,
-                  const float4* __restrict__ trigA, const float4* __restrict__ trigB,
-                  float* __restrict__ out, int TR, int TC, int col_tiles, unsigned int ntiles,
-                  StreamCtl* ctl, uint2* __restrict__ queue, unsigned int qcap) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    StreamSmem& sm = *reinterpret_cast<StreamSmem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) sm.lqcount = 0;
-    bool producing = true;
-    for (;;) {
-        if (producing) {
-            if (tid == 0) sm.tile = (int)atomicAdd(&ctl->tile_next, 1u);
-            __syncthreads();
-            const unsigned int tile = (unsigned int)sm.tile;
-            if (tile >= ntiles) {
-                producing = false;                            // uniform
-            } else {
-                const int tile_r = tile / col_tiles, tile_c = tile - tile_r * col_tiles;
-                const int r0 = tile_r * TR, c0 = tile_c * TC;
-                const int tr = min(TR, na - r0), tc = min(TC, nb - c0);
-                // ---- stage boxes + bounding box of the row centres
-                float minx = FLT_MAX, maxx = -FLT_MAX, miny = FLT_MAX, maxy = -FLT_MAX, maxr = 0.f;
-                for (int i = tid; i < tr + tc; i += IOU_THREADS) {
-                    const bool is_row = i < tr;
-                    const int k = is_row ? i : i - tr;
-                    const float* box = (is_row ? A + (size_t)(r0 + k) * 7 : B + (size_t)(c0 + k) * 7);
-                    const float cx = box[0], cy = box[1], rad = cull_radius(box);
-                    if (is_row) {
-                        sm.row[k] = make_float4(cx, cy, rad, 0.f);
-                        minx = fminf(minx, cx); maxx = fmaxf(maxx, cx); miny = fminf(miny, cy); maxy = fmaxf(maxy, cy);
-                        maxr = (rad != rad) ? CUDART_INF_F : fmaxf(maxr, rad);
-                    } else { sm.ccx[k] = cx; sm.ccy[k] = cy; sm.crad[k] = rad; }
-                }
-                // ---- zero fill (fire-and-forget; drains while the CTA culls and clips)
-                float* out_tile = out + (size_t)r0 * nb + c0;
-                const bool vec = ((nb & 3) == 0) && ((c0 & 3) == 0) && ((tc & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
-                if (vec) {
-                    const int nq = tc >> 2, nquads = tr * nq;
-                    if (nq * 4 == nb) {
-                        float4* dst = reinterpret_cast<float4*>(out_tile);
-#pragma unroll 4
-                        for (int q = tid; q < nquads; q += IOU_THREADS) dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    } else {
-                        for (int q = tid; q < nquads; q += IOU_THREADS) {
-                            const int r = q / nq;
-                            reinterpret_cast<float4*>(out_tile + (size_t)r * nb)[q - r * nq] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    }
-                } else {
-                    for (int p = tid; p < tr * tc; p += IOU_THREADS) { const int r = p / tc; out_tile[(size_t)r * nb + (p - r * tc)] = 0.f; }
-                }
-#pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    minx = fminf(minx, __shfl_xor_sync(0xffffffffu, minx, o)); maxx = fmaxf(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
-                    miny = fminf(miny, __shfl_xor_sync(0xffffffffu, miny, o)); maxy = fmaxf(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
-                    maxr = fmaxf(maxr, __shfl_xor_sync(0xffffffffu, maxr, o));
-                }
-                if (lane == 0) { sm.red[warp][0] = minx; sm.red[warp][1] = maxx; sm.red[warp][2] = miny; sm.red[warp][3] = maxy; sm.red[warp][4] = maxr; }
-                if (tid == 0) sm.nact = 0;
-                __syncthreads();
-                minx = sm.red[0][0]; maxx = sm.red[0][1]; miny = sm.red[0][2]; maxy = sm.red[0][3]; maxr = sm.red[0][4];
-#pragma unroll
-                for (int w = 1; w < STREAM_WARPS; ++w) {
-                    minx = fminf(minx, sm.red[w][0]); maxx = fmaxf(maxx, sm.red[w][1]);
-                    miny = fminf(miny, sm.red[w][2]); maxy = fmaxf(maxy, sm.red[w][3]); maxr = fmaxf(maxr, sm.red[w][4]);
-                }
-                // ---- active columns (one exact-conservative test per column against the rows' bounding box)
-                for (int c = tid; c < tc; c += IOU_THREADS) {
-                    const float cx = sm.ccx[c], cy = sm.ccy[c];
-                    const float ddx = fmaxf(fmaxf(minx - cx, cx - maxx), 0.f), ddy = fmaxf(fmaxf(miny - cy, cy - maxy), 0.f);
-                    const float rr = maxr + sm.crad[c];
-                    const bool far = (cx == cx) && (cy == cy) && (ddx * ddx + ddy * ddy > rr * rr);
-                    if (!far) sm.act[atomicAdd(&sm.nact, 1)] = (unsigned char)c;
-                }
-                __syncthreads();
-                // ---- pair tests on rows x active columns -> local queue -> global queue
-                const int nact = sm.nact;
-                int trp = 32;
-                while (trp < tr) trp <<= 1;
-                const int groups = IOU_THREADS / trp, row = tid & (trp - 1), grp = tid / trp;
-                const bool has_row = row < tr;
-                const float4 rw = has_row ? sm.row[row] : make_float4(0.f, 0.f, 0.f, 0.f);
-                const int iters = (nact + groups - 1) / groups;
-                for (int it0 = 0; it0 < iters; it0 += 2) {
-                    const int qc = sm.lqcount;
-                    __syncthreads();       // everyone has read the count before anyone appends again
-                    if (qc > STREAM_LQ - 2 * IOU_THREADS) {   // uniform; dense tiles only
-                        stream_publish<MODE, FMA>(sm, ctl, queue, qcap, A, B, trigA, trigB, r0, c0, nb, out);
-                    }
-                    const int it1 = min(iters, it0 + 2);
-                    for (int it = it0; it < it1; ++it) {
-                        const int k = it * groups + grp;
-                        const bool valid = has_row && k < nact;
-                        const int c = valid ? sm.act[k] : 0;
-                        const float dx = rw.x - sm.ccx[c], dy = rw.y - sm.ccy[c], rr = rw.z + sm.crad[c];
-                        // NaN anywhere => comparison false => not culled => the clip decides, like the reference
-                        const bool heavy = valid && !(dx * dx + dy * dy > rr * rr);
-                        const unsigned int m = __ballot_sync(0xffffffffu, heavy);
-                        if (m) {
-                            int qb = 0;
-                            if (lane == 0) qb = atomicAdd(&sm.lqcount, __popc(m));
-                            qb = __shfl_sync(0xffffffffu, qb, 0);
-                            if (heavy) sm.lq[qb + __popc(m & ((1u << lane) - 1))] = (unsigned short)((row << 8) | c);
-                        }
-                    }
-                    __syncthreads();
-                }
-                stream_publish<MODE, FMA>(sm, ctl, queue, qcap, A, B, trigA, trigB, r0, c0, nb, out);
-                __syncthreads();           // every thread's entries are written and fenced
-                if (tid == 0) { __threadfence(); atomicAdd(&ctl->tiles_done, 1u); }
-            }
-        }
-        // ---------- consume up to 256 pooled pairs (from any tile); the tile's stores drain meanwhile
-        const int did = stream_consume<MODE, FMA>(sm, ctl, queue, qcap, ntiles, A, B, trigA, trigB, nb, out);
-        if (!producing && did == 0) {
-            if (tid == 0) {
-                const bool all_done = ld_volatile_u32(&ctl->tiles_done) == ntiles;
-                const unsigned int c = ld_volatile_u32(&ctl->reserve);
-                const unsigned int h = ld_volatile_u32(&ctl->head);
-                sm.ccount = (all_done && h >= c) ? -1 : 0;
-            }
-            __syncthreads();
-            const bool fin = sm.ccount < 0;
-            __syncthreads();
-            if (fin) break;
-            __nanosleep(200);
-        }
-    }
-}
-
 // out[i] = f(a[i], b[i / group]) -- every pair is "heavy" by construction (CVAE samples vs their GT)
 constexpr int ALIGNED_THREADS = 128;
 template <int MODE, bool FMA>
@@ -536,6 +292,9 @@ iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict_
     out[i] = out_v;
 }
 
+#ifdef GLENET_PHASE_TIMING
+static int g_debug_tile_rows = 0;   // developer override (debug build only)
+#endif
 static void pick_tiles(int na, int nb, int& TR, int& TC, int& row_tiles, int& col_tiles) {
     col_tiles = (nb + IOU_TC_MAX - 1) / IOU_TC_MAX;
     TC = ((nb + col_tiles - 1) / col_tiles + 3) / 4 * 4;   // multiple of 4 keeps every tile on the 16-byte store path
@@ -546,59 +305,21 @@ static void pick_tiles(int na, int nb, int& TR, int& TC, int& row_tiles, int& co
     if (tr < 32) tr = 32;
     if (tr > IOU_TR_MAX) tr = IOU_TR_MAX;
     TR = (int)tr;
+#ifdef GLENET_PHASE_TIMING
+    if (g_debug_tile_rows) TR = g_debug_tile_rows;
+#endif
     row_tiles = (na + TR - 1) / TR;
-}
-
-constexpr long STREAM_MIN_PAIRS = 1L << 62;     // EXPERIMENTAL path, disabled: claim latency still dominates
-
-static size_t iou_queue_capacity(long na, long nb) {
-    const long pairs = na * nb;
-    long cap = 2 * na + 65536;     // ~4x the survivors of an anchor sweep; a full queue degrades gracefully
-    if (cap > pairs) cap = pairs;
-    if (cap > (1L << 28)) cap = 1L << 28;
-    return (size_t)cap;
 }
 
 template <int MODE, bool FMA>
 static int launch_iou(const float* A, const float* trigA, int na, const float* B, const float* trigB, int nb,
-                      float* out, void* ws, size_t ws_bytes, cudaStream_t stream, const char* what) {
+                      float* out, cudaStream_t stream, const char* what) {
     if (na < 0 || nb < 0) return fail(GLENET_EINVAL, "%s: negative box count", what);
     if (na == 0 || nb == 0) return GLENET_OK;
     if (!A || !B || !out) return fail(GLENET_EINVAL, "%s: null pointer", what);
     if (!FMA && (!trigA || !trigB)) return fail(GLENET_EINVAL, "%s: CPU dialect needs host-evaluated trig tables", what);
-    if (ws && (((uintptr_t)ws) & 15)) return fail(GLENET_EALIGN, "%s: workspace must be 16-byte aligned", what);
     int TR, TC, row_tiles, col_tiles;
     pick_tiles(na, nb, TR, TC, row_tiles, col_tiles);
-    const long pairs = (long)na * nb;
-    if (ws && ws_bytes >= sizeof(StreamCtl) + 8 * 1024 && pairs >= STREAM_MIN_PAIRS && pairs < (1L << 31)) {
-        // persistent producer/consumer kernel, full-height row tiles
-        TR = IOU_TR_MAX;
-        row_tiles = (na + TR - 1) / TR;
-        const long tiles = (long)row_tiles * col_tiles;
-        StreamCtl* ctl = reinterpret_cast<StreamCtl*>(ws);
-        uint2* queue = reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(ws) + sizeof(StreamCtl));
-        size_t qcap = (ws_bytes - sizeof(StreamCtl)) / sizeof(uint2);
-        if (qcap > (1u << 30)) qcap = 1u << 30;
-        auto kernel = iou_stream_kernel<MODE, FMA>;
-        static bool attr_done = false;
-        static int ctas_per_sm = 3;
-        if (!attr_done) {
-            int rc = set_smem(kernel, sizeof(StreamSmem), what);
-            if (rc) return rc;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, IOU_THREADS, sizeof(StreamSmem)) != cudaSuccess || ctas_per_sm < 1) ctas_per_sm = 1;
-            attr_done = true;
-        }
-        cudaError_t e = cudaMemsetAsync(queue, 0xff, qcap * sizeof(uint2), stream);
-        if (e == cudaSuccess) e = cudaMemsetAsync(ctl, 0, sizeof(StreamCtl), stream);
-        if (e != cudaSuccess) return fail(-(int)e, "%s: workspace memset failed", what);
-        int sms = 148;
-        long grid = (long)ctas_per_sm * sms;
-        if (grid > tiles) grid = tiles;
-        kernel<<<(unsigned)grid, IOU_THREADS, sizeof(StreamSmem), stream>>>(
-            A, na, B, nb, reinterpret_cast<const float4*>(trigA), reinterpret_cast<const float4*>(trigB), out, TR, TC,
-            col_tiles, (unsigned int)tiles, ctl, queue, (unsigned int)qcap);
-        return check_launch(what);
-    }
     auto kernel = iou_tile_kernel<MODE, FMA>;
     static bool attr_done = false;   // per template instantiation
     if (!attr_done) {
@@ -621,6 +342,8 @@ using namespace glenet;
 extern "C" {
 
 #ifdef GLENET_PHASE_TIMING
+void glenet_debug_set_tile_rows(int tr) { g_debug_tile_rows = tr; }
+void glenet_debug_set_flags(int f) { cudaMemcpyToSymbol(g_dbg_flags, &f, sizeof(int)); }
 // developer-only: read and reset the per-phase cycle accumulators of iou_tile_kernel
 int glenet_debug_iou_phase_cycles(unsigned long long* host_out8) {
     cudaDeviceSynchronize();
@@ -631,27 +354,19 @@ int glenet_debug_iou_phase_cycles(unsigned long long* host_out8) {
 }
 #endif
 
-size_t glenet_boxes_iou_workspace_bytes(int na, int nb) {
-    if (na <= 0 || nb <= 0 || (long)na * nb < STREAM_MIN_PAIRS) return 16;
-    return align_up(sizeof(StreamCtl) + iou_queue_capacity(na, nb) * sizeof(uint2), 16);
+int glenet_boxes_overlap_bev_gpu(const float* a, int na, const float* b, int nb, float* out, glenet_stream_t s) {
+    return launch_iou<MODE_OVERLAP, true>(a, nullptr, na, b, nullptr, nb, out, (cudaStream_t)s, "glenet_boxes_overlap_bev_gpu");
 }
-
-int glenet_boxes_overlap_bev_gpu(const float* a, int na, const float* b, int nb, float* out, void* ws, size_t ws_bytes,
-                                 glenet_stream_t s) {
-    return launch_iou<MODE_OVERLAP, true>(a, nullptr, na, b, nullptr, nb, out, ws, ws_bytes, (cudaStream_t)s, "glenet_boxes_overlap_bev_gpu");
+int glenet_boxes_iou_bev_gpu(const float* a, int na, const float* b, int nb, float* out, glenet_stream_t s) {
+    return launch_iou<MODE_IOU_BEV, true>(a, nullptr, na, b, nullptr, nb, out, (cudaStream_t)s, "glenet_boxes_iou_bev_gpu");
 }
-int glenet_boxes_iou_bev_gpu(const float* a, int na, const float* b, int nb, float* out, void* ws, size_t ws_bytes,
-                             glenet_stream_t s) {
-    return launch_iou<MODE_IOU_BEV, true>(a, nullptr, na, b, nullptr, nb, out, ws, ws_bytes, (cudaStream_t)s, "glenet_boxes_iou_bev_gpu");
-}
-int glenet_boxes_iou3d_gpu(const float* a, int na, const float* b, int nb, float* out, void* ws, size_t ws_bytes,
-                           glenet_stream_t s) {
-    return launch_iou<MODE_IOU3D, true>(a, nullptr, na, b, nullptr, nb, out, ws, ws_bytes, (cudaStream_t)s, "glenet_boxes_iou3d_gpu");
+int glenet_boxes_iou3d_gpu(const float* a, int na, const float* b, int nb, float* out, glenet_stream_t s) {
+    return launch_iou<MODE_IOU3D, true>(a, nullptr, na, b, nullptr, nb, out, (cudaStream_t)s, "glenet_boxes_iou3d_gpu");
 }
 int glenet_boxes_iou_bev_cpu_dialect(const float* a, const float* trig_a, int na, const float* b, const float* trig_b,
-                                     int nb, float* out, void* ws, size_t ws_bytes, glenet_stream_t s) {
+                                     int nb, float* out, glenet_stream_t s) {
     if (((uintptr_t)trig_a | (uintptr_t)trig_b) & 15) return fail(GLENET_EALIGN, "%s: trig tables must be 16-byte aligned", "glenet_boxes_iou_bev_cpu_dialect");
-    return launch_iou<MODE_IOU_BEV, false>(a, trig_a, na, b, trig_b, nb, out, ws, ws_bytes, (cudaStream_t)s, "glenet_boxes_iou_bev_cpu_dialect");
+    return launch_iou<MODE_IOU_BEV, false>(a, trig_a, na, b, trig_b, nb, out, (cudaStream_t)s, "glenet_boxes_iou_bev_cpu_dialect");
 }
 
 int glenet_boxes_iou_aligned_gpu(int mode, const float* a, int na, const float* b, int group, float* out,

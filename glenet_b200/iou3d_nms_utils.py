@@ -62,10 +62,8 @@ def _pairwise(fn_name: str, boxes_a: torch.Tensor, boxes_b: torch.Tensor) -> tor
     out = torch.empty((na, nb), dtype=torch.float32, device=a.device)
     if na and nb:
         lib = _lib.load()
-        ws_bytes = lib.glenet_boxes_iou_workspace_bytes(na, nb)
-        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=a.device)
         with torch.cuda.device(a.device):
-            rc = getattr(lib, fn_name)(a.data_ptr(), na, b.data_ptr(), nb, out.data_ptr(), ws.data_ptr(), ws_bytes, _stream(a.device))
+            rc = getattr(lib, fn_name)(a.data_ptr(), na, b.data_ptr(), nb, out.data_ptr(), _stream(a.device))
         _lib.check(rc, fn_name)
     return out
 
@@ -112,11 +110,9 @@ def boxes_bev_iou_cpu(boxes_a, boxes_b):
         d = host.to(dev, non_blocking=True)
         out = torch.empty((na, nb), dtype=torch.float32, device=dev)
         p = d.data_ptr()
-        ws_bytes = lib.glenet_boxes_iou_workspace_bytes(na, nb)
-        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             rc = lib.glenet_boxes_iou_bev_cpu_dialect(p, p + 4 * o_ta, na, p + 4 * o_b, p + 4 * o_tb, nb,
-                                                      out.data_ptr(), ws.data_ptr(), ws_bytes, _stream(dev))
+                                                      out.data_ptr(), _stream(dev))
         _lib.check(rc, "glenet_boxes_iou_bev_cpu_dialect")
         ans_iou.copy_(out)   # D2H, synchronising
     return ans_iou.numpy() if is_numpy else ans_iou

@@ -39,27 +39,18 @@ const char* glenet_last_error(void);
  * boxes_overlap_bev_gpu(boxes_a, boxes_b, ans_overlap)   pcdet/ops/iou3d_nms/src/iou3d_nms.cpp:49-68
  * boxes_iou_bev_gpu(boxes_a, boxes_b, ans_iou)           pcdet/ops/iou3d_nms/src/iou3d_nms.cpp:70-88
  * out is (na, nb) float32; every element is written (no pre-zeroing needed).
- * GPU dialect: libdevice trig + the reference kernels' FMA contraction.
- *
- * workspace is OPTIONAL (NULL / 0 allowed): with glenet_boxes_iou_workspace_bytes(na, nb) bytes, matrices
- * of >= 2^21 pairs run through the persistent producer/consumer kernel (streaming stores overlapped with
- * the clipping of the surviving pairs, pooled over the whole matrix); without it, or for small matrices,
- * the one-pass tile kernel is used.  Results are identical either way. */
-size_t glenet_boxes_iou_workspace_bytes(int na, int nb);
+ * GPU dialect: libdevice trig + the reference kernels' FMA contraction. */
 int glenet_boxes_overlap_bev_gpu(const float* boxes_a, int na, const float* boxes_b, int nb,
-                                 float* ans_overlap, void* workspace, size_t workspace_bytes,
-                                 glenet_stream_t stream);
+                                 float* ans_overlap, glenet_stream_t stream);
 int glenet_boxes_iou_bev_gpu(const float* boxes_a, int na, const float* boxes_b, int nb,
-                             float* ans_iou, void* workspace, size_t workspace_bytes,
-                             glenet_stream_t stream);
+                             float* ans_iou, glenet_stream_t stream);
 
 /* boxes_iou3d_gpu(boxes_a, boxes_b): the reference composes it in Python from
  * boxes_overlap_bev_gpu plus ~10 elementwise torch kernels
  * (pcdet/ops/iou3d_nms/iou3d_nms_utils.py:88-121); here it is one fused kernel with the
  * same per-step rounding. */
 int glenet_boxes_iou3d_gpu(const float* boxes_a, int na, const float* boxes_b, int nb,
-                           float* ans_iou3d, void* workspace, size_t workspace_bytes,
-                           glenet_stream_t stream);
+                           float* ans_iou3d, glenet_stream_t stream);
 
 /* Row-aligned variants: out[i] = f(boxes_a[i], boxes_b[i / group]) for i < na, where boxes_b
  * holds ceil(na / group) rows.  Additive API for the CVAE label-uncertainty workload
@@ -75,8 +66,7 @@ int glenet_boxes_iou_aligned_gpu(int mode, const float* boxes_a, int na, const f
  * trig_a / trig_b: (n, 4) float32 rows {cosf(h), sinf(h), cosf(-h), sinf(-h)}, device pointers. */
 int glenet_boxes_iou_bev_cpu_dialect(const float* boxes_a, const float* trig_a, int na,
                                      const float* boxes_b, const float* trig_b, int nb,
-                                     float* ans_iou, void* workspace, size_t workspace_bytes,
-                                     glenet_stream_t stream);
+                                     float* ans_iou, glenet_stream_t stream);
 
 /* ---------------------------------------------------------------- NMS
  * nms_gpu(boxes, keep, thresh)        pcdet/ops/iou3d_nms/src/iou3d_nms.cpp:90-136  (rotated)

@@ -4,7 +4,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from glenet_b200 import synth
 lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "glenet_b200/lib/libglenet_geom_dbg.so"))
-lib.glenet_boxes_iou_bev_gpu.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+lib.glenet_boxes_iou_bev_gpu.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
 dev = torch.device("cuda:0")
 a = synth.anchors_kitti3().to(dev); b = synth.kitti_boxes(100, 4).to(dev)
 out = torch.empty((a.shape[0], b.shape[0]), device=dev)
@@ -12,7 +12,7 @@ buf = (ctypes.c_ulonglong * 8)()
 names = ["0 stage+reduce", "1 active cols", "2 pair tests", "3 lazy prepare", "4 zero fill tail+barrier", "5 write results", "6 (unused)", "7 clip"]
 for it in range(3):
     lib.glenet_debug_iou_phase_cycles(buf)
-    lib.glenet_boxes_iou_bev_gpu(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], out.data_ptr(), None, 0, None)
+    lib.glenet_boxes_iou_bev_gpu(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], out.data_ptr(), None)
     lib.glenet_debug_iou_phase_cycles(buf)
     tot = sum(buf)
     print(f"iter {it}: total CTA cycles (sum over 825 CTAs) {tot}, per CTA {tot / 825:.0f}")
