@@ -27,6 +27,7 @@ __all__ = [
     "boxes_bev_iou_cpu", "boxes_iou_bev", "boxes_iou3d_gpu", "boxes_overlap_bev",
     "boxes_iou_bev_aligned", "boxes_iou3d_aligned",
     "nms_gpu", "nms_normal_gpu", "nms_gpu_batch", "nms_normal_gpu_batch",
+    "new_nms_gpu", "nms_func", "softnms_gpu", "softnms", "scale_by_iou",
 ]
 
 
@@ -258,3 +259,7 @@ def nms_gpu_batch(boxes, scores, thresh):
 def nms_normal_gpu_batch(boxes, scores, thresh):
     """Batched nms_normal_gpu, see nms_gpu_batch."""
     return _nms_batch("glenet_nms_normal_gpu", boxes, scores, thresh)
+
+
+# GLENet's variance-voting NMS / soft-NMS (iou3d_nms_utils.py:200-356): host control flow over the IoU functions above
+from .variance_nms import new_nms_gpu, nms_func, scale_by_iou, softnms, softnms_gpu  # noqa: E402,F401

@@ -99,6 +99,15 @@ def make_cpu():
     out["cpu_iou_waymo"] = iou.boxes_bev_iou_cpu(d["waymo_p"], d["waymo_gt"]).numpy()
     for f in range(2):
         out[f"cpu_pib_mask_{f}"] = np.packbits(roi.points_in_boxes_cpu(d["pib_points"][f], d["pib_boxes"][f]).numpy().astype(np.uint8), axis=1)
+    # GLENet's variance-voting NMS (new_nms_gpu -> nms_func, iou3d_nms_utils.py:200-273), reference Python on CPU
+    g = torch.Generator().manual_seed(11)
+    vb, vs = synth.proposals(300, 10, 4)
+    vvar = torch.rand((300, 7), generator=g) * 0.5 + 0.05
+    out["vnms_boxes"], out["vnms_scores"], out["vnms_var"] = vb.numpy(), vs.numpy(), vvar.numpy()
+    for name, kw in (("var", dict(variance=vvar.clone())), ("novar", dict()), ("thr", dict(variance=vvar.clone(), score_threshold=0.2))):
+        keep, _, nb = iou.new_nms_gpu(vb.clone(), vs.clone(), 0.25, NMS_TYPE="new_nms_gpu", NMS_PRE_MAXSIZE=4096, **kw)
+        out[f"vnms_keep_{name}"] = np.asarray(keep).astype(np.int64)
+        out[f"vnms_newboxes_{name}"] = np.asarray(nb)[np.asarray(keep)]
     np.savez_compressed(os.path.join(HERE, "cpu_golden.npz"), **out)
     print("wrote cpu_golden.npz", {k: v.shape for k, v in out.items()})
 

@@ -233,6 +233,22 @@ def test_points_in_boxes_properties_full_size(cuda):
     assert bool((R.points_in_boxes_gpu(pts_nan, boxes[None].to(cuda))[0, :7] == -1).all())
 
 
+def test_glenet_variance_voting_nms_on_gpu(cuda, cpu_golden):
+    """NMS_TYPE new_nms_gpu (every shipped GLENet config) through the GPU IoU matrix vs the reference's Python + CPU IoU."""
+    boxes, scores, var = (torch.from_numpy(cpu_golden[k]).to(cuda) for k in ("vnms_boxes", "vnms_scores", "vnms_var"))
+    for name, kw in (("var", dict(variance=var.clone())), ("novar", dict()), ("thr", dict(variance=var.clone(), score_threshold=0.2))):
+        keep, none, new_boxes = I.new_nms_gpu(boxes.clone(), scores.clone(), 0.25, NMS_TYPE="new_nms_gpu", NMS_PRE_MAXSIZE=4096, **kw)
+        assert none is None and isinstance(keep, np.ndarray) and isinstance(new_boxes, np.ndarray)
+        np.testing.assert_array_equal(keep, cpu_golden[f"vnms_keep_{name}"])
+        np.testing.assert_allclose(new_boxes[keep], cpu_golden[f"vnms_newboxes_{name}"], rtol=0, atol=2e-5)
+    # indexable the way model_nms_utils.py:44-45 does it
+    idx = torch.arange(boxes.shape[0], device=cuda)
+    assert idx[keep[:50]].shape[0] == min(50, len(keep))
+    # soft-NMS: same 3-tuple convention, scores only ever decay, kept boxes sorted by score
+    k2, none, nb2 = I.softnms_gpu(boxes.clone(), scores.clone(), 0.25, score_threshold=0.1, variance=var[:, :6].clone())
+    assert none is None and k2.is_cuda and nb2.shape == boxes.shape and k2.numel() > 5
+
+
 # ------------------------------------------------------------------ edge cases and error behaviour
 def test_empty_and_ragged_inputs(cuda, capi):
     e7 = torch.zeros((0, 7), device=cuda)

@@ -64,3 +64,34 @@ def test_synthetic_generators_are_seeded_and_shaped():
     assert smp.shape == (210, 7) and gt.shape == (7, 7)
     pts = synth.points(1000, synth.kitti_boxes(4, 0))
     assert pts.shape == (1000, 3) and pts.dtype == torch.float32
+
+
+def test_variance_voting_nms_matches_reference_python(cpu_golden, capi):
+    """new_nms_gpu / nms_func (GLENet's NMS_TYPE) against the reference's own Python run on its CPU IoU
+    (tests/golden/make_golden.py).  The IoU matrix is injected from the C oracle (bit-exact with the
+    reference CPU function), so this checks the host control flow without a GPU."""
+    from glenet_b200 import variance_nms as V
+    boxes, scores, var = cpu_golden["vnms_boxes"], cpu_golden["vnms_scores"], cpu_golden["vnms_var"]
+
+    def run(variance, score_threshold=0):
+        b = boxes.copy()
+        b[:, 6] = V._limit_period(b[:, 6], offset=0.5, period=np.pi * 2)
+        s, nb = V.nms_func(b, scores.copy(), 0.25, score_threshold, variance=variance,
+                           iou_fn=lambda x, y: capi.boxes_iou_bev(x, y, dialect=capi.CPU))
+        keep = (s > 0).nonzero()[0]
+        keep = keep[s[keep].argsort()[::-1]]
+        return keep, nb[keep]
+
+    for name, kw in (("var", dict(variance=var.copy())), ("novar", dict(variance=None)), ("thr", dict(variance=var.copy(), score_threshold=0.2))):
+        keep, nb = run(**kw)
+        np.testing.assert_array_equal(keep, cpu_golden[f"vnms_keep_{name}"])
+        np.testing.assert_array_equal(nb, cpu_golden[f"vnms_newboxes_{name}"])
+    assert len(cpu_golden["vnms_keep_var"]) > 5
+
+
+def test_scale_by_iou_modes():
+    from glenet_b200 import variance_nms as V
+    iou = torch.tensor([0.0, 0.2, 0.5, 0.9])
+    lin = V.scale_by_iou(iou, 0.3, "linear")
+    assert torch.allclose(lin, torch.tensor([1.0, 1.0, 0.5, 0.1]))
+    assert torch.allclose(V.scale_by_iou(iou, 0.3, "gaussian"), torch.exp(-iou ** 2 / 0.3))
