@@ -51,11 +51,12 @@ enum {
     BP_PX = 7,                 // 4 rotated corner x
     BP_PY = 11,                // 4 rotated corner y
     BP_ZMIN = 15, BP_ZMAX = 16, BP_VOL = 17,   // boxes_iou3d_gpu terms (iou3d_nms_utils.py:100-117)
-    BP_STRIDE = 21
+    BP_STRIDE = 21,            // record stride with the z terms (3D IoU)
+    BP_STRIDE_BEV = 17         // BEV-only kernels drop them: 20 % less shared memory => one more CTA per SM
 };
 
 // trig4 = {cos(h), sin(h), cos(-h), sin(-h)}
-template <bool FMA>
+template <bool FMA, bool WITH_Z = true>
 __device__ __forceinline__ void box_prepare(const float* __restrict__ box, const float4 trig4,
                                             float* __restrict__ o) {
     const float cx = box[0], cy = box[1], z = box[2], dx = box[3], dy = box[4], dz = box[5];
@@ -81,10 +82,12 @@ __device__ __forceinline__ void box_prepare(const float* __restrict__ box, const
     o[BP_THX] = __fmaf_rn(dx, 0.5f, 0.01f);   // == dx/2 + MARGIN, single rounding in both dialects
     o[BP_THY] = __fmaf_rn(dy, 0.5f, 0.01f);
     o[BP_AREA] = __fmul_rn(dx, dy);
-    const float hz = __fmul_rn(dz, 0.5f);
-    o[BP_ZMIN] = __fsub_rn(z, hz);
-    o[BP_ZMAX] = __fadd_rn(z, hz);
-    o[BP_VOL] = __fmul_rn(__fmul_rn(dx, dy), dz);
+    if (WITH_Z) {
+        const float hz = __fmul_rn(dz, 0.5f);
+        o[BP_ZMIN] = __fsub_rn(z, hz);
+        o[BP_ZMAX] = __fadd_rn(z, hz);
+        o[BP_VOL] = __fmul_rn(__fmul_rn(dx, dy), dz);
+    }
 }
 
 __device__ __forceinline__ float4 device_trig(float heading) {
@@ -255,9 +258,12 @@ __device__ __forceinline__ float polygon_area(int cnt, VertexFn V) {
 }
 
 // box_overlap (:104-225): overlap area of prepared boxes a (row) and b (column), one thread per pair.
-// The vertex list (<= 16 entries, dynamically indexed) lives in per-thread local memory.  The 4 x 4 edge
-// loops are kept ROLLED (corners re-read from the BoxPre records in shared memory): the unrolled form is
-// ~6000 SASS instructions and thrashes the instruction cache when warps diverge.
+// The vertex list (<= 16 entries, dynamically indexed) lives in per-thread local memory.
+//   box_overlap         : 4 x 4 edge loops ROLLED, corners re-read from the BoxPre records in shared memory.
+//                         For kernels where only some warps clip while others stream (tile / NMS kernels):
+//                         the unrolled form is ~6000 SASS instructions and thrashes the instruction cache.
+//   box_overlap_unrolled: everything inlined and unrolled, corners in registers.  For the aligned kernel,
+//                         where every warp runs the same clip code over register-resident records.
 template <bool FMA>
 __device__ __noinline__ float box_overlap(const float* __restrict__ a, const float* __restrict__ b) {
     float2 v[MAX_POLY];
@@ -278,6 +284,35 @@ __device__ __noinline__ float box_overlap(const float* __restrict__ a, const flo
         const float bxk = b[BP_PX + k], byk = b[BP_PY + k], axk = a[BP_PX + k], ayk = a[BP_PY + k];
         if (corner_in_box<FMA>(a, bxk, byk) && cnt < MAX_POLY) v[cnt++] = make_float2(bxk, byk);
         if (corner_in_box<FMA>(b, axk, ayk) && cnt < MAX_POLY) v[cnt++] = make_float2(axk, ayk);
+    }
+    return polygon_area<FMA>(cnt, [&](int k) { return v[k]; });
+}
+
+template <bool FMA>
+__device__ __forceinline__ float box_overlap_unrolled(const float* __restrict__ a, const float* __restrict__ b) {
+    float ax[4], ay[4], bx[4], by[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ax[k] = a[BP_PX + k]; ay[k] = a[BP_PY + k];
+        bx[k] = b[BP_PX + k]; by[k] = b[BP_PY + k];
+    }
+    float2 v[MAX_POLY];
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float ox, oy;
+            if (edge_intersection<FMA>(ax[i], ay[i], ax[(i + 1) & 3], ay[(i + 1) & 3],
+                                       bx[j], by[j], bx[(j + 1) & 3], by[(j + 1) & 3], ox, oy)) {
+                if (cnt < MAX_POLY) v[cnt++] = make_float2(ox, oy);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (corner_in_box<FMA>(a, bx[k], by[k]) && cnt < MAX_POLY) v[cnt++] = make_float2(bx[k], by[k]);
+        if (corner_in_box<FMA>(b, ax[k], ay[k]) && cnt < MAX_POLY) v[cnt++] = make_float2(ax[k], ay[k]);
     }
     return polygon_area<FMA>(cnt, [&](int k) { return v[k]; });
 }

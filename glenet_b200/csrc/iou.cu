@@ -30,7 +30,8 @@ namespace glenet {
 constexpr int IOU_THREADS = 256;
 constexpr int IOU_TR_MAX = 256;            // tile rows (boxes_a)
 constexpr int IOU_TC_MAX = 128;            // tile cols (boxes_b)
-constexpr int IOU_QCAP = 6 * IOU_THREADS;  // queue capacity; drained when 4 more column steps could overflow it
+constexpr int IOU_QCAP = 4 * IOU_THREADS;  // queue capacity; drained when 2 more column steps could overflow it
+constexpr int IOU_CTAS_PER_SM = 4;         // register budget the kernel is compiled for (5 was measured: spills, no gain)
 constexpr int IOU_ZCHUNK = 4 * 32;         // float4 stores per warp and zero-fill chunk
 
 enum { MODE_OVERLAP = 0, MODE_IOU_BEV = 1, MODE_IOU3D = 2 };
@@ -45,11 +46,12 @@ __device__ int g_dbg_flags;   // bit 0: skip the clip pass, bit 1: skip the zero
 #define PHASE_INIT do { } while (0)
 #endif
 
+template <int BPS>
 struct __align__(16) IouSmem {
     float4 row[IOU_TR_MAX];                // {cx, cy, cull radius, -}
     float ccx[IOU_TC_MAX], ccy[IOU_TC_MAX], crad[IOU_TC_MAX];   // SoA so that 4 consecutive columns are one LDS.128
-    float rpre[IOU_TR_MAX * BP_STRIDE];
-    float cpre[IOU_TC_MAX * BP_STRIDE];
+    float rpre[IOU_TR_MAX * BPS];
+    float cpre[IOU_TC_MAX * BPS];
     float qres[IOU_QCAP];                  // clipped results, parked until the tile's zero fill is complete
     unsigned short queue[IOU_QCAP];        // (row << 8) | col  (row < 256, col < 128)
     float red[IOU_THREADS / 32][5];
@@ -66,7 +68,8 @@ __device__ __forceinline__ float finish_pair(const float* a, const float* b, flo
 
 // Zero-fill of the tile, chunked so that any warp can take part whenever it has nothing else to do:
 // the stores are fire-and-forget, which is what lets them overlap the clip pass of the other warps.
-__device__ __forceinline__ void zero_fill_tile(IouSmem& sm, float* __restrict__ out_tile, int tr, int tc, int nb, bool vec) {
+template <typename SM>
+__device__ __forceinline__ void zero_fill_tile(SM& sm, float* __restrict__ out_tile, int tr, int tc, int nb, bool vec) {
     const int lane = threadIdx.x & 31;
     if (vec) {
         const int nq = tc >> 2, nquads = tr * nq;
@@ -109,9 +112,10 @@ __device__ __forceinline__ void zero_fill_tile(IouSmem& sm, float* __restrict__ 
 // then overwrite the zeros (parked in shared memory meanwhile).  Warps without queued pairs go straight to zero filling, the others join
 // when their pairs are done -- streaming stores and clipping overlap inside the CTA.
 template <int MODE, bool FMA>
-__device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict__ A, const float* __restrict__ B,
+__device__ __forceinline__ void drain_queue(IouSmem<MODE == MODE_IOU3D ? BP_STRIDE : BP_STRIDE_BEV>& sm, const float* __restrict__ A, const float* __restrict__ B,
                                             const float4* __restrict__ trigA, const float4* __restrict__ trigB,
                                             int r0, int c0, int tr, int tc, int nb, float* __restrict__ out, bool vec) {
+    constexpr int BPS = (MODE == MODE_IOU3D) ? BP_STRIDE : BP_STRIDE_BEV;
     const int tid = threadIdx.x;
     const int n = sm.qcount;
     PHASE_INIT;
@@ -125,7 +129,7 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
             const float* box = (is_row ? A : B) + (size_t)g * 7;
             const float4* trig = is_row ? trigA : trigB;
             const float4 t4 = trig ? trig[g] : device_trig(box[6]);
-            box_prepare<FMA>(box, t4, (is_row ? sm.rpre : sm.cpre) + k * BP_STRIDE);
+            box_prepare<FMA, MODE == MODE_IOU3D>(box, t4, (is_row ? sm.rpre : sm.cpre) + k * BPS);
             *flag = 2;
         }
     }
@@ -138,8 +142,8 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
 #endif
     for (int q = tid; q < ((dbg & 1) ? 0 : n); q += IOU_THREADS) {
         const unsigned int e = sm.queue[q];
-        const float* a = sm.rpre + (e >> 8) * BP_STRIDE;
-        const float* b = sm.cpre + (e & 255) * BP_STRIDE;
+        const float* a = sm.rpre + (e >> 8) * BPS;
+        const float* b = sm.cpre + (e & 255) * BPS;
         sm.qres[q] = finish_pair<MODE>(a, b, box_overlap<FMA>(a, b));
     }
     PHASE_MARK(7);
@@ -157,7 +161,8 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
 }
 
 // append the lanes' surviving pairs with one atomic per warp
-__device__ __forceinline__ void enqueue_heavy(IouSmem& sm, unsigned int heavy, int r, int c, int lane) {
+template <typename SM>
+__device__ __forceinline__ void enqueue_heavy(SM& sm, unsigned int heavy, int r, int c, int lane) {
     const unsigned int m = __ballot_sync(0xffffffffu, heavy != 0);
     if (!m) return;
     int qb = 0;
@@ -171,12 +176,13 @@ __device__ __forceinline__ void enqueue_heavy(IouSmem& sm, unsigned int heavy, i
 }
 
 template <int MODE, bool FMA>
-__global__ void __launch_bounds__(IOU_THREADS, 4)
+__global__ void __launch_bounds__(IOU_THREADS, IOU_CTAS_PER_SM)
 iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int nb,
                 const float4* __restrict__ trigA, const float4* __restrict__ trigB,
                 float* __restrict__ out, int TR, int TC, int col_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    IouSmem& sm = *reinterpret_cast<IouSmem*>(smem_raw);
+    using Smem = IouSmem<MODE == MODE_IOU3D ? BP_STRIDE : BP_STRIDE_BEV>;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_r = blockIdx.x / col_tiles, tile_c = blockIdx.x - tile_r * col_tiles;
     const int r0 = tile_r * TR, c0 = tile_c * TC;
@@ -232,7 +238,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
 
     // ---- per-pair circle test on the active columns only; survivors go to the queue.
     //      One row per thread (TR <= 256 = block size), uniform loop over the active columns whose
-    //      data is a shared-memory broadcast; the queue is checked every 4 columns (<= 1024 appends).
+    //      data is a shared-memory broadcast; the queue is checked every 2 columns (<= 512 appends).
     const int nact = sm.nact;
     {
         // thread -> (row, column group): rows padded to a power of two so that small tiles still use all threads
@@ -242,13 +248,13 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
         const bool has_row = row < tr;
         const float4 rw = has_row ? sm.row[row] : make_float4(0.f, 0.f, 0.f, 0.f);
         const int iters = (nact + groups - 1) / groups;
-        for (int it0 = 0; it0 < iters; it0 += 4) {
+        for (int it0 = 0; it0 < iters; it0 += 2) {
             const int qc = sm.qcount;
             __syncthreads();   // everyone has read the count before anyone appends again => the branch is uniform
-            if (qc > IOU_QCAP - 4 * IOU_THREADS) {   // dense tiles only
+            if (qc > IOU_QCAP - 2 * IOU_THREADS) {   // dense tiles only
                 drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, vec);
             }
-            const int it1 = min(iters, it0 + 4);
+            const int it1 = min(iters, it0 + 2);
             for (int it = it0; it < it1; ++it) {
                 const int k = it * groups + grp;
                 const bool valid = has_row && k < nact;
@@ -275,9 +281,7 @@ iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict_
     const int tid = threadIdx.x;
     const int i = blockIdx.x * ALIGNED_THREADS + tid;
     if (i >= na) return;
-    __shared__ float s_pre[2 * ALIGNED_THREADS * BP_STRIDE];
-    float* a = s_pre + tid * BP_STRIDE;
-    float* b = s_pre + (ALIGNED_THREADS + tid) * BP_STRIDE;
+    float a[BP_STRIDE], b[BP_STRIDE];   // statically indexed => registers
     const float* ba = A + (size_t)i * 7;
     const float* bb = B + (size_t)(i / group) * 7;
     float out_v = 0.f;
@@ -286,7 +290,7 @@ iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict_
     if (!(ddx * ddx + ddy * ddy > rr * rr)) {
         box_prepare<FMA>(ba, device_trig(ba[6]), a);
         box_prepare<FMA>(bb, device_trig(bb[6]), b);
-        const float ov = box_overlap<FMA>(a, b);
+        const float ov = box_overlap_unrolled<FMA>(a, b);
         out_v = finish_pair<MODE>(a, b, ov);
     }
     out[i] = out_v;
@@ -299,7 +303,7 @@ static void pick_tiles(int na, int nb, int& TR, int& TC, int& row_tiles, int& co
     col_tiles = (nb + IOU_TC_MAX - 1) / IOU_TC_MAX;
     TC = ((nb + col_tiles - 1) / col_tiles + 3) / 4 * 4;   // multiple of 4 keeps every tile on the 16-byte store path
     // aim for >= 4 CTAs per SM (148 SMs) before growing the row tile
-    long want = 4L * 148;
+    long want = (long)IOU_CTAS_PER_SM * 148;
     long tr = ((long)na * col_tiles + want - 1) / want;
     tr = (tr + 31) / 32 * 32;
     if (tr < 32) tr = 32;
@@ -323,13 +327,13 @@ static int launch_iou(const float* A, const float* trigA, int na, const float* B
     auto kernel = iou_tile_kernel<MODE, FMA>;
     static bool attr_done = false;   // per template instantiation
     if (!attr_done) {
-        int rc = set_smem(kernel, sizeof(IouSmem), what);
+        int rc = set_smem(kernel, sizeof(IouSmem<MODE == MODE_IOU3D ? BP_STRIDE : BP_STRIDE_BEV>), what);
         if (rc) return rc;
         attr_done = true;
     }
     const long tiles = (long)row_tiles * col_tiles;
     if (tiles > 0x7fffffffL) return fail(GLENET_EINVAL, "%s: too many tiles", what);
-    kernel<<<(unsigned)tiles, IOU_THREADS, sizeof(IouSmem), stream>>>(
+    kernel<<<(unsigned)tiles, IOU_THREADS, sizeof(IouSmem<MODE == MODE_IOU3D ? BP_STRIDE : BP_STRIDE_BEV>), stream>>>(
         A, na, B, nb, reinterpret_cast<const float4*>(trigA), reinterpret_cast<const float4*>(trigB), out, TR, TC,
         col_tiles);
     return check_launch(what);
