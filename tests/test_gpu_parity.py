@@ -249,6 +249,45 @@ def test_glenet_variance_voting_nms_on_gpu(cuda, cpu_golden):
     assert none is None and k2.is_cuda and nb2.shape == boxes.shape and k2.numel() > 5
 
 
+def test_rarely_taken_kernel_paths(cuda, capi, ref_so):
+    """Paths the headline configs never reach: NMS with more boxes than the staged sweep holds (n > 12 700),
+    points-in-boxes with box records in global memory (N > 512), the per-frame exhaustive fallback (non-finite
+    box extents) next to binned frames, > 255 boxes in one cell, and IoU with several / ragged column tiles."""
+    # NMS: RoI-head training size (9000) and beyond the shared-memory staging limit (14000)
+    for n in (9000, 14000):
+        boxes, scores = synth.proposals(n, 60, n)
+        boxes[:, :2] += torch.randn(n, 2, generator=torch.Generator().manual_seed(n)) * 2.0
+        boxes, scores = boxes.to(cuda), scores.to(cuda)
+        assert torch.equal(I.nms_gpu(boxes, scores, 0.7)[0], ref_so.nms_gpu(boxes, scores, 0.7)[0])
+        assert torch.equal(I.nms_normal_gpu(boxes, scores, 0.5)[0], ref_so.nms_normal_gpu(boxes, scores, 0.5)[0])
+    # PIB: 700 boxes (records stay in global memory), 3 frames, one of them degenerate
+    bx = torch.stack([synth.waymo_boxes(700, 50 + f) for f in range(3)])
+    bx[1, 5, 3] = float("inf")            # infinite extent => this frame cannot be binned => exhaustive loop on the device
+    bx[2, 7, 0] = float("nan")            # a NaN box never matches; the frame is still binned
+    pts = torch.stack([synth.points(50000, bx[f, :100], synth.WAYMO_RANGE, 0.3, seed=f) for f in range(3)])
+    bx, pts = bx.to(cuda), pts.to(cuda)
+    assert torch.equal(R.points_in_boxes_gpu(pts, bx), ref_so.points_in_boxes_gpu(pts, bx))
+    # PIB: 400 boxes piled on one spot => hundreds of candidates in a cell (> 255 => exhaustive flag)
+    pile = synth.kitti_boxes(400, 3)
+    pile[:, :2] = pile[:1, :2] + torch.randn(400, 2, generator=torch.Generator().manual_seed(3)) * 0.3
+    pp = synth.points(30000, pile, synth.KITTI_RANGE, 0.6, seed=4)[None].to(cuda)
+    assert torch.equal(R.points_in_boxes_gpu(pp, pile[None].to(cuda)), ref_so.points_in_boxes_gpu(pp, pile[None].to(cuda)))
+    # IoU: 3 ragged column tiles (nb = 301, not a multiple of 4 => scalar store path), odd row count
+    a, _ = synth.proposals(1111, 30, 5)
+    b, _ = synth.proposals(301, 30, 5)
+    a, b = a.to(cuda), b.to(cuda)
+    assert torch.equal(I.boxes_iou_bev(a, b), ref_so.boxes_iou_bev(a, b))
+    assert torch.equal(I.boxes_iou3d_gpu(a, b), ref_so.boxes_iou3d_gpu(a, b))
+    # unaligned output view (16-byte vector stores must not be used): write into a column slice of a wider tensor
+    wide = torch.empty((64, 104), device=cuda)
+    import glenet_b200
+    lib = glenet_b200.load()
+    tmp = torch.empty((64 * 100 + 1,), device=cuda)[1:]          # 4-byte aligned only
+    assert lib.glenet_boxes_iou_bev_gpu(a.data_ptr(), 64, b.data_ptr(), 100, tmp.data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
+    assert torch.equal(tmp.view(64, 100), I.boxes_iou_bev(a[:64], b[:100]))
+    del wide
+
+
 # ------------------------------------------------------------------ edge cases and error behaviour
 def test_empty_and_ragged_inputs(cuda, capi):
     e7 = torch.zeros((0, 7), device=cuda)
