@@ -36,6 +36,7 @@ inline int set_smem(K kernel, size_t bytes, const char* what) {
         snprintf(last_error_buf(), 512, "%s: cudaFuncSetAttribute(%zu B): %s", what, bytes, cudaGetErrorString(e));
         return -(int)e;
     }
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   // a hint; failure is harmless
     return GLENET_OK;
 }
 

@@ -104,11 +104,11 @@ __device__ __forceinline__ float4 device_trig(float heading) {
 // (a corner may be admitted up to MARGIN outside, in both axes) plus slack for the
 // rounding of absolute corner coordinates.  Two boxes whose centres are farther apart
 // than r_a + r_b produce no polygon vertex in the reference => overlap is exactly +0.
-__device__ __forceinline__ float cull_radius(const float* __restrict__ box) {
-    const float dx = box[3], dy = box[4];
+__device__ __forceinline__ float cull_radius(float cx, float cy, float dx, float dy) {
     const float r = 0.5f * sqrtf(dx * dx + dy * dy);
-    return r * 1.0001f + 0.03f + 2e-6f * (fabsf(box[0]) + fabsf(box[1]));
+    return r * 1.0001f + 0.03f + 2e-6f * (fabsf(cx) + fabsf(cy));
 }
+__device__ __forceinline__ float cull_radius(const float* __restrict__ box) { return cull_radius(box[0], box[1], box[3], box[4]); }
 
 // ---------------------------------------------------------------- polygon
 // cross_points[16] of the reference (:155)
@@ -162,6 +162,27 @@ __device__ __forceinline__ bool corner_in_box(const float* __restrict__ b, float
     const float rx = mul_sub<FMA>(cn, dxp, sn, dyp);   // dxp*cos + dyp*(-sin)
     const float ry = mul_add<FMA>(cn, dyp, sn, dxp);   // dxp*sin + dyp*cos (dyp*cos is the fused product)
     return fabsf(rx) < b[BP_THX] && fabsf(ry) < b[BP_THY];
+}
+
+// Separating-axis test with a safety margin.  True only when the two rectangles are further apart along
+// one of their four edge normals than every tolerance of the reference's clipping code (MARGIN 0.01 of
+// check_in_box2d :53, EPS 1e-8 of intersection() :57-89) plus the rounding of this test itself; the
+// reference then finds no corner inside the other box and no edge crossing, i.e. cnt == 0 and the overlap
+// is exactly +0.  Any NaN/Inf makes every comparison false => "not separated" => the clip code decides.
+// Budget of the 0.05 slack: 0.01 MARGIN, 2 x 0.01 for |dx/2 + 0.01| < |dx|/2 when an extent is negative,
+// the rest plus the relative terms for float rounding (coordinates up to 1e6 m).
+__device__ __forceinline__ bool sat_separated(const float* __restrict__ a, const float* __restrict__ b) {
+    const float acx = a[BP_CX], acy = a[BP_CY], bcx = b[BP_CX], bcy = b[BP_CY];
+    const float dx = bcx - acx, dy = bcy - acy;
+    const float ca = a[BP_CN], sa = a[BP_SN], cb = b[BP_CN], sb = b[BP_SN];
+    const float C = fabsf(ca * cb + sa * sb), S = fabsf(sa * cb - ca * sb);
+    const float ax = fabsf(a[BP_THX]), ay = fabsf(a[BP_THY]), bx = fabsf(b[BP_THX]), by = fabsf(b[BP_THY]);
+    const float slack = 0.05f + 4e-6f * (fabsf(acx) + fabsf(acy) + fabsf(bcx) + fabsf(bcy));
+    const float k = 1.0002f;
+    const float pax = fabsf(ca * dx - sa * dy), pay = fabsf(sa * dx + ca * dy);
+    const float pbx = fabsf(cb * dx - sb * dy), pby = fabsf(sb * dx + cb * dy);
+    return pax > (ax + bx * C + by * S) * k + slack || pay > (ay + bx * S + by * C) * k + slack ||
+           pbx > (bx + ax * C + ay * S) * k + slack || pby > (by + ax * S + ay * C) * k + slack;
 }
 
 // Monotone stand-in for atan2f(dy, dx) on (-pi, pi]: same ordering of the polygon vertices about the
@@ -328,13 +349,16 @@ __device__ __forceinline__ float max_nan(float a, float b) { return (a != a || b
 __device__ __forceinline__ float min_nan(float a, float b) { return (a != a || b != b) ? (a + b) : fminf(a, b); }
 
 // boxes_iou3d_gpu (iou3d_nms_utils.py:100-119), every step separately rounded as torch does
-__device__ __forceinline__ float iou3d_from_overlap(const float* __restrict__ a, const float* __restrict__ b, float ov) {
-    const float max_of_min = max_nan(a[BP_ZMIN], b[BP_ZMIN]);
-    const float min_of_max = min_nan(a[BP_ZMAX], b[BP_ZMAX]);
+__device__ __forceinline__ float iou3d_from_terms(float a_zmin, float a_zmax, float a_vol, float b_zmin, float b_zmax, float b_vol, float ov) {
+    const float max_of_min = max_nan(a_zmin, b_zmin);
+    const float min_of_max = min_nan(a_zmax, b_zmax);
     const float oh = clamp_min_nan(__fsub_rn(min_of_max, max_of_min), 0.f);
     const float o3 = __fmul_rn(ov, oh);
-    const float den = clamp_min_nan(__fsub_rn(__fadd_rn(a[BP_VOL], b[BP_VOL]), o3), 1e-6f);
+    const float den = clamp_min_nan(__fsub_rn(__fadd_rn(a_vol, b_vol), o3), 1e-6f);
     return __fdiv_rn(o3, den);
+}
+__device__ __forceinline__ float iou3d_from_overlap(const float* __restrict__ a, const float* __restrict__ b, float ov) {
+    return iou3d_from_terms(a[BP_ZMIN], a[BP_ZMAX], a[BP_VOL], b[BP_ZMIN], b[BP_ZMAX], b[BP_VOL], ov);
 }
 
 }  // namespace glenet

@@ -4,19 +4,24 @@
 // pcdet/ops/iou3d_nms/src/iou3d_nms_kernel.cu:236-265,378-398 and the ~10 torch
 // elementwise kernels of boxes_iou3d_gpu (pcdet/ops/iou3d_nms/iou3d_nms_utils.py:88-121).
 //
-// Design (one CTA = one TR x TC tile of the (na, nb) matrix):
+// Design (one CTA = one TR x TC tile of the (na, nb) matrix; the grid is sized to ONE wave of resident
+// CTAs whenever the problem allows it, because the kernel is bound by the latency of a CTA's phase chain):
+//   0. zero fill   : > 99 % of an anchor sweep is exactly +0.0 and that regime is HBM-write bound
+//                    (4 B / pair).  The tile is zero-filled by the bulk-copy engine (cp.async.bulk
+//                    shared -> global from a 4 KB block of zeros): a handful of instructions per CTA,
+//                    fully asynchronous, so the stores drain while the CTA works through 1-4.
 //   1. cull pass   : two-level exact-conservative circle test on box tiles staged in shared
 //                    memory.  First one test per COLUMN against the bounding box of the tile's
 //                    row centres (an anchor tile sees ~4 of 100 GT boxes), then one test per
-//                    (row, active column).  The tile itself is zero-filled with 16-byte streaming
-//                    stores -- > 99 % of an anchor sweep is exactly +0.0 and this regime is
-//                    HBM-write bound (4 B / pair).
-//   2. compaction  : surviving pairs are appended to a shared-memory queue with one
-//                    warp-aggregated atomic per warp, and their boxes are flagged.
+//                    (row, active column), 32 columns at a time into a register bitmask.
+//   2. compaction  : surviving pairs are appended to a shared-memory queue (one atomic per warp and
+//                    32 columns), their boxes are flagged.
 //   3. lazy prepare: only flagged boxes get their BoxPre record (4 trig calls, corners,
-//                    margin thresholds) -- once per box per tile, never per pair.
-//   4. clip pass   : the queue is drained with all lanes busy (no divergence between
-//                    "far" and "near" pairs).
+//                    margin thresholds) -- once per box per tile, never per pair, on full warps.
+//   4. SAT filter  : a separating-axis test on the prepared records drops the pairs whose overlap is
+//                    exactly 0 in the reference too; the rest is compacted again.
+//   5. clip pass   : one pair per thread, results parked in shared memory and written once the
+//                    zero fill has landed.
 // The reference instead runs the full clipping code, incl. 20 sinf/cosf evaluations, for
 // every pair in a 16x16 thread block with 208 B of local-memory stack per thread.
 #include "common.cuh"
@@ -27,17 +32,21 @@
 
 namespace glenet {
 
-constexpr int IOU_THREADS = 256;
-constexpr int IOU_TR_MAX = 256;            // tile rows (boxes_a)
+constexpr int IOU_THREADS = 256;           // 7 "chain" warps (cull, prepare, clip) + 1 fill warp
+constexpr int IOU_CHAIN = IOU_THREADS - 32;
+constexpr int IOU_TR_MAX = 384;            // tile rows (boxes_a)
 constexpr int IOU_TC_MAX = 128;            // tile cols (boxes_b)
-constexpr int IOU_QCAP = 4 * IOU_THREADS;  // queue capacity; drained when 2 more column steps could overflow it
+constexpr int IOU_RPT = (IOU_TR_MAX + IOU_CHAIN - 1) / IOU_CHAIN;   // rows per thread in the circle tests of tall tiles
+constexpr int IOU_QCAP = 512;              // circle-test survivors per drain
+constexpr int IOU_Q2CAP = IOU_QCAP + IOU_CHAIN;   // + the partial clip pass carried over from the previous drain
 constexpr int IOU_CTAS_PER_SM = 4;         // register budget the kernel is compiled for (5 was measured: spills, no gain)
-constexpr int IOU_ZCHUNK = 4 * 32;         // float4 stores per warp and zero-fill chunk
+constexpr int IOU_ZBYTES = 4096;           // block of zeros in shared memory = largest bulk store of the zero fill
+constexpr int BPS = BP_STRIDE_BEV;         // BoxPre stride in shared memory (the z terms of 3D IoU are read per clipped pair)
 
 enum { MODE_OVERLAP = 0, MODE_IOU_BEV = 1, MODE_IOU3D = 2 };
 
 #ifdef GLENET_PHASE_TIMING   // developer instrumentation: accumulated clock64() per phase, thread 0 of every CTA
-__device__ unsigned long long g_phase_cycles[8];
+__device__ unsigned long long g_phase_cycles[12];   // [0..7] phase cycles, [8] queued pairs, [9] pairs clipped, [10] boxes prepared, [11] drains
 __device__ int g_dbg_flags;   // bit 0: skip the clip pass, bit 1: skip the zero fill (timing experiments only)
 #define PHASE_MARK(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_phase_cycles[k], (unsigned long long)(now_ - t_phase_)); t_phase_ = now_; } } while (0)
 #define PHASE_INIT long long t_phase_ = clock64()
@@ -46,133 +55,173 @@ __device__ int g_dbg_flags;   // bit 0: skip the clip pass, bit 1: skip the zero
 #define PHASE_INIT do { } while (0)
 #endif
 
-template <int BPS>
-struct __align__(16) IouSmem {
+struct __align__(128) IouSmem {
+    float4 zero[IOU_ZBYTES / 16];          // source of the bulk zero fill
     float4 row[IOU_TR_MAX];                // {cx, cy, cull radius, -}
-    float ccx[IOU_TC_MAX], ccy[IOU_TC_MAX], crad[IOU_TC_MAX];   // SoA so that 4 consecutive columns are one LDS.128
+    float ccx[IOU_TC_MAX], ccy[IOU_TC_MAX], crad[IOU_TC_MAX];
     float rpre[IOU_TR_MAX * BPS];
     float cpre[IOU_TC_MAX * BPS];
-    float qres[IOU_QCAP];                  // clipped results, parked until the tile's zero fill is complete
-    unsigned short queue[IOU_QCAP];        // (row << 8) | col  (row < 256, col < 128)
+    float qres[IOU_Q2CAP];                 // clipped results, parked until the zero fill has landed
+    unsigned short queue[IOU_QCAP];        // (row << 7) | col  (row < 384, col < 128): survivors of the circle test
+    unsigned short queue2[IOU_Q2CAP];      // survivors of the separating-axis test: the pairs that are clipped
+    unsigned short plist[IOU_TR_MAX + IOU_TC_MAX];   // boxes to prepare in the current drain
     float red[IOU_THREADS / 32][5];
-    unsigned char rflag[IOU_TR_MAX], cflag[IOU_TC_MAX], act[IOU_TC_MAX];
-    int qcount, nact, zchunk;
+    unsigned char rflag[IOU_TR_MAX], cflag[IOU_TC_MAX], act[IOU_TC_MAX];   // flags: 0 = unused, 1 = wanted, 2 = prepared
+    int qcount, q2count, nact, nprep;
 };
+static_assert(IOU_TR_MAX * IOU_TC_MAX <= 65536 && IOU_TC_MAX == 128, "queue entries are (row << 7) | col in 16 bits");
+
+// ---- bulk-copy engine (TMA without a tensor map): shared -> global, tracked by bulk async-groups
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned int bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(__cvta_generic_to_global(gdst)), "r"((unsigned int)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// ---- named barriers: 1 = the chain warps among themselves, 2 = "the tile's zero fill has landed" (fill warp arrives, chain warps wait)
+__device__ __forceinline__ void chain_sync() { asm volatile("bar.sync 1, %0;" :: "n"(IOU_CHAIN) : "memory"); }
+__device__ __forceinline__ void fill_arrive() { asm volatile("bar.arrive 2, %0;" :: "n"(IOU_THREADS) : "memory"); }
+__device__ __forceinline__ void fill_wait() { asm volatile("bar.sync 2, %0;" :: "n"(IOU_THREADS) : "memory"); }
+
+// z terms of boxes_iou3d_gpu (iou3d_nms_utils.py:100-117) for one box, every step separately rounded as torch does
+struct ZTerms { float zmin, zmax, vol; };
+__device__ __forceinline__ ZTerms z_terms(float z, float dz, float area) {
+    const float hz = __fmul_rn(dz, 0.5f);
+    ZTerms t;
+    t.zmin = __fsub_rn(z, hz); t.zmax = __fadd_rn(z, hz); t.vol = __fmul_rn(area, dz);
+    return t;
+}
+__device__ __forceinline__ bool z_terms_finite(const ZTerms& t) { return fabsf(t.zmin) + fabsf(t.zmax) + fabsf(t.vol) < CUDART_INF_F; }
 
 template <int MODE>
-__device__ __forceinline__ float finish_pair(const float* a, const float* b, float ov) {
+__device__ __forceinline__ float finish_pair(const float* a, const float* b, float ov, const float* __restrict__ boxa, const float* __restrict__ boxb) {
     if (MODE == MODE_OVERLAP) return ov;
     if (MODE == MODE_IOU_BEV) return iou_from_overlap(a[BP_AREA], b[BP_AREA], ov);
-    return iou3d_from_overlap(a, b, ov);
+    const ZTerms za = z_terms(boxa[2], boxa[5], a[BP_AREA]), zb = z_terms(boxb[2], boxb[5], b[BP_AREA]);
+    return iou3d_from_terms(za.zmin, za.zmax, za.vol, zb.zmin, zb.zmax, zb.vol, ov);
 }
 
-// Zero-fill of the tile, chunked so that any warp can take part whenever it has nothing else to do:
-// the stores are fire-and-forget, which is what lets them overlap the clip pass of the other warps.
-template <typename SM>
-__device__ __forceinline__ void zero_fill_tile(SM& sm, float* __restrict__ out_tile, int tr, int tc, int nb, bool vec) {
-    const int lane = threadIdx.x & 31;
+// Zero fill of the tile, executed by ONE warp while the other seven work on the tile's pairs.  16-byte aligned
+// tiles go through the bulk-copy engine (a few dozen 4 KB shared -> global copies from a block of zeros);
+// everything else falls back to plain stores.  Either way the warp blocks on back-pressure from the memory
+// system -- a wave of tiles is ~85 MB of stores -- and nobody waits for it until the results are due.
+__device__ __forceinline__ void zero_fill_tile(IouSmem& sm, float* __restrict__ out_tile, int tr, int tc, int nb, bool vec, int lane) {
     if (vec) {
-        const int nq = tc >> 2, nquads = tr * nq;
-        const int nchunks = (nquads + IOU_ZCHUNK - 1) / IOU_ZCHUNK;
-        const bool contiguous = (nq * 4 == nb);
-        for (;;) {
-            int ch = 0;
-            if (lane == 0) ch = atomicAdd(&sm.zchunk, 1);
-            ch = __shfl_sync(0xffffffffu, ch, 0);
-            if (ch >= nchunks) break;
-#pragma unroll
-            for (int k = 0; k < IOU_ZCHUNK / 32; ++k) {
-                const int q = ch * IOU_ZCHUNK + k * 32 + lane;
-                if (q < nquads) {
-                    float4* dst;
-                    if (contiguous) dst = reinterpret_cast<float4*>(out_tile) + q;
-                    else { const int r = q / nq; dst = reinterpret_cast<float4*>(out_tile + (size_t)r * nb) + (q - r * nq); }
-                    *dst = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+        if (tc == nb) {   // the tile is one contiguous range of the matrix
+            const size_t total = (size_t)tr * nb * sizeof(float);
+            char* dst = reinterpret_cast<char*>(out_tile);
+            for (size_t off = (size_t)lane * IOU_ZBYTES; off < total; off += (size_t)32 * IOU_ZBYTES) {
+                const size_t left = total - off;
+                bulk_store(dst + off, sm.zero, (unsigned int)(left < (size_t)IOU_ZBYTES ? left : (size_t)IOU_ZBYTES));
             }
+        } else {
+            for (int r = lane; r < tr; r += 32) bulk_store(out_tile + (size_t)r * nb, sm.zero, (unsigned int)tc * sizeof(float));
         }
+        bulk_commit();
+        bulk_wait_all();       // writes of this thread's bulk copies are complete ...
+        fence_proxy_async();   // ... and ordered before generic-proxy accesses that follow the barrier
     } else {
         const int npairs = tr * tc;
-        const int nchunks = (npairs + IOU_ZCHUNK - 1) / IOU_ZCHUNK;
-        for (;;) {
-            int ch = 0;
-            if (lane == 0) ch = atomicAdd(&sm.zchunk, 1);
-            ch = __shfl_sync(0xffffffffu, ch, 0);
-            if (ch >= nchunks) break;
-#pragma unroll
-            for (int k = 0; k < IOU_ZCHUNK / 32; ++k) {
-                const int p = ch * IOU_ZCHUNK + k * 32 + lane;
-                if (p < npairs) { const int r = p / tc; out_tile[(size_t)r * nb + (p - r * tc)] = 0.f; }
-            }
-        }
+        for (int p = lane; p < npairs; p += 32) { const int r = p / tc; out_tile[(size_t)r * nb + (p - r * tc)] = 0.f; }
     }
 }
 
-// Clip the queued pairs.  Results are parked until the tile's zero fill is complete (barrier),
-// then overwrite the zeros (parked in shared memory meanwhile).  Warps without queued pairs go straight to zero filling, the others join
-// when their pairs are done -- streaming stores and clipping overlap inside the CTA.
+// Drain the first n queue entries (survivors of the circle test).  Chain warps only.
+//   1. the boxes they touch are compacted into a list and prepared (BoxPre) on full warps,
+//   2. a separating-axis test on the prepared records drops the pairs whose overlap is exactly 0 in the
+//      reference too (sat_separated); the rest is appended to queue2,
+//   3. queue2 is clipped one pair per thread -- in full passes only unless this is the tile's last drain; the
+//      remainder stays in queue2 for the next drain -- and the results are parked in shared memory,
+//   4. once the fill warp has signalled that the tile's zeros have landed (first drain only) they are written.
 template <int MODE, bool FMA>
-__device__ __forceinline__ void drain_queue(IouSmem<MODE == MODE_IOU3D ? BP_STRIDE : BP_STRIDE_BEV>& sm, const float* __restrict__ A, const float* __restrict__ B,
+__device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict__ A, const float* __restrict__ B,
                                             const float4* __restrict__ trigA, const float4* __restrict__ trigB,
-                                            int r0, int c0, int tr, int tc, int nb, float* __restrict__ out, bool vec) {
-    constexpr int BPS = (MODE == MODE_IOU3D) ? BP_STRIDE : BP_STRIDE_BEV;
-    const int tid = threadIdx.x;
-    const int n = sm.qcount;
+                                            int r0, int c0, int tr, int tc, int nb, float* __restrict__ out, int n, bool last, bool& fill_pending) {
+    const int tid = threadIdx.x, lane = tid & 31;
     PHASE_INIT;
-    // lazy per-box preparation of the boxes that take part in at least one queued pair
-    for (int i = tid; i < tr + tc; i += IOU_THREADS) {
+    for (int i0 = 0; i0 < tr + tc; i0 += IOU_CHAIN) {
+        const int i = i0 + tid;
+        const bool want = i < tr + tc && (i < tr ? sm.rflag[i] : sm.cflag[i - tr]) == 1;
+        const unsigned int m = __ballot_sync(0xffffffffu, want);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&sm.nprep, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (want) sm.plist[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)i;
+        }
+    }
+    chain_sync();
+    const int nprep = sm.nprep;
+    for (int j = tid; j < nprep; j += IOU_CHAIN) {
+        const int i = sm.plist[j];
         const bool is_row = i < tr;
         const int k = is_row ? i : i - tr;
-        unsigned char* flag = is_row ? &sm.rflag[k] : &sm.cflag[k];
-        if (*flag == 1) {
-            const int g = is_row ? r0 + k : c0 + k;
-            const float* box = (is_row ? A : B) + (size_t)g * 7;
-            const float4* trig = is_row ? trigA : trigB;
-            const float4 t4 = trig ? trig[g] : device_trig(box[6]);
-            box_prepare<FMA, MODE == MODE_IOU3D>(box, t4, (is_row ? sm.rpre : sm.cpre) + k * BPS);
-            *flag = 2;
+        float* rec = (is_row ? sm.rpre : sm.cpre) + k * BPS;
+        float raw[7];   // staged in the record's first slots by the tile prologue: no global load behind the zero fill's stores
+#pragma unroll
+        for (int f = 0; f < 7; ++f) raw[f] = rec[f];
+        const float4* trig = is_row ? trigA : trigB;
+        const float4 t4 = trig ? trig[is_row ? r0 + k : c0 + k] : device_trig(raw[6]);
+        box_prepare<FMA, false>(raw, t4, rec);
+        *(is_row ? &sm.rflag[k] : &sm.cflag[k]) = 2;
+    }
+    chain_sync();
+    PHASE_MARK(3);
+    for (int q0 = 0; q0 < n; q0 += IOU_CHAIN) {
+        const int q = q0 + tid;
+        unsigned int e = 0;
+        bool keep = false;
+        if (q < n) {
+            e = sm.queue[q];
+            const float* a = sm.rpre + (e >> 7) * BPS;
+            const float* b = sm.cpre + (e & 127) * BPS;
+            keep = !sat_separated(a, b);
+            if (MODE == MODE_IOU3D && !keep) {   // 0 * NaN: a non-finite z term turns even a zero BEV overlap into NaN (iou3d_nms_utils.py:107-117)
+                const float* boxa = A + (size_t)(r0 + (e >> 7)) * 7;
+                const float* boxb = B + (size_t)(c0 + (e & 127)) * 7;
+                keep = !z_terms_finite(z_terms(boxa[2], boxa[5], a[BP_AREA])) || !z_terms_finite(z_terms(boxb[2], boxb[5], b[BP_AREA]));
+            }
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&sm.q2count, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) sm.queue2[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)e;
         }
     }
-    __syncthreads();
-    PHASE_MARK(3);
-#ifdef GLENET_PHASE_TIMING
-    const int dbg = g_dbg_flags;
-#else
-    const int dbg = 0;
-#endif
-    for (int q = tid; q < ((dbg & 1) ? 0 : n); q += IOU_THREADS) {
-        const unsigned int e = sm.queue[q];
-        const float* a = sm.rpre + (e >> 8) * BPS;
-        const float* b = sm.cpre + (e & 255) * BPS;
-        sm.qres[q] = finish_pair<MODE>(a, b, box_overlap<FMA>(a, b));
-    }
+    chain_sync();
     PHASE_MARK(7);
-    if (!(dbg & 2)) zero_fill_tile(sm, out + (size_t)r0 * nb + c0, tr, tc, nb, vec);   // no-op once every chunk has been taken
-    __syncthreads();
+    const int n2 = sm.q2count;
+    int nclip = last ? n2 : n2 / IOU_CHAIN * IOU_CHAIN;
+#ifdef GLENET_PHASE_TIMING
+    if (g_dbg_flags & 1) nclip = 0;
+    if (tid == 0) { atomicAdd(&g_phase_cycles[8], (unsigned long long)n); atomicAdd(&g_phase_cycles[9], (unsigned long long)nclip);
+                    atomicAdd(&g_phase_cycles[10], (unsigned long long)nprep); atomicAdd(&g_phase_cycles[11], 1ull); }
+#endif
+    for (int q = tid; q < nclip; q += IOU_CHAIN) {
+        const unsigned int e = sm.queue2[q];
+        const float* a = sm.rpre + (e >> 7) * BPS;
+        const float* b = sm.cpre + (e & 127) * BPS;
+        sm.qres[q] = finish_pair<MODE>(a, b, box_overlap<FMA>(a, b), A + (size_t)(r0 + (e >> 7)) * 7, B + (size_t)(c0 + (e & 127)) * 7);
+    }
     PHASE_MARK(4);
-    for (int q = tid; q < n; q += IOU_THREADS) {
-        const unsigned int e = sm.queue[q];
-        out[(size_t)(r0 + (e >> 8)) * nb + (c0 + (e & 255))] = sm.qres[q];
+    unsigned short carry = 0;
+    const int rem = n2 - nclip;   // < IOU_CHAIN unless the clip pass is disabled for a timing experiment
+    if (tid < rem) carry = sm.queue2[nclip + tid];
+    if (fill_pending && (nclip > 0 || last)) { fill_wait(); fill_pending = false; }   // also a barrier among the chain warps
+    else chain_sync();
+    PHASE_MARK(6);
+    for (int q = tid; q < nclip; q += IOU_CHAIN) {
+        const unsigned int e = sm.queue2[q];
+        out[(size_t)(r0 + (e >> 7)) * nb + (c0 + (e & 127))] = sm.qres[q];
     }
-    __syncthreads();
-    if (tid == 0) sm.qcount = 0;
-    __syncthreads();
+    chain_sync();   // queue2[0, nclip) has been read by everyone
+    if (tid < rem) sm.queue2[tid] = carry;
+    if (tid == 0) { sm.qcount = 0; sm.q2count = rem < IOU_CHAIN ? rem : 0; sm.nprep = 0; }
+    chain_sync();
     PHASE_MARK(5);
-}
-
-// append the lanes' surviving pairs with one atomic per warp
-template <typename SM>
-__device__ __forceinline__ void enqueue_heavy(SM& sm, unsigned int heavy, int r, int c, int lane) {
-    const unsigned int m = __ballot_sync(0xffffffffu, heavy != 0);
-    if (!m) return;
-    int qb = 0;
-    if (lane == 0) qb = atomicAdd(&sm.qcount, __popc(m));
-    qb = __shfl_sync(0xffffffffu, qb, 0);
-    if (heavy) {
-        sm.queue[qb + __popc(m & ((1u << lane) - 1))] = (unsigned short)((r << 8) | c);
-        if (sm.rflag[r] == 0) sm.rflag[r] = 1;   // 0 = unused, 1 = wanted, 2 = prepared
-        if (sm.cflag[c] == 0) sm.cflag[c] = 1;
-    }
 }
 
 template <int MODE, bool FMA>
@@ -180,22 +229,33 @@ __global__ void __launch_bounds__(IOU_THREADS, IOU_CTAS_PER_SM)
 iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int nb,
                 const float4* __restrict__ trigA, const float4* __restrict__ trigB,
                 float* __restrict__ out, int TR, int TC, int col_tiles) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    using Smem = IouSmem<MODE == MODE_IOU3D ? BP_STRIDE : BP_STRIDE_BEV>;
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    IouSmem& sm = *reinterpret_cast<IouSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_r = blockIdx.x / col_tiles, tile_c = blockIdx.x - tile_r * col_tiles;
     const int r0 = tile_r * TR, c0 = tile_c * TC;
     const int tr = min(TR, na - r0), tc = min(TC, nb - c0);
     PHASE_INIT;
 
-    // ---- stage the tile's boxes (centre + cull radius) and the bounding box of the row centres
+    // ---- stage the tile's boxes: centre + cull radius for the circle tests, the raw box in the first slots of
+    //      its BoxPre record (prepared in place if a pair needs it), and the bounding box of the row centres.
+    //      All eight warps take part, so every global load of the tile is back before the zero fill starts.
     float minx = FLT_MAX, maxx = -FLT_MAX, miny = FLT_MAX, maxy = -FLT_MAX, maxr = 0.f;
     for (int i = tid; i < tr + tc; i += IOU_THREADS) {
         const bool is_row = i < tr;
         const int k = is_row ? i : i - tr;
         const float* box = (is_row ? A + (size_t)(r0 + k) * 7 : B + (size_t)(c0 + k) * 7);
-        const float cx = box[0], cy = box[1], rad = cull_radius(box);
+        float raw[7];
+#pragma unroll
+        for (int f = 0; f < 7; ++f) raw[f] = box[f];
+        float* rec = (is_row ? sm.rpre : sm.cpre) + k * BPS;
+#pragma unroll
+        for (int f = 0; f < 7; ++f) rec[f] = raw[f];
+        const float cx = raw[0], cy = raw[1];
+        float rad = cull_radius(cx, cy, raw[3], raw[4]);
+        // 3D IoU multiplies the BEV overlap by the z overlap in torch: 0 * NaN = NaN, so a box with a
+        // non-finite z term must reach finish_pair for every pair
+        if (MODE == MODE_IOU3D && !z_terms_finite(z_terms(raw[2], raw[5], __fmul_rn(raw[3], raw[4])))) rad = CUDART_INF_F;
         if (is_row) {
             sm.row[k] = make_float4(cx, cy, rad, 0.f); sm.rflag[k] = 0;
             minx = fminf(minx, cx); maxx = fmaxf(maxx, cx); miny = fminf(miny, cy); maxy = fmaxf(maxy, cy);
@@ -209,8 +269,22 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
         maxr = fmaxf(maxr, __shfl_xor_sync(0xffffffffu, maxr, o));
     }
     if (lane == 0) { sm.red[warp][0] = minx; sm.red[warp][1] = maxx; sm.red[warp][2] = miny; sm.red[warp][3] = maxy; sm.red[warp][4] = maxr; }
-    if (tid == 0) { sm.qcount = 0; sm.nact = 0; sm.zchunk = 0; }
+    static_assert(IOU_ZBYTES == IOU_THREADS * 16, "one float4 of zeros per thread");
+    sm.zero[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) { sm.qcount = 0; sm.q2count = 0; sm.nact = 0; sm.nprep = 0; }
+    fence_proxy_async();   // the zeros were written through the generic proxy, the bulk engine reads through the async proxy
     __syncthreads();
+
+    if (warp == IOU_CHAIN / 32) {   // ---- the fill warp
+        const bool vec = ((nb & 3) == 0) && ((c0 & 3) == 0) && ((tc & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
+#ifdef GLENET_PHASE_TIMING
+        if (!(g_dbg_flags & 2))
+#endif
+        zero_fill_tile(sm, out + (size_t)r0 * nb + c0, tr, tc, nb, vec, lane);
+        __threadfence_block();
+        fill_arrive();
+        return;
+    }
     PHASE_MARK(0);
     minx = sm.red[0][0]; maxx = sm.red[0][1]; miny = sm.red[0][2]; maxy = sm.red[0][3]; maxr = sm.red[0][4];
 #pragma unroll
@@ -222,54 +296,89 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     // ---- active columns: a column whose circle cannot reach the rows' bounding box is culled for the
     //      whole tile with ONE test (rows with a NaN centre produce no polygon vertex in the reference
     //      either, so leaving them out of the bounding box is exact).  NaN in the column => stays active.
-    for (int c = tid; c < tc; c += IOU_THREADS) {
+    for (int c = tid; c < tc; c += IOU_CHAIN) {
         const float cx = sm.ccx[c], cy = sm.ccy[c];
         const float ddx = fmaxf(fmaxf(minx - cx, cx - maxx), 0.f), ddy = fmaxf(fmaxf(miny - cy, cy - maxy), 0.f);
         const float rr = maxr + sm.crad[c];
         const bool far = (cx == cx) && (cy == cy) && (ddx * ddx + ddy * ddy > rr * rr);
         if (!far) sm.act[atomicAdd(&sm.nact, 1)] = (unsigned char)c;
     }
-
-    float* out_tile = out + (size_t)r0 * nb + c0;
-    (void)out_tile;
-    const bool vec = ((nb & 3) == 0) && ((c0 & 3) == 0) && ((tc & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
-    __syncthreads();   // act[] / nact complete
+    chain_sync();   // act[] / nact complete
     PHASE_MARK(1);
 
-    // ---- per-pair circle test on the active columns only; survivors go to the queue.
-    //      One row per thread (TR <= 256 = block size), uniform loop over the active columns whose
-    //      data is a shared-memory broadcast; the queue is checked every 2 columns (<= 512 appends).
+    // ---- per-pair circle test on the active columns.  Warps are laid out as (row warps) x (column groups):
+    //      every thread tests its row(s) against up to 32 columns of its group into a register bitmask, then the
+    //      survivors are appended to the queue with one atomic per warp.  Slots are reserved optimistically:
+    //      entries that fall beyond the queue's capacity stay in the bitmask, the queue is drained and they are
+    //      appended in the next round (dense tiles only).
     const int nact = sm.nact;
-    {
-        // thread -> (row, column group): rows padded to a power of two so that small tiles still use all threads
-        int trp = 32;
-        while (trp < tr) trp <<= 1;
-        const int groups = IOU_THREADS / trp, row = tid & (trp - 1), grp = tid / trp;
-        const bool has_row = row < tr;
-        const float4 rw = has_row ? sm.row[row] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const int iters = (nact + groups - 1) / groups;
-        for (int it0 = 0; it0 < iters; it0 += 2) {
-            const int qc = sm.qcount;
-            __syncthreads();   // everyone has read the count before anyone appends again => the branch is uniform
-            if (qc > IOU_QCAP - 2 * IOU_THREADS) {   // dense tiles only
-                drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, vec);
-            }
-            const int it1 = min(iters, it0 + 2);
-            for (int it = it0; it < it1; ++it) {
-                const int k = it * groups + grp;
-                const bool valid = has_row && k < nact;
-                const int c = valid ? sm.act[k] : 0;
-                const float dx = rw.x - sm.ccx[c], dy = rw.y - sm.ccy[c], rr = rw.z + sm.crad[c];
+    const int rwarps = (tr + 31) >> 5;                                   // <= 12
+    const int groups = rwarps <= IOU_CHAIN / 32 ? (IOU_CHAIN / 32) / rwarps : 1;
+    const bool tall = rwarps > IOU_CHAIN / 32;                           // two rows per thread, one column group
+    const int grp = tall ? 0 : warp / rwarps;
+    const bool idle = !tall && grp >= groups;
+    int rows[IOU_RPT];
+    float4 rw[IOU_RPT];
+#pragma unroll
+    for (int j = 0; j < IOU_RPT; ++j) {
+        rows[j] = tall ? tid + j * IOU_CHAIN : (j == 0 ? (warp - grp * rwarps) * 32 + lane : IOU_TR_MAX);
+        if (idle || rows[j] >= tr) rows[j] = -1;
+        rw[j] = rows[j] >= 0 ? sm.row[rows[j]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    bool fill_pending = true;
+    for (int cb = 0; cb < nact;) {
+        const int per = min(32, (nact - cb + groups - 1) / groups);     // columns per group in this round
+        const int k0 = min(nact, cb + grp * per), k1 = idle ? k0 : min(nact, k0 + per);
+        cb += per * groups;
+        unsigned int m[IOU_RPT];
+#pragma unroll
+        for (int j = 0; j < IOU_RPT; ++j) m[j] = 0u;
+#pragma unroll 4
+        for (int k = k0; k < k1; ++k) {
+            const int c = sm.act[k];
+            const float cx = sm.ccx[c], cy = sm.ccy[c], cr = sm.crad[c];
+#pragma unroll
+            for (int j = 0; j < IOU_RPT; ++j) {
+                const float dx = rw[j].x - cx, dy = rw[j].y - cy, rr = rw[j].z + cr;
                 // NaN anywhere => the comparison is false => not culled => the clip pass decides, like the reference
-                const unsigned int heavy = (valid && !(dx * dx + dy * dy > rr * rr)) ? 1u : 0u;
-                enqueue_heavy(sm, heavy, row, c, lane);
+                if (!(dx * dx + dy * dy > rr * rr)) m[j] |= 1u << (k - k0);
             }
-            __syncthreads();
+        }
+#pragma unroll
+        for (int j = 0; j < IOU_RPT; ++j) if (rows[j] < 0) m[j] = 0u;
+        for (;;) {
+            int cnt = 0;
+#pragma unroll
+            for (int j = 0; j < IOU_RPT; ++j) cnt += __popc(m[j]);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
+            int base = 0;
+            if (wtotal) {
+                if (lane == 31) base = atomicAdd(&sm.qcount, wtotal);
+                base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+            }
+            chain_sync();
+            const int total = sm.qcount;   // the same value in every thread: nobody adds again before the next barrier
+#pragma unroll
+            for (int j = 0; j < IOU_RPT; ++j) {
+                while (m[j] && base < IOU_QCAP) {
+                    const int k = __ffs(m[j]) - 1;
+                    m[j] &= m[j] - 1;
+                    const int c = sm.act[k0 + k];
+                    sm.queue[base++] = (unsigned short)((rows[j] << 7) | c);
+                    if (sm.rflag[rows[j]] == 0) sm.rflag[rows[j]] = 1;
+                    if (sm.cflag[c] == 0) sm.cflag[c] = 1;
+                }
+            }
+            chain_sync();
+            if (total <= IOU_QCAP) break;
+            drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, IOU_QCAP, false, fill_pending);
         }
     }
     PHASE_MARK(2);
-    drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, vec);
-    PHASE_MARK(6);
+    drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, sm.qcount, true, fill_pending);
 }
 
 // out[i] = f(a[i], b[i / group]) -- every pair is "heavy" by construction (CVAE samples vs their GT)
@@ -291,7 +400,7 @@ iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict_
         box_prepare<FMA>(ba, device_trig(ba[6]), a);
         box_prepare<FMA>(bb, device_trig(bb[6]), b);
         const float ov = box_overlap_unrolled<FMA>(a, b);
-        out_v = finish_pair<MODE>(a, b, ov);
+        out_v = (MODE == MODE_OVERLAP) ? ov : (MODE == MODE_IOU_BEV) ? iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) : iou3d_from_overlap(a, b, ov);
     }
     out[i] = out_v;
 }
@@ -299,16 +408,39 @@ iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict_
 #ifdef GLENET_PHASE_TIMING
 static int g_debug_tile_rows = 0;   // developer override (debug build only)
 #endif
-static void pick_tiles(int na, int nb, int& TR, int& TC, int& row_tiles, int& col_tiles) {
+// The kernel is bound by the latency of one CTA's phase chain (~13 us) unless the zero fill of a whole wave
+// of tiles takes longer, so the row-tile height is chosen to minimise  waves x max(chain, fill of one wave):
+// a problem that fits one wave of resident CTAs gets exactly one, with the smallest tile that achieves it.
+static int g_col_split = 1;
+template <typename K>
+static int resident_ctas(K kernel) {
+    int dev = 0, sms = 148, per_sm = IOU_CTAS_PER_SM;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, IOU_THREADS, sizeof(IouSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return sms * per_sm;
+}
+static void pick_tiles(int na, int nb, int resident, int& TR, int& TC, int& row_tiles, int& col_tiles) {
     col_tiles = (nb + IOU_TC_MAX - 1) / IOU_TC_MAX;
+    {   // very small problems (< 1/4 wave): split the columns further -- a small dense matrix
+        // is bound by the clip passes of its few tiles, and more CTAs are more clip lanes
+        const long rt32 = (na + 31) / 32;
+        const long want = resident / rt32, most = (nb + 31) / 32;
+        if (g_col_split && rt32 * col_tiles * 4 < resident && want > col_tiles) col_tiles = (int)(want < most ? want : most);
+    }
     TC = ((nb + col_tiles - 1) / col_tiles + 3) / 4 * 4;   // multiple of 4 keeps every tile on the 16-byte store path
-    // aim for >= 4 CTAs per SM (148 SMs) before growing the row tile
-    long want = (long)IOU_CTAS_PER_SM * 148;
-    long tr = ((long)na * col_tiles + want - 1) / want;
-    tr = (tr + 31) / 32 * 32;
-    if (tr < 32) tr = 32;
-    if (tr > IOU_TR_MAX) tr = IOU_TR_MAX;
-    TR = (int)tr;
+    col_tiles = (nb + TC - 1) / TC;
+    const double slots = resident;
+    const double chain_us = 13.0, fill_bytes_per_us = 6.0e6;
+    double best = 0.0;
+    TR = 32;
+    for (int tr = 32; tr <= IOU_TR_MAX; tr += 32) {
+        const double tiles = (double)((na + tr - 1) / tr) * col_tiles;
+        const double waves = ceil(tiles / slots);
+        const double fill_us = (double)tr * TC * 4.0 * (tiles < slots ? tiles : slots) / fill_bytes_per_us;
+        const double cost = waves * (chain_us > fill_us ? chain_us : fill_us) + 0.002 * tr;   // ties go to the smaller tile
+        if (tr == 32 || cost < best) { best = cost; TR = tr; }
+    }
 #ifdef GLENET_PHASE_TIMING
     if (g_debug_tile_rows) TR = g_debug_tile_rows;
 #endif
@@ -322,18 +454,18 @@ static int launch_iou(const float* A, const float* trigA, int na, const float* B
     if (na == 0 || nb == 0) return GLENET_OK;
     if (!A || !B || !out) return fail(GLENET_EINVAL, "%s: null pointer", what);
     if (!FMA && (!trigA || !trigB)) return fail(GLENET_EINVAL, "%s: CPU dialect needs host-evaluated trig tables", what);
-    int TR, TC, row_tiles, col_tiles;
-    pick_tiles(na, nb, TR, TC, row_tiles, col_tiles);
     auto kernel = iou_tile_kernel<MODE, FMA>;
-    static bool attr_done = false;   // per template instantiation
-    if (!attr_done) {
-        int rc = set_smem(kernel, sizeof(IouSmem<MODE == MODE_IOU3D ? BP_STRIDE : BP_STRIDE_BEV>), what);
+    static int resident = 0;   // per template instantiation
+    if (!resident) {
+        int rc = set_smem(kernel, sizeof(IouSmem), what);
         if (rc) return rc;
-        attr_done = true;
+        resident = resident_ctas(kernel);
     }
+    int TR, TC, row_tiles, col_tiles;
+    pick_tiles(na, nb, resident, TR, TC, row_tiles, col_tiles);
     const long tiles = (long)row_tiles * col_tiles;
     if (tiles > 0x7fffffffL) return fail(GLENET_EINVAL, "%s: too many tiles", what);
-    kernel<<<(unsigned)tiles, IOU_THREADS, sizeof(IouSmem<MODE == MODE_IOU3D ? BP_STRIDE : BP_STRIDE_BEV>), stream>>>(
+    kernel<<<(unsigned)tiles, IOU_THREADS, sizeof(IouSmem), stream>>>(
         A, na, B, nb, reinterpret_cast<const float4*>(trigA), reinterpret_cast<const float4*>(trigB), out, TR, TC,
         col_tiles);
     return check_launch(what);
@@ -347,12 +479,18 @@ extern "C" {
 
 #ifdef GLENET_PHASE_TIMING
 void glenet_debug_set_tile_rows(int tr) { g_debug_tile_rows = tr; }
+void glenet_debug_set_col_split(int on) { g_col_split = on; }
 void glenet_debug_set_flags(int f) { cudaMemcpyToSymbol(g_dbg_flags, &f, sizeof(int)); }
+int glenet_debug_iou_resident_ctas() {
+    auto kernel = iou_tile_kernel<MODE_IOU_BEV, true>;
+    set_smem(kernel, sizeof(IouSmem), "debug");
+    return resident_ctas(kernel);
+}
 // developer-only: read and reset the per-phase cycle accumulators of iou_tile_kernel
 int glenet_debug_iou_phase_cycles(unsigned long long* host_out8) {
     cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(host_out8, g_phase_cycles, sizeof(unsigned long long) * 8);
-    unsigned long long z[8] = {0};
+    cudaMemcpyFromSymbol(host_out8, g_phase_cycles, sizeof(unsigned long long) * 12);
+    unsigned long long z[12] = {0};
     cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
     return 0;
 }
