@@ -22,6 +22,8 @@ _SIGNATURES = {
     "glenet_boxes_overlap_bev_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "glenet_boxes_iou_bev_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "glenet_boxes_iou3d_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "glenet_boxes_iou_frames_gpu": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_longlong, ctypes.c_int, c_float_p, ctypes.c_longlong,
+                                                   ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_void_p]),
     "glenet_boxes_iou_aligned_gpu": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "glenet_boxes_iou_bev_cpu_dialect": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "glenet_host_trig4": (None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
@@ -35,7 +37,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 def lib_path() -> str:

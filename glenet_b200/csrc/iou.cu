@@ -47,6 +47,7 @@ enum { MODE_OVERLAP = 0, MODE_IOU_BEV = 1, MODE_IOU3D = 2 };
 
 #ifdef GLENET_PHASE_TIMING   // developer instrumentation: accumulated clock64() per phase, thread 0 of every CTA
 __device__ unsigned long long g_phase_cycles[12];   // [0..7] phase cycles, [8] queued pairs, [9] pairs clipped, [10] boxes prepared, [11] drains
+__device__ unsigned long long g_cta_log[4096 * 4];   // per CTA: start ns, end ns, queued pairs, clipped pairs
 __device__ int g_dbg_flags;   // bit 0: skip the clip pass, bit 1: skip the zero fill (timing experiments only)
 #define PHASE_MARK(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_phase_cycles[k], (unsigned long long)(now_ - t_phase_)); t_phase_ = now_; } } while (0)
 #define PHASE_INIT long long t_phase_ = clock64()
@@ -54,6 +55,8 @@ __device__ int g_dbg_flags;   // bit 0: skip the clip pass, bit 1: skip the zero
 #define PHASE_MARK(k) do { } while (0)
 #define PHASE_INIT do { } while (0)
 #endif
+
+struct IouFrames { long long stride_a, stride_b, stride_out; int tiles_per_frame; };   // strides in floats
 
 struct __align__(128) IouSmem {
     float4 zero[IOU_ZBYTES / 16];          // source of the bulk zero fill
@@ -197,6 +200,7 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
     int nclip = last ? n2 : n2 / IOU_CHAIN * IOU_CHAIN;
 #ifdef GLENET_PHASE_TIMING
     if (g_dbg_flags & 1) nclip = 0;
+    if (tid == 0 && blockIdx.x < 4096) { g_cta_log[blockIdx.x * 4 + 2] += n; g_cta_log[blockIdx.x * 4 + 3] += nclip; }
     if (tid == 0) { atomicAdd(&g_phase_cycles[8], (unsigned long long)n); atomicAdd(&g_phase_cycles[9], (unsigned long long)nclip);
                     atomicAdd(&g_phase_cycles[10], (unsigned long long)nprep); atomicAdd(&g_phase_cycles[11], 1ull); }
 #endif
@@ -228,14 +232,24 @@ template <int MODE, bool FMA>
 __global__ void __launch_bounds__(IOU_THREADS, IOU_CTAS_PER_SM)
 iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int nb,
                 const float4* __restrict__ trigA, const float4* __restrict__ trigB,
-                float* __restrict__ out, int TR, int TC, int col_tiles) {
+                float* __restrict__ out, int TR, int TC, int col_tiles, IouFrames fr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     IouSmem& sm = *reinterpret_cast<IouSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile_r = blockIdx.x / col_tiles, tile_c = blockIdx.x - tile_r * col_tiles;
+    // frames: independent (na, nb) problems of one launch, e.g. the GT sets of a batch against the same anchors
+    const int frame = blockIdx.x / fr.tiles_per_frame, tile = blockIdx.x - frame * fr.tiles_per_frame;
+    A += (size_t)frame * fr.stride_a; B += (size_t)frame * fr.stride_b; out += (size_t)frame * fr.stride_out;
+    const int tile_r = tile / col_tiles, tile_c = tile - tile_r * col_tiles;
+    // Programmatic dependent launch: this grid may have been made resident while the previous kernel of the
+    // stream was still draining; everything below reads or writes global memory, so wait for it here.  The
+    // launch latency and the CTA scheduling of back-to-back calls is what gets hidden.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int r0 = tile_r * TR, c0 = tile_c * TC;
     const int tr = min(TR, na - r0), tc = min(TC, nb - c0);
     PHASE_INIT;
+#ifdef GLENET_PHASE_TIMING
+    if (tid == 0 && blockIdx.x < 4096) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_cta_log[blockIdx.x * 4] = t; g_cta_log[blockIdx.x * 4 + 2] = 0; g_cta_log[blockIdx.x * 4 + 3] = 0; }
+#endif
 
     // ---- stage the tile's boxes: centre + cull radius for the circle tests, the raw box in the first slots of
     //      its BoxPre record (prepared in place if a pair needs it), and the bounding box of the row centres.
@@ -274,6 +288,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     if (tid == 0) { sm.qcount = 0; sm.q2count = 0; sm.nact = 0; sm.nprep = 0; }
     fence_proxy_async();   // the zeros were written through the generic proxy, the bulk engine reads through the async proxy
     __syncthreads();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel of the stream may be scheduled as SMs free up
 
     if (warp == IOU_CHAIN / 32) {   // ---- the fill warp
         const bool vec = ((nb & 3) == 0) && ((c0 & 3) == 0) && ((tc & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
@@ -379,6 +394,9 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     }
     PHASE_MARK(2);
     drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, sm.qcount, true, fill_pending);
+#ifdef GLENET_PHASE_TIMING
+    if (tid == 0 && blockIdx.x < 4096) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_cta_log[blockIdx.x * 4 + 1] = t; }
+#endif
 }
 
 // out[i] = f(a[i], b[i / group]) -- every pair is "heavy" by construction (CVAE samples vs their GT)
@@ -420,11 +438,11 @@ static int resident_ctas(K kernel) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, IOU_THREADS, sizeof(IouSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
     return sms * per_sm;
 }
-static void pick_tiles(int na, int nb, int resident, int& TR, int& TC, int& row_tiles, int& col_tiles) {
+static void pick_tiles(int na, int nb, int frames, int resident, int& TR, int& TC, int& row_tiles, int& col_tiles) {
     col_tiles = (nb + IOU_TC_MAX - 1) / IOU_TC_MAX;
     {   // very small problems (< 1/4 wave): split the columns further -- a small dense matrix
         // is bound by the clip passes of its few tiles, and more CTAs are more clip lanes
-        const long rt32 = (na + 31) / 32;
+        const long rt32 = (long)((na + 31) / 32) * frames;
         const long want = resident / rt32, most = (nb + 31) / 32;
         if (g_col_split && rt32 * col_tiles * 4 < resident && want > col_tiles) col_tiles = (int)(want < most ? want : most);
     }
@@ -435,7 +453,7 @@ static void pick_tiles(int na, int nb, int resident, int& TR, int& TC, int& row_
     double best = 0.0;
     TR = 32;
     for (int tr = 32; tr <= IOU_TR_MAX; tr += 32) {
-        const double tiles = (double)((na + tr - 1) / tr) * col_tiles;
+        const double tiles = (double)((na + tr - 1) / tr) * col_tiles * frames;
         const double waves = ceil(tiles / slots);
         const double fill_us = (double)tr * TC * 4.0 * (tiles < slots ? tiles : slots) / fill_bytes_per_us;
         const double cost = waves * (chain_us > fill_us ? chain_us : fill_us) + 0.002 * tr;   // ties go to the smaller tile
@@ -449,9 +467,10 @@ static void pick_tiles(int na, int nb, int resident, int& TR, int& TC, int& row_
 
 template <int MODE, bool FMA>
 static int launch_iou(const float* A, const float* trigA, int na, const float* B, const float* trigB, int nb,
-                      float* out, cudaStream_t stream, const char* what) {
-    if (na < 0 || nb < 0) return fail(GLENET_EINVAL, "%s: negative box count", what);
-    if (na == 0 || nb == 0) return GLENET_OK;
+                      float* out, cudaStream_t stream, const char* what,
+                      int frames = 1, long long stride_a = 0, long long stride_b = 0, long long stride_out = 0) {
+    if (na < 0 || nb < 0 || frames < 0) return fail(GLENET_EINVAL, "%s: negative count", what);
+    if (na == 0 || nb == 0 || frames == 0) return GLENET_OK;
     if (!A || !B || !out) return fail(GLENET_EINVAL, "%s: null pointer", what);
     if (!FMA && (!trigA || !trigB)) return fail(GLENET_EINVAL, "%s: CPU dialect needs host-evaluated trig tables", what);
     auto kernel = iou_tile_kernel<MODE, FMA>;
@@ -462,12 +481,24 @@ static int launch_iou(const float* A, const float* trigA, int na, const float* B
         resident = resident_ctas(kernel);
     }
     int TR, TC, row_tiles, col_tiles;
-    pick_tiles(na, nb, resident, TR, TC, row_tiles, col_tiles);
-    const long tiles = (long)row_tiles * col_tiles;
-    if (tiles > 0x7fffffffL) return fail(GLENET_EINVAL, "%s: too many tiles", what);
-    kernel<<<(unsigned)tiles, IOU_THREADS, sizeof(IouSmem), stream>>>(
-        A, na, B, nb, reinterpret_cast<const float4*>(trigA), reinterpret_cast<const float4*>(trigB), out, TR, TC,
-        col_tiles);
+    pick_tiles(na, nb, frames, resident, TR, TC, row_tiles, col_tiles);
+    const long long tiles = (long long)row_tiles * col_tiles;
+    if (tiles * frames > 0x7fffffffLL) return fail(GLENET_EINVAL, "%s: too many tiles", what);
+    IouFrames fr;
+    fr.stride_a = stride_a; fr.stride_b = stride_b; fr.stride_out = stride_out; fr.tiles_per_frame = (int)tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(tiles * frames)); cfg.blockDim = dim3(IOU_THREADS);
+    cfg.dynamicSmemBytes = sizeof(IouSmem); cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, A, na, B, nb, reinterpret_cast<const float4*>(trigA),
+                                       reinterpret_cast<const float4*>(trigB), out, TR, TC, col_tiles, fr);
+    if (e != cudaSuccess) {
+        snprintf(last_error_buf(), 512, "%s: launch failed: %s", what, cudaGetErrorString(e));
+        return -(int)e;
+    }
     return check_launch(what);
 }
 
@@ -481,6 +512,10 @@ extern "C" {
 void glenet_debug_set_tile_rows(int tr) { g_debug_tile_rows = tr; }
 void glenet_debug_set_col_split(int on) { g_col_split = on; }
 void glenet_debug_set_flags(int f) { cudaMemcpyToSymbol(g_dbg_flags, &f, sizeof(int)); }
+int glenet_debug_iou_cta_log(unsigned long long* host_out, int n) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(host_out, g_cta_log, sizeof(unsigned long long) * 4 * n);
+}
 int glenet_debug_iou_resident_ctas() {
     auto kernel = iou_tile_kernel<MODE_IOU_BEV, true>;
     set_smem(kernel, sizeof(IouSmem), "debug");
@@ -504,6 +539,17 @@ int glenet_boxes_iou_bev_gpu(const float* a, int na, const float* b, int nb, flo
 }
 int glenet_boxes_iou3d_gpu(const float* a, int na, const float* b, int nb, float* out, glenet_stream_t s) {
     return launch_iou<MODE_IOU3D, true>(a, nullptr, na, b, nullptr, nb, out, (cudaStream_t)s, "glenet_boxes_iou3d_gpu");
+}
+int glenet_boxes_iou_frames_gpu(int mode, const float* a, long long a_frame_stride, int na, const float* b, long long b_frame_stride,
+                                int nb, float* out, int frames, glenet_stream_t s) {
+    const char* what = "glenet_boxes_iou_frames_gpu";
+    if (a_frame_stride < 0 || b_frame_stride < 0) return fail(GLENET_EINVAL, "%s: negative stride", what);
+    const long long so = (long long)na * nb;
+    cudaStream_t st = (cudaStream_t)s;
+    if (mode == 0) return launch_iou<MODE_OVERLAP, true>(a, nullptr, na, b, nullptr, nb, out, st, what, frames, a_frame_stride, b_frame_stride, so);
+    if (mode == 1) return launch_iou<MODE_IOU_BEV, true>(a, nullptr, na, b, nullptr, nb, out, st, what, frames, a_frame_stride, b_frame_stride, so);
+    if (mode == 2) return launch_iou<MODE_IOU3D, true>(a, nullptr, na, b, nullptr, nb, out, st, what, frames, a_frame_stride, b_frame_stride, so);
+    return fail(GLENET_EINVAL, "%s: mode must be 0 (overlap), 1 (BEV IoU) or 2 (3D IoU)", what);
 }
 int glenet_boxes_iou_bev_cpu_dialect(const float* a, const float* trig_a, int na, const float* b, const float* trig_b,
                                      int nb, float* out, glenet_stream_t s) {

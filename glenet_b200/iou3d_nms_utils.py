@@ -26,6 +26,7 @@ from . import _lib
 __all__ = [
     "boxes_bev_iou_cpu", "boxes_iou_bev", "boxes_iou3d_gpu", "boxes_overlap_bev",
     "boxes_iou_bev_aligned", "boxes_iou3d_aligned",
+    "boxes_iou_bev_frames", "boxes_overlap_bev_frames", "boxes_iou3d_gpu_frames",
     "nms_gpu", "nms_normal_gpu", "nms_gpu_batch", "nms_normal_gpu_batch",
     "new_nms_gpu", "nms_func", "softnms_gpu", "softnms", "scale_by_iou",
 ]
@@ -155,6 +156,57 @@ def boxes_iou3d_gpu(boxes_a, boxes_b):
     """
     assert boxes_a.shape[1] == boxes_b.shape[1] == 7
     return _pairwise("glenet_boxes_iou3d_gpu", boxes_a, boxes_b)
+
+
+def _frames(mode: int, boxes_a: torch.Tensor, boxes_b: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    _check_cuda_f32(boxes_a, "boxes_a")
+    _check_cuda_f32(boxes_b, "boxes_b")
+    if boxes_a.device != boxes_b.device:
+        raise RuntimeError("boxes_a and boxes_b must be on the same device")
+    assert boxes_b.dim() == 3 and boxes_b.shape[2] == 7, "boxes_b must be (F, M, 7)"
+    assert boxes_a.shape[-1] == 7 and boxes_a.dim() in (2, 3), "boxes_a must be (N, 7) or (F, N, 7)"
+    frames, nb = boxes_b.shape[0], boxes_b.shape[1]
+    a, b = boxes_a.contiguous(), boxes_b.contiguous()
+    if a.dim() == 3:
+        assert a.shape[0] == frames, "boxes_a and boxes_b disagree on the number of frames"
+        na, stride_a = a.shape[1], a.shape[1] * 7
+    else:
+        na, stride_a = a.shape[0], 0
+    if out is None:
+        out = torch.empty((frames, na, nb), dtype=torch.float32, device=a.device)
+    else:
+        assert out.shape == (frames, na, nb) and out.dtype == torch.float32 and out.is_contiguous() and out.device == a.device
+    if frames and na and nb:
+        lib = _lib.load()
+        with torch.cuda.device(a.device):
+            rc = lib.glenet_boxes_iou_frames_gpu(mode, a.data_ptr(), stride_a, na, b.data_ptr(), nb * 7, nb, out.data_ptr(), frames, _stream(a.device))
+        _lib.check(rc, "glenet_boxes_iou_frames_gpu")
+    return out
+
+
+def boxes_iou_bev_frames(boxes_a, boxes_b, out=None):
+    """BEV IoU of every frame of a batch in ONE launch.
+
+    Args:
+        boxes_a: (N, 7) shared by all frames (e.g. the anchors) or (F, N, 7)
+        boxes_b: (F, M, 7) e.g. the zero-padded ``gt_boxes`` of a batch
+    Returns:
+        (F, N, M); frame f equals ``boxes_iou_bev(boxes_a[f], boxes_b[f])`` bit for bit.
+
+    Additive API.  The reference loops over the batch in Python and launches one kernel per frame
+    (axis_aligned_target_assigner.py:60-105, proposal_target_layer.py:116-160); with one grid for all
+    frames the tiles of different frames overlap on the SMs."""
+    return _frames(1, boxes_a, boxes_b, out)
+
+
+def boxes_overlap_bev_frames(boxes_a, boxes_b, out=None):
+    """Frame-batched :func:`boxes_overlap_bev`."""
+    return _frames(0, boxes_a, boxes_b, out)
+
+
+def boxes_iou3d_gpu_frames(boxes_a, boxes_b, out=None):
+    """Frame-batched :func:`boxes_iou3d_gpu`: (N, 7) or (F, N, 7) x (F, M, 7) -> (F, N, M)."""
+    return _frames(2, boxes_a, boxes_b, out)
 
 
 def _aligned(mode: int, boxes_a: torch.Tensor, boxes_b: torch.Tensor, group: int) -> torch.Tensor:

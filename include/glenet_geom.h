@@ -52,6 +52,18 @@ int glenet_boxes_iou_bev_gpu(const float* boxes_a, int na, const float* boxes_b,
 int glenet_boxes_iou3d_gpu(const float* boxes_a, int na, const float* boxes_b, int nb,
                            float* ans_iou3d, glenet_stream_t stream);
 
+/* Frame-batched variant: `frames` independent (na, nb) problems in ONE launch, frame f reading
+ * boxes_a + f * a_frame_stride and boxes_b + f * b_frame_stride (strides in floats; 0 = the same
+ * boxes for every frame) and writing the dense (na, nb) block out + f * na * nb.
+ * This is the loop `for k in range(batch_size)` of the target assigner
+ * (pcdet/models/dense_heads/target_assigner/axis_aligned_target_assigner.py:60-105: the same anchors
+ * against each frame's padded GT boxes) as one grid: the tiles of all frames share the SMs, so the
+ * per-launch latency chain of a single frame no longer bounds the throughput.
+ * mode 0 = overlap, 1 = BEV IoU, 2 = 3D IoU; same arithmetic as the single-frame entry points. */
+int glenet_boxes_iou_frames_gpu(int mode, const float* boxes_a, long long a_frame_stride, int na,
+                                const float* boxes_b, long long b_frame_stride, int nb,
+                                float* out, int frames, glenet_stream_t stream);
+
 /* Row-aligned variants: out[i] = f(boxes_a[i], boxes_b[i / group]) for i < na, where boxes_b
  * holds ceil(na / group) rows.  Additive API for the CVAE label-uncertainty workload
  * (30 sampled boxes per GT object); mode 0 = overlap, 1 = BEV IoU, 2 = 3D IoU.

@@ -147,6 +147,64 @@ def test_everything_bit_exact_vs_reference_kernels(cuda, ref_so):
     del g
 
 
+def test_frame_batched_iou_equals_per_frame_calls(cuda, ref_so):
+    """boxes_*_frames: one launch for a batch of frames == the per-frame drop-in calls, bit for bit."""
+    anchors = synth.anchors_kitti3()[:30000].to(cuda)
+    for nb in (100, 37, 131):                                             # 16-byte rows, ragged rows, two column tiles
+        gts = torch.stack([synth.kitti_boxes(nb, 50 + f) for f in range(5)]).to(cuda)
+        gts[3, nb // 2:] = 0                                               # zero padding as the dataloader produces it
+        for fr, one in ((I.boxes_iou_bev_frames, I.boxes_iou_bev), (I.boxes_overlap_bev_frames, I.boxes_overlap_bev),
+                        (I.boxes_iou3d_gpu_frames, I.boxes_iou3d_gpu)):
+            got = fr(anchors, gts)
+            assert got.shape == (5, 30000, nb)
+            for f in range(5):
+                assert torch.equal(got[f], one(anchors, gts[f]))
+        assert torch.equal(I.boxes_iou_bev_frames(anchors, gts)[2], ref_so.boxes_iou_bev(anchors, gts[2]))
+    # per-frame boxes_a, dense proposals, caller-provided output
+    props = torch.stack([synth.proposals(512, 12, 70 + f)[0] for f in range(3)]).to(cuda)
+    gts = torch.stack([synth.kitti_boxes(40, 80 + f) for f in range(3)]).to(cuda)
+    out = torch.full((3, 512, 40), -1.0, device=cuda)
+    assert I.boxes_iou3d_gpu_frames(props, gts, out=out) is out
+    for f in range(3):
+        assert torch.equal(out[f], I.boxes_iou3d_gpu(props[f], gts[f]))
+    assert I.boxes_iou_bev_frames(anchors, torch.zeros((0, 10, 7), device=cuda)).shape == (0, 30000, 10)
+    assert I.boxes_iou_bev_frames(anchors, torch.zeros((4, 0, 7), device=cuda)).shape == (4, 30000, 0)
+
+
+def test_non_finite_heights_propagate_like_torch(cuda, ref_so):
+    """boxes_iou3d_gpu multiplies the BEV overlap by the z overlap in torch: 0 * NaN = NaN even for far-apart boxes."""
+    a = synth.kitti_boxes(300, 0).to(cuda)
+    b = synth.kitti_boxes(64, 1).to(cuda)
+    a[5, 2] = float("nan"); a[17, 5] = float("inf"); a[40, 2] = float("inf"); a[41, 5] = float("nan")
+    b[3, 5] = float("nan"); b[9, 2] = float("-inf"); b[11, 3] = float("inf"); b[11, 5] = 0.0
+    got, want = I.boxes_iou3d_gpu(a, b), ref_so.boxes_iou3d_gpu(a, b)
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.equal(torch.nan_to_num(got, nan=-1.0), torch.nan_to_num(want, nan=-1.0))
+    assert torch.isnan(got[5]).all() and torch.isnan(got[:, 3]).all()
+    # the BEV functions ignore z: same inputs, no NaN from the z columns
+    assert torch.equal(I.boxes_iou_bev(a, b), ref_so.boxes_iou_bev(a, b))
+
+
+def test_back_to_back_launches_on_one_buffer(cuda):
+    """Programmatic dependent launch must not let a launch start writing before its predecessor finished:
+    alternate two different problems on ONE output buffer and check the last writer wins every time."""
+    anchors = synth.anchors_kitti3().to(cuda)
+    g0, g1 = synth.kitti_boxes(100, 4).to(cuda), synth.kitti_boxes(100, 5).to(cuda)
+    w0, w1 = I.boxes_iou_bev(anchors, g0).clone(), I.boxes_iou_bev(anchors, g1).clone()
+    out = torch.empty((1, anchors.shape[0], 100), device=cuda)
+    for it in range(6):
+        for _ in range(3):
+            I.boxes_iou_bev_frames(anchors, g0[None], out=out)
+            I.boxes_iou_bev_frames(anchors, g1[None], out=out)
+        if it % 2:
+            I.boxes_iou_bev_frames(anchors, g0[None], out=out)
+        assert torch.equal(out[0], w0 if it % 2 else w1)
+    # a torch kernel in between (fill) and a consumer right behind (sum) see ordinary stream order
+    out.fill_(7.0)
+    I.boxes_iou_bev_frames(anchors, g0[None], out=out)
+    assert float(out.sum()) == float(w0.sum())
+
+
 def test_dense_matrix_many_queue_drains(cuda):
     """Dense tiles (thousands of clipped pairs per tile => several queue drains per CTA): the result must be
     reproducible run after run and equal to a row-slab evaluation, which tiles the matrix differently

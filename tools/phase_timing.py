@@ -45,10 +45,10 @@ def timed(iters=20):
 if len(sys.argv) > 2:
     lib.glenet_debug_set_col_split(int(sys.argv[2]))
     print("column split", sys.argv[2])
-for flags, label in ((0, "full kernel"), (1, "no clip"), (2, "no zero fill"), (3, "neither")):
+for flags, label in ((0, "full kernel"), (1, "no clip"), (2, "no zero fill"), (3, "neither"), (4, "STG fill"), (5, "STG fill, no clip")):
     lib.glenet_debug_set_flags(flags)
     print(f"{label:14s} {timed():7.2f} us / launch")
-lib.glenet_debug_set_flags(0)
+lib.glenet_debug_set_flags(int(os.environ.get('PHASE_FLAGS', '0')))
 lib.glenet_debug_iou_phase_cycles(buf)
 run(outs[0])
 lib.glenet_debug_iou_phase_cycles(buf)
@@ -58,3 +58,18 @@ print(f"drains {buf[11]}  queued pairs/drain {buf[8] / ncta:.1f}  clipped pairs/
 print(f"cycles per CTA {tot / ncta:.0f}")
 for n, v in zip(names, list(buf)[:8]):
     print(f"   {n:28s} {v / ncta:10.0f} cycles/CTA  {100 * v / max(tot, 1):5.1f}%")
+
+import numpy as np
+log = (ctypes.c_ulonglong * (4096 * 4))()
+lib.glenet_debug_iou_cta_log(log, 4096)
+L = np.array(log, dtype=np.uint64).reshape(4096, 4).astype(np.int64)
+L = L[L[:, 0] > 0]
+t0 = L[:, 0].min()
+start, end, nq, nc = (L[:, 0] - t0) / 1e3, (L[:, 1] - t0) / 1e3, L[:, 2], L[:, 3]
+dur = end - start
+print(f"CTA start offset us: min {start.min():.1f} p50 {np.median(start):.1f} max {start.max():.1f};  end: p50 {np.median(end):.1f} p90 {np.percentile(end, 90):.1f} max {end.max():.1f}")
+print(f"CTA duration us: min {dur.min():.1f} p50 {np.median(dur):.1f} p90 {np.percentile(dur, 90):.1f} max {dur.max():.1f}")
+for lo, hi in ((0, 1), (1, 113), (113, 225), (225, 449), (449, 100000)):
+    m = (nc >= lo) & (nc < hi)
+    if m.any():
+        print(f"   clipped pairs in [{lo},{hi}): {m.sum():4d} CTAs, duration p50 {np.median(dur[m]):.1f} max {dur[m].max():.1f} us, end max {end[m].max():.1f}")

@@ -1,6 +1,6 @@
 """Tiny driver for ncu captures: runs one named workload a few times.
 
-    ncu --set full ... python tools/prof_workloads.py pib|iou_sparse|iou_dense|nms [iters]
+    ncu --set full ... python tools/prof_workloads.py pib|iou_sparse|iou_frames|iou_dense|nms [iters]
 """
 import os
 import sys
@@ -24,6 +24,11 @@ elif what == "iou_sparse":
     a = synth.anchors_kitti3().to(dev)
     b = synth.kitti_boxes(100, 4).to(dev)
     fn = lambda: I.boxes_iou_bev(a, b)
+elif what == "iou_frames":   # the bench's step: 16 frames of the anchor sweep in one launch, 1.35 GB of result slabs
+    a = synth.anchors_kitti3().to(dev)
+    b = torch.stack([synth.kitti_boxes(100, 100 + f + 1) for f in range(16)]).to(dev)
+    out = torch.empty((16, a.shape[0], 100), device=dev)
+    fn = lambda: I.boxes_iou_bev_frames(a, b, out=out)
 elif what == "iou_dense":
     s, g = synth.cvae_samples(20000, 30, 0)
     s, g = s.to(dev), g.to(dev)
