@@ -283,15 +283,18 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
         maxr = fmaxf(maxr, __shfl_xor_sync(0xffffffffu, maxr, o));
     }
     if (lane == 0) { sm.red[warp][0] = minx; sm.red[warp][1] = maxx; sm.red[warp][2] = miny; sm.red[warp][3] = maxy; sm.red[warp][4] = maxr; }
-    static_assert(IOU_ZBYTES == IOU_THREADS * 16, "one float4 of zeros per thread");
-    sm.zero[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) { sm.qcount = 0; sm.q2count = 0; sm.nact = 0; sm.nprep = 0; }
-    fence_proxy_async();   // the zeros were written through the generic proxy, the bulk engine reads through the async proxy
     __syncthreads();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel of the stream may be scheduled as SMs free up
 
     if (warp == IOU_CHAIN / 32) {   // ---- the fill warp
         const bool vec = ((nb & 3) == 0) && ((c0 & 3) == 0) && ((tc & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
+        if (vec) {   // the block of zeros the bulk copies read: written and fenced by the warp that issues them
+#pragma unroll
+            for (int k = 0; k < IOU_ZBYTES / 16 / 32; ++k) sm.zero[k * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            fence_proxy_async();   // generic-proxy writes -> async-proxy reads
+            __syncwarp();
+        }
 #ifdef GLENET_PHASE_TIMING
         if (!(g_dbg_flags & 2))
 #endif

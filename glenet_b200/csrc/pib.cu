@@ -448,14 +448,15 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
             if (res != 0x7fffffff) out[__float_as_int(e.w)] = res;
         };
         int qn = 0;                                           // warp-uniform fill of the warp's queue
-        Pts4 cur;
+        Pts4 cur, nxt;   // register prefetch two batches ahead: one batch of cold points is shorter than an L2 round trip
         load_pts4(pts, p_begin + warp * PIB_WBATCH + lane * 4, p_end, vec, cur);
+        if (NB > 1) load_pts4(pts, p_begin + ((PIB_THREADS / 32) + warp) * PIB_WBATCH + lane * 4, p_end, vec, nxt);
 #pragma unroll 1
         for (int j = 0; j < NB; ++j) {
             const int p0 = p_begin + (j * (PIB_THREADS / 32) + warp) * PIB_WBATCH + lane * 4;
             const int nvalid = max(0, min(4, p_end - p0));
-            Pts4 nxt;
-            if (j + 1 < NB) load_pts4(pts, p0 + (PIB_THREADS / 32) * PIB_WBATCH, p_end, vec, nxt);
+            Pts4 nxt2;
+            if (j + 2 < NB) load_pts4(pts, p0 + 2 * (PIB_THREADS / 32) * PIB_WBATCH, p_end, vec, nxt2);
             // branch-free fine-bitmap lookup: floor -> one unsigned range test for both axes -> one LDS.
             // NaN maps to cell 0 (harmless: the exact predicate rejects it), out-of-grid to "cold".
             unsigned int hot = 0;
@@ -499,7 +500,8 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
                     __syncwarp();
                 }
             }
-            if (j + 1 < NB) cur = nxt;
+            cur = nxt;
+            nxt = nxt2;
         }
         if (qn) {                                              // leftovers of the chunk
             if (lane < qn) resolve(wq[lane]);

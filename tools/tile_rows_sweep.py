@@ -1,35 +1,32 @@
-"""Developer aid: time the anchor sweep for several row-tile heights (debug library)."""
+"""Developer aid: sweep the row-tile height of iou_tile_kernel on the bench's 16-frame anchor sweep (needs the debug lib)."""
 import ctypes, os, sys
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from glenet_b200 import synth
-lib = ctypes.CDLL(os.path.join(ROOT, "glenet_b200/lib/libglenet_geom_dbg.so"))
-lib.glenet_boxes_iou_bev_gpu.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "glenet_b200/lib/libglenet_geom_dbg.so"))
+lib.glenet_boxes_iou_frames_gpu.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong,
+                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
 dev = torch.device("cuda:0")
+F = 16
 a = synth.anchors_kitti3().to(dev)
-gts = [synth.kitti_boxes(100, 100 + f).to(dev) for f in range(16)]
-outs = [torch.empty((a.shape[0], 100), device=dev) for _ in range(16)]
-for tr, fl in ((0, 0), (0, 1), (0, 2), (0, 3), (128, 1), (128, 2)):
-    lib.glenet_debug_set_tile_rows(tr); lib.glenet_debug_set_flags(fl)
-    def run():
-        for f in range(16):
-            lib.glenet_boxes_iou_bev_gpu(a.data_ptr(), a.shape[0], gts[f].data_ptr(), 100, outs[f].data_ptr(), None)
-    for _ in range(3): run()
-    torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(10): run()
-    
-    e.record(); torch.cuda.synchronize()
-    print(f"TR={tr:4d} flags={fl} (1=no clip, 2=no zero fill): {s.elapsed_time(e) / 160 * 1000:.1f} us per launch", flush=True)
-# reference points: plain memset of one output matrix, and 16 of them
-torch.cuda.synchronize()
-s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for _ in range(3):
-    for o in outs: o.zero_()
-s.record()
-for _ in range(10):
-    for o in outs: o.zero_()
-e.record(); torch.cuda.synchronize()
-print(f"torch zero_() of one (211200,100) f32 matrix: {s.elapsed_time(e) / 160 * 1000:.1f} us", flush=True)
+b = torch.stack([synth.kitti_boxes(100, 100 + f + 1) for f in range(F)]).to(dev)
+out = torch.empty((F, a.shape[0], 100), device=dev)
+
+
+def run(frames):
+    lib.glenet_boxes_iou_frames_gpu(1, a.data_ptr(), 0, a.shape[0], b.data_ptr(), 700, 100, out.data_ptr(), frames, None)
+
+
+for frames in (16, 1):
+    for tr in (0, 384, 352, 320, 288, 256, 224, 192, 160, 128, 96, 64):
+        lib.glenet_debug_set_tile_rows(tr)
+        for _ in range(3):
+            run(frames)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(10):
+            run(frames)
+        e.record(); torch.cuda.synchronize()
+        us = s.elapsed_time(e) / 10 * 1e3
+        print(f"frames {frames:2d} TR {tr:3d} ({'auto' if tr == 0 else 'forced'}): {us:8.1f} us / launch, {us / frames:6.2f} us / frame")
