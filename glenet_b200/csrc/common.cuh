@@ -30,13 +30,15 @@ inline int check_launch(const char* what) {
 }
 
 template <typename K>
-inline int set_smem(K kernel, size_t bytes, const char* what) {
+inline int set_smem(K kernel, size_t bytes, const char* what, bool max_carveout = false) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) {
         snprintf(last_error_buf(), 512, "%s: cudaFuncSetAttribute(%zu B): %s", what, bytes, cudaGetErrorString(e));
         return -(int)e;
     }
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   // a hint; failure is harmless
+    // a hint (failure is harmless): kernels sized to fill the SM's shared memory with resident CTAs ask for the largest carveout;
+    // the others keep the driver's choice, i.e. more L1 for the clip code's local-memory vertex lists
+    if (max_carveout) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     return GLENET_OK;
 }
 

@@ -20,6 +20,7 @@
 // polygon is the only per-thread array left, and the angular sort
 // evaluates one atan2f per vertex instead of two per comparison.
 #pragma once
+#include <math_constants.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -183,6 +184,31 @@ __device__ __forceinline__ bool sat_separated(const float* __restrict__ a, const
     const float pbx = fabsf(cb * dx - sb * dy), pby = fabsf(sb * dx + cb * dy);
     return pax > (ax + bx * C + by * S) * k + slack || pay > (ay + bx * S + by * C) * k + slack ||
            pbx > (bx + ax * C + ay * S) * k + slack || pby > (by + ax * S + ay * C) * k + slack;
+}
+
+// Upper bound of the overlap area the reference's clipping code can return for two prepared boxes.
+// Every vertex of its polygon is an edge crossing or a corner that check_in_box2d admits, so all of them lie
+// inside BOTH rectangles grown by MARGIN; that intersection is convex, hence the fan area is at most the area
+// of the intersection, which in turn is at most (its extent along a's length axis) x (its extent along a's
+// width axis) -- and the same in b's frame.  The extents are those of a grown by MARGIN (+ slack, as in
+// sat_separated) clipped against the projection of the grown b.  Used by NMS to skip the clip of pairs whose
+// IoU cannot exceed the threshold; NaN/Inf inputs give NaN/Inf, which callers must treat as "cannot skip".
+__device__ __forceinline__ float overlap_upper_bound(const float* __restrict__ a, const float* __restrict__ b) {
+    const float acx = a[BP_CX], acy = a[BP_CY], bcx = b[BP_CX], bcy = b[BP_CY];
+    const float dx = bcx - acx, dy = bcy - acy;
+    const float ca = a[BP_CN], sa = a[BP_SN], cb = b[BP_CN], sb = b[BP_SN];
+    const float C = fabsf(ca * cb + sa * sb), S = fabsf(sa * cb - ca * sb);
+    const float slack = 0.03f + 4e-6f * (fabsf(acx) + fabsf(acy) + fabsf(bcx) + fabsf(bcy));
+    const float ax = fabsf(a[BP_THX]) + slack, ay = fabsf(a[BP_THY]) + slack, bx = fabsf(b[BP_THX]) + slack, by = fabsf(b[BP_THY]) + slack;
+    const float pax = ca * dx - sa * dy, pay = sa * dx + ca * dy;     // centre of b in a's frame
+    const float pbx = -(cb * dx - sb * dy), pby = -(sb * dx + cb * dy);   // centre of a in b's frame
+    const float rbx = bx * C + by * S, rby = bx * S + by * C;         // half extents of b along a's axes
+    const float rax = ax * C + ay * S, ray = ax * S + ay * C;
+    const float oax = fminf(ax, pax + rbx) - fmaxf(-ax, pax - rbx), oay = fminf(ay, pay + rby) - fmaxf(-ay, pay - rby);
+    const float obx = fminf(bx, pbx + rax) - fmaxf(-bx, pbx - rax), oby = fminf(by, pby + ray) - fmaxf(-by, pby - ray);
+    const float ua = (oax > 0.f && oay > 0.f) ? oax * oay : ((oax != oax || oay != oay) ? CUDART_NAN_F : 0.f);
+    const float ub = (obx > 0.f && oby > 0.f) ? obx * oby : ((obx != obx || oby != oby) ? CUDART_NAN_F : 0.f);
+    return (ua != ua || ub != ub) ? CUDART_NAN_F : fminf(ua, ub) * 1.001f;
 }
 
 // Monotone stand-in for atan2f(dy, dx) on (-pi, pi]: same ordering of the polygon vertices about the

@@ -479,7 +479,7 @@ static int launch_iou(const float* A, const float* trigA, int na, const float* B
     auto kernel = iou_tile_kernel<MODE, FMA>;
     static int resident = 0;   // per template instantiation
     if (!resident) {
-        int rc = set_smem(kernel, sizeof(IouSmem), what);
+        int rc = set_smem(kernel, sizeof(IouSmem), what, true);
         if (rc) return rc;
         resident = resident_ctas(kernel);
     }
@@ -521,7 +521,7 @@ int glenet_debug_iou_cta_log(unsigned long long* host_out, int n) {
 }
 int glenet_debug_iou_resident_ctas() {
     auto kernel = iou_tile_kernel<MODE_IOU_BEV, true>;
-    set_smem(kernel, sizeof(IouSmem), "debug");
+    set_smem(kernel, sizeof(IouSmem), "debug", true);
     return resident_ctas(kernel);
 }
 // developer-only: read and reset the per-phase cycle accumulators of iou_tile_kernel

@@ -205,6 +205,20 @@ def test_back_to_back_launches_on_one_buffer(cuda):
     assert float(out.sum()) == float(w0.sum())
 
 
+def test_nms_threshold_corner_cases_vs_reference(cuda, ref_so):
+    """Thresholds around the IoU-bound filter of the mask kernel, and a negative one (IoU 0 > thresh: only the top box survives)."""
+    boxes, scores = synth.proposals(2500, 14, 33)
+    boxes, scores = boxes.to(cuda), scores.to(cuda)
+    for thr in (-0.1, 0.0, 1e-4, 0.3, 0.5, 0.55, 0.7, 0.9, 0.999, 1.0):
+        got, want = I.nms_gpu(boxes, scores, thr)[0], ref_so.nms_gpu(boxes, scores, thr)[0]
+        assert torch.equal(got, want), thr
+    # many near-duplicates: IoU close to 1 everywhere inside a cluster
+    dup = boxes[:40].repeat_interleave(30, dim=0) + torch.randn((1200, 7), device=cuda, generator=None) * 0.004
+    sc = torch.rand(1200, device=cuda)
+    for thr in (0.7, 0.95, 0.99):
+        assert torch.equal(I.nms_gpu(dup, sc, thr)[0], ref_so.nms_gpu(dup, sc, thr)[0]), thr
+
+
 def test_dense_matrix_many_queue_drains(cuda):
     """Dense tiles (thousands of clipped pairs per tile => several queue drains per CTA): the result must be
     reproducible run after run and equal to a row-slab evaluation, which tiles the matrix differently

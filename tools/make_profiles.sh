@@ -11,6 +11,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 # 2. full captures
 K='regex:pib_query|iou_tile|iou_aligned|nms_mask|nms_sweep|pib_build'
 cap() { timeout 300 ncu --set full --clock-control none --import-source on -k "$K" -s $2 -c $3 -f -o gpurun_out/${R}_$1 python tools/prof_workloads.py $1 3 2>&1 | tail -1; }
+cap iou_frames 2 1
 cap iou_sparse 2 1
 cap pib 4 2
 cap nms 4 2
