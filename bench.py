@@ -308,6 +308,17 @@ def side_runs(torch, I, R, synth, dev, hbm_gbs):
         torch.cuda.synchronize()
         return s.elapsed_time(e) / iters
 
+    # cfg4 without the matrix: the assigner's reductions (row / column max + argmax) from the sparse IoU list
+    anchors = synth.anchors_kitti3().to(dev)
+    gts16 = torch.stack([synth.kitti_boxes(100, 101 + f) for f in range(16)]).to(dev)
+    ms_sp = ev(lambda: I.boxes_iou_frames_sparse(anchors, gts16, "bev"), 10)
+    ms_mx = ev(lambda: I.iou_max_overlaps_frames(anchors, gts16, "bev"), 10)
+    npairs = 16 * anchors.shape[0] * 100
+    out["anchor_sweep_sparse"] = {"workload": "cfg4 anchor sweep, 16 frames, non-zero IoU list instead of the dense matrix (incl. the host sync for its length)",
+                                  "pairs_per_s_list": npairs / (ms_sp * 1e-3), "ms_list": ms_sp,
+                                  "pairs_per_s_max_overlaps": npairs / (ms_mx * 1e-3), "ms_max_overlaps": ms_mx,
+                                  "note": "row/col max+argmax (F,N)+(F,M) as consumed by axis_aligned_target_assigner.py:141-165; no 4 B/pair write"}
+    del anchors, gts16
     # cfg2: points_in_boxes, 128 frames x 180k points x 200 boxes (276 MB of points > L2)
     B, M, N = 128, 180000, 200
     boxes = torch.stack([synth.waymo_boxes(N, 100 + f) for f in range(B)]).to(dev)

@@ -24,6 +24,10 @@ _SIGNATURES = {
     "glenet_boxes_iou3d_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "glenet_boxes_iou_frames_gpu": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_longlong, ctypes.c_int, c_float_p, ctypes.c_longlong,
                                                    ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_void_p]),
+    "glenet_boxes_iou_frames_sparse_gpu": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_longlong, ctypes.c_int, c_float_p, ctypes.c_longlong,
+                                                          ctypes.c_int, ctypes.c_int, ctypes.c_void_p, c_float_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p]),
+    "glenet_boxes_iou_frames_max_gpu": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_longlong, ctypes.c_int, c_float_p, ctypes.c_longlong,
+                                                       ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "glenet_boxes_iou_aligned_gpu": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "glenet_boxes_iou_bev_cpu_dialect": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "glenet_host_trig4": (None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
@@ -37,7 +41,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
-ABI_VERSION = 3
+ABI_VERSION = 5
 
 
 def lib_path() -> str:

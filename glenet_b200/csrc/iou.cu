@@ -56,7 +56,17 @@ __device__ int g_dbg_flags;   // bit 0: skip the clip pass, bit 1: skip the zero
 #define PHASE_INIT do { } while (0)
 #endif
 
-struct IouFrames { long long stride_a, stride_b, stride_out; int tiles_per_frame; };   // strides in floats
+struct IouFrames {
+    long long stride_a, stride_b, stride_out;   // per-frame strides in floats
+    int tiles_per_frame, na;
+    // sparse output (sp_count != nullptr): instead of the dense matrix, the non-zero elements are appended as
+    // (flat index frame * na * nb + row * nb + col, value) in no particular order; sp_count keeps counting past sp_cap
+    long long* sp_idx; float* sp_val; unsigned long long* sp_count; long long sp_cap;
+    // reduced output (row_key != nullptr): per row / per column  max over the other axis of
+    // (value bits << 32) | (0xffffffff - index), i.e. the maximum and the FIRST index attaining it; 0 = no non-zero element
+    unsigned long long* row_key; unsigned long long* col_key;
+};
+__device__ __forceinline__ bool iou_no_matrix(const IouFrames& fr) { return fr.sp_count != nullptr || fr.row_key != nullptr; }
 
 struct __align__(128) IouSmem {
     float4 zero[IOU_ZBYTES / 16];          // source of the bulk zero fill
@@ -140,7 +150,8 @@ __device__ __forceinline__ void zero_fill_tile(IouSmem& sm, float* __restrict__ 
 template <int MODE, bool FMA>
 __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict__ A, const float* __restrict__ B,
                                             const float4* __restrict__ trigA, const float4* __restrict__ trigB,
-                                            int r0, int c0, int tr, int tc, int nb, float* __restrict__ out, int n, bool last, bool& fill_pending) {
+                                            int r0, int c0, int tr, int tc, int nb, float* __restrict__ out, int n, bool last, bool& fill_pending,
+                                            const IouFrames& fr, long long frame_base) {
     const int tid = threadIdx.x, lane = tid & 31;
     PHASE_INIT;
     for (int i0 = 0; i0 < tr + tc; i0 += IOU_CHAIN) {
@@ -217,9 +228,42 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
     if (fill_pending && (nclip > 0 || last)) { fill_wait(); fill_pending = false; }   // also a barrier among the chain warps
     else chain_sync();
     PHASE_MARK(6);
-    for (int q = tid; q < nclip; q += IOU_CHAIN) {
-        const unsigned int e = sm.queue2[q];
-        out[(size_t)(r0 + (e >> 7)) * nb + (c0 + (e & 127))] = sm.qres[q];
+    if (fr.row_key) {
+        const int frame = blockIdx.x / fr.tiles_per_frame;
+        for (int q = tid; q < nclip; q += IOU_CHAIN) {
+            const unsigned int e = sm.queue2[q];
+            const float v = sm.qres[q];
+            if (!(v == 0.f)) {
+                const unsigned int r = r0 + (e >> 7), c = c0 + (e & 127);
+                const unsigned long long hi = (unsigned long long)__float_as_uint(v) << 32;
+                atomicMax(fr.row_key + (size_t)frame * fr.na + r, hi | (0xffffffffu - c));
+                atomicMax(fr.col_key + (size_t)frame * nb + c, hi | (0xffffffffu - r));
+            }
+        }
+    }
+    if (fr.sp_count) {
+        for (int q0 = 0; q0 < nclip; q0 += IOU_CHAIN) {
+            const int q = q0 + tid;
+            unsigned int e = 0;
+            float v = 0.f;
+            if (q < nclip) { e = sm.queue2[q]; v = sm.qres[q]; }
+            const bool nz = !(v == 0.f);   // NaN counts: the dense matrix would hold it too
+            const unsigned int m = __ballot_sync(0xffffffffu, nz);
+            if (m) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(fr.sp_count, (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0) + __popc(m & ((1u << lane) - 1));
+                if (nz && (long long)base < fr.sp_cap) {
+                    fr.sp_idx[base] = frame_base + (long long)(r0 + (e >> 7)) * nb + (c0 + (e & 127));
+                    fr.sp_val[base] = v;
+                }
+            }
+        }
+    } else if (!fr.row_key) {
+        for (int q = tid; q < nclip; q += IOU_CHAIN) {
+            const unsigned int e = sm.queue2[q];
+            out[(size_t)(r0 + (e >> 7)) * nb + (c0 + (e & 127))] = sm.qres[q];
+        }
     }
     chain_sync();   // queue2[0, nclip) has been read by everyone
     if (tid < rem) sm.queue2[tid] = carry;
@@ -239,6 +283,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     // frames: independent (na, nb) problems of one launch, e.g. the GT sets of a batch against the same anchors
     const int frame = blockIdx.x / fr.tiles_per_frame, tile = blockIdx.x - frame * fr.tiles_per_frame;
     A += (size_t)frame * fr.stride_a; B += (size_t)frame * fr.stride_b; out += (size_t)frame * fr.stride_out;
+    const long long frame_base = (long long)frame * na * nb;
     const int tile_r = tile / col_tiles, tile_c = tile - tile_r * col_tiles;
     // Programmatic dependent launch: this grid may have been made resident while the previous kernel of the
     // stream was still draining; everything below reads or writes global memory, so wait for it here.  The
@@ -289,7 +334,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
 
     if (warp == IOU_CHAIN / 32) {   // ---- the fill warp
         const bool vec = ((nb & 3) == 0) && ((c0 & 3) == 0) && ((tc & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
-        if (vec) {   // the block of zeros the bulk copies read: written and fenced by the warp that issues them
+        if (vec && !iou_no_matrix(fr)) {   // the block of zeros the bulk copies read: written and fenced by the warp that issues them
 #pragma unroll
             for (int k = 0; k < IOU_ZBYTES / 16 / 32; ++k) sm.zero[k * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
             fence_proxy_async();   // generic-proxy writes -> async-proxy reads
@@ -298,7 +343,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
 #ifdef GLENET_PHASE_TIMING
         if (!(g_dbg_flags & 2))
 #endif
-        zero_fill_tile(sm, out + (size_t)r0 * nb + c0, tr, tc, nb, vec, lane);
+        if (!iou_no_matrix(fr)) zero_fill_tile(sm, out + (size_t)r0 * nb + c0, tr, tc, nb, vec, lane);
         __threadfence_block();
         fill_arrive();
         return;
@@ -392,11 +437,11 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
             }
             chain_sync();
             if (total <= IOU_QCAP) break;
-            drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, IOU_QCAP, false, fill_pending);
+            drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, IOU_QCAP, false, fill_pending, fr, frame_base);
         }
     }
     PHASE_MARK(2);
-    drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, sm.qcount, true, fill_pending);
+    drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, sm.qcount, true, fill_pending, fr, frame_base);
 #ifdef GLENET_PHASE_TIMING
     if (tid == 0 && blockIdx.x < 4096) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_cta_log[blockIdx.x * 4 + 1] = t; }
 #endif
@@ -471,10 +516,23 @@ static void pick_tiles(int na, int nb, int frames, int resident, int& TR, int& T
 template <int MODE, bool FMA>
 static int launch_iou(const float* A, const float* trigA, int na, const float* B, const float* trigB, int nb,
                       float* out, cudaStream_t stream, const char* what,
-                      int frames = 1, long long stride_a = 0, long long stride_b = 0, long long stride_out = 0) {
+                      int frames = 1, long long stride_a = 0, long long stride_b = 0, long long stride_out = 0,
+                      long long* sp_idx = nullptr, float* sp_val = nullptr, unsigned long long* sp_count = nullptr, long long sp_cap = 0,
+                      unsigned long long* row_key = nullptr, unsigned long long* col_key = nullptr) {
     if (na < 0 || nb < 0 || frames < 0) return fail(GLENET_EINVAL, "%s: negative count", what);
+    if (sp_count) {
+        if (sp_cap < 0 || (sp_cap > 0 && (!sp_idx || !sp_val))) return fail(GLENET_EINVAL, "%s: bad sparse buffers", what);
+        cudaError_t e = cudaMemsetAsync(sp_count, 0, sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return fail(-(int)e, "%s: cudaMemsetAsync failed", what);
+    }
+    if (row_key || col_key) {
+        if (!row_key || !col_key) return fail(GLENET_EINVAL, "%s: row and column keys go together", what);
+        cudaError_t e = cudaMemsetAsync(row_key, 0, sizeof(unsigned long long) * (size_t)frames * na, stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(col_key, 0, sizeof(unsigned long long) * (size_t)frames * nb, stream);
+        if (e != cudaSuccess) return fail(-(int)e, "%s: cudaMemsetAsync failed", what);
+    }
     if (na == 0 || nb == 0 || frames == 0) return GLENET_OK;
-    if (!A || !B || !out) return fail(GLENET_EINVAL, "%s: null pointer", what);
+    if (!A || !B || (!out && !sp_count && !row_key)) return fail(GLENET_EINVAL, "%s: null pointer", what);
     if (!FMA && (!trigA || !trigB)) return fail(GLENET_EINVAL, "%s: CPU dialect needs host-evaluated trig tables", what);
     auto kernel = iou_tile_kernel<MODE, FMA>;
     static int resident = 0;   // per template instantiation
@@ -488,7 +546,9 @@ static int launch_iou(const float* A, const float* trigA, int na, const float* B
     const long long tiles = (long long)row_tiles * col_tiles;
     if (tiles * frames > 0x7fffffffLL) return fail(GLENET_EINVAL, "%s: too many tiles", what);
     IouFrames fr;
-    fr.stride_a = stride_a; fr.stride_b = stride_b; fr.stride_out = stride_out; fr.tiles_per_frame = (int)tiles;
+    fr.stride_a = stride_a; fr.stride_b = stride_b; fr.stride_out = (sp_count || row_key) ? 0 : stride_out; fr.tiles_per_frame = (int)tiles; fr.na = na;
+    fr.row_key = row_key; fr.col_key = col_key;
+    fr.sp_idx = sp_idx; fr.sp_val = sp_val; fr.sp_count = sp_count; fr.sp_cap = sp_cap;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(tiles * frames)); cfg.blockDim = dim3(IOU_THREADS);
     cfg.dynamicSmemBytes = sizeof(IouSmem); cfg.stream = stream;
@@ -552,6 +612,29 @@ int glenet_boxes_iou_frames_gpu(int mode, const float* a, long long a_frame_stri
     if (mode == 0) return launch_iou<MODE_OVERLAP, true>(a, nullptr, na, b, nullptr, nb, out, st, what, frames, a_frame_stride, b_frame_stride, so);
     if (mode == 1) return launch_iou<MODE_IOU_BEV, true>(a, nullptr, na, b, nullptr, nb, out, st, what, frames, a_frame_stride, b_frame_stride, so);
     if (mode == 2) return launch_iou<MODE_IOU3D, true>(a, nullptr, na, b, nullptr, nb, out, st, what, frames, a_frame_stride, b_frame_stride, so);
+    return fail(GLENET_EINVAL, "%s: mode must be 0 (overlap), 1 (BEV IoU) or 2 (3D IoU)", what);
+}
+int glenet_boxes_iou_frames_sparse_gpu(int mode, const float* a, long long a_frame_stride, int na, const float* b, long long b_frame_stride,
+                                       int nb, int frames, long long* idx, float* val, long long cap, unsigned long long* count,
+                                       glenet_stream_t s) {
+    const char* what = "glenet_boxes_iou_frames_sparse_gpu";
+    if (a_frame_stride < 0 || b_frame_stride < 0) return fail(GLENET_EINVAL, "%s: negative stride", what);
+    if (!count) return fail(GLENET_EINVAL, "%s: null count pointer", what);
+    cudaStream_t st = (cudaStream_t)s;
+    if (mode == 0) return launch_iou<MODE_OVERLAP, true>(a, nullptr, na, b, nullptr, nb, nullptr, st, what, frames, a_frame_stride, b_frame_stride, 0, idx, val, count, cap);
+    if (mode == 1) return launch_iou<MODE_IOU_BEV, true>(a, nullptr, na, b, nullptr, nb, nullptr, st, what, frames, a_frame_stride, b_frame_stride, 0, idx, val, count, cap);
+    if (mode == 2) return launch_iou<MODE_IOU3D, true>(a, nullptr, na, b, nullptr, nb, nullptr, st, what, frames, a_frame_stride, b_frame_stride, 0, idx, val, count, cap);
+    return fail(GLENET_EINVAL, "%s: mode must be 0 (overlap), 1 (BEV IoU) or 2 (3D IoU)", what);
+}
+int glenet_boxes_iou_frames_max_gpu(int mode, const float* a, long long a_frame_stride, int na, const float* b, long long b_frame_stride,
+                                    int nb, int frames, unsigned long long* row_key, unsigned long long* col_key, glenet_stream_t s) {
+    const char* what = "glenet_boxes_iou_frames_max_gpu";
+    if (a_frame_stride < 0 || b_frame_stride < 0) return fail(GLENET_EINVAL, "%s: negative stride", what);
+    if (!row_key || !col_key) return fail(GLENET_EINVAL, "%s: null key pointer", what);
+    cudaStream_t st = (cudaStream_t)s;
+    if (mode == 0) return launch_iou<MODE_OVERLAP, true>(a, nullptr, na, b, nullptr, nb, nullptr, st, what, frames, a_frame_stride, b_frame_stride, 0, nullptr, nullptr, nullptr, 0, row_key, col_key);
+    if (mode == 1) return launch_iou<MODE_IOU_BEV, true>(a, nullptr, na, b, nullptr, nb, nullptr, st, what, frames, a_frame_stride, b_frame_stride, 0, nullptr, nullptr, nullptr, 0, row_key, col_key);
+    if (mode == 2) return launch_iou<MODE_IOU3D, true>(a, nullptr, na, b, nullptr, nb, nullptr, st, what, frames, a_frame_stride, b_frame_stride, 0, nullptr, nullptr, nullptr, 0, row_key, col_key);
     return fail(GLENET_EINVAL, "%s: mode must be 0 (overlap), 1 (BEV IoU) or 2 (3D IoU)", what);
 }
 int glenet_boxes_iou_bev_cpu_dialect(const float* a, const float* trig_a, int na, const float* b, const float* trig_b,

@@ -27,6 +27,7 @@ __all__ = [
     "boxes_bev_iou_cpu", "boxes_iou_bev", "boxes_iou3d_gpu", "boxes_overlap_bev",
     "boxes_iou_bev_aligned", "boxes_iou3d_aligned",
     "boxes_iou_bev_frames", "boxes_overlap_bev_frames", "boxes_iou3d_gpu_frames",
+    "boxes_iou_frames_sparse", "iou_max_overlaps_frames",
     "nms_gpu", "nms_normal_gpu", "nms_gpu_batch", "nms_normal_gpu_batch",
     "new_nms_gpu", "nms_func", "softnms_gpu", "softnms", "scale_by_iou",
 ]
@@ -207,6 +208,96 @@ def boxes_overlap_bev_frames(boxes_a, boxes_b, out=None):
 def boxes_iou3d_gpu_frames(boxes_a, boxes_b, out=None):
     """Frame-batched :func:`boxes_iou3d_gpu`: (N, 7) or (F, N, 7) x (F, M, 7) -> (F, N, M)."""
     return _frames(2, boxes_a, boxes_b, out)
+
+
+_MODES = {"overlap": 0, "bev": 1, "3d": 2}
+
+
+def boxes_iou_frames_sparse(boxes_a, boxes_b, mode="bev", cap=None):
+    """The non-zero elements of the frame-batched IoU matrix as a coordinate list -- the (F, N, M) matrix itself is
+    never written.
+
+    Args:
+        boxes_a: (N, 7) shared by all frames or (F, N, 7);  boxes_b: (F, M, 7) or (M, 7) for a single frame
+        mode: "bev" (boxes_iou_bev), "3d" (boxes_iou3d_gpu) or "overlap" (boxes_overlap_bev)
+        cap: initial capacity of the list (grown and re-run automatically if too small)
+    Returns:
+        idx (K,) int64 flat indices ``f * N * M + row * M + col`` and val (K,) float32, in no particular order;
+        ``val[k]`` is bit-identical to the dense call's element, every other element of the dense matrix is +0.0.
+
+    Additive API for the reference's consumers that only reduce the matrix (see :func:`iou_max_overlaps_frames`)."""
+    _check_cuda_f32(boxes_a, "boxes_a")
+    _check_cuda_f32(boxes_b, "boxes_b")
+    if boxes_b.dim() == 2:
+        boxes_b = boxes_b.unsqueeze(0)
+    assert boxes_b.dim() == 3 and boxes_b.shape[2] == 7 and boxes_a.shape[-1] == 7 and boxes_a.dim() in (2, 3)
+    frames, nb = boxes_b.shape[0], boxes_b.shape[1]
+    a, b = boxes_a.contiguous(), boxes_b.contiguous()
+    if a.dim() == 3:
+        assert a.shape[0] == frames
+        na, stride_a = a.shape[1], a.shape[1] * 7
+    else:
+        na, stride_a = a.shape[0], 0
+    dev = a.device
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    if cap is None:
+        cap = max(1 << 16, 32 * frames * (na + nb))
+    cap = int(min(cap, max(1, frames * na * nb)))
+    lib = _lib.load()
+    while True:
+        idx = torch.empty((cap,), dtype=torch.int64, device=dev)
+        val = torch.empty((cap,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.glenet_boxes_iou_frames_sparse_gpu(_MODES[mode], a.data_ptr(), stride_a, na, b.data_ptr(), nb * 7, nb, frames,
+                                                        idx.data_ptr(), val.data_ptr(), cap, count.data_ptr(), _stream(dev))
+        _lib.check(rc, "glenet_boxes_iou_frames_sparse_gpu")
+        k = int(count.item())      # the list's length is data dependent: one sync, like the reference's nonzero() calls
+        if k <= cap:
+            return idx[:k], val[:k]
+        cap = k
+
+
+def iou_max_overlaps_frames(boxes_a, boxes_b, mode="bev"):
+    """Row / column maxima of the IoU matrix of every frame without materialising it.
+
+    Returns ``(a_max, a_argmax, b_max, b_argmax)`` with shapes (F, N), (F, N), (F, M), (F, M): exactly
+    ``iou.max(dim=2)``, ``iou.argmax(dim=2)`` (first index among ties, numpy's rule -- the reference goes through
+    numpy, axis_aligned_target_assigner.py:141-150), ``iou.max(dim=1)``, ``iou.argmax(dim=1)`` of
+    ``iou = boxes_iou_*_frames(boxes_a, boxes_b)``.  Rows / columns without any overlap report max 0, argmax 0.
+    These four vectors are what the anchor assignment and the RoI sampler consume
+    (axis_aligned_target_assigner.py:141-165, proposal_target_layer.py:113-114).  One kernel launch (atomic max on
+    packed (value, index) keys) plus the decode; no host sync."""
+    _check_cuda_f32(boxes_a, "boxes_a")
+    _check_cuda_f32(boxes_b, "boxes_b")
+    if boxes_b.dim() == 2:
+        boxes_b = boxes_b.unsqueeze(0)
+    assert boxes_b.dim() == 3 and boxes_b.shape[2] == 7 and boxes_a.shape[-1] == 7 and boxes_a.dim() in (2, 3)
+    frames, nb = boxes_b.shape[0], boxes_b.shape[1]
+    a, b = boxes_a.contiguous(), boxes_b.contiguous()
+    if a.dim() == 3:
+        assert a.shape[0] == frames
+        na, stride_a = a.shape[1], a.shape[1] * 7
+    else:
+        na, stride_a = a.shape[0], 0
+    dev = a.device
+    row_key = torch.empty((frames, na), dtype=torch.int64, device=dev)
+    col_key = torch.empty((frames, nb), dtype=torch.int64, device=dev)
+    if frames:
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            rc = lib.glenet_boxes_iou_frames_max_gpu(_MODES[mode], a.data_ptr(), stride_a, na, b.data_ptr(), nb * 7, nb, frames,
+                                                     row_key.data_ptr(), col_key.data_ptr(), _stream(dev))
+        _lib.check(rc, "glenet_boxes_iou_frames_max_gpu")
+
+    def decode(key):
+        # key = (float bits << 32) | (0xffffffff - index); key == 0 <=> nothing non-zero on that row / column
+        val = (key >> 32).to(torch.int32).view(torch.float32)
+        arg = torch.where(key == 0, torch.zeros_like(key), 0xffffffff - (key & 0xffffffff))
+        return val, arg
+
+    a_max, a_arg = decode(row_key)
+    b_max, b_arg = decode(col_key)
+    return a_max, a_arg, b_max, b_arg
 
 
 def _aligned(mode: int, boxes_a: torch.Tensor, boxes_b: torch.Tensor, group: int) -> torch.Tensor:

@@ -64,6 +64,27 @@ int glenet_boxes_iou_frames_gpu(int mode, const float* boxes_a, long long a_fram
                                 const float* boxes_b, long long b_frame_stride, int nb,
                                 float* out, int frames, glenet_stream_t stream);
 
+/* Sparse variant of the frame-batched call: the (frames, na, nb) matrix is NOT materialised; every element that
+ * is not exactly +0.0 (NaN included) is appended to a coordinate list instead,
+ *     idx[k] = f * na * nb + row * nb + col   (int64),   val[k] = the value the dense call would store there,
+ * in no particular order.  *count (device, zeroed by the call on `stream`) ends up as the number of such elements
+ * and keeps counting past `cap`, so count > cap tells the caller to retry with larger buffers.
+ * For the consumers of the reference that only reduce the matrix -- row / column max + argmax of the target
+ * assigner (axis_aligned_target_assigner.py:141-165), RoI sampling (proposal_target_layer.py:113-114), recall
+ * counting (detector3d_template.py:344-359) -- this removes the 4 B / pair HBM-write bound of the dense call. */
+int glenet_boxes_iou_frames_sparse_gpu(int mode, const float* boxes_a, long long a_frame_stride, int na,
+                                       const float* boxes_b, long long b_frame_stride, int nb, int frames,
+                                       long long* idx, float* val, long long cap, unsigned long long* count,
+                                       glenet_stream_t stream);
+
+/* Reduced variant: per frame, the maximum of every row and of every column of the (na, nb) matrix together with the
+ * FIRST index attaining it (numpy's argmax rule, which is what the reference's assigner applies), again without
+ * materialising the matrix.  row_key: (frames, na) u64, col_key: (frames, nb) u64, both zeroed by the call on `stream`;
+ * key = (IEEE bits of the maximum << 32) | (0xffffffff - argmax); key == 0 means "no non-zero element": max 0, argmax 0. */
+int glenet_boxes_iou_frames_max_gpu(int mode, const float* boxes_a, long long a_frame_stride, int na,
+                                    const float* boxes_b, long long b_frame_stride, int nb, int frames,
+                                    unsigned long long* row_key, unsigned long long* col_key, glenet_stream_t stream);
+
 /* Row-aligned variants: out[i] = f(boxes_a[i], boxes_b[i / group]) for i < na, where boxes_b
  * holds ceil(na / group) rows.  Additive API for the CVAE label-uncertainty workload
  * (30 sampled boxes per GT object); mode 0 = overlap, 1 = BEV IoU, 2 = 3D IoU.

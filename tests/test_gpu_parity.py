@@ -171,6 +171,44 @@ def test_frame_batched_iou_equals_per_frame_calls(cuda, ref_so):
     assert I.boxes_iou_bev_frames(anchors, torch.zeros((4, 0, 7), device=cuda)).shape == (4, 30000, 0)
 
 
+def test_sparse_iou_and_max_overlaps_equal_the_dense_matrix(cuda):
+    """boxes_iou_frames_sparse lists exactly the non-zero elements of the dense matrix (bit-identical values);
+    iou_max_overlaps_frames equals max / numpy-argmax of the dense matrix along both axes."""
+    anchors = synth.anchors_kitti3()[:50000].to(cuda)
+    gts = torch.stack([synth.kitti_boxes(60, 90 + f) for f in range(4)]).to(cuda)
+    gts[1, 30:] = 0
+    gts[2, 5] = gts[2, 4]                                                    # duplicate GT: ties along the row
+    for mode, dense_fn in (("bev", I.boxes_iou_bev_frames), ("3d", I.boxes_iou3d_gpu_frames), ("overlap", I.boxes_overlap_bev_frames)):
+        dense = dense_fn(anchors, gts)
+        idx, val = I.boxes_iou_frames_sparse(anchors, gts, mode)
+        assert idx.dtype == torch.int64 and val.dtype == torch.float32 and idx.shape == val.shape
+        assert idx.numel() == int((dense != 0).sum()) and idx.unique().numel() == idx.numel()
+        rebuilt = torch.zeros_like(dense).view(-1)
+        rebuilt[idx] = val
+        assert torch.equal(rebuilt.view_as(dense), dense)
+        # a capacity that is too small is grown transparently
+        idx2, val2 = I.boxes_iou_frames_sparse(anchors, gts, mode, cap=100)
+        o1, o2 = torch.argsort(idx), torch.argsort(idx2)
+        assert torch.equal(idx[o1], idx2[o2]) and torch.equal(val[o1], val2[o2])
+        if mode == "overlap":
+            continue
+        a_max, a_arg, b_max, b_arg = I.iou_max_overlaps_frames(anchors, gts, mode)
+        d = dense.cpu().numpy()
+        np.testing.assert_array_equal(a_max.cpu().numpy(), d.max(axis=2))
+        np.testing.assert_array_equal(a_arg.cpu().numpy(), d.argmax(axis=2))
+        np.testing.assert_array_equal(b_max.cpu().numpy(), d.max(axis=1))
+        np.testing.assert_array_equal(b_arg.cpu().numpy(), d.argmax(axis=1))
+    # single frame given as (M, 7); dense proposals (most elements non-zero inside clusters)
+    props = synth.proposals(700, 6, 3)[0].to(cuda)
+    idx, val = I.boxes_iou_frames_sparse(props, props, "bev")
+    dense = I.boxes_iou_bev(props, props)
+    rebuilt = torch.zeros(700 * 700, device=cuda)
+    rebuilt[idx] = val
+    assert torch.equal(rebuilt.view(700, 700), dense)
+    e_idx, e_val = I.boxes_iou_frames_sparse(anchors, torch.zeros((3, 0, 7), device=cuda))
+    assert e_idx.numel() == 0 and e_val.numel() == 0
+
+
 def test_non_finite_heights_propagate_like_torch(cuda, ref_so):
     """boxes_iou3d_gpu multiplies the BEV overlap by the z overlap in torch: 0 * NaN = NaN even for far-apart boxes."""
     a = synth.kitti_boxes(300, 0).to(cuda)
