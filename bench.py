@@ -319,6 +319,13 @@ def side_runs(torch, I, R, synth, dev, hbm_gbs):
                                   "pairs_per_s_max_overlaps": npairs / (ms_mx * 1e-3), "ms_max_overlaps": ms_mx,
                                   "note": "row/col max+argmax (F,N)+(F,M) as consumed by axis_aligned_target_assigner.py:141-165; no 4 B/pair write"}
     del anchors, gts16
+    # pcdet/ops/iou3d boxes_aligned_iou3d_gpu: predictions vs regression targets of the positive anchors (IoU-aware heads)
+    from glenet_b200 import iou3d_utils as I1
+    pred, tgt = synth.head_pairs(20000, 3)
+    pred, tgt = pred.to(dev), tgt.to(dev)
+    ms_v1 = ev(lambda: I1.boxes_aligned_iou3d_gpu(pred, tgt), 50)
+    out["aligned_iou3d_heads"] = {"workload": "boxes_aligned_iou3d_gpu (pcdet/ops/iou3d), 20000 prediction/target pairs", "value": 20000 / (ms_v1 * 1e-3),
+                                  "unit": "pairs/s", "ms": ms_v1}
     # cfg2: points_in_boxes, 128 frames x 180k points x 200 boxes (276 MB of points > L2)
     B, M, N = 128, 180000, 200
     boxes = torch.stack([synth.waymo_boxes(N, 100 + f) for f in range(B)]).to(dev)

@@ -28,6 +28,10 @@ _SIGNATURES = {
                                                           ctypes.c_int, ctypes.c_int, ctypes.c_void_p, c_float_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p]),
     "glenet_boxes_iou_frames_max_gpu": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_longlong, ctypes.c_int, c_float_p, ctypes.c_longlong,
                                                        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "glenet_iou3d_v1_boxes_aligned_gpu": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                         c_float_p, c_float_p, c_float_p, ctypes.c_void_p]),
+    "glenet_iou3d_v1_aligned_overlap_bev_gpu": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "glenet_iou3d_v1_aligned_overlap_bev_cpu_dialect": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "glenet_boxes_iou_aligned_gpu": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "glenet_boxes_iou_bev_cpu_dialect": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "glenet_host_trig4": (None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
@@ -41,7 +45,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 def lib_path() -> str:

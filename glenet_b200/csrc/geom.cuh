@@ -335,7 +335,58 @@ __device__ __noinline__ float box_overlap(const float* __restrict__ a, const flo
     return polygon_area<FMA>(cnt, [&](int k) { return v[k]; });
 }
 
+// ---------------------------------------------------------------- pcdet/ops/iou3d dialect ("V1")
+// The older op behind boxes_aligned_iou3d_gpu (pcdet/ops/iou3d/src/iou3d_kernel.cu): boxes arrive as
+// [x1, y1, x2, y2, angle], corners are rotated CLOCKWISE about the box centre (rotate_around_center :122-126) and
+// check_in_box2d (:50-66) compares the back-rotated point against the box edges -/+ MARGIN = 1e-5.  Contraction
+// pattern read from the SASS of boxes_aligned_overlap_kernel (nvcc 12.9, sm_100a):
+//   ex = p.x - cx with cx = (x1 + x2) / 2 (the halving is exact, so fma(x1 + x2, -0.5, p.x) == p.x - cx)
+//   rotate : x' = fma(cos, ex, sin*ey) + cx          y' = fma(cos, ey, -(sin*ex)) + cy
+//   in box : rx = fma(cn, dxp, sn*dyp) + cx          ry = fma(cn, dyp, -(sn*dxp)) + cy      (cn, sn = cos/sin(-angle))
+//   intersection(), the fan and the final |area| / 2 are the expressions of the iou3d_nms kernels (edge_intersection).
+enum { BP1_X1M = BP_THX, BP1_Y1M = BP_THY, BP1_X2P = BP_ZMIN, BP1_Y2P = BP_ZMAX };   // box edges -/+ MARGIN
 template <bool FMA>
+__device__ __forceinline__ void box_prepare_v1(float x1, float y1, float x2, float y2, const float4 trig4, float* __restrict__ o) {
+    const float cx = __fmul_rn(__fadd_rn(x1, x2), 0.5f), cy = __fmul_rn(__fadd_rn(y1, y2), 0.5f);
+    const float ex1 = __fsub_rn(x1, cx), ex2 = __fsub_rn(x2, cx), ey1 = __fsub_rn(y1, cy), ey2 = __fsub_rn(y2, cy);
+    const float c = trig4.x, s = trig4.y;
+    const float exs[4] = {ex1, ex2, ex2, ex1};
+    const float eys[4] = {ey1, ey1, ey2, ey2};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (FMA) {
+            o[BP_PX + k] = __fadd_rn(__fmaf_rn(c, exs[k], __fmul_rn(s, eys[k])), cx);
+            o[BP_PY + k] = __fadd_rn(__fmaf_rn(c, eys[k], -__fmul_rn(s, exs[k])), cy);
+        } else {   // (ex*cos + ey*sin) + cx ; (-ex*sin + ey*cos) + cy, every operation rounded
+            o[BP_PX + k] = __fadd_rn(__fadd_rn(__fmul_rn(exs[k], c), __fmul_rn(eys[k], s)), cx);
+            o[BP_PY + k] = __fadd_rn(__fadd_rn(-__fmul_rn(exs[k], s), __fmul_rn(eys[k], c)), cy);
+        }
+    }
+    o[BP_CX] = cx; o[BP_CY] = cy; o[BP_CN] = trig4.z; o[BP_SN] = trig4.w;
+    o[BP1_X1M] = __fadd_rn(x1, -1e-5f); o[BP1_Y1M] = __fadd_rn(y1, -1e-5f);
+    o[BP1_X2P] = __fadd_rn(x2, 1e-5f);  o[BP1_Y2P] = __fadd_rn(y2, 1e-5f);
+    o[BP_AREA] = 0.f;
+}
+template <bool FMA>
+__device__ __forceinline__ bool corner_in_box_v1(const float* __restrict__ b, float px, float py) {
+    const float cx = b[BP_CX], cy = b[BP_CY], cn = b[BP_CN], sn = b[BP_SN];
+    const float dxp = __fsub_rn(px, cx), dyp = __fsub_rn(py, cy);
+    float rx, ry;
+    if (FMA) {
+        rx = __fadd_rn(__fmaf_rn(cn, dxp, __fmul_rn(sn, dyp)), cx);
+        ry = __fadd_rn(__fmaf_rn(cn, dyp, -__fmul_rn(sn, dxp)), cy);
+    } else {
+        rx = __fadd_rn(__fadd_rn(__fmul_rn(dxp, cn), __fmul_rn(dyp, sn)), cx);
+        ry = __fadd_rn(__fadd_rn(-__fmul_rn(dxp, sn), __fmul_rn(dyp, cn)), cy);
+    }
+    return rx > b[BP1_X1M] && rx < b[BP1_X2P] && ry > b[BP1_Y1M] && ry < b[BP1_Y2P];
+}
+template <bool FMA, bool V1>
+__device__ __forceinline__ bool corner_test(const float* __restrict__ b, float px, float py) {
+    return V1 ? corner_in_box_v1<FMA>(b, px, py) : corner_in_box<FMA>(b, px, py);
+}
+
+template <bool FMA, bool V1 = false>
 __device__ __forceinline__ float box_overlap_unrolled(const float* __restrict__ a, const float* __restrict__ b) {
     float ax[4], ay[4], bx[4], by[4];
 #pragma unroll
@@ -358,8 +409,8 @@ __device__ __forceinline__ float box_overlap_unrolled(const float* __restrict__ 
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (corner_in_box<FMA>(a, bx[k], by[k]) && cnt < MAX_POLY) v[cnt++] = make_float2(bx[k], by[k]);
-        if (corner_in_box<FMA>(b, ax[k], ay[k]) && cnt < MAX_POLY) v[cnt++] = make_float2(ax[k], ay[k]);
+        if (corner_test<FMA, V1>(a, bx[k], by[k]) && cnt < MAX_POLY) v[cnt++] = make_float2(bx[k], by[k]);
+        if (corner_test<FMA, V1>(b, ax[k], ay[k]) && cnt < MAX_POLY) v[cnt++] = make_float2(ax[k], ay[k]);
     }
     return polygon_area<FMA>(cnt, [&](int k) { return v[k]; });
 }
@@ -375,12 +426,13 @@ __device__ __forceinline__ float max_nan(float a, float b) { return (a != a || b
 __device__ __forceinline__ float min_nan(float a, float b) { return (a != a || b != b) ? (a + b) : fminf(a, b); }
 
 // boxes_iou3d_gpu (iou3d_nms_utils.py:100-119), every step separately rounded as torch does
-__device__ __forceinline__ float iou3d_from_terms(float a_zmin, float a_zmax, float a_vol, float b_zmin, float b_zmax, float b_vol, float ov) {
+__device__ __forceinline__ float iou3d_from_terms(float a_zmin, float a_zmax, float a_vol, float b_zmin, float b_zmax, float b_vol, float ov,
+                                                  float eps = 1e-6f) {
     const float max_of_min = max_nan(a_zmin, b_zmin);
     const float min_of_max = min_nan(a_zmax, b_zmax);
     const float oh = clamp_min_nan(__fsub_rn(min_of_max, max_of_min), 0.f);
     const float o3 = __fmul_rn(ov, oh);
-    const float den = clamp_min_nan(__fsub_rn(__fadd_rn(a_vol, b_vol), o3), 1e-6f);
+    const float den = clamp_min_nan(__fsub_rn(__fadd_rn(a_vol, b_vol), o3), eps);
     return __fdiv_rn(o3, den);
 }
 __device__ __forceinline__ float iou3d_from_overlap(const float* __restrict__ a, const float* __restrict__ b, float ov) {

@@ -1,0 +1,99 @@
+"""Drop-in for the row-aligned IoU of ``pcdet.ops.iou3d.iou3d_utils``.
+
+GLENet's IoU-aware heads call ``boxes_aligned_iou3d_gpu(pred_boxes[pos], gt_boxes[pos])`` once per training step
+(``pcdet/models/dense_heads/anchor_head_kl_label.py:428``, ``anchor_head_iou.py:209``).  The reference builds the result
+from ``boxes3d_to_bev_torch`` (``iou3d_utils.py:79-106``), the native ``boxes_aligned_overlap_bev_gpu``
+(``pcdet/ops/iou3d/src/iou3d.cpp:55-73``, one 16-thread block per 16 pairs) and ~25 torch elementwise kernels
+(``iou3d_utils.py:332-387``); here it is one kernel launch with the same per-step float32 rounding.
+
+This op is NOT the arithmetic of ``pcdet.ops.iou3d_nms``: boxes are ``[x1, y1, x2, y2, ry]`` rectangles rotated
+clockwise about their centre, and ``check_in_box2d`` uses a 1e-5 margin on the box edges
+(``iou3d_kernel.cu:50-66,122-126``) -- reproduced from the reference kernel's SASS, see ``csrc/geom.cuh``.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .iou3d_nms_utils import _check_cuda_f32, _stream
+
+__all__ = ["boxes_aligned_iou3d_gpu", "boxes_aligned_overlap_bev_gpu", "boxes3d_to_bev_torch"]
+
+
+def boxes3d_to_bev_torch(boxes3d, box_mode='wlh', rect=False):
+    """
+    Input(torch):
+        boxes3d: (N, 7) [x, y, z, h, w, l, ry]
+        rect: True/False means boxes in camera/velodyne coord system.
+    Output:
+        boxes_bev: (N, 5) [x1, y1, x2, y2, ry/rz], left-bottom: (x1, y1), right-top: (x2, y2), ry/rz: clockwise rotation angle
+
+    Reference: iou3d_utils.py:79-106 (plain torch there too; kept for callers that want the BEV rows).
+    """
+    boxes_bev = boxes3d.new(torch.Size((boxes3d.shape[0], 5)))
+    if boxes3d.shape[-1] == 5:
+        w_index, l_index = box_mode.index('w') + 2, box_mode.index('l') + 2
+    elif boxes3d.shape[-1] == 7:
+        w_index, l_index = box_mode.index('w') + 3, box_mode.index('l') + 3
+    else:
+        raise NotImplementedError
+    half_w, half_l = boxes3d[:, w_index] / 2., boxes3d[:, l_index] / 2.
+    if rect:
+        cu, cv = boxes3d[:, 0], boxes3d[:, 2]
+        boxes_bev[:, 0], boxes_bev[:, 1] = cu - half_l, cv - half_w
+        boxes_bev[:, 2], boxes_bev[:, 3] = cu + half_l, cv + half_w
+    else:
+        cu, cv = boxes3d[:, 0], boxes3d[:, 1]
+        boxes_bev[:, 0], boxes_bev[:, 1] = cu - half_w, cv - half_l
+        boxes_bev[:, 2], boxes_bev[:, 3] = cu + half_w, cv + half_l
+    boxes_bev[:, 4] = boxes3d[:, -1]
+    return boxes_bev
+
+
+def boxes_aligned_overlap_bev_gpu(boxes_a_bev, boxes_b_bev):
+    """The native call of the reference (iou3d.cpp:55-73): (N, 5) x (N, 5) ``[x1, y1, x2, y2, ry]`` -> (N, 1) overlap areas."""
+    _check_cuda_f32(boxes_a_bev, "boxes_a")
+    _check_cuda_f32(boxes_b_bev, "boxes_b")
+    assert boxes_a_bev.shape == boxes_b_bev.shape and boxes_a_bev.shape[1] == 5
+    a, b = boxes_a_bev.contiguous(), boxes_b_bev.contiguous()
+    out = torch.empty((a.shape[0], 1), dtype=torch.float32, device=a.device)
+    if a.shape[0]:
+        lib = _lib.load()
+        with torch.cuda.device(a.device):
+            rc = lib.glenet_iou3d_v1_aligned_overlap_bev_gpu(a.data_ptr(), b.data_ptr(), a.shape[0], out.data_ptr(), _stream(a.device))
+        _lib.check(rc, "glenet_iou3d_v1_aligned_overlap_bev_gpu")
+    return out
+
+
+def boxes_aligned_iou3d_gpu(boxes_a, boxes_b, box_mode='wlh', rect=False, need_bev=False):
+    """
+    Input (torch):
+        boxes_a: (N, 7) [x, y, z, w, l, h, ry], torch tensor with type float32.
+        boxes_b: (N, 7) [x, y, z, w, l, h, ry], torch tensor with type float32.
+        rect: True/False means boxes in camera/velodyne coord system.
+        Notice: (x, y, z) are real center.
+    Output:
+        iou_3d: (N, 1)   [and iou_bev: (N, 1) with need_bev]
+
+    Reference: iou3d_utils.py:332-387.  ``rect=True`` raises NotImplementedError there as well (:356-357).
+    """
+    assert boxes_a.shape[0] == boxes_b.shape[0]
+    w_index, l_index, h_index = box_mode.index('w') + 3, box_mode.index('l') + 3, box_mode.index('h') + 3
+    if rect:
+        raise NotImplementedError
+    _check_cuda_f32(boxes_a, "boxes_a")
+    _check_cuda_f32(boxes_b, "boxes_b")
+    assert boxes_a.dim() == 2 and boxes_a.shape[1] == 7 and boxes_b.shape[1] == 7
+    a, b = boxes_a.contiguous(), boxes_b.contiguous()
+    n = a.shape[0]
+    iou3d = torch.empty((n, 1), dtype=torch.float32, device=a.device)
+    iou_bev = torch.empty((n, 1), dtype=torch.float32, device=a.device) if need_bev else None
+    if n:
+        lib = _lib.load()
+        with torch.cuda.device(a.device):
+            rc = lib.glenet_iou3d_v1_boxes_aligned_gpu(a.data_ptr(), b.data_ptr(), n, w_index, l_index, h_index, iou3d.data_ptr(),
+                                                       iou_bev.data_ptr() if need_bev else None, None, _stream(a.device))
+        _lib.check(rc, "glenet_iou3d_v1_boxes_aligned_gpu")
+    if need_bev:
+        return iou3d, iou_bev
+    return iou3d

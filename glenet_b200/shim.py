@@ -3,6 +3,7 @@
     import glenet_b200.shim; glenet_b200.shim.install()
     from pcdet.ops.iou3d_nms import iou3d_nms_utils          # -> glenet_b200.iou3d_nms_utils
     from pcdet.ops.roiaware_pool3d import roiaware_pool3d_utils
+    from pcdet.ops.iou3d.iou3d_utils import boxes_aligned_iou3d_gpu   # -> glenet_b200.iou3d_utils
 
 Inside a real OpenPCDet/GLENet checkout the two modules are replaced in ``sys.modules`` (call
 ``install()`` before anything imports ``pcdet.ops``); without pcdet installed, stub parent
@@ -15,11 +16,13 @@ import importlib
 import sys
 import types
 
-from . import iou3d_nms_utils, roiaware_pool3d_utils
+from . import iou3d_nms_utils, iou3d_utils, roiaware_pool3d_utils
 
 _TARGETS = {
     "pcdet.ops.iou3d_nms.iou3d_nms_utils": iou3d_nms_utils,
     "pcdet.ops.roiaware_pool3d.roiaware_pool3d_utils": roiaware_pool3d_utils,
+    # only boxes_aligned_iou3d_gpu (+ its two helpers) of pcdet/ops/iou3d is provided: the one function GLENet imports from it
+    "pcdet.ops.iou3d.iou3d_utils": iou3d_utils,
 }
 
 

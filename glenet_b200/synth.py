@@ -100,3 +100,23 @@ def cvae_samples(g_objects, r, seed=0):
     sigma = torch.tensor([0.15, 0.15, 0.05, 0.1, 0.05, 0.05, 0.05], dtype=torch.float32)
     samples = gt.repeat_interleave(r, dim=0) + torch.randn((g_objects * r, 7), generator=g, dtype=torch.float32) * sigma
     return samples.contiguous(), gt
+
+
+def head_pairs(n, seed=0):
+    """Row-aligned (prediction, regression target) boxes as the IoU-aware heads see them
+    (anchor_head_kl_label.py:417-428: decoded predictions vs decoded targets of the positive anchors):
+    targets = kitti_boxes, predictions = targets + noise; a few exact copies, tiny offsets, quarter turns and
+    far misses are mixed in.  Returns (pred (n, 7), target (n, 7))."""
+    g = _gen(seed + 4000)
+    tgt = kitti_boxes(n, seed + 7)
+    sigma = torch.tensor([0.25, 0.25, 0.1, 0.15, 0.08, 0.08, 0.12], dtype=torch.float32)
+    pred = tgt + torch.randn((n, 7), generator=g, dtype=torch.float32) * sigma
+    k = torch.arange(n)
+    pred[k % 11 == 0] = tgt[k % 11 == 0]                                  # exact copies
+    m = k % 11 == 1
+    pred[m] = tgt[m]; pred[m, 0] += 1e-5                                  # one margin to the side
+    m = k % 11 == 2
+    pred[m] = tgt[m]; pred[m, 6] += 3.14159265 / 2                        # quarter turn about the same centre
+    m = k % 11 == 3
+    pred[m, 0] += 6.0                                                     # miss
+    return pred.contiguous(), tgt.contiguous()

@@ -92,6 +92,26 @@ int glenet_boxes_iou_frames_max_gpu(int mode, const float* boxes_a, long long a_
 int glenet_boxes_iou_aligned_gpu(int mode, const float* boxes_a, int na, const float* boxes_b,
                                  int group, float* out, glenet_stream_t stream);
 
+/* ---------------------------------------------------------------- pcdet/ops/iou3d (row-aligned IoU of the IoU-aware heads)
+ * boxes_aligned_iou3d_gpu(boxes_a, boxes_b, box_mode, rect=False, need_bev)   pcdet/ops/iou3d/iou3d_utils.py:332-387
+ *   = boxes3d_to_bev_torch (:79-106) + boxes_aligned_overlap_bev_gpu (pcdet/ops/iou3d/src/iou3d.cpp:55-73,
+ *     kernel iou3d_kernel.cu:284-293) + ~25 torch elementwise kernels, here one kernel with the same per-step rounding.
+ * boxes_a, boxes_b: (n, 7) [x, y, z, d3, d4, d5, ry]; w_index / l_index / h_index (a permutation of 3, 4, 5) say
+ * which of d3..d5 is the extent along x, along y and the height ('wlh' -> 3, 4, 5).  Each of the three outputs may
+ * be NULL: iou3d (n), iou_bev (n), overlap_bev (n).  This op has its own arithmetic (clockwise rotation,
+ * [x1, y1, x2, y2] edges -/+ 1e-5 in check_in_box2d), reproduced from the SASS of the reference kernel. */
+int glenet_iou3d_v1_boxes_aligned_gpu(const float* boxes_a, const float* boxes_b, int n, int w_index, int l_index,
+                                      int h_index, float* iou3d, float* iou_bev, float* overlap_bev,
+                                      glenet_stream_t stream);
+/* boxes_aligned_overlap_bev_gpu(boxes_a, boxes_b, ans_overlap) itself: (n, 5) [x1, y1, x2, y2, ry] rows. */
+int glenet_iou3d_v1_aligned_overlap_bev_gpu(const float* boxes_a_bev, const float* boxes_b_bev, int n,
+                                            float* ans_overlap, glenet_stream_t stream);
+/* The same in the CPU dialect of pcdet/ops/iou3d/src/iou3d_cpu.cpp (box_overlap :126-247; no FMA contraction, host
+ * libm trig tables as for glenet_boxes_iou_bev_cpu_dialect): row i of boxes_overlap_bev_cpu's diagonal. */
+int glenet_iou3d_v1_aligned_overlap_bev_cpu_dialect(const float* boxes_a_bev, const float* trig_a,
+                                                    const float* boxes_b_bev, const float* trig_b, int n,
+                                                    float* ans_overlap, glenet_stream_t stream);
+
 /* boxes_iou_bev_cpu(boxes_a, boxes_b, ans_iou)           pcdet/ops/iou3d_nms/src/iou3d_cpu.cpp:232-252
  * The reference runs this single-threaded on the host.  Here it executes on the GPU in the
  * "CPU dialect" (no FMA contraction; cos/sin supplied by the host's libm so that the

@@ -1,12 +1,13 @@
 """Build recipe for ``oracle/_ref`` -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 Compiles the *unmodified* reference sources where they lie under
-``/root/reference`` into two torch extension modules:
+``/root/reference`` into three torch extension modules:
 
 * ``oracle/_ref/iou3d_nms_cuda.so``       <- pcdet/ops/iou3d_nms/src/{iou3d_cpu.cpp,
                                               iou3d_nms_api.cpp, iou3d_nms.cpp, iou3d_nms_kernel.cu}
 * ``oracle/_ref/roiaware_pool3d_cuda.so`` <- pcdet/ops/roiaware_pool3d/src/{roiaware_pool3d.cpp,
                                               roiaware_pool3d_kernel.cu}
+* ``oracle/_ref/iou3d_cuda.so``           <- pcdet/ops/iou3d/src/{iou3d.cpp, iou3d_cpu.cpp, iou3d_kernel.cu}
 
 (the same source lists as the reference's ``setup.py:58-76``).  Nothing is copied
 into the repository: only build products land in ``oracle/_ref`` which is
@@ -41,6 +42,14 @@ EXTS = {
         "pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp",
         "pcdet/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu",
     ],
+    # pcdet/ops/iou3d (the [x1, y1, x2, y2, ry] variant behind boxes_aligned_iou3d_gpu of the IoU-aware heads).
+    # The reference's own setup.py (pcdet/ops/iou3d/setup.py:9-13) lists only iou3d.cpp + iou3d_kernel.cu, which leaves
+    # the *_cpu symbols that iou3d.cpp:264-277 binds undefined; iou3d_cpu.cpp next to them defines those.
+    "iou3d_cuda": [
+        "pcdet/ops/iou3d/src/iou3d.cpp",
+        "pcdet/ops/iou3d/src/iou3d_cpu.cpp",
+        "pcdet/ops/iou3d/src/iou3d_kernel.cu",
+    ],
 }
 
 
@@ -64,6 +73,8 @@ def build(force: bool = False, verbose: bool = False) -> bool:
 
     os.makedirs(OUT, exist_ok=True)
     for name, srcs in EXTS.items():
+        if os.path.isfile(os.path.join(OUT, name + ".so")) and not force:
+            continue
         bdir = os.path.join(OUT, "build_" + name)
         os.makedirs(bdir, exist_ok=True)
         load(

@@ -52,6 +52,8 @@ def load():
         lib.oracle_points_in_boxes_mask_rows.argtypes = [ctypes.c_int, fp, ctypes.c_int, ctypes.c_int, fp, ctypes.c_int, ip]
         lib.oracle_points_in_boxes_index.argtypes = [ctypes.c_int, fp, ctypes.c_int, ctypes.c_int, fp, ctypes.c_int, ip]
         lib.oracle_count_circle_pass.argtypes = [fp, ctypes.c_int, fp, ctypes.c_int]
+        lib.oracle_iou3d_v1_overlap_bev.argtypes = [ctypes.c_int, fp, ctypes.c_int, fp, ctypes.c_int, fp]
+        lib.oracle_iou3d_v1_overlap_aligned.argtypes = [ctypes.c_int, fp, fp, ctypes.c_int, fp]
         lib.oracle_count_circle_pass.restype = ctypes.c_uint64
         lib.oracle_abi_version.restype = ctypes.c_int
         _lib = lib
@@ -122,3 +124,20 @@ def points_in_boxes_index(points, boxes, dialect=GPU):
 def count_circle_pass(a, b):
     a, b = _f32(a), _f32(b)
     return int(load().oracle_count_circle_pass(a.ctypes.data, a.shape[0], b.ctypes.data, b.shape[0]))
+
+
+def iou3d_v1_overlap_bev(a5, b5, dialect=CPU):
+    """pcdet/ops/iou3d boxes_overlap_bev_cpu: (N, 5) x (M, 5) [x1, y1, x2, y2, angle] -> (N, M)."""
+    a5, b5 = _f32(a5), _f32(b5)
+    out = np.zeros((a5.shape[0], b5.shape[0]), dtype=np.float32)
+    load().oracle_iou3d_v1_overlap_bev(dialect, a5.ctypes.data, a5.shape[0], b5.ctypes.data, b5.shape[0], out.ctypes.data)
+    return out
+
+
+def iou3d_v1_overlap_aligned(a5, b5, dialect=GPU):
+    """pcdet/ops/iou3d boxes_aligned_overlap_bev_gpu: row i of a5 against row i of b5 -> (N,)."""
+    a5, b5 = _f32(a5), _f32(b5)
+    assert a5.shape == b5.shape
+    out = np.zeros((a5.shape[0],), dtype=np.float32)
+    load().oracle_iou3d_v1_overlap_aligned(dialect, a5.ctypes.data, b5.ctypes.data, a5.shape[0], out.ctypes.data)
+    return out

@@ -56,6 +56,15 @@ def roiaware_pool3d_cuda():
     return _load("roiaware_pool3d_cuda")
 
 
+def iou3d_available() -> bool:
+    return os.path.isfile(os.path.join(REF_DIR, "iou3d_cuda.so"))
+
+
+def iou3d_cuda():
+    """pcdet/ops/iou3d (the [x1, y1, x2, y2, ry] variant used by boxes_aligned_iou3d_gpu)."""
+    return _load("iou3d_cuda")
+
+
 def _np2t(x):
     # common_utils.py:15-18
     if isinstance(x, np.ndarray):
@@ -149,3 +158,56 @@ def points_in_boxes_gpu(points, boxes):
     if out.numel() and boxes.shape[1]:
         roiaware_pool3d_cuda().points_in_boxes_gpu(boxes.contiguous(), points.contiguous(), out)
     return out
+
+
+# ---------------------------------------------------------------- pcdet/ops/iou3d (row-aligned IoU of the IoU-aware heads)
+def boxes3d_to_bev_torch(boxes3d, box_mode='wlh', rect=False):
+    """pcdet/ops/iou3d/iou3d_utils.py:79-106."""
+    boxes_bev = boxes3d.new(torch.Size((boxes3d.shape[0], 5)))
+    w_index, l_index = box_mode.index('w') + 3, box_mode.index('l') + 3
+    half_w, half_l = boxes3d[:, w_index] / 2., boxes3d[:, l_index] / 2.
+    assert not rect
+    cu, cv = boxes3d[:, 0], boxes3d[:, 1]
+    boxes_bev[:, 0], boxes_bev[:, 1] = cu - half_w, cv - half_l
+    boxes_bev[:, 2], boxes_bev[:, 3] = cu + half_w, cv + half_l
+    boxes_bev[:, 4] = boxes3d[:, -1]
+    return boxes_bev
+
+
+def boxes_aligned_iou3d_gpu(boxes_a, boxes_b, box_mode='wlh', rect=False, need_bev=False):
+    """pcdet/ops/iou3d/iou3d_utils.py:332-387 (rect=False; rect=True raises there too)."""
+    assert boxes_a.shape[0] == boxes_b.shape[0]
+    w_index, l_index, h_index = box_mode.index('w') + 3, box_mode.index('l') + 3, box_mode.index('h') + 3
+    boxes_a_bev = boxes3d_to_bev_torch(boxes_a, box_mode, rect)
+    boxes_b_bev = boxes3d_to_bev_torch(boxes_b, box_mode, rect)
+    overlaps_bev = torch.zeros((boxes_a.shape[0], 1), dtype=torch.float32, device=boxes_a.device)
+    if boxes_a.shape[0]:
+        iou3d_cuda().boxes_aligned_overlap_bev_gpu(boxes_a_bev.contiguous(), boxes_b_bev.contiguous(), overlaps_bev)
+    area_a = (boxes_a[:, w_index] * boxes_a[:, l_index]).view(-1, 1)
+    area_b = (boxes_b[:, w_index] * boxes_b[:, l_index]).view(-1, 1)
+    iou_bev = overlaps_bev / torch.clamp(area_a + area_b - overlaps_bev, min=1e-7)
+    if rect:
+        raise NotImplementedError
+    half_h_a = boxes_a[:, h_index] / 2.0
+    half_h_b = boxes_b[:, h_index] / 2.0
+    a_hmin = (boxes_a[:, 2] - half_h_a).view(-1, 1)
+    a_hmax = (boxes_a[:, 2] + half_h_a).view(-1, 1)
+    b_hmin = (boxes_b[:, 2] - half_h_b).view(-1, 1)
+    b_hmax = (boxes_b[:, 2] + half_h_b).view(-1, 1)
+    max_of_min = torch.max(a_hmin, b_hmin)
+    min_of_max = torch.min(a_hmax, b_hmax)
+    overlaps_h = torch.clamp(min_of_max - max_of_min, min=0)
+    overlaps_3d = overlaps_bev * overlaps_h
+    vol_a = (boxes_a[:, 3] * boxes_a[:, 4] * boxes_a[:, 5]).view(-1, 1)
+    vol_b = (boxes_b[:, 3] * boxes_b[:, 4] * boxes_b[:, 5]).view(-1, 1)
+    iou3d = overlaps_3d / torch.clamp(vol_a + vol_b - overlaps_3d, min=1e-7)
+    if need_bev:
+        return iou3d, iou_bev
+    return iou3d
+
+
+def iou3d_v1_overlap_bev_cpu(boxes_a_bev, boxes_b_bev):
+    """boxes_overlap_bev_cpu of pcdet/ops/iou3d/src/iou3d_cpu.cpp:258-281: (N, 5) x (M, 5) CPU tensors -> (N, M)."""
+    ans = torch.zeros((boxes_a_bev.shape[0], boxes_b_bev.shape[0]), dtype=torch.float32)
+    iou3d_cuda().boxes_overlap_bev_cpu(boxes_a_bev.contiguous(), boxes_b_bev.contiguous(), ans)
+    return ans

@@ -29,6 +29,28 @@ def gpu_golden():
 
 
 @pytest.fixture(scope="session")
+def cpu_golden_v1():
+    return dict(np.load(os.path.join(GOLDEN_DIR, "cpu_golden_v1.npz")))
+
+
+@pytest.fixture(scope="session")
+def gpu_golden_v1():
+    path = os.path.join(GOLDEN_DIR, "gpu_golden_v1.npz")
+    if not os.path.isfile(path):
+        pytest.skip("tests/golden/gpu_golden_v1.npz missing (generate with make_golden.py gpu_v1 on a B200)")
+    return dict(np.load(path))
+
+
+@pytest.fixture(scope="session")
+def ref_iou3d():
+    """pcdet/ops/iou3d compiled into oracle/_ref/iou3d_cuda.so (skips when it was not built/shipped)."""
+    from oracle import ref
+    if not ref.iou3d_available():
+        pytest.skip("oracle/_ref/iou3d_cuda.so not built (needs /root/reference; run python oracle/build_ref.py)")
+    return ref
+
+
+@pytest.fixture(scope="session")
 def capi():
     from oracle import capi as c
     c.load()

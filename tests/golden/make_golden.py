@@ -6,6 +6,10 @@
     gpurun -- python tests/golden/make_golden.py gpu
                                                # on a B200: the reference's CUDA kernels (oracle/_ref)
                                                # -> gpurun_out/gpu_golden.npz (copy it to tests/golden/)
+    python tests/golden/make_golden.py cpu_v1  # pcdet/ops/iou3d (boxes_aligned_iou3d_gpu's op), CPU function
+                                               # -> tests/golden/cpu_golden_v1.npz
+    gpurun -- python tests/golden/make_golden.py gpu_v1    # the same op's CUDA kernel through the reference's
+                                               # wrapper imported verbatim -> gpurun_out/gpu_golden_v1.npz
 
 The inputs are produced by the seeded generators of glenet_b200.synth plus a hand-written
 adversarial set (identical boxes, shared edges, corners at 0.01 +- ulp from an edge, zero
@@ -89,6 +93,56 @@ def load_reference_wrappers():
     return iou, roi
 
 
+def load_reference_iou3d_utils():
+    """pcdet/ops/iou3d/iou3d_utils.py imported verbatim (its only native dependency is iou3d_cuda)."""
+    def pkg(name):
+        if name not in sys.modules:
+            m = types.ModuleType(name); m.__path__ = []; sys.modules[name] = m
+        return sys.modules[name]
+    for n in ("pcdet", "pcdet.ops", "pcdet.ops.iou3d"):
+        pkg(n)
+    sys.modules["pcdet.ops.iou3d.iou3d_cuda"] = oref.iou3d_cuda()
+    sys.modules["pcdet.ops.iou3d"].iou3d_cuda = oref.iou3d_cuda()
+    spec = importlib.util.spec_from_file_location("pcdet.ops.iou3d.iou3d_utils", os.path.join(REF, "pcdet/ops/iou3d/iou3d_utils.py"))
+    m = importlib.util.module_from_spec(spec); sys.modules["pcdet.ops.iou3d.iou3d_utils"] = m; spec.loader.exec_module(m)
+    return m
+
+
+def v1_inputs():
+    pred, tgt = synth.head_pairs(600, 0)
+    return {"v1_pred": pred, "v1_tgt": tgt}
+
+
+def make_cpu_v1():
+    """pcdet/ops/iou3d: the reference's own boxes3d_to_bev_torch + its CPU overlap (boxes_overlap_bev_cpu, diagonal)."""
+    u = load_reference_iou3d_utils()
+    d = v1_inputs()
+    a5, b5 = u.boxes3d_to_bev_torch(d["v1_pred"]), u.boxes3d_to_bev_torch(d["v1_tgt"])
+    full = torch.zeros((a5.shape[0], b5.shape[0]))
+    oref.iou3d_cuda().boxes_overlap_bev_cpu(a5.contiguous(), b5.contiguous(), full)
+    out = {k: v.numpy() for k, v in d.items()}
+    out["v1_pred_bev"], out["v1_tgt_bev"] = a5.numpy(), b5.numpy()
+    out["cpu_v1_overlap_aligned"] = full.diagonal().numpy().copy()
+    out["cpu_v1_overlap_block"] = full[:64, :64].numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "cpu_golden_v1.npz"), **out)
+    print("wrote cpu_golden_v1.npz", {k: v.shape for k, v in out.items()})
+
+
+def make_gpu_v1():
+    """pcdet/ops/iou3d on a B200: the reference's Python wrapper verbatim around its compiled kernel."""
+    # /root/reference does not exist on the GPU box: there the wrapper is oracle.ref's restatement of
+    # iou3d_utils.py:332-387 (checked against the file itself wherever the reference tree is present)
+    u = load_reference_iou3d_utils() if os.path.isdir(REF) else oref
+    dev = torch.device("cuda:0")
+    d = {k: v.to(dev) for k, v in v1_inputs().items()}
+    iou3d, iou_bev = u.boxes_aligned_iou3d_gpu(d["v1_pred"], d["v1_tgt"], need_bev=True)
+    iou3d_lwh = u.boxes_aligned_iou3d_gpu(d["v1_pred"], d["v1_tgt"], box_mode="lwh")
+    out = {"gpu_v1_iou3d": iou3d.cpu().numpy(), "gpu_v1_iou_bev": iou_bev.cpu().numpy(), "gpu_v1_iou3d_lwh": iou3d_lwh.cpu().numpy()}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    np.savez_compressed(os.path.join(ROOT, "gpurun_out", "gpu_golden_v1.npz"), **out)
+    print("wrote gpurun_out/gpu_golden_v1.npz", {k: v.shape for k, v in out.items()})
+
+
 def make_cpu():
     iou, roi = load_reference_wrappers()
     d = inputs()
@@ -133,4 +187,4 @@ def make_gpu():
 
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "cpu"
-    make_cpu() if mode == "cpu" else make_gpu()
+    {"cpu": make_cpu, "gpu": make_gpu, "cpu_v1": make_cpu_v1, "gpu_v1": make_gpu_v1}[mode]()

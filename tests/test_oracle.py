@@ -108,3 +108,34 @@ def test_flop_model_counts(capi):
     assert st.pairs == 100 * 100
     assert sum(st.cnt_hist) == st.pairs
     assert st.flops() > 151 * st.pairs
+
+
+# ------------------------------------------------------------------ pcdet/ops/iou3d (boxes_aligned_iou3d_gpu's op)
+def test_v1_overlap_cpu_dialect_matches_reference_golden(cpu_golden_v1, capi):
+    g = cpu_golden_v1
+    np.testing.assert_array_equal(capi.iou3d_v1_overlap_aligned(g["v1_pred_bev"], g["v1_tgt_bev"], dialect=capi.CPU), g["cpu_v1_overlap_aligned"])
+    np.testing.assert_array_equal(capi.iou3d_v1_overlap_bev(g["v1_pred_bev"][:64], g["v1_tgt_bev"][:64], dialect=capi.CPU), g["cpu_v1_overlap_block"])
+    assert (g["cpu_v1_overlap_aligned"] > 0).mean() > 0.8 and (g["cpu_v1_overlap_aligned"] == 0).sum() > 20   # overlapping pairs and misses
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_v1_oracle_bitexact_vs_reference_cpu(ref_iou3d, capi, seed):
+    pred, tgt = synth.head_pairs(300, seed)
+    a5, b5 = ref_iou3d.boxes3d_to_bev_torch(pred), ref_iou3d.boxes3d_to_bev_torch(tgt)
+    want = ref_iou3d.iou3d_v1_overlap_bev_cpu(a5, b5[:120]).numpy()
+    np.testing.assert_array_equal(capi.iou3d_v1_overlap_bev(a5.numpy(), b5[:120].numpy(), dialect=capi.CPU), want)
+    np.testing.assert_array_equal(capi.iou3d_v1_overlap_aligned(a5.numpy()[:120], b5.numpy()[:120], dialect=capi.CPU), want.diagonal())
+
+
+def test_v1_restated_python_wrapper_equals_reference_file(ref_iou3d):
+    """oracle.ref.boxes3d_to_bev_torch restates pcdet/ops/iou3d/iou3d_utils.py:79-106; check it against the file itself."""
+    import os
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference tree not present")
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden
+    u = make_golden.load_reference_iou3d_utils()
+    pred, _ = synth.head_pairs(50, 5)
+    for mode in ("wlh", "lwh", "hwl"):
+        assert torch.equal(u.boxes3d_to_bev_torch(pred, mode), ref_iou3d.boxes3d_to_bev_torch(pred, mode))

@@ -4,5 +4,5 @@
 set -e
 cd "$(dirname "$0")/../glenet_b200/csrc"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -DGLENET_PHASE_TIMING -Xcompiler -fPIC \
-     -I ../../include -shared iou.cu nms.cu pib.cu host.cpp -o ../lib/libglenet_geom_dbg.so
+     -I ../../include -shared iou.cu iou3d_v1.cu nms.cu pib.cu host.cpp -o ../lib/libglenet_geom_dbg.so
 echo built glenet_b200/lib/libglenet_geom_dbg.so
