@@ -35,6 +35,7 @@ _SIGNATURES = {
     "glenet_boxes_iou_aligned_gpu": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "glenet_boxes_iou_bev_cpu_dialect": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "glenet_host_trig4": (None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "glenet_host_trig4_strided": (None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "glenet_host_trig2": (None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "glenet_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "glenet_nms_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
@@ -45,7 +46,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 def lib_path() -> str:

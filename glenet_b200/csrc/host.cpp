@@ -14,6 +14,18 @@
 extern "C" {
 
 // out: (n, 4) rows {cos(h), sin(h), cos(-h), sin(-h)}; boxes: (n, 7) host floats
+void glenet_host_trig4_strided(const float* angles_host, int stride, int n, float* out_host) {
+    for (int i = 0; i < n; ++i) {
+        const float h = angles_host[(size_t)i * stride];
+        float s, c;
+        sincosf(h, &s, &c);
+        out_host[4 * (size_t)i + 0] = c;
+        out_host[4 * (size_t)i + 1] = s;
+        out_host[4 * (size_t)i + 2] = cosf(-h);
+        out_host[4 * (size_t)i + 3] = sinf(-h);
+    }
+}
+
 void glenet_host_trig4(const float* boxes_host, int n, float* out_host) {
     for (int i = 0; i < n; ++i) {
         const float h = boxes_host[(size_t)i * 7 + 6];

@@ -17,7 +17,7 @@ import torch
 from . import _lib
 from .iou3d_nms_utils import _check_cuda_f32, _stream
 
-__all__ = ["boxes_aligned_iou3d_gpu", "boxes_aligned_overlap_bev_gpu", "boxes3d_to_bev_torch"]
+__all__ = ["boxes_aligned_iou3d_gpu", "boxes_aligned_overlap_bev_gpu", "boxes_aligned_overlap_bev_cpu", "boxes3d_to_bev_torch"]
 
 
 def boxes3d_to_bev_torch(boxes3d, box_mode='wlh', rect=False):
@@ -97,3 +97,37 @@ def boxes_aligned_iou3d_gpu(boxes_a, boxes_b, box_mode='wlh', rect=False, need_b
     if need_bev:
         return iou3d, iou_bev
     return iou3d
+
+
+def boxes_aligned_overlap_bev_cpu(boxes_a_bev, boxes_b_bev):
+    """Row-aligned counterpart of the op's CPU function ``boxes_overlap_bev_cpu`` (``pcdet/ops/iou3d/src/iou3d_cpu.cpp:258-281``):
+    CPU tensors (N, 5) ``[x1, y1, x2, y2, ry]`` in, (N, 1) CPU tensor out, element i = ``box_overlap(a[i], b[i])`` of
+    ``iou3d_cpu.cpp:126-247`` bit for bit.  Executes on the GPU in that file's CPU dialect (every operation rounded
+    separately; cos/sin of the angles evaluated by the host's libm, as for ``iou3d_nms_utils.boxes_bev_iou_cpu``)."""
+    assert not (boxes_a_bev.is_cuda or boxes_b_bev.is_cuda), 'Only support CPU tensors'
+    assert boxes_a_bev.shape == boxes_b_bev.shape and boxes_a_bev.shape[1] == 5
+    if boxes_a_bev.dtype != torch.float32 or boxes_b_bev.dtype != torch.float32:
+        raise RuntimeError("boxes must be float32")
+    a, b = boxes_a_bev.contiguous(), boxes_b_bev.contiguous()
+    n = a.shape[0]
+    ans = a.new_zeros((n, 1))
+    if n:
+        lib = _lib.load()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        # one pinned host buffer [boxes_a | boxes_b | pad | trig_a | trig_b] -> one H2D copy; trig tables 16-byte aligned
+        o_b, o_ta = n * 5, (2 * n * 5 + 3) // 4 * 4
+        o_tb = o_ta + 4 * n
+        host = torch.empty((o_tb + 4 * n,), dtype=torch.float32).pin_memory()
+        host[:o_b].copy_(a.view(-1))
+        host[o_b:o_b + n * 5].copy_(b.view(-1))
+        base = host.data_ptr()
+        lib.glenet_host_trig4_strided(a.data_ptr() + 16, 5, n, base + 4 * o_ta)
+        lib.glenet_host_trig4_strided(b.data_ptr() + 16, 5, n, base + 4 * o_tb)
+        d = host.to(dev, non_blocking=True)
+        out = torch.empty((n, 1), dtype=torch.float32, device=dev)
+        p = d.data_ptr()
+        with torch.cuda.device(dev):
+            rc = lib.glenet_iou3d_v1_aligned_overlap_bev_cpu_dialect(p, p + 4 * o_ta, p + 4 * o_b, p + 4 * o_tb, n, out.data_ptr(), _stream(dev))
+        _lib.check(rc, "glenet_iou3d_v1_aligned_overlap_bev_cpu_dialect")
+        ans.copy_(out)   # D2H, synchronising
+    return ans

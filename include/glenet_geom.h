@@ -163,6 +163,8 @@ int glenet_points_in_boxes_cpu_dialect(const float* boxes, const float* trig, in
  * code makes (iou3d_cpu.cpp:74-84,146-151; roiaware_pool3d.cpp:121-125).  boxes_host: (n, 7)
  * host floats.  trig4 rows: {cosf(h), sinf(h), cosf(-h), sinf(-h)}; trig2 rows: {cosf(-h), sinf(-h)}. */
 void glenet_host_trig4(const float* boxes_host, int n, float* out_host);
+/* the same table for angles stored with an arbitrary stride (in floats), e.g. column 4 of (n, 5) [x1, y1, x2, y2, ry] rows */
+void glenet_host_trig4_strided(const float* angles_host, int stride, int n, float* out_host);
 void glenet_host_trig2(const float* boxes_host, int n, float* out_host);
 
 #ifdef __cplusplus

@@ -539,6 +539,22 @@ def test_v1_aligned_iou_bit_exact_vs_reference_kernel(cuda, ref_iou3d, capi):
     assert torch.equal(g2[generic], w2[generic]) and float((g2 - w2).abs().max()) <= IOU_TOL
 
 
+def test_v1_cpu_dialect_bit_exact_vs_reference_cpu_code(cuda, capi, cpu_golden_v1):
+    g = cpu_golden_v1
+    got = I1.boxes_aligned_overlap_bev_cpu(torch.from_numpy(g["v1_pred_bev"]), torch.from_numpy(g["v1_tgt_bev"]))
+    assert got.shape == (600, 1) and not got.is_cuda
+    generic = (np.arange(600) % 11) != 1
+    np.testing.assert_array_equal(got.numpy()[generic, 0], g["cpu_v1_overlap_aligned"][generic])      # golden = the reference's CPU function
+    assert np.abs(got.numpy()[:, 0] - g["cpu_v1_overlap_aligned"]).max() <= 1e-5
+    pred, tgt = synth.head_pairs(5000, 12)
+    a5, b5 = I1.boxes3d_to_bev_torch(pred), I1.boxes3d_to_bev_torch(tgt)
+    want = capi.iou3d_v1_overlap_aligned(a5.numpy(), b5.numpy(), dialect=capi.CPU)
+    got = I1.boxes_aligned_overlap_bev_cpu(a5, b5).numpy()[:, 0]
+    generic = (np.arange(5000) % 11) != 1
+    np.testing.assert_array_equal(got[generic], want[generic])
+    assert np.abs(got - want).max() <= 1e-5
+
+
 def test_v1_api_behaviour(cuda):
     pred, tgt = synth.head_pairs(10, 1)
     pred, tgt = pred.to(cuda), tgt.to(cuda)
