@@ -11,7 +11,7 @@ import torch
 from . import _lib
 from .iou3d_nms_utils import _stream, check_numpy_to_torch
 
-__all__ = ["points_in_boxes_cpu", "points_in_boxes_gpu"]
+__all__ = ["points_in_boxes_cpu", "points_in_boxes_cpu_lists", "points_in_boxes_gpu"]
 
 
 def points_in_boxes_cpu(points, boxes):
@@ -34,25 +34,56 @@ def points_in_boxes_cpu(points, boxes):
     n, m = boxes.shape[0], points.shape[0]
     point_indices = points.new_zeros((n, m), dtype=torch.int)
     if n and m:
-        b = boxes.float().contiguous()
-        p = points.float().contiguous()
-        if b.is_cuda or p.is_cuda:
-            raise RuntimeError("points_in_boxes_cpu expects CPU tensors / numpy arrays")
-        lib = _lib.load()
-        dev = torch.device("cuda", torch.cuda.current_device())
-        host = torch.empty(n * 7 + n * 2 + m * 3, dtype=torch.float32).pin_memory()
-        o_t, o_p = n * 7, n * 9
-        host[:o_t].copy_(b.view(-1))
-        lib.glenet_host_trig2(b.data_ptr(), n, host.data_ptr() + 4 * o_t)
-        host[o_p:].copy_(p.view(-1))
-        d = host.to(dev, non_blocking=True)
-        out = torch.empty((n, m), dtype=torch.int32, device=dev)
-        base = d.data_ptr()
-        with torch.cuda.device(dev):
-            rc = lib.glenet_points_in_boxes_cpu_dialect(base, base + 4 * o_t, n, base + 4 * o_p, m, out.data_ptr(), _stream(dev))
-        _lib.check(rc, "glenet_points_in_boxes_cpu_dialect")
-        point_indices.copy_(out)   # D2H, synchronising
+        point_indices.copy_(_cpu_dialect_mask_on_device(points, boxes))   # D2H, synchronising
     return point_indices.numpy() if is_numpy else point_indices
+
+
+def _cpu_dialect_mask_on_device(points: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
+    """(N, M) int32 0/1 mask of points_in_boxes_cpu, left on the GPU."""
+    n, m = boxes.shape[0], points.shape[0]
+    b = boxes.float().contiguous()
+    p = points.float().contiguous()
+    if b.is_cuda or p.is_cuda:
+        raise RuntimeError("points_in_boxes_cpu expects CPU tensors / numpy arrays")
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    host = torch.empty(n * 7 + n * 2 + m * 3, dtype=torch.float32).pin_memory()
+    o_t, o_p = n * 7, n * 9
+    host[:o_t].copy_(b.view(-1))
+    lib.glenet_host_trig2(b.data_ptr(), n, host.data_ptr() + 4 * o_t)
+    host[o_p:].copy_(p.view(-1))
+    d = host.to(dev, non_blocking=True)
+    out = torch.empty((n, m), dtype=torch.int32, device=dev)
+    base = d.data_ptr()
+    with torch.cuda.device(dev):
+        rc = lib.glenet_points_in_boxes_cpu_dialect(base, base + 4 * o_t, n, base + 4 * o_p, m, out.data_ptr(), _stream(dev))
+    _lib.check(rc, "glenet_points_in_boxes_cpu_dialect")
+    return out
+
+
+def points_in_boxes_cpu_lists(points, boxes):
+    """Per-box index lists instead of the (N, num_points) mask of :func:`points_in_boxes_cpu`.
+
+    Returns ``(offsets, indices)``: ``indices[offsets[i]:offsets[i + 1]]`` are, in ascending order, the points with
+    ``points_in_boxes_cpu(points, boxes)[i] > 0`` -- i.e. ``np.nonzero(point_indices[i])[0]``, the selection the
+    GT-database builders make per object (``kitti_dataset.py:236-259``: ``gt_points = points[point_indices[i] > 0]``,
+    ``waymo_dataset.py:342-395``).  Same predicate and dialect as points_in_boxes_cpu (MARGIN 1e-2, a point may belong to
+    several boxes); the mask is compacted on the GPU, so only the few thousand indices of the objects' points cross
+    PCIe instead of N x num_points int32.  numpy in -> numpy out, like the mask function.  Additive API."""
+    assert boxes.shape[1] == 7
+    assert points.shape[1] == 3
+    points, is_numpy = check_numpy_to_torch(points)
+    boxes, is_numpy = check_numpy_to_torch(boxes)
+    n, m = boxes.shape[0], points.shape[0]
+    offsets = torch.zeros((n + 1,), dtype=torch.int64)
+    indices = torch.zeros((0,), dtype=torch.int64)
+    if n and m:
+        mask = _cpu_dialect_mask_on_device(points, boxes)
+        nz = mask.nonzero()                                   # row-major: boxes ascending, points ascending within a box
+        counts = torch.bincount(nz[:, 0], minlength=n)
+        offsets[1:] = torch.cumsum(counts, 0).cpu()
+        indices = nz[:, 1].contiguous().cpu()
+    return (offsets.numpy(), indices.numpy()) if is_numpy else (offsets, indices)
 
 
 def points_in_boxes_gpu(points, boxes):

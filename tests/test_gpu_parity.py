@@ -555,6 +555,22 @@ def test_v1_cpu_dialect_bit_exact_vs_reference_cpu_code(cuda, capi, cpu_golden_v
     assert np.abs(got - want).max() <= 1e-5
 
 
+def test_points_in_boxes_cpu_lists_equal_mask_rows(cuda, ref_so):
+    """GT-database cropping building block: per-object point lists == nonzero() of the reference's CPU mask rows."""
+    boxes = synth.kitti_boxes(25, 40)
+    boxes[7] = boxes[6]; boxes[7, 0] += 0.3                                  # overlapping boxes: a point may be in both
+    pts = synth.points(80000, boxes, synth.KITTI_RANGE, 0.2, seed=4)
+    want = ref_so.points_in_boxes_cpu(pts, boxes).numpy()
+    off, idx = R.points_in_boxes_cpu_lists(pts, boxes)
+    assert off.shape == (26,) and off[0] == 0 and off[-1] == idx.numel() == int(want.sum())
+    for i in range(25):
+        np.testing.assert_array_equal(idx[off[i]:off[i + 1]].numpy(), np.nonzero(want[i])[0])
+    o2, i2 = R.points_in_boxes_cpu_lists(pts.numpy(), boxes.numpy())          # numpy in -> numpy out
+    assert isinstance(o2, np.ndarray) and np.array_equal(o2, off.numpy()) and np.array_equal(i2, idx.numpy())
+    o3, i3 = R.points_in_boxes_cpu_lists(pts, boxes[:0])
+    assert o3.tolist() == [0] and i3.numel() == 0
+
+
 def test_v1_api_behaviour(cuda):
     pred, tgt = synth.head_pairs(10, 1)
     pred, tgt = pred.to(cuda), tgt.to(cuda)
