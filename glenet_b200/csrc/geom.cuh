@@ -155,6 +155,47 @@ __device__ __forceinline__ bool edge_intersection(float p0x, float p0y, float p1
     return true;
 }
 
+// The two halves of intersection() separately, for box_overlap's deferred intersection points: edge_crosses = the
+// three early-outs (check_rect_cross, s1*s2 > 0, s3*s4 > 0), edge_point = the point of a pair that passed.  Same
+// expressions as edge_intersection (which the unrolled clip keeps using).
+template <bool FMA>
+__device__ __forceinline__ bool edge_crosses(float p0x, float p0y, float p1x, float p1y,
+                                             float q0x, float q0y, float q1x, float q1y) {
+    const bool rc = fminf(p0x, p1x) <= fmaxf(q0x, q1x) && fminf(q0x, q1x) <= fmaxf(p0x, p1x) &&
+                    fminf(p0y, p1y) <= fmaxf(q0y, q1y) && fminf(q0y, q1y) <= fmaxf(p0y, p1y);
+    if (!rc) return false;
+    const float pdx = __fsub_rn(p1x, p0x), pdy = __fsub_rn(p1y, p0y);
+    const float qdx = __fsub_rn(q1x, q0x), qdy = __fsub_rn(q1y, q0y);
+    const float s1 = mul_sub<FMA>(__fsub_rn(q0x, p0x), pdy, pdx, __fsub_rn(q0y, p0y));
+    const float s2 = __fsub_rn(__fmul_rn(pdx, __fsub_rn(q1y, p0y)), __fmul_rn(pdy, __fsub_rn(q1x, p0x)));
+    if (!(__fmul_rn(s1, s2) > 0.f)) return false;
+    const float s3 = mul_sub<FMA>(__fsub_rn(p0x, q0x), qdy, __fsub_rn(p0y, q0y), qdx);
+    const float s4 = mul_sub<FMA>(qdx, __fsub_rn(p1y, q0y), qdy, __fsub_rn(p1x, q0x));
+    return __fmul_rn(s3, s4) > 0.f;
+}
+template <bool FMA>
+__device__ __forceinline__ float2 edge_point(float p0x, float p0y, float p1x, float p1y,
+                                             float q0x, float q0y, float q1x, float q1y) {
+    const float pdx = __fsub_rn(p1x, p0x), pdy = __fsub_rn(p1y, p0y);
+    const float s1 = mul_sub<FMA>(__fsub_rn(q0x, p0x), pdy, pdx, __fsub_rn(q0y, p0y));
+    const float m1 = __fmul_rn(pdx, __fsub_rn(q1y, p0y));
+    const float m2 = __fmul_rn(pdy, __fsub_rn(q1x, p0x));
+    const float s5 = __fsub_rn(m2, m1);
+    const float den = __fsub_rn(s5, s1);
+    float2 o;
+    if (fabsf(den) > 1e-8f) {
+        o.x = __fdiv_rn(mul_sub<FMA>(q0x, s5, q1x, s1), den);
+        o.y = __fdiv_rn(mul_sub<FMA>(q0y, s5, q1y, s1), den);
+    } else {
+        const float a0 = __fsub_rn(p0y, p1y), b0 = pdx, c0 = mul_sub<FMA>(p0x, p1y, p1x, p0y);
+        const float a1 = __fsub_rn(q0y, q1y), b1 = __fsub_rn(q1x, q0x), c1 = mul_sub<FMA>(q0x, q1y, q0y, q1x);
+        const float D = mul_sub<FMA>(b1, a0, b0, a1);
+        o.x = __fdiv_rn(mul_sub<FMA>(b0, c1, b1, c0), D);
+        o.y = __fdiv_rn(mul_sub<FMA>(c0, a1, a0, c1), D);
+    }
+    return o;
+}
+
 // check_in_box2d (:50-60) of point (px,py) against a prepared box.
 template <bool FMA>
 __device__ __forceinline__ bool corner_in_box(const float* __restrict__ b, float px, float py) {
@@ -315,16 +356,24 @@ template <bool FMA>
 __device__ __noinline__ float box_overlap(const float* __restrict__ a, const float* __restrict__ b) {
     float2 v[MAX_POLY];
     int cnt = 0;
+    // Pass 1: which of the 16 edge pairs cross (cheap early-outs).  Pass 2: the intersection points -- two IEEE
+    // divisions each -- only for the pairs that do, every lane walking ITS OWN hit list: the warp iterates
+    // max(hits per lane) ~ 4 times with most lanes busy instead of 16 times with ~5 of 32.
+    unsigned int hits = 0u;
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
         const float p0x = a[BP_PX + i], p0y = a[BP_PY + i], p1x = a[BP_PX + ((i + 1) & 3)], p1y = a[BP_PY + ((i + 1) & 3)];
 #pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-            float ox, oy;
-            if (edge_intersection<FMA>(p0x, p0y, p1x, p1y, b[BP_PX + j], b[BP_PY + j], b[BP_PX + ((j + 1) & 3)], b[BP_PY + ((j + 1) & 3)], ox, oy)) {
-                if (cnt < MAX_POLY) v[cnt++] = make_float2(ox, oy);
-            }
-        }
+        for (int j = 0; j < 4; ++j)
+            if (edge_crosses<FMA>(p0x, p0y, p1x, p1y, b[BP_PX + j], b[BP_PY + j], b[BP_PX + ((j + 1) & 3)], b[BP_PY + ((j + 1) & 3)]))
+                hits |= 1u << (i * 4 + j);
+    }
+#pragma unroll 1
+    while (hits) {   // ascending (i, j): the reference's order of discovery
+        const int e = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int i = e >> 2, j = e & 3, i1 = (i + 1) & 3, j1 = (j + 1) & 3;
+        v[cnt++] = edge_point<FMA>(a[BP_PX + i], a[BP_PY + i], a[BP_PX + i1], a[BP_PY + i1], b[BP_PX + j], b[BP_PY + j], b[BP_PX + j1], b[BP_PY + j1]);
     }
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
