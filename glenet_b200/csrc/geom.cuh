@@ -360,12 +360,15 @@ __device__ __noinline__ float box_overlap(const float* __restrict__ a, const flo
     // divisions each -- only for the pairs that do, every lane walking ITS OWN hit list: the warp iterates
     // max(hits per lane) ~ 4 times with most lanes busy instead of 16 times with ~5 of 32.
     unsigned int hits = 0u;
+    float bx[4], by[4];   // b's corners in registers: the j loop is unrolled, the i loop is not
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { bx[k] = b[BP_PX + k]; by[k] = b[BP_PY + k]; }
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
         const float p0x = a[BP_PX + i], p0y = a[BP_PY + i], p1x = a[BP_PX + ((i + 1) & 3)], p1y = a[BP_PY + ((i + 1) & 3)];
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (edge_crosses<FMA>(p0x, p0y, p1x, p1y, b[BP_PX + j], b[BP_PY + j], b[BP_PX + ((j + 1) & 3)], b[BP_PY + ((j + 1) & 3)]))
+            if (edge_crosses<FMA>(p0x, p0y, p1x, p1y, bx[j], by[j], bx[(j + 1) & 3], by[(j + 1) & 3]))
                 hits |= 1u << (i * 4 + j);
     }
 #pragma unroll 1
