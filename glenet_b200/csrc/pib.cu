@@ -126,7 +126,7 @@ __device__ __forceinline__ Footprint footprint(const float* __restrict__ r) {
 // -- O(rows) instead of O(cells) work -- and the row's bits are set word-wise.  Everything is padded
 // outwards (strip and span), so the bitmap is a superset of the cells any inside point can map to.
 __device__ __forceinline__ void raster_fine_rows(const Footprint& f, float gx0, float gy0, float finv_x, float finv_y,
-                                                 unsigned int* __restrict__ s_bits) {
+                                                 unsigned int* __restrict__ s_bits, int row_phase = 0, int row_stride = 1) {
     const int iy0 = max(0, min(PIB_FG - 1, (int)floorf((f.y0 - gy0) * finv_y)));
     const int iy1 = max(0, min(PIB_FG - 1, (int)floorf((f.y1 - gy0) * finv_y)));
     const float ch = 1.f / finv_y, cw = 1.f / finv_x;
@@ -141,7 +141,7 @@ __device__ __forceinline__ void raster_fine_rows(const Footprint& f, float gx0, 
         px[k] = lx * f.c + ly * f.s;
         py[k] = -lx * f.s + ly * f.c;
     }
-    for (int iy = iy0; iy <= iy1; ++iy) {
+    for (int iy = iy0 + row_phase; iy <= iy1; iy += row_stride) {
         const float ylo = gy0 + (float)iy * ch - f.cy - eps_y, yhi = gy0 + (float)(iy + 1) * ch - f.cy + eps_y;
         float xmin = FLT_MAX, xmax = -FLT_MAX;
 #pragma unroll
@@ -262,11 +262,18 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
         // One box per thread (N <= 512 boxes is one round): with a few hundred boxes per frame, box-level
         // parallelism beats splitting one box's ~15 rows / ~15 cells over a warp (measured both ways).
         //   pass 0: fine occupancy bitmap + coarse counts      pass 1: coarse fill (after the scan)
+        // With few boxes the CTA has threads to spare: `parts` threads share one box in pass 0 -- part 0 counts the
+        // coarse cells, the others rasterise interleaved fine rows -- laid out so that a warp holds one part only.
+        const int parts = N * 4 <= PIB_BUILD_THREADS ? 4 : (N * 2 <= PIB_BUILD_THREADS ? 2 : 1);
         for (int pass = 0; pass < 2; ++pass) {
-            for (int k = tid; k < N; k += PIB_BUILD_THREADS) {
+            const int items = pass == 0 ? N * parts : N;
+            for (int it = tid; it < items; it += PIB_BUILD_THREADS) {
+                const int part = it / N, k = it - part * N;
                 const Footprint fp = footprint(rec + (size_t)k * 8);
                 if (fp.never) continue;
-                if (pass == 0) raster_fine_rows(fp, bx0, by0, finv_x, finv_y, s_bits);
+                if (pass == 0 && (parts == 1 || part > 0))
+                    raster_fine_rows(fp, bx0, by0, finv_x, finv_y, s_bits, parts == 1 ? 0 : part - 1, parts == 1 ? 1 : parts - 1);
+                if (part > 0) continue;
                 for_cells<PIB_G>(fp, bx0, by0, inv_x, inv_y, [&](int cell) {
                     const unsigned int pos = atomicAdd(&cnt[cell], 1u);
                     if (pass == 1) list[pos] = (unsigned int)k;

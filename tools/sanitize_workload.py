@@ -1,0 +1,25 @@
+"""Small run of every kernel for compute-sanitizer (memcheck / racecheck):  compute-sanitizer --tool memcheck python tools/sanitize_workload.py"""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from glenet_b200 import iou3d_nms_utils as I, iou3d_utils as I1, roiaware_pool3d_utils as R, synth
+dev = torch.device("cuda:0")
+a = synth.anchors_kitti3()[:3000].to(dev)
+g = torch.stack([synth.kitti_boxes(37, 5 + f) for f in range(3)]).to(dev)
+I.boxes_iou_bev_frames(a, g); I.boxes_iou3d_gpu_frames(a, g); I.boxes_overlap_bev(a, g[0])
+g4 = torch.stack([synth.kitti_boxes(100, 9 + f) for f in range(2)]).to(dev)
+I.boxes_iou_bev_frames(a, g4)                                   # bulk-copy zero fill path
+p, s = synth.proposals(700, 6, 1)
+p, s = p.to(dev), s.to(dev)
+I.boxes_iou_bev(p, p)                                           # dense tiles: queue overflow rounds, carried clip passes
+I.boxes_iou_frames_sparse(a, g4); I.iou_max_overlaps_frames(a, g4)
+I.nms_gpu(p, s, 0.7); I.nms_normal_gpu(p, s, 0.7); I.nms_gpu_batch(torch.stack([p, p]), torch.stack([s, s]), 0.5)
+I.boxes_iou3d_aligned(p[:600], p[:20], 30)
+pr, tg = synth.head_pairs(500, 0)
+I1.boxes_aligned_iou3d_gpu(pr.to(dev), tg.to(dev), need_bev=True)
+bx = torch.stack([synth.waymo_boxes(40, 30 + f) for f in range(2)])
+pts = torch.stack([synth.points(9000, bx[f], synth.WAYMO_RANGE, 0.1, seed=f) for f in range(2)])
+R.points_in_boxes_gpu(pts.to(dev), bx.to(dev)); R.points_in_boxes_gpu(pts.to(dev), bx[:, :5].contiguous().to(dev))
+R.points_in_boxes_cpu(pts[0], bx[0]); I.boxes_bev_iou_cpu(p[:50].cpu(), p[:40].cpu())
+torch.cuda.synchronize()
+print("sanitize workload done")
