@@ -201,6 +201,7 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
     __shared__ unsigned int s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = blockIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the query grid be scheduled behind this one
     const float* boxes = boxes_all + (size_t)f * N * 7;
     float* rec = ws.rec + (size_t)f * N * 8;
     unsigned int* start = ws.start + (size_t)f * (PIB_CELLS + 1);
@@ -365,6 +366,7 @@ __global__ void __launch_bounds__(PIB_THREADS, 4)
 pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace ws, int* __restrict__ out_all,
                  int chunks_per_frame, int total_chunks) {
     extern __shared__ __align__(16) unsigned char pib_smem[];
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the build kernel (previous in the stream) has completed and flushed
     float4* s_q = reinterpret_cast<float4*>(pib_smem);                                        // [warps][PIB_WQ] {x, y, z, index}
     unsigned int* s_cells = reinterpret_cast<unsigned int*>(s_q + (PIB_THREADS / 32) * PIB_WQ); // [PIB_CELLS] id0:16 | id1:16
     unsigned int* s_bits = s_cells + PIB_CELLS;                                               // [PIB_FWORDS]
@@ -638,7 +640,20 @@ int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int 
     }
     const long resident = 4L * 148;   // persistent: 4 CTAs per SM
     const unsigned grid = (unsigned)(total < resident ? total : resident);
-    pib_query_kernel<<<grid, PIB_THREADS, smem, st>>>(pts, N, M, w, out, chunks, (int)total);
+    // programmatic dependent launch: the query grid is scheduled while the build kernel drains and waits
+    // (griddepcontrol.wait) before it touches the workspace -- hides the launch gap between the two kernels
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PIB_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const int total_i = (int)total;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, pib_query_kernel, pts, N, M, w, out, chunks, total_i);
+    if (le != cudaSuccess) {
+        snprintf(last_error_buf(), 512, "%s: launch failed: %s", what, cudaGetErrorString(le));
+        return -(int)le;
+    }
     return check_launch(what);
 }
 
