@@ -32,15 +32,31 @@
 
 namespace glenet {
 
-constexpr int IOU_THREADS = 256;           // 7 "chain" warps (cull, prepare, clip) + 1 fill warp
+// CTA shape (overridable for tuning experiments: -DGLENET_IOU_THREADS=128 -DGLENET_IOU_TR_MAX=192 -DGLENET_IOU_CTAS=7 ...)
+#ifndef GLENET_IOU_THREADS
+#define GLENET_IOU_THREADS 256
+#endif
+#ifndef GLENET_IOU_TR_MAX
+#define GLENET_IOU_TR_MAX 384
+#endif
+#ifndef GLENET_IOU_CTAS
+#define GLENET_IOU_CTAS 4
+#endif
+#ifndef GLENET_IOU_QCAP
+#define GLENET_IOU_QCAP 512
+#endif
+#ifndef GLENET_IOU_ZBYTES
+#define GLENET_IOU_ZBYTES 4096
+#endif
+constexpr int IOU_THREADS = GLENET_IOU_THREADS;   // (threads / 32 - 1) "chain" warps (cull, prepare, clip) + 1 fill warp
 constexpr int IOU_CHAIN = IOU_THREADS - 32;
-constexpr int IOU_TR_MAX = 384;            // tile rows (boxes_a)
-constexpr int IOU_TC_MAX = 128;            // tile cols (boxes_b)
+constexpr int IOU_TR_MAX = GLENET_IOU_TR_MAX;     // tile rows (boxes_a)
+constexpr int IOU_TC_MAX = 128;                   // tile cols (boxes_b)
 constexpr int IOU_RPT = (IOU_TR_MAX + IOU_CHAIN - 1) / IOU_CHAIN;   // rows per thread in the circle tests of tall tiles
-constexpr int IOU_QCAP = 512;              // circle-test survivors per drain
+constexpr int IOU_QCAP = GLENET_IOU_QCAP;         // circle-test survivors per drain
 constexpr int IOU_Q2CAP = IOU_QCAP + IOU_CHAIN;   // + the partial clip pass carried over from the previous drain
-constexpr int IOU_CTAS_PER_SM = 4;         // register budget the kernel is compiled for (5 was measured: spills, no gain)
-constexpr int IOU_ZBYTES = 4096;           // block of zeros in shared memory = largest bulk store of the zero fill
+constexpr int IOU_CTAS_PER_SM = GLENET_IOU_CTAS;  // register budget the kernel is compiled for
+constexpr int IOU_ZBYTES = GLENET_IOU_ZBYTES;     // block of zeros in shared memory = largest bulk store of the zero fill
 constexpr int BPS = BP_STRIDE_BEV;         // BoxPre stride in shared memory (the z terms of 3D IoU are read per clipped pair)
 
 enum { MODE_OVERLAP = 0, MODE_IOU_BEV = 1, MODE_IOU3D = 2 };
