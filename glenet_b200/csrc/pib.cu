@@ -483,18 +483,16 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
                 for (int i = 0; i < 4; ++i) if (i < nvalid) out[p0 + i] = -1;
             }
             if (__any_sync(0xffffffffu, hot != 0)) {
-                const int nh = __popc(hot);
-                int pre = nh;
+                // append the hot points: one ballot per point slot gives every lane its queue position (the order of the
+                // queue is irrelevant) -- cheaper than a 5-step prefix sum followed by per-lane sequential writes
+                const unsigned int lt = (1u << lane) - 1u;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
-                const int total = __shfl_sync(0xffffffffu, pre, 31);
-                if (hot) {
-                    int qb = qn + pre - nh;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if ((hot >> i) & 1u) wq[qb++] = make_float4(cur.x[i], cur.y[i], cur.z[i], __int_as_float(p0 + i));
+                for (int i = 0; i < 4; ++i) {
+                    const bool hi = (hot >> i) & 1u;
+                    const unsigned int m = __ballot_sync(0xffffffffu, hi);
+                    if (hi) wq[qn + __popc(m & lt)] = make_float4(cur.x[i], cur.y[i], cur.z[i], __int_as_float(p0 + i));
+                    qn += __popc(m);
                 }
-                qn += total;
                 __syncwarp();   // queue visible; also orders the provisional -1 stores before the results
                 // drain whole warps only; the remainder (< 32 entries) waits for the next batch
                 int head = 0;

@@ -29,10 +29,14 @@ def main():
             hdr = r; continue
         if hdr is None or cur_fn is None or ksub not in cur_fn or not r[0].strip().isdigit():
             continue
-        si, ii, ti = hdr.index('# Samples'), hdr.index('Instructions Executed'), hdr.index('Thread Instructions Executed')
+        shift = len(r) - len(hdr)   # source text with quotes / commas is not escaped by ncu: count columns from the right
+        si, ii, ti = (hdr.index(c) + shift for c in ('# Samples', 'Instructions Executed', 'Thread Instructions Executed'))
         key = (cur_file, int(r[0]))
         a = agg.setdefault(key, [0, 0, 0, r[1].strip()[:90]])
-        a[0] += int(r[si]); a[1] += int(r[ii]); a[2] += int(r[ti])
+        try:
+            a[0] += int(r[si]); a[1] += int(r[ii]); a[2] += int(r[ti])
+        except ValueError:
+            pass
     ts, tin = sum(a[0] for a in agg.values()), sum(a[1] for a in agg.values())
     print(f"kernel *{ksub}*: {len(agg)} source lines, {ts} stall samples, {tin} warp instructions")
     byfile = collections.Counter()
