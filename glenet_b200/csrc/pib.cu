@@ -446,9 +446,13 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
             if (k1 == 0xfffe) {          // > 2 candidates: walk the whole list
                 const unsigned long long c64 = __ldg(cells64 + ci);
                 const unsigned int s0 = (unsigned int)(c64 >> 32) & 0xffffffu, n = (unsigned int)(c64 >> 56);
-                for (unsigned int i = 0; i < n; ++i) {
-                    const int k = (int)__ldg(list + s0 + i);
-                    if (k < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k * 8)) res = k;
+                for (unsigned int i = 0; i < n; i += 4) {   // four independent list loads per round trip to L2
+                    int kk[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) kk[u] = (i + u < n) ? (int)__ldg(list + s0 + i + u) : 0x7fffffff;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (kk[u] < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)kk[u] * 8)) res = kk[u];
                 }
             } else {
                 if (k0 != 0xffff && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k0 * 8)) res = k0;
