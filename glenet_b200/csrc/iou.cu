@@ -108,6 +108,9 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigne
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// ---- single-instruction warp reductions of sm_100a (CREDUX.F32); NaN inputs are ignored like fminf / fmaxf do
+__device__ __forceinline__ float warp_min(float v) { float r; asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float warp_max(float v) { float r; asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
 // ---- named barriers: 1 = the chain warps among themselves, 2 = "the tile's zero fill has landed" (fill warp arrives, chain warps wait)
 __device__ __forceinline__ void chain_sync() { asm volatile("bar.sync 1, %0;" :: "n"(IOU_CHAIN) : "memory"); }
 __device__ __forceinline__ void fill_arrive() { asm volatile("bar.arrive 2, %0;" :: "n"(IOU_THREADS) : "memory"); }
@@ -227,7 +230,8 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
     int nclip = last ? n2 : n2 / IOU_CHAIN * IOU_CHAIN;
 #ifdef GLENET_PHASE_TIMING
     if (g_dbg_flags & 1) nclip = 0;
-    if (tid == 0 && blockIdx.x < 4096) { g_cta_log[blockIdx.x * 4 + 2] += n; g_cta_log[blockIdx.x * 4 + 3] += nclip; }
+    { const unsigned int cl = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+      if (tid == 0 && cl < 4096) { g_cta_log[cl * 4 + 2] += n; g_cta_log[cl * 4 + 3] += nclip; } }
     if (tid == 0) { atomicAdd(&g_phase_cycles[8], (unsigned long long)n); atomicAdd(&g_phase_cycles[9], (unsigned long long)nclip);
                     atomicAdd(&g_phase_cycles[10], (unsigned long long)nprep); atomicAdd(&g_phase_cycles[11], 1ull); }
 #endif
@@ -245,7 +249,7 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
     else chain_sync();
     PHASE_MARK(6);
     if (fr.row_key) {
-        const int frame = blockIdx.x / fr.tiles_per_frame;
+        const int frame = blockIdx.z;
         for (int q = tid; q < nclip; q += IOU_CHAIN) {
             const unsigned int e = sm.queue2[q];
             const float v = sm.qres[q];
@@ -297,10 +301,10 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     IouSmem& sm = *reinterpret_cast<IouSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // frames: independent (na, nb) problems of one launch, e.g. the GT sets of a batch against the same anchors
-    const int frame = blockIdx.x / fr.tiles_per_frame, tile = blockIdx.x - frame * fr.tiles_per_frame;
+    // grid = (column tiles, row tiles, frames): no integer division to find the tile
+    const int frame = blockIdx.z, tile_r = blockIdx.y, tile_c = blockIdx.x;
     A += (size_t)frame * fr.stride_a; B += (size_t)frame * fr.stride_b; out += (size_t)frame * fr.stride_out;
     const long long frame_base = (long long)frame * na * nb;
-    const int tile_r = tile / col_tiles, tile_c = tile - tile_r * col_tiles;
     // Programmatic dependent launch: this grid may have been made resident while the previous kernel of the
     // stream was still draining; everything below reads or writes global memory, so wait for it here.  The
     // launch latency and the CTA scheduling of back-to-back calls is what gets hidden.
@@ -309,7 +313,8 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     const int tr = min(TR, na - r0), tc = min(TC, nb - c0);
     PHASE_INIT;
 #ifdef GLENET_PHASE_TIMING
-    if (tid == 0 && blockIdx.x < 4096) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_cta_log[blockIdx.x * 4] = t; g_cta_log[blockIdx.x * 4 + 2] = 0; g_cta_log[blockIdx.x * 4 + 3] = 0; }
+    const unsigned int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (tid == 0 && cta_lin < 4096) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_cta_log[cta_lin * 4] = t; g_cta_log[cta_lin * 4 + 2] = 0; g_cta_log[cta_lin * 4 + 3] = 0; }
 #endif
 
     // ---- stage the tile's boxes: centre + cull radius for the circle tests, the raw box in the first slots of
@@ -337,12 +342,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
             maxr = (rad != rad) ? CUDART_INF_F : fmaxf(maxr, rad);   // a NaN radius must not be dropped by fmaxf
         } else { sm.ccx[k] = cx; sm.ccy[k] = cy; sm.crad[k] = rad; sm.cflag[k] = 0; }
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        minx = fminf(minx, __shfl_xor_sync(0xffffffffu, minx, o)); maxx = fmaxf(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
-        miny = fminf(miny, __shfl_xor_sync(0xffffffffu, miny, o)); maxy = fmaxf(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
-        maxr = fmaxf(maxr, __shfl_xor_sync(0xffffffffu, maxr, o));
-    }
+    minx = warp_min(minx); maxx = warp_max(maxx); miny = warp_min(miny); maxy = warp_max(maxy); maxr = warp_max(maxr);
     if (lane == 0) { sm.red[warp][0] = minx; sm.red[warp][1] = maxx; sm.red[warp][2] = miny; sm.red[warp][3] = maxy; sm.red[warp][4] = maxr; }
     if (tid == 0) { sm.qcount = 0; sm.q2count = 0; sm.nact = 0; sm.nprep = 0; }
     __syncthreads();
@@ -459,7 +459,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     PHASE_MARK(2);
     drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, sm.qcount, true, fill_pending, fr, frame_base);
 #ifdef GLENET_PHASE_TIMING
-    if (tid == 0 && blockIdx.x < 4096) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_cta_log[blockIdx.x * 4 + 1] = t; }
+    if (tid == 0 && cta_lin < 4096) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_cta_log[cta_lin * 4 + 1] = t; }
 #endif
 }
 
@@ -566,7 +566,8 @@ static int launch_iou(const float* A, const float* trigA, int na, const float* B
     fr.row_key = row_key; fr.col_key = col_key;
     fr.sp_idx = sp_idx; fr.sp_val = sp_val; fr.sp_count = sp_count; fr.sp_cap = sp_cap;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(tiles * frames)); cfg.blockDim = dim3(IOU_THREADS);
+    if (row_tiles > 65535 || frames > 65535) return fail(GLENET_EINVAL, "%s: more than 65535 row tiles or frames", what);
+    cfg.gridDim = dim3((unsigned)col_tiles, (unsigned)row_tiles, (unsigned)frames); cfg.blockDim = dim3(IOU_THREADS);
     cfg.dynamicSmemBytes = sizeof(IouSmem); cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
