@@ -222,7 +222,9 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
         float tx, ty, tz;
         box_thresholds<false>(b[3], b[4], b[5], tx, ty, tz);
         float* r = rec + (size_t)k * 8;
-        r[0] = b[0]; r[1] = b[1]; r[2] = b[2]; r[3] = cosf(-rz); r[4] = sinf(-rz); r[5] = tx; r[6] = ty; r[7] = tz;
+        float sn, cs;
+        sincosf(-rz, &sn, &cs);   // == cosf(-rz), sinf(-rz) bit for bit (tools/cuda/trig_symmetry.cu)
+        r[0] = b[0]; r[1] = b[1]; r[2] = b[2]; r[3] = cs; r[4] = sn; r[5] = tx; r[6] = ty; r[7] = tz;
         const Footprint fp = footprint(r);
         if (fp.never) continue;
         if (fp.bad) { bad = true; continue; }
@@ -537,7 +539,9 @@ pib_direct_kernel(const float* __restrict__ boxes_all, const float* __restrict__
         float tx, ty, tz;
         box_thresholds<false>(b[3], b[4], b[5], tx, ty, tz);
         float* r = s_rec + tid * 8;
-        r[0] = b[0]; r[1] = b[1]; r[2] = b[2]; r[3] = cosf(-b[6]); r[4] = sinf(-b[6]); r[5] = tx; r[6] = ty; r[7] = tz;
+        float sn, cs;
+        sincosf(-b[6], &sn, &cs);
+        r[0] = b[0]; r[1] = b[1]; r[2] = b[2]; r[3] = cs; r[4] = sn; r[5] = tx; r[6] = ty; r[7] = tz;
     }
     const int p_begin = chunk * PIB_DIRECT_PTS, p_end = min(M, p_begin + PIB_DIRECT_PTS);
     const bool vec = ((((uintptr_t)pts) & 15) == 0) && ((((uintptr_t)out) & 15) == 0);
