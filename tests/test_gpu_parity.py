@@ -258,6 +258,42 @@ def test_nms_threshold_corner_cases_vs_reference(cuda, ref_so):
         assert torch.equal(I.nms_gpu(dup, sc, thr)[0], ref_so.nms_gpu(dup, sc, thr)[0]), thr
 
 
+def _fuzz_boxes(n, g, centre_scale, dim_lo, dim_hi, heading_scale):
+    c = (torch.rand((n, 3), generator=g) - 0.5) * 2 * centre_scale
+    c[:, 2] *= 0.02
+    d = torch.exp(torch.rand((n, 3), generator=g) * (math.log(dim_hi) - math.log(dim_lo)) + math.log(dim_lo))
+    h = (torch.rand((n, 1), generator=g) - 0.5) * 2 * heading_scale
+    return torch.cat([c, d, h], dim=1).float().contiguous()
+
+
+@pytest.mark.parametrize("centre_scale,dim_lo,dim_hi,heading_scale", [
+    (30.0, 0.2, 12.0, 3.2),        # ordinary scenes, boxes from pedestrians to trucks, dense
+    (3.0, 1e-3, 5.0, 50.0),        # tiny and ordinary boxes piled up, headings far outside (-pi, pi]
+    (2e4, 5.0, 4e3, 1e4),          # far coordinates, building-sized boxes, huge headings
+    (0.5, 1e-4, 1e-2, 7.0),        # everything below the 0.01 m margin of check_in_box2d
+])
+def test_fuzz_extreme_scales_vs_reference_kernels(cuda, ref_so, centre_scale, dim_lo, dim_hi, heading_scale):
+    """The conservative culls (circle, separating axis, IoU upper bound) must stay exact far away from KITTI-like scales."""
+    g = torch.Generator().manual_seed(int(centre_scale * 7 + dim_hi))
+    a = _fuzz_boxes(1500, g, centre_scale, dim_lo, dim_hi, heading_scale).to(cuda)
+    b = _fuzz_boxes(333, g, centre_scale, dim_lo, dim_hi, heading_scale).to(cuda)
+    for mine, theirs in ((I.boxes_iou_bev, ref_so.boxes_iou_bev), (I.boxes_overlap_bev, ref_so.boxes_overlap_bev), (I.boxes_iou3d_gpu, ref_so.boxes_iou3d_gpu)):
+        got, want = mine(a, b), theirs(a, b)
+        assert torch.equal(got == 0, want == 0)
+        scale = float(want.abs().max().clamp(min=1.0))
+        assert float((got - want).abs().max()) <= IOU_TOL * scale
+        assert float((got == want).float().mean()) > 0.999
+    scores = torch.rand(1500, generator=g).to(cuda)
+    for thr in (0.7, 0.25, 0.01):
+        assert torch.equal(I.nms_gpu(a, scores, thr)[0], ref_so.nms_gpu(a, scores, thr)[0])
+        assert torch.equal(I.nms_normal_gpu(a, scores, thr)[0], ref_so.nms_normal_gpu(a, scores, thr)[0])
+    pts = ((torch.rand((1, 50000, 3), generator=g) - 0.5) * 2 * centre_scale)
+    pts[..., 2] *= 0.02
+    pts[0, :333] = b[:, :3].cpu()                                  # every box centre is a query point
+    pts = pts.to(cuda)
+    assert torch.equal(R.points_in_boxes_gpu(pts, b[None]), ref_so.points_in_boxes_gpu(pts, b[None]))
+
+
 def test_dense_matrix_many_queue_drains(cuda):
     """Dense tiles (thousands of clipped pairs per tile => several queue drains per CTA): the result must be
     reproducible run after run and equal to a row-slab evaluation, which tiles the matrix differently
