@@ -319,6 +319,22 @@ def side_runs(torch, I, R, synth, dev, hbm_gbs):
                                   "pairs_per_s_list": npairs / (ms_sp * 1e-3), "ms_list": ms_sp,
                                   "pairs_per_s_max_overlaps": npairs / (ms_mx * 1e-3), "ms_max_overlaps": ms_mx,
                                   "note": "row/col max+argmax (F,N)+(F,M) as consumed by axis_aligned_target_assigner.py:141-165; no 4 B/pair write"}
+    # the same reductions end to end: pinned host boxes in, pinned host vectors out (what the assigner would receive)
+    a_h = synth.anchors_kitti3().pin_memory()
+    g_h = torch.stack([synth.kitti_boxes(100, 101 + f) for f in range(16)]).pin_memory()
+    res_h = [torch.empty((16, a_h.shape[0]), dtype=torch.float32).pin_memory(), torch.empty((16, a_h.shape[0]), dtype=torch.int64).pin_memory(),
+             torch.empty((16, 100), dtype=torch.float32).pin_memory(), torch.empty((16, 100), dtype=torch.int64).pin_memory()]
+
+    def e2e_max():
+        res = I.iou_max_overlaps_frames(a_h.to(dev, non_blocking=True), g_h.to(dev, non_blocking=True), "bev")
+        for dst, src in zip(res_h, res):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms_e2e_mx = ev(e2e_max, 5)
+    out["anchor_sweep_sparse"]["e2e_max_overlaps"] = {"pairs_per_s": npairs / (ms_e2e_mx * 1e-3), "ms": ms_e2e_mx,
+                                                     "h2d_bytes": a_h.numel() * 4 + g_h.numel() * 4, "d2h_bytes": sum(t.numel() * t.element_size() for t in res_h),
+                                                     "note": "matrix-free API end to end; NOT the headline e2e (which returns the dense matrix like the reference call)"}
     del anchors, gts16
     # pcdet/ops/iou3d boxes_aligned_iou3d_gpu: predictions vs regression targets of the positive anchors (IoU-aware heads)
     from glenet_b200 import iou3d_utils as I1
