@@ -9,9 +9,6 @@ build() { # name threads tr_max ctas qcap zbytes
        iou.cu iou3d_v1.cu nms.cu pib.cu host.cpp -o ../lib/libglenet_geom_shape_$1.so 2>&1 | grep -v "warning\|nms.cu\|\^\|detected\|^$\|Remark" || true
   echo "built $1"
 }
-build base 256 384 4 512 4096 &
-build t128 128 192 7 256 2048 &
-build t192 192 288 5 384 4096 &
-build t160 160 224 6 320 2048 &
-build t512 512 512 2 1024 4096 &
+VARIANTS=${VARIANTS:-"base:256:384:4:512:4096 t128:128:192:7:256:2048 t192:192:288:5:384:4096 t160:160:224:6:320:2048 t512:512:512:2:1024:4096"}
+for v in $VARIANTS; do IFS=: read n t r c q z <<< "$v"; build $n $t $r $c $q $z & done
 wait
