@@ -74,7 +74,7 @@ __device__ int g_dbg_flags;   // bit 0: skip the clip pass, bit 1: skip the zero
 
 struct IouFrames {
     long long stride_a, stride_b, stride_out;   // per-frame strides in floats
-    int tiles_per_frame, na;
+    int na;
     // sparse output (sp_count != nullptr): instead of the dense matrix, the non-zero elements are appended as
     // (flat index frame * na * nb + row * nb + col, value) in no particular order; sp_count keeps counting past sp_cap
     long long* sp_idx; float* sp_val; unsigned long long* sp_count; long long sp_cap;
@@ -562,7 +562,7 @@ static int launch_iou(const float* A, const float* trigA, int na, const float* B
     const long long tiles = (long long)row_tiles * col_tiles;
     if (tiles * frames > 0x7fffffffLL) return fail(GLENET_EINVAL, "%s: too many tiles", what);
     IouFrames fr;
-    fr.stride_a = stride_a; fr.stride_b = stride_b; fr.stride_out = (sp_count || row_key) ? 0 : stride_out; fr.tiles_per_frame = (int)tiles; fr.na = na;
+    fr.stride_a = stride_a; fr.stride_b = stride_b; fr.stride_out = (sp_count || row_key) ? 0 : stride_out; fr.na = na;
     fr.row_key = row_key; fr.col_key = col_key;
     fr.sp_idx = sp_idx; fr.sp_val = sp_val; fr.sp_count = sp_count; fr.sp_cap = sp_cap;
     cudaLaunchConfig_t cfg = {};
