@@ -466,7 +466,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
 // out[i] = f(a[i], b[i / group]) -- every pair is "heavy" by construction (CVAE samples vs their GT)
 constexpr int ALIGNED_THREADS = 128;
 template <int MODE, bool FMA>
-__global__ void __launch_bounds__(ALIGNED_THREADS)
+__global__ void __launch_bounds__(ALIGNED_THREADS, 8)
 iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int group,
                    float* __restrict__ out) {
     const int tid = threadIdx.x;

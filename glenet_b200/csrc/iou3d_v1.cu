@@ -24,7 +24,7 @@ __device__ __forceinline__ void v1_to_bev(const float* __restrict__ box, int wi,
 }
 
 template <bool FMA>
-__global__ void __launch_bounds__(V1_THREADS)
+__global__ void __launch_bounds__(V1_THREADS, 8)
 iou3d_v1_aligned_kernel(const float* __restrict__ A, const float* __restrict__ B, int n, int wi, int li, int hi,
                         float* __restrict__ iou3d, float* __restrict__ iou_bev, float* __restrict__ overlap_bev) {
     const int i = blockIdx.x * V1_THREADS + threadIdx.x;
@@ -52,7 +52,7 @@ iou3d_v1_aligned_kernel(const float* __restrict__ A, const float* __restrict__ B
 
 // (N, 5) [x1, y1, x2, y2, angle] x (N, 5) -> overlap; the native call of the reference (boxes_aligned_overlap_bev_gpu)
 template <bool FMA>
-__global__ void __launch_bounds__(V1_THREADS)
+__global__ void __launch_bounds__(V1_THREADS, 8)
 iou3d_v1_aligned_overlap_bev_kernel(const float* __restrict__ A, const float* __restrict__ B, const float4* __restrict__ trigA,
                                     const float4* __restrict__ trigB, int n, float* __restrict__ out) {
     const int i = blockIdx.x * V1_THREADS + threadIdx.x;
