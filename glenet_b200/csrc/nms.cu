@@ -64,7 +64,7 @@ __device__ __forceinline__ void tri_decode(int t, int nblk, int& rb, int& cb) {
 }
 
 template <bool NORMAL>
-__global__ void __launch_bounds__(NMS_THREADS)
+__global__ void __launch_bounds__(NMS_THREADS, 5)
 nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsigned long long* __restrict__ mask_all,
                 int col_blocks, int tiles_per_frame) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
