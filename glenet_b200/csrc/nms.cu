@@ -21,6 +21,10 @@
 
 namespace glenet {
 
+#ifdef GLENET_PHASE_TIMING   // developer instrumentation of the sweep (tools/nms_sweep_timing.py)
+__device__ unsigned long long g_sweep_cycles[4];   // [0] warp 0 busy, [1] whole loop, [2] job warps busy (warp 1), [3] steps
+#endif
+
 constexpr int NMS_THREADS = 256;
 constexpr int NMS_TILE = 64;
 constexpr int SWEEP_THREADS = 512;
@@ -224,8 +228,15 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask_all, int n, int col
     int num_keep = 0;   // tracked by warp 0
     __syncthreads();
 
+#ifdef GLENET_PHASE_TIMING
+    const long long t_loop0 = clock64();
+    long long busy = 0;
+#endif
     for (int c = 0; c < col_blocks; ++c) {
         const int rows = min(NMS_TILE, n - c * NMS_TILE);
+#ifdef GLENET_PHASE_TIMING
+        const long long t_step0 = clock64();
+#endif
         if (warp == 0) {
             // resolve the diagonal tile: one iteration per KEPT box (find-first-set over the unsuppressed bits)
             const int r_lo = c * NMS_TILE + lane, r_hi = r_lo + 32;
@@ -235,23 +246,36 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask_all, int n, int col
             const unsigned long long u_lo = (has_next && lane < rows) ? (PRE ? s_sup[r_lo] : mask[(size_t)r_lo * col_blocks + c + 1]) : 0ull;
             const unsigned long long u_hi = (has_next && lane + 32 < rows) ? (PRE ? s_sup[r_hi] : mask[(size_t)r_hi * col_blocks + c + 1]) : 0ull;
             const unsigned long long valid = (rows == NMS_TILE) ? ~0ull : ((1ull << rows) - 1ull);
-            unsigned long long w = remv[c];
-            unsigned long long cand = ~w & valid, kept = 0ull;
-            while (cand) {
-                const int i = __ffsll((long long)cand) - 1;
-                kept |= 1ull << i;
-                const unsigned long long lo = __shfl_sync(0xffffffffu, d_lo, i & 31), hi = __shfl_sync(0xffffffffu, d_hi, i & 31);
-                w |= (i < 32) ? lo : hi;
-                cand = ~w & valid & ~((2ull << i) - 1ull);
+            // The serial chain (one iteration per kept box) runs on 32-bit halves: rows 0..31 first -- a kept row ORs both
+            // halves of its diagonal word into the suppression word --, then rows 32..63, whose words only have bits in the
+            // upper half (the mask holds j > i only).
+            const unsigned long long w0 = remv[c];
+            unsigned int wl = (unsigned int)w0, wh = (unsigned int)(w0 >> 32);
+            const unsigned int vl = (unsigned int)valid, vh = (unsigned int)(valid >> 32);
+            const unsigned int dll = (unsigned int)d_lo, dlh = (unsigned int)(d_lo >> 32), dhh = (unsigned int)(d_hi >> 32);
+            unsigned int kl = 0u, kh = 0u;
+            for (unsigned int cand = ~wl & vl; cand;) {
+                const int i = __ffs((int)cand) - 1;
+                kl |= 1u << i;
+                wl |= __shfl_sync(0xffffffffu, dll, i);
+                wh |= __shfl_sync(0xffffffffu, dlh, i);
+                cand = ~wl & vl & ~((2u << i) - 1u);
             }
+            for (unsigned int cand = ~wh & vh; cand;) {
+                const int i = __ffs((int)cand) - 1;
+                kh |= 1u << i;
+                wh |= __shfl_sync(0xffffffffu, dhh, i);
+                cand = ~wh & vh & ~((2u << i) - 1u);
+            }
+            const unsigned long long kept = (unsigned long long)kl | ((unsigned long long)kh << 32);
             // kept rows of this chunk -> next chunk's suppression word, straight from registers
-            unsigned long long nx = (((kept >> lane) & 1ull) ? u_lo : 0ull) | (((kept >> (lane + 32)) & 1ull) ? u_hi : 0ull);
-#pragma unroll
-            for (int o = 16; o; o >>= 1) nx |= __shfl_xor_sync(0xffffffffu, nx, o);
+            const unsigned long long nxl = (((kept >> lane) & 1ull) ? u_lo : 0ull) | (((kept >> (lane + 32)) & 1ull) ? u_hi : 0ull);
+            const unsigned long long nx = (unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned int)nxl) |
+                                          ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned int)(nxl >> 32)) << 32);
             if (lane == 0 && has_next && nx) atomicOr(&remv[c + 1], nx);
             // emit kept indices in ascending order; remember the rows for the lagging propagation
             const int slot = c & 1;
-            for (int i = lane; i < NMS_TILE; i += 32) {
+            if (kept) for (int i = lane; i < NMS_TILE; i += 32) {
                 if ((kept >> i) & 1ull) {
                     const int pos = __popcll(kept & ((1ull << i) - 1ull));
                     keep[num_keep + pos] = (long long)(c * NMS_TILE + i);
@@ -271,8 +295,17 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask_all, int n, int col
                 if (m) atomicOr(&remv[j], m);
             }
         }
+#ifdef GLENET_PHASE_TIMING
+        busy += clock64() - t_step0;
+#endif
         __syncthreads();
     }
+#ifdef GLENET_PHASE_TIMING
+    if (frame == 0 && lane == 0) {
+        if (warp == 0) { atomicAdd(&g_sweep_cycles[0], (unsigned long long)busy); atomicAdd(&g_sweep_cycles[1], (unsigned long long)(clock64() - t_loop0)); atomicAdd(&g_sweep_cycles[3], (unsigned long long)col_blocks); }
+        if (warp == 1) atomicAdd(&g_sweep_cycles[2], (unsigned long long)busy);
+    }
+#endif
     if (tid == 0) num_keep_all[frame] = num_keep;
 }
 
@@ -336,6 +369,16 @@ size_t glenet_nms_workspace_bytes(int frames, int n) {
     const size_t col_blocks = ((size_t)n + NMS_TILE - 1) / NMS_TILE;
     return align_up((size_t)frames * n * col_blocks * sizeof(unsigned long long), 16);
 }
+
+#ifdef GLENET_PHASE_TIMING
+int glenet_debug_sweep_cycles(unsigned long long* host_out4) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host_out4, g_sweep_cycles, sizeof(unsigned long long) * 4);
+    unsigned long long z[4] = {0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_sweep_cycles, z, sizeof(z));
+    return 0;
+}
+#endif
 
 int glenet_nms_gpu(const float* boxes, int frames, int n, float thresh, int64_t* keep, int32_t* num_keep, void* ws,
                    size_t ws_bytes, glenet_stream_t s) {
