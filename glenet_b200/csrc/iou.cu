@@ -296,7 +296,7 @@ template <int MODE, bool FMA>
 __global__ void __launch_bounds__(IOU_THREADS, IOU_CTAS_PER_SM)
 iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int nb,
                 const float4* __restrict__ trigA, const float4* __restrict__ trigB,
-                float* __restrict__ out, int TR, int TC, int col_tiles, IouFrames fr) {
+                float* __restrict__ out, int TR, int TC, IouFrames fr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     IouSmem& sm = *reinterpret_cast<IouSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -574,7 +574,7 @@ static int launch_iou(const float* A, const float* trigA, int na, const float* B
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, A, na, B, nb, reinterpret_cast<const float4*>(trigA),
-                                       reinterpret_cast<const float4*>(trigB), out, TR, TC, col_tiles, fr);
+                                       reinterpret_cast<const float4*>(trigB), out, TR, TC, fr);
     if (e != cudaSuccess) {
         snprintf(last_error_buf(), 512, "%s: launch failed: %s", what, cudaGetErrorString(e));
         return -(int)e;

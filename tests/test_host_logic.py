@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from glenet_b200 import iou3d_nms_utils as I
+from glenet_b200 import iou3d_utils as I1
 from glenet_b200 import roiaware_pool3d_utils as R
 from glenet_b200 import shim, synth
 
@@ -38,6 +39,34 @@ def test_wrappers_reject_bad_input_before_any_launch():
         R.points_in_boxes_cpu(np.zeros((4, 2), np.float32), np.zeros((2, 7), np.float32))
     with pytest.raises(AssertionError):
         R.points_in_boxes_gpu(torch.zeros(1, 4, 3), torch.zeros(2, 2, 7))
+
+
+def test_additive_apis_reject_bad_input_before_any_launch():
+    a = synth.kitti_boxes(6, 0)
+    g = torch.stack([synth.kitti_boxes(4, 1), synth.kitti_boxes(4, 2)])
+    for fn in (I.boxes_iou_bev_frames, I.boxes_iou3d_gpu_frames, I.boxes_overlap_bev_frames, I.iou_max_overlaps_frames, I.boxes_iou_frames_sparse):
+        with pytest.raises(RuntimeError):
+            fn(a, g)                           # CPU tensors: raise, never compute on the host
+    pred, tgt = synth.head_pairs(5, 0)
+    with pytest.raises(NotImplementedError):
+        I1.boxes_aligned_iou3d_gpu(pred, tgt, rect=True)        # as the reference (iou3d_utils.py:356-357)
+    with pytest.raises(AssertionError):
+        I1.boxes_aligned_iou3d_gpu(pred, tgt[:3])
+    with pytest.raises(RuntimeError):
+        I1.boxes_aligned_iou3d_gpu(pred, tgt)
+    with pytest.raises(ValueError):
+        I1.boxes_aligned_iou3d_gpu(pred, tgt, box_mode="xyz")   # str.index, as in the reference
+    with pytest.raises(AssertionError):
+        I1.boxes_aligned_overlap_bev_cpu(pred[:, :5].cuda() if torch.cuda.is_available() else pred[:, :4], tgt[:, :5])
+    bev = I1.boxes3d_to_bev_torch(pred, "lwh")
+    assert bev.shape == (5, 5) and torch.equal(bev[:, 4], pred[:, 6])
+    assert torch.equal(bev[:, 2] - bev[:, 0], (pred[:, 0] + pred[:, 4] / 2) - (pred[:, 0] - pred[:, 4] / 2))   # 'lwh': w = column 4
+
+
+def test_shim_registers_the_aligned_iou_module():
+    shim.install()
+    from pcdet.ops.iou3d.iou3d_utils import boxes_aligned_iou3d_gpu
+    assert boxes_aligned_iou3d_gpu is I1.boxes_aligned_iou3d_gpu
 
 
 def test_empty_inputs_do_not_need_a_gpu():
