@@ -28,6 +28,8 @@
 #include "geom.cuh"
 #include "../../include/glenet_geom.h"
 #include <float.h>
+#include <stdlib.h>
+#include <string.h>
 #include <math_constants.h>
 
 namespace glenet {
@@ -44,6 +46,9 @@ namespace glenet {
 #endif
 #ifndef GLENET_IOU_QCAP
 #define GLENET_IOU_QCAP 512
+#endif
+#ifndef GLENET_IOU_WARP_MIN_CTAS
+#define GLENET_IOU_WARP_MIN_CTAS 2000000000   // warp-autonomous kernel off by default until validated on the GPU (GLENET_IOU_KERNEL=warp forces it)
 #endif
 #ifndef GLENET_IOU_ZBYTES
 #define GLENET_IOU_ZBYTES 4096
@@ -463,6 +468,8 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
 #endif
 }
 
+#include "iou_warp.cuh"
+
 // out[i] = f(a[i], b[i / group]) -- every pair is "heavy" by construction (CVAE samples vs their GT)
 constexpr int ALIGNED_THREADS = 128;
 template <int MODE, bool FMA>
@@ -550,6 +557,48 @@ static int launch_iou(const float* A, const float* trigA, int na, const float* B
     if (na == 0 || nb == 0 || frames == 0) return GLENET_OK;
     if (!A || !B || (!out && !sp_count && !row_key)) return fail(GLENET_EINVAL, "%s: null pointer", what);
     if (!FMA && (!trigA || !trigB)) return fail(GLENET_EINVAL, "%s: CPU dialect needs host-evaluated trig tables", what);
+    // Large sweeps go to the warp-autonomous kernel (iou_warp.cuh); everything else to the tile kernel, whose
+    // small tiles spread a small problem over more SMs.  GLENET_IOU_KERNEL=tile|warp overrides (tests, tuning).
+    {
+        static int forced = -1;   // 0 = auto, 1 = tile, 2 = warp
+        if (forced < 0) {
+            const char* e = getenv("GLENET_IOU_KERNEL");
+            forced = !e ? 0 : (!strcmp(e, "tile") ? 1 : (!strcmp(e, "warp") ? 2 : 0));
+        }
+        const long long wk_ctas = (long long)((na + WK_TR - 1) / WK_TR) * ((nb + IOU_TC_MAX - 1) / IOU_TC_MAX) * frames;
+        const bool use_warp = forced == 2 || (forced == 0 && wk_ctas >= GLENET_IOU_WARP_MIN_CTAS);
+        if (use_warp) {
+            auto wk = iou_warp_kernel<MODE, FMA>;
+            static bool wk_ready = false;
+            if (!wk_ready) {
+                int rc = set_smem(wk, sizeof(WkSmem), what, true);
+                if (rc) return rc;
+                wk_ready = true;
+            }
+            const int col_tiles = (nb + IOU_TC_MAX - 1) / IOU_TC_MAX;
+            const int TC = ((nb + col_tiles - 1) / col_tiles + 3) / 4 * 4;
+            const int ct = (nb + TC - 1) / TC, rt = (na + WK_TR - 1) / WK_TR;
+            if (rt > 65535 || frames > 65535) return fail(GLENET_EINVAL, "%s: more than 65535 row tiles or frames", what);
+            IouFrames fr;
+            fr.stride_a = stride_a; fr.stride_b = stride_b; fr.stride_out = (sp_count || row_key) ? 0 : stride_out; fr.na = na;
+            fr.sp_idx = sp_idx; fr.sp_val = sp_val; fr.sp_count = sp_count; fr.sp_cap = sp_cap;
+            fr.row_key = row_key; fr.col_key = col_key;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)ct, (unsigned)rt, (unsigned)frames); cfg.blockDim = dim3(WK_THREADS);
+            cfg.dynamicSmemBytes = sizeof(WkSmem); cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, wk, A, na, B, nb, reinterpret_cast<const float4*>(trigA),
+                                               reinterpret_cast<const float4*>(trigB), out, TC, fr);
+            if (e != cudaSuccess) {
+                snprintf(last_error_buf(), 512, "%s: launch failed: %s", what, cudaGetErrorString(e));
+                return -(int)e;
+            }
+            return check_launch(what);
+        }
+    }
     auto kernel = iou_tile_kernel<MODE, FMA>;
     static int resident = 0;   // per template instantiation
     if (!resident) {
