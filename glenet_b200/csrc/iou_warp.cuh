@@ -11,9 +11,10 @@
 #pragma once
 
 constexpr int WK_THREADS = 256;
-constexpr int WK_WARPS = WK_THREADS / 32;
-constexpr int WK_RW = 64;                   // rows per warp (two per lane)
-constexpr int WK_TR = WK_WARPS * WK_RW;     // rows per CTA
+constexpr int WK_WARPS = WK_THREADS / 32 - 1;   // worker warps; the last warp of the CTA only feeds the zero fill
+constexpr int WK_WORKERS = WK_WARPS * 32;
+constexpr int WK_RW = 64;                   // rows per worker warp (two per lane)
+constexpr int WK_TR = WK_WARPS * WK_RW;     // rows per CTA (448)
 constexpr int WK_Q = 128;                   // circle-test survivors per warp and drain
 constexpr int WK_CCH = 32;                  // active columns per chunk = column BoxPre records resident at a time
 constexpr int WK_CTAS_PER_SM = 4;
@@ -31,8 +32,15 @@ struct __align__(128) WkSmem {
     float red[WK_WARPS][5];
     unsigned char act[IOU_TC_MAX];
     int nact;
+    int fill_done;                          // set by the fill warp once the tile's zeros have landed
     WkWarp w[WK_WARPS];
 };
+
+__device__ __forceinline__ void wk_sync() { asm volatile("bar.sync 1, %0;" :: "n"(WK_WORKERS) : "memory"); }   // worker warps only
+__device__ __forceinline__ void wk_wait_fill(WkSmem& sm) {
+    while (*reinterpret_cast<volatile int*>(&sm.fill_done) == 0) __nanosleep(200);
+    __threadfence_block();
+}
 
 // Everything a warp needs to drain its queue; kept in one struct so that the drain is a plain function.
 struct WkCtx {
@@ -98,9 +106,8 @@ __device__ __forceinline__ void wk_drain(WkSmem& sm, WkWarp& ws, const WkCtx& cx
                                            cx.B + (size_t)(cx.c0 + sm.act[e & 127u]) * 7);
         }
     }
-    if (fill_pending) {   // this warp's slice of the zero fill has landed (each lane waits for the bulk copies it issued)
-        bulk_wait_all();
-        fence_proxy_async();
+    if (fill_pending) {   // the tile's zero fill has landed (flag set by the fill warp)
+        wk_wait_fill(sm);
         fill_pending = false;
     }
     __syncwarp();
@@ -149,9 +156,45 @@ iou_warp_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     WkWarp& ws = sm.w[warp];
     const int wr0 = warp * WK_RW, wrows = max(0, min(WK_RW, tr - wr0));
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    const bool no_matrix = iou_no_matrix(fr);
+    if (tid == 0) { sm.fill_done = 0; sm.nact = 0; }
+    __syncthreads();   // the only CTA-wide barrier: the flag is clear before anybody can set or poll it
 
-    // ---- prologue: columns (centre + cull radius) by the CTA, each warp its own rows (raw box into the record slots)
-    for (int c = tid; c < tc; c += WK_THREADS) {
+    if (warp == WK_WARPS) {   // ---- the fill warp: zero block, bulk copies for the whole tile, completion flag
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (no_matrix) return;
+        const bool vec = ((nb & 3) == 0) && ((c0 & 3) == 0) && ((tc & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
+        float* ot = out + (size_t)r0 * nb + c0;
+        if (vec) {
+#pragma unroll
+            for (int k = 0; k < IOU_ZBYTES / 16 / 32; ++k) sm.zero[k * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            fence_proxy_async();
+            __syncwarp();
+            if (tc == nb) {
+                const size_t total = (size_t)tr * nb * sizeof(float);
+                char* dst = reinterpret_cast<char*>(ot);
+                for (size_t off = (size_t)lane * IOU_ZBYTES; off < total; off += (size_t)32 * IOU_ZBYTES) {
+                    const size_t left = total - off;
+                    bulk_store(dst + off, sm.zero, (unsigned int)(left < (size_t)IOU_ZBYTES ? left : (size_t)IOU_ZBYTES));
+                }
+            } else {
+                for (int r = lane; r < tr; r += 32) bulk_store(ot + (size_t)r * nb, sm.zero, (unsigned int)tc * sizeof(float));
+            }
+            bulk_commit();
+            bulk_wait_all();
+            fence_proxy_async();
+        } else {
+            const int npairs = tr * tc;
+            for (int p = lane; p < npairs; p += 32) { const int r = p / tc; ot[(size_t)r * nb + (p - r * tc)] = 0.f; }
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile int*>(&sm.fill_done) = 1;
+        return;
+    }
+
+    // ---- prologue (worker warps): columns (centre + cull radius) together, each warp its own rows (raw box into the record slots)
+    for (int c = tid; c < tc; c += WK_WORKERS) {
         const float* box = B + (size_t)(c0 + c) * 7;
         const float cx = box[0], cy = box[1], dx = box[3], dy = box[4];
         float rad = cull_radius(cx, cy, dx, dy);
@@ -181,42 +224,8 @@ iou_warp_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     }
     minx = warp_min(minx); maxx = warp_max(maxx); miny = warp_min(miny); maxy = warp_max(maxy); maxr = warp_max(maxr);
     if (lane == 0) { sm.red[warp][0] = minx; sm.red[warp][1] = maxx; sm.red[warp][2] = miny; sm.red[warp][3] = maxy; sm.red[warp][4] = maxr; }
-    const bool no_matrix = iou_no_matrix(fr);
-    const bool vec = ((nb & 3) == 0) && ((c0 & 3) == 0) && ((tc & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
-    if (warp == 0) {
-        if (lane == 0) sm.nact = 0;
-        if (vec && !no_matrix) {
-#pragma unroll
-            for (int k = 0; k < IOU_ZBYTES / 16 / 32; ++k) sm.zero[k * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-            fence_proxy_async();
-        }
-    }
-    __syncthreads();
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
-    // ---- this warp's slice of the zero fill: asynchronous bulk copies (or plain stores when the tile is not 16-byte aligned)
-    bool fill_pending = false;
-    if (!no_matrix && wrows > 0) {
-        float* ot = out + (size_t)(r0 + wr0) * nb + c0;
-        if (vec) {
-            if (tc == nb) {
-                const size_t total = (size_t)wrows * nb * sizeof(float);
-                char* dst = reinterpret_cast<char*>(ot);
-                for (size_t off = (size_t)lane * IOU_ZBYTES; off < total; off += (size_t)32 * IOU_ZBYTES) {
-                    const size_t left = total - off;
-                    bulk_store(dst + off, sm.zero, (unsigned int)(left < (size_t)IOU_ZBYTES ? left : (size_t)IOU_ZBYTES));
-                }
-            } else {
-                for (int r = lane; r < wrows; r += 32) bulk_store(ot + (size_t)r * nb, sm.zero, (unsigned int)tc * sizeof(float));
-            }
-            bulk_commit();
-            fill_pending = true;
-        } else {
-            const int npairs = wrows * tc;
-            for (int p = lane; p < npairs; p += 32) { const int r = p / tc; ot[(size_t)r * nb + (p - r * tc)] = 0.f; }
-            __syncwarp();
-        }
-    }
+    wk_sync();
+    bool fill_pending = !no_matrix;
 
     // ---- active columns of the tile (against the bounding box of all its rows)
     minx = sm.red[0][0]; maxx = sm.red[0][1]; miny = sm.red[0][2]; maxy = sm.red[0][3]; maxr = sm.red[0][4];
@@ -225,14 +234,14 @@ iou_warp_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
         minx = fminf(minx, sm.red[w][0]); maxx = fmaxf(maxx, sm.red[w][1]);
         miny = fminf(miny, sm.red[w][2]); maxy = fmaxf(maxy, sm.red[w][3]); maxr = fmaxf(maxr, sm.red[w][4]);
     }
-    for (int c = tid; c < tc; c += WK_THREADS) {
+    for (int c = tid; c < tc; c += WK_WORKERS) {
         const float cx = sm.ccx[c], cy = sm.ccy[c];
         const float ddx = fmaxf(fmaxf(minx - cx, cx - maxx), 0.f), ddy = fmaxf(fmaxf(miny - cy, cy - maxy), 0.f);
         const float rr = maxr + sm.crad[c];
         const bool far = (cx == cx) && (cy == cy) && (ddx * ddx + ddy * ddy > rr * rr);
         if (!far) sm.act[atomicAdd(&sm.nact, 1)] = (unsigned char)c;
     }
-    __syncthreads();
+    wk_sync();
     const int nact = sm.nact;
 
     WkCtx cx;
@@ -243,7 +252,7 @@ iou_warp_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     const unsigned int lt = (1u << lane) - 1u;
     for (int cb = 0; cb < nact; cb += WK_CCH) {
         const int ncol = min(WK_CCH, nact - cb);
-        if (cb > 0) __syncthreads();   // every warp has clipped what referred to the previous chunk's column records
+        if (cb > 0) wk_sync();   // every warp has clipped what referred to the previous chunk's column records
         if (tid < ncol) {
             const int c = sm.act[cb + tid];
             const float* box = B + (size_t)(c0 + c) * 7;
@@ -253,7 +262,7 @@ iou_warp_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
             const float4 t4 = trigB ? trigB[c0 + c] : device_trig(raw[6]);
             box_prepare<FMA, false>(raw, t4, sm.cpre + tid * BPS);
         }
-        __syncthreads();
+        wk_sync();
         if (wrows > 0) {
             cx.cb = cb;
             unsigned int m[2] = {0u, 0u};
@@ -297,9 +306,6 @@ iou_warp_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
             }
         }
     }
-    if (wrows > 0) {
-        if (qn) wk_drain<MODE, FMA>(sm, ws, cx, fr, qn, need, done, fill_pending, lane);
-        if (fill_pending) bulk_wait_all();   // the block of zeros must outlive the copies that read it
-    }
+    if (wrows > 0 && qn) wk_drain<MODE, FMA>(sm, ws, cx, fr, qn, need, done, fill_pending, lane);
     (void)lt;
 }
