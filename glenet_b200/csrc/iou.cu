@@ -457,12 +457,17 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
                 }
             }
             chain_sync();
-            if (total <= IOU_QCAP) break;
-            drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, IOU_QCAP, false, fill_pending, fr, frame_base);
+            // ONE call site for the drain (it is ~2000 instructions; a second inlined copy costs instruction-cache space):
+            // a full queue is drained and the round repeated; after the last chunk's round the tile's final drain runs.
+            const bool overflow = total > IOU_QCAP;
+            const bool final_drain = !overflow && cb >= nact;
+            if (overflow || final_drain)
+                drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, overflow ? IOU_QCAP : total, final_drain, fill_pending, fr, frame_base);
+            if (!overflow) break;
         }
     }
     PHASE_MARK(2);
-    drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, sm.qcount, true, fill_pending, fr, frame_base);
+    // (a tile without active columns has nothing to write: its chain warps leave, the fill warp finishes on its own)
 #ifdef GLENET_PHASE_TIMING
     if (tid == 0 && cta_lin < 4096) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_cta_log[cta_lin * 4 + 1] = t; }
 #endif
