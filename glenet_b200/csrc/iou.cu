@@ -64,6 +64,7 @@ constexpr int IOU_CTAS_PER_SM = GLENET_IOU_CTAS;  // register budget the kernel 
 constexpr int IOU_ZBYTES = GLENET_IOU_ZBYTES;     // block of zeros in shared memory = largest bulk store of the zero fill
 constexpr int BPS = BP_STRIDE_BEV;         // BoxPre stride in shared memory (the z terms of 3D IoU are read per clipped pair)
 
+enum { OUT_DENSE = 0, OUT_REDUCED = 1 };   // kernel output: the (na, nb) matrix, or the coordinate list / row-column maxima
 enum { MODE_OVERLAP = 0, MODE_IOU_BEV = 1, MODE_IOU3D = 2 };
 
 #ifdef GLENET_PHASE_TIMING   // developer instrumentation: accumulated clock64() per phase, thread 0 of every CTA
@@ -171,7 +172,7 @@ __device__ __forceinline__ void zero_fill_tile(IouSmem& sm, float* __restrict__ 
 //   3. queue2 is clipped one pair per thread -- in full passes only unless this is the tile's last drain; the
 //      remainder stays in queue2 for the next drain -- and the results are parked in shared memory,
 //   4. once the fill warp has signalled that the tile's zeros have landed (first drain only) they are written.
-template <int MODE, bool FMA>
+template <int MODE, bool FMA, int OUT>
 __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict__ A, const float* __restrict__ B,
                                             const float4* __restrict__ trigA, const float4* __restrict__ trigB,
                                             int r0, int c0, int tr, int tc, int nb, float* __restrict__ out, int n, bool last, bool& fill_pending,
@@ -200,7 +201,7 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
 #pragma unroll
         for (int f = 0; f < 7; ++f) raw[f] = rec[f];
         const float4* trig = is_row ? trigA : trigB;
-        const float4 t4 = trig ? trig[is_row ? r0 + k : c0 + k] : device_trig(raw[6]);
+        const float4 t4 = FMA ? device_trig(raw[6]) : trig[is_row ? r0 + k : c0 + k];   // CPU dialect: host-libm table (launcher checks it is there)
         box_prepare<FMA, false>(raw, t4, rec);
         *(is_row ? &sm.rflag[k] : &sm.cflag[k]) = 2;
     }
@@ -250,10 +251,10 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
     unsigned short carry = 0;
     const int rem = n2 - nclip;   // < IOU_CHAIN unless the clip pass is disabled for a timing experiment
     if (tid < rem) carry = sm.queue2[nclip + tid];
-    if (fill_pending && (nclip > 0 || last)) { fill_wait(); fill_pending = false; }   // also a barrier among the chain warps
+    if (OUT == OUT_DENSE && fill_pending && (nclip > 0 || last)) { fill_wait(); fill_pending = false; }   // also a barrier among the chain warps
     else chain_sync();
     PHASE_MARK(6);
-    if (fr.row_key) {
+    if (OUT == OUT_REDUCED && fr.row_key) {
         const int frame = blockIdx.z;
         for (int q = tid; q < nclip; q += IOU_CHAIN) {
             const unsigned int e = sm.queue2[q];
@@ -266,7 +267,7 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
             }
         }
     }
-    if (fr.sp_count) {
+    if (OUT == OUT_REDUCED && fr.sp_count) {
         for (int q0 = 0; q0 < nclip; q0 += IOU_CHAIN) {
             const int q = q0 + tid;
             unsigned int e = 0;
@@ -284,7 +285,8 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
                 }
             }
         }
-    } else if (!fr.row_key) {
+    }
+    if (OUT == OUT_DENSE) {
         for (int q = tid; q < nclip; q += IOU_CHAIN) {
             const unsigned int e = sm.queue2[q];
             out[(size_t)(r0 + (e >> 7)) * nb + (c0 + (e & 127))] = sm.qres[q];
@@ -297,7 +299,7 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
     PHASE_MARK(5);
 }
 
-template <int MODE, bool FMA>
+template <int MODE, bool FMA, int OUT>
 __global__ void __launch_bounds__(IOU_THREADS, IOU_CTAS_PER_SM)
 iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int nb,
                 const float4* __restrict__ trigA, const float4* __restrict__ trigB,
@@ -354,8 +356,9 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel of the stream may be scheduled as SMs free up
 
     if (warp == IOU_CHAIN / 32) {   // ---- the fill warp
+        if (OUT != OUT_DENSE) return;   // no matrix, nothing to fill, and nobody waits for this warp
         const bool vec = ((nb & 3) == 0) && ((c0 & 3) == 0) && ((tc & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
-        if (vec && !iou_no_matrix(fr)) {   // the block of zeros the bulk copies read: written and fenced by the warp that issues them
+        if (vec) {   // the block of zeros the bulk copies read: written and fenced by the warp that issues them
 #pragma unroll
             for (int k = 0; k < IOU_ZBYTES / 16 / 32; ++k) sm.zero[k * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
             fence_proxy_async();   // generic-proxy writes -> async-proxy reads
@@ -364,7 +367,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
 #ifdef GLENET_PHASE_TIMING
         if (!(g_dbg_flags & 2))
 #endif
-        if (!iou_no_matrix(fr)) zero_fill_tile(sm, out + (size_t)r0 * nb + c0, tr, tc, nb, vec, lane);
+        zero_fill_tile(sm, out + (size_t)r0 * nb + c0, tr, tc, nb, vec, lane);
         __threadfence_block();
         fill_arrive();
         return;
@@ -462,7 +465,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
             const bool overflow = total > IOU_QCAP;
             const bool final_drain = !overflow && cb >= nact;
             if (overflow || final_drain)
-                drain_queue<MODE, FMA>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, overflow ? IOU_QCAP : total, final_drain, fill_pending, fr, frame_base);
+                drain_queue<MODE, FMA, OUT>(sm, A, B, trigA, trigB, r0, c0, tr, tc, nb, out, overflow ? IOU_QCAP : total, final_drain, fill_pending, fr, frame_base);
             if (!overflow) break;
         }
     }
@@ -541,6 +544,43 @@ static void pick_tiles(int na, int nb, int frames, int resident, int& TR, int& T
     row_tiles = (na + TR - 1) / TR;
 }
 
+template <int MODE, bool FMA, int OUT>
+static int launch_tile(const float* A, const float* trigA, int na, const float* B, const float* trigB, int nb, float* out, cudaStream_t stream,
+                       const char* what, int frames, long long stride_a, long long stride_b, long long stride_out,
+                       long long* sp_idx, float* sp_val, unsigned long long* sp_count, long long sp_cap,
+                       unsigned long long* row_key, unsigned long long* col_key) {
+    auto kernel = iou_tile_kernel<MODE, FMA, OUT>;
+    static int resident = 0;   // per template instantiation
+    if (!resident) {
+        int rc = set_smem(kernel, sizeof(IouSmem), what, true);
+        if (rc) return rc;
+        resident = resident_ctas(kernel);
+    }
+    int TR, TC, row_tiles, col_tiles;
+    pick_tiles(na, nb, frames, resident, TR, TC, row_tiles, col_tiles);
+    const long long tiles = (long long)row_tiles * col_tiles;
+    if (tiles * frames > 0x7fffffffLL) return fail(GLENET_EINVAL, "%s: too many tiles", what);
+    IouFrames fr;
+    fr.stride_a = stride_a; fr.stride_b = stride_b; fr.stride_out = (sp_count || row_key) ? 0 : stride_out; fr.na = na;
+    fr.row_key = row_key; fr.col_key = col_key;
+    fr.sp_idx = sp_idx; fr.sp_val = sp_val; fr.sp_count = sp_count; fr.sp_cap = sp_cap;
+    cudaLaunchConfig_t cfg = {};
+    if (row_tiles > 65535 || frames > 65535) return fail(GLENET_EINVAL, "%s: more than 65535 row tiles or frames", what);
+    cfg.gridDim = dim3((unsigned)col_tiles, (unsigned)row_tiles, (unsigned)frames); cfg.blockDim = dim3(IOU_THREADS);
+    cfg.dynamicSmemBytes = sizeof(IouSmem); cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, A, na, B, nb, reinterpret_cast<const float4*>(trigA),
+                                       reinterpret_cast<const float4*>(trigB), out, TR, TC, fr);
+    if (e != cudaSuccess) {
+        snprintf(last_error_buf(), 512, "%s: launch failed: %s", what, cudaGetErrorString(e));
+        return -(int)e;
+    }
+    return check_launch(what);
+}
+
 template <int MODE, bool FMA>
 static int launch_iou(const float* A, const float* trigA, int na, const float* B, const float* trigB, int nb,
                       float* out, cudaStream_t stream, const char* what,
@@ -604,36 +644,9 @@ static int launch_iou(const float* A, const float* trigA, int na, const float* B
             return check_launch(what);
         }
     }
-    auto kernel = iou_tile_kernel<MODE, FMA>;
-    static int resident = 0;   // per template instantiation
-    if (!resident) {
-        int rc = set_smem(kernel, sizeof(IouSmem), what, true);
-        if (rc) return rc;
-        resident = resident_ctas(kernel);
-    }
-    int TR, TC, row_tiles, col_tiles;
-    pick_tiles(na, nb, frames, resident, TR, TC, row_tiles, col_tiles);
-    const long long tiles = (long long)row_tiles * col_tiles;
-    if (tiles * frames > 0x7fffffffLL) return fail(GLENET_EINVAL, "%s: too many tiles", what);
-    IouFrames fr;
-    fr.stride_a = stride_a; fr.stride_b = stride_b; fr.stride_out = (sp_count || row_key) ? 0 : stride_out; fr.na = na;
-    fr.row_key = row_key; fr.col_key = col_key;
-    fr.sp_idx = sp_idx; fr.sp_val = sp_val; fr.sp_count = sp_count; fr.sp_cap = sp_cap;
-    cudaLaunchConfig_t cfg = {};
-    if (row_tiles > 65535 || frames > 65535) return fail(GLENET_EINVAL, "%s: more than 65535 row tiles or frames", what);
-    cfg.gridDim = dim3((unsigned)col_tiles, (unsigned)row_tiles, (unsigned)frames); cfg.blockDim = dim3(IOU_THREADS);
-    cfg.dynamicSmemBytes = sizeof(IouSmem); cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, A, na, B, nb, reinterpret_cast<const float4*>(trigA),
-                                       reinterpret_cast<const float4*>(trigB), out, TR, TC, fr);
-    if (e != cudaSuccess) {
-        snprintf(last_error_buf(), 512, "%s: launch failed: %s", what, cudaGetErrorString(e));
-        return -(int)e;
-    }
-    return check_launch(what);
+    if (sp_count || row_key)
+        return launch_tile<MODE, FMA, OUT_REDUCED>(A, trigA, na, B, trigB, nb, out, stream, what, frames, stride_a, stride_b, stride_out, sp_idx, sp_val, sp_count, sp_cap, row_key, col_key);
+    return launch_tile<MODE, FMA, OUT_DENSE>(A, trigA, na, B, trigB, nb, out, stream, what, frames, stride_a, stride_b, stride_out, sp_idx, sp_val, sp_count, sp_cap, row_key, col_key);
 }
 
 }  // namespace glenet
@@ -651,7 +664,7 @@ int glenet_debug_iou_cta_log(unsigned long long* host_out, int n) {
     return (int)cudaMemcpyFromSymbol(host_out, g_cta_log, sizeof(unsigned long long) * 4 * n);
 }
 int glenet_debug_iou_resident_ctas() {
-    auto kernel = iou_tile_kernel<MODE_IOU_BEV, true>;
+    auto kernel = iou_tile_kernel<MODE_IOU_BEV, true, OUT_DENSE>;
     set_smem(kernel, sizeof(IouSmem), "debug", true);
     return resident_ctas(kernel);
 }
