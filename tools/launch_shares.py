@@ -13,8 +13,8 @@ for r in rows:
     a = agg.setdefault(name[:80], [0, 0.0])
     a[0] += 1
     a[1] += us
-    if "iou_tile_kernel<1, 1>" in name:
-        grids[grid].append(us)
+    if "iou_tile_kernel<1, 1" in name:
+        grids[(name.split("(")[0].replace("void glenet::", ""), grid)].append(us)
 total = sum(a[1] for a in agg.values())
 with open(sys.argv[2], "w") as f:
     w = csv.writer(f)
@@ -22,4 +22,4 @@ with open(sys.argv[2], "w") as f:
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         w.writerow([k, n, round(t, 1), round(t / total, 3)])
 for g, v in grids.items():
-    print(f"iou_tile_kernel<1,1> grid {g}: {len(v)} launches, mean {sum(v) / len(v):.1f} us")
+    print(f"{g[0]} grid {g[1]}: {len(v)} launches, mean {sum(v) / len(v):.1f} us")
