@@ -294,6 +294,36 @@ def test_fuzz_extreme_scales_vs_reference_kernels(cuda, ref_so, centre_scale, di
     assert torch.equal(R.points_in_boxes_gpu(pts, b[None]), ref_so.points_in_boxes_gpu(pts, b[None]))
 
 
+def test_experimental_warp_kernel_matches_tile_kernel(cuda, tmp_path):
+    """csrc/iou_warp.cuh (off by default) must stay bit-identical to the tile kernel: run a few shapes
+    in a subprocess with GLENET_IOU_KERNEL=warp and compare with this process's (tile kernel) results."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "from glenet_b200 import iou3d_nms_utils as I, synth\n"
+        "dev = torch.device('cuda:0'); out = {}\n"
+        "a = synth.anchors_kitti3()[:20000].to(dev)\n"
+        "g = torch.stack([synth.kitti_boxes(100, 60 + f) for f in range(3)]).to(dev)\n"
+        "out['frames'] = I.boxes_iou_bev_frames(a, g).cpu(); out['f3d'] = I.boxes_iou3d_gpu_frames(a, g[:, :37].contiguous()).cpu()\n"
+        "p = synth.proposals(900, 8, 2)[0].to(dev)\n"
+        "out['dense'] = I.boxes_iou_bev(p, p).cpu(); out['wide'] = I.boxes_overlap_bev(p[:300], synth.kitti_boxes(301, 4).to(dev)).cpu()\n"
+        "out['max'] = torch.stack([t.float() for t in I.iou_max_overlaps_frames(a, g)[:2]]).cpu()\n"
+        "torch.save(out, %r)\n"
+    )
+    res = {}
+    for kernel in ("tile", "warp"):
+        path = str(tmp_path / (kernel + ".pt"))
+        env = dict(os.environ, GLENET_IOU_KERNEL=kernel)
+        subprocess.run([sys.executable, "-c", script % (root, path)], check=True, env=env, timeout=300)
+        res[kernel] = torch.load(path)
+    for k in res["tile"]:
+        assert torch.equal(res["tile"][k], res["warp"][k]), k
+    assert float(res["tile"]["frames"].max()) > 0.5
+
+
 def test_dense_matrix_many_queue_drains(cuda):
     """Dense tiles (thousands of clipped pairs per tile => several queue drains per CTA): the result must be
     reproducible run after run and equal to a row-slab evaluation, which tiles the matrix differently
