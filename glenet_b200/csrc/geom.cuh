@@ -103,6 +103,14 @@ __device__ __forceinline__ float4 device_trig(float heading) {
     return t;
 }
 
+// The same four values from ONE sincosf (bit-identical for every float, see above).  Used by the thread-per-pair kernels,
+// which evaluate the trig of two boxes per pair and gain ~10 % from it.
+__device__ __forceinline__ float4 device_trig_fused(float heading) {
+    float sn, cs;
+    sincosf(heading, &sn, &cs);
+    return make_float4(cs, sn, cs, -sn);
+}
+
 // Conservative cull radius: circumscribed circle of the box grown by the 0.01 margin
 // (a corner may be admitted up to MARGIN outside, in both axes) plus slack for the
 // rounding of absolute corner coordinates.  Two boxes whose centres are farther apart

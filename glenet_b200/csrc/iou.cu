@@ -494,8 +494,8 @@ iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict_
     const float ddx = ba[0] - bb[0], ddy = ba[1] - bb[1];
     const float rr = cull_radius(ba) + cull_radius(bb);
     if (!(ddx * ddx + ddy * ddy > rr * rr)) {
-        box_prepare<FMA>(ba, device_trig(ba[6]), a);
-        box_prepare<FMA>(bb, device_trig(bb[6]), b);
+        box_prepare<FMA>(ba, device_trig_fused(ba[6]), a);
+        box_prepare<FMA>(bb, device_trig_fused(bb[6]), b);
         const float ov = box_overlap_unrolled<FMA>(a, b);
         out_v = (MODE == MODE_OVERLAP) ? ov : (MODE == MODE_IOU_BEV) ? iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) : iou3d_from_overlap(a, b, ov);
     }

@@ -34,9 +34,9 @@ iou3d_v1_aligned_kernel(const float* __restrict__ A, const float* __restrict__ B
     float a[BP_STRIDE], b[BP_STRIDE];   // statically indexed => registers
     float x1, y1, x2, y2;
     v1_to_bev(ba, wi, li, x1, y1, x2, y2);
-    box_prepare_v1<FMA>(x1, y1, x2, y2, device_trig(ba[6]), a);
+    box_prepare_v1<FMA>(x1, y1, x2, y2, device_trig_fused(ba[6]), a);
     v1_to_bev(bb, wi, li, x1, y1, x2, y2);
-    box_prepare_v1<FMA>(x1, y1, x2, y2, device_trig(bb[6]), b);
+    box_prepare_v1<FMA>(x1, y1, x2, y2, device_trig_fused(bb[6]), b);
     const float ov = box_overlap_unrolled<FMA, true>(a, b);
     if (overlap_bev) overlap_bev[i] = ov;
     if (iou_bev) {   // iou3d_utils.py:351-353
@@ -60,8 +60,8 @@ iou3d_v1_aligned_overlap_bev_kernel(const float* __restrict__ A, const float* __
     const float* ba = A + (size_t)i * 5;
     const float* bb = B + (size_t)i * 5;
     float a[BP_STRIDE], b[BP_STRIDE];
-    box_prepare_v1<FMA>(ba[0], ba[1], ba[2], ba[3], trigA ? trigA[i] : device_trig(ba[4]), a);
-    box_prepare_v1<FMA>(bb[0], bb[1], bb[2], bb[3], trigB ? trigB[i] : device_trig(bb[4]), b);
+    box_prepare_v1<FMA>(ba[0], ba[1], ba[2], ba[3], trigA ? trigA[i] : device_trig_fused(ba[4]), a);
+    box_prepare_v1<FMA>(bb[0], bb[1], bb[2], bb[3], trigB ? trigB[i] : device_trig_fused(bb[4]), b);
     out[i] = box_overlap_unrolled<FMA, true>(a, b);
 }
 
