@@ -121,25 +121,38 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
     // cull pass over the 64 x 64 pairs (only j > i on the diagonal tile, iou3d_nms_kernel.cu:300-302)
     const bool diag = rb == cb;
     const bool all_pairs = thresh < 0.f;   // an IoU of exactly 0 exceeds a negative threshold: nothing may be culled
-#pragma unroll 4
-    for (int k = 0; k < NMS_TILE * NMS_TILE / NMS_THREADS; ++k) {
-        const int p = k * NMS_THREADS + tid;
-        const int r = p >> 6, c = p & 63;
-        bool heavy = false;
-        if (r < tr && c < tc && !(diag && c <= r)) {
-            const float ddx = sm.rcx[r] - sm.ccx[c], ddy = sm.rcy[r] - sm.ccy[c];
-            const float rr = sm.rrad[r] + sm.crad[c];
-            heavy = all_pairs || !(ddx * ddx + ddy * ddy > rr * rr);
+    // thread = one column c and 16 rows (r = 4 k + tid / 64): the circle tests go into a register bitmask, then ONE
+    // warp-aggregated reservation appends all survivors (the queue holds the whole tile, so it cannot overflow)
+    constexpr int NMS_RPT = NMS_TILE * NMS_TILE / NMS_THREADS;   // 16 rows per thread
+    const int c = tid & (NMS_TILE - 1), rq = tid >> 6;
+    unsigned int hits = 0u;
+    if (c < tc) {
+        const float ccx = sm.ccx[c], ccy = sm.ccy[c], ccr = sm.crad[c];
+#pragma unroll
+        for (int k = 0; k < NMS_RPT; ++k) {
+            const int r = k * (NMS_THREADS / NMS_TILE) + rq;
+            const float ddx = sm.rcx[r] - ccx, ddy = sm.rcy[r] - ccy, rr = sm.rrad[r] + ccr;
+            const bool heavy = r < tr && !(diag && c <= r) && (all_pairs || !(ddx * ddx + ddy * ddy > rr * rr));
+            hits |= (heavy ? 1u : 0u) << k;
         }
-        const unsigned int m = __ballot_sync(0xffffffffu, heavy);
-        if (m) {
+    }
+    {
+        const int cnt = __popc(hits);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
+        if (wtotal) {
             int qb = 0;
-            if (lane == 0) qb = atomicAdd(&sm.qcount, __popc(m));
-            qb = __shfl_sync(0xffffffffu, qb, 0);
-            if (heavy) {
-                sm.queue[qb + __popc(m & ((1u << lane) - 1))] = (unsigned short)p;
+            if (lane == 31) qb = atomicAdd(&sm.qcount, wtotal);
+            qb = __shfl_sync(0xffffffffu, qb, 31) + incl - cnt;
+            if (hits && sm.cflag[c] == 0) sm.cflag[c] = 1;
+            while (hits) {
+                const int k = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const int r = k * (NMS_THREADS / NMS_TILE) + rq;
+                sm.queue[qb++] = (unsigned short)((r << 6) | c);
                 if (sm.rflag[r] == 0) sm.rflag[r] = 1;
-                if (sm.cflag[c] == 0) sm.cflag[c] = 1;
             }
         }
     }
@@ -185,7 +198,8 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
         const float* a = sm.rpre + (p >> 6) * BP_STRIDE;
         const float* b = sm.cpre + (p & 63) * BP_STRIDE;
         const float ov = box_overlap<true>(a, b);
-        if (iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) > thresh) atomicOr(&sm.bits[p >> 6], 1ull << (p & 63));
+        if (iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) > thresh)   // 32-bit halves: a native shared-memory atomic instead of a 64-bit CAS loop
+            atomicOr(reinterpret_cast<unsigned int*>(&sm.bits[p >> 6]) + ((p >> 5) & 1), 1u << (p & 31));
     }
     __syncthreads();
     if (tid < tr) mask[(size_t)(r0 + tid) * col_blocks + cb] = sm.bits[tid];
