@@ -32,7 +32,31 @@ constexpr int PIB_FWORDS = PIB_FG * PIB_FG / 32;
 constexpr int PIB_ROUND = 4 * 256;              // points per CTA round of the direct kernel (4 per thread)
 constexpr int PIB_WBATCH = 128;                 // points per warp batch (4 per lane)
 constexpr int PIB_WQ = PIB_WBATCH + 32;         // warp queue: one batch of hot points + a remainder of < 32
-constexpr int PIB_CHUNK = 4096;                 // points per work item of the query kernel
+#ifndef GLENET_PIB_CHUNK
+#define GLENET_PIB_CHUNK 1024
+#endif
+#ifndef GLENET_PIB_RUNS          // 1: a CTA's chunks of one frame are streamed as one run (no pipeline refill per chunk)
+#define GLENET_PIB_RUNS 1
+#endif
+#ifndef GLENET_PIB_UNROLL3       // 1: three prefetch buffers in a loop unrolled by three (no register copies)
+#define GLENET_PIB_UNROLL3 0
+#endif
+#ifndef GLENET_PIB_SMEM_HDR      // 1: frame header re-read from shared memory instead of living in registers
+#define GLENET_PIB_SMEM_HDR 0
+#endif
+#ifndef GLENET_PIB_SLOTSKIP      // 1: skip the queue-append code of a point slot in which no lane is hot
+#define GLENET_PIB_SLOTSKIP 0
+#endif
+#ifndef GLENET_PIB_DBG           // timing experiments only (results invalid): 1 no raster, 2 no coarse cells, 4 no scan, 8 no cell pack, 16 no query launch
+#define GLENET_PIB_DBG 0
+#endif
+#ifndef GLENET_PIB_ZWINDOW       // 1: points outside the z window of all boxes of the frame are cold without a table lookup result
+#define GLENET_PIB_ZWINDOW 1
+#endif
+#ifndef GLENET_PIB_CTAS          // resident CTAs per SM the query kernel is compiled and launched for
+#define GLENET_PIB_CTAS 3
+#endif
+constexpr int PIB_CHUNK = GLENET_PIB_CHUNK;     // points per work item of the query kernel
 constexpr int PIB_THREADS = 256;
 constexpr int PIB_DIRECT_BOXES = 32;            // at most this many boxes => single-launch direct kernel for small calls
 constexpr int PIB_DIRECT_PTS = 4096;            // points per CTA of the direct kernel
@@ -40,11 +64,13 @@ constexpr long PIB_DIRECT_MAX_POINTS = 1 << 20; // ... when the whole call has a
 constexpr int PIB_BUILD_THREADS = 512;
 constexpr int PIB_SMEM_BOXES = 512;             // box records cached in shared memory by the query kernel
 
-struct PibFrame {          // 32 B header per frame
+struct PibFrame {          // 48 B header per frame
     float gx0, gy0, inv_x, inv_y;   // coarse mapping: cell = floor((x - gx0) * inv_x)
     int exhaustive;        // 1 => query kernel loops over all boxes
     int list_len;          // < 0 => no box of the frame can contain any point
     float finv_x, finv_y;  // fine bitmap mapping
+    float zc, zh;          // z window of all boxes together: |z - zc| > zh => the point is in no box (zh = +inf: no window)
+    float pad0, pad1;
 };
 
 __host__ __device__ inline size_t pib_list_cap(int n) { return (size_t)32 * n + 2 * PIB_CELLS; }
@@ -195,9 +221,9 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
     __shared__ unsigned int cnt[PIB_CELLS];
     __shared__ unsigned int s_bits[PIB_FWORDS];
     __shared__ unsigned int scan_tmp[PIB_BUILD_THREADS];
-    __shared__ float red[4][PIB_BUILD_THREADS / 32];
-    __shared__ float s_bounds[4];
-    __shared__ int s_bad;
+    __shared__ float red[6][PIB_BUILD_THREADS / 32];
+    __shared__ float s_bounds[6];
+    __shared__ int s_bad, s_zwide;
     __shared__ unsigned int s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = blockIdx.x;
@@ -210,12 +236,13 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
 
     for (int i = tid; i < PIB_CELLS; i += PIB_BUILD_THREADS) cnt[i] = 0;
     for (int i = tid; i < PIB_FWORDS; i += PIB_BUILD_THREADS) s_bits[i] = 0;
-    if (tid == 0) s_bad = 0;
+    if (tid == 0) { s_bad = 0; s_zwide = 0; }
     __syncthreads();
 
     // pass 1: records + frame bounds
     float bx0 = FLT_MAX, by0 = FLT_MAX, bx1 = -FLT_MAX, by1 = -FLT_MAX;
-    bool bad = false;
+    float zlo = FLT_MAX, zhi = -FLT_MAX;   // union of the boxes' z intervals [cz - tz, cz + tz]
+    bool bad = false, zwide = false;
     for (int k = tid; k < N; k += PIB_BUILD_THREADS) {
         const float* b = boxes + (size_t)k * 7;
         const float rz = b[6];
@@ -228,24 +255,37 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
         const Footprint fp = footprint(r);
         if (fp.never) continue;
         if (fp.bad) { bad = true; continue; }
+        // `|z - cz| > tz` rejects: a NaN on either side never rejects (no window then), tz < 0 always does
+        if (!(fabsf(b[2]) <= FLT_MAX) || !(tz <= FLT_MAX)) zwide = true;
+        else if (tz >= 0.f) { zlo = fminf(zlo, b[2] - tz); zhi = fmaxf(zhi, b[2] + tz); }
         bx0 = fminf(bx0, fp.x0); bx1 = fmaxf(bx1, fp.x1); by0 = fminf(by0, fp.y0); by1 = fmaxf(by1, fp.y1);
     }
     if (bad) s_bad = 1;
+    if (zwide) s_zwide = 1;
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
+        zlo = fminf(zlo, __shfl_xor_sync(0xffffffffu, zlo, o));
+        zhi = fmaxf(zhi, __shfl_xor_sync(0xffffffffu, zhi, o));
         bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
         by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o));
         bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
         by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
     }
-    if (lane == 0) { red[0][warp] = bx0; red[1][warp] = by0; red[2][warp] = bx1; red[3][warp] = by1; }
+    if (lane == 0) { red[0][warp] = bx0; red[1][warp] = by0; red[2][warp] = bx1; red[3][warp] = by1; red[4][warp] = zlo; red[5][warp] = zhi; }
     __syncthreads();
     if (tid == 0) {
         for (int w = 1; w < PIB_BUILD_THREADS / 32; ++w) {
             bx0 = fminf(bx0, red[0][w]); by0 = fminf(by0, red[1][w]);
             bx1 = fmaxf(bx1, red[2][w]); by1 = fmaxf(by1, red[3][w]);
+            zlo = fminf(zlo, red[4][w]); zhi = fmaxf(zhi, red[5][w]);
         }
         s_bounds[0] = bx0; s_bounds[1] = by0; s_bounds[2] = bx1; s_bounds[3] = by1;
+        // conservative window: the slack (1e-3 + 1e-5 of the width + 1e-6 of the magnitude) is far above the rounding
+        // of `z - cz`, `cz -+ tz` and `z - zc`; anything non-finite => no window
+        float zc = 0.5f * zlo + 0.5f * zhi;
+        float zh = (0.5f * zhi - 0.5f * zlo) * 1.00001f + 1e-3f + 1e-6f * fmaxf(fabsf(zlo), fabsf(zhi));
+        if (s_zwide || !(zhi >= zlo) || !(zh <= FLT_MAX) || !(fabsf(zc) <= FLT_MAX)) { zc = 0.f; zh = __int_as_float(0x7f800000); }
+        s_bounds[4] = zc; s_bounds[5] = zh;
     }
     __syncthreads();   // also publishes the records written above to the whole CTA
     bx0 = s_bounds[0]; by0 = s_bounds[1]; bx1 = s_bounds[2]; by1 = s_bounds[3];
@@ -274,9 +314,9 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
                 const int part = it / N, k = it - part * N;
                 const Footprint fp = footprint(rec + (size_t)k * 8);
                 if (fp.never) continue;
-                if (pass == 0 && (parts == 1 || part > 0))
+                if (!(GLENET_PIB_DBG & 1) && pass == 0 && (parts == 1 || part > 0))
                     raster_fine_rows(fp, bx0, by0, finv_x, finv_y, s_bits, parts == 1 ? 0 : part - 1, parts == 1 ? 1 : parts - 1);
-                if (part > 0) continue;
+                if (part > 0 || (GLENET_PIB_DBG & 2)) continue;
                 for_cells<PIB_G>(fp, bx0, by0, inv_x, inv_y, [&](int cell) {
                     const unsigned int pos = atomicAdd(&cnt[cell], 1u);
                     if (pass == 1) list[pos] = (unsigned int)k;
@@ -291,7 +331,7 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
                 for (int i = 0; i < PER; ++i) { local[i] = cnt[tid * PER + i]; sum += local[i]; }
                 scan_tmp[tid] = sum;
                 __syncthreads();
-                for (int o = 1; o < PIB_BUILD_THREADS; o <<= 1) {
+                for (int o = 1; o < ((GLENET_PIB_DBG & 4) ? 0 : PIB_BUILD_THREADS); o <<= 1) {
                     unsigned int v = (tid >= o) ? scan_tmp[tid - o] : 0u;
                     __syncthreads();
                     scan_tmp[tid] += v;
@@ -312,7 +352,7 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
             }
         }
         for (int i = tid; i < PIB_FWORDS; i += PIB_BUILD_THREADS) bits[i] = s_bits[i];
-        if (!exhaustive) {
+        if (!exhaustive && !(GLENET_PIB_DBG & 8)) {
             // packed coarse cells: the first two candidates inline (most cells hold <= 2), the rest via the list
             unsigned long long* cells = ws.cells + (size_t)f * PIB_CELLS;
             bool too_many = false;
@@ -333,6 +373,7 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
         h.exhaustive = exhaustive ? 1 : 0;
         h.list_len = empty ? -1 : (int)total;   // -1: nothing can match in this frame
         h.finv_x = finv_x; h.finv_y = finv_y;
+        h.zc = s_bounds[4]; h.zh = s_bounds[5]; h.pad0 = h.pad1 = 0.f;
         ws.frames[f] = h;
     }
 }
@@ -364,7 +405,7 @@ __device__ __forceinline__ void load_pts4(const float* __restrict__ pts, int p0,
 //   3. the ~13 % of points whose fine cell is occupied go to the warp's private queue
 //      (warp prefix sum, no atomics), and the warp drains it at once: coarse cell -> candidate
 //      list -> exact predicate -> minimum index over the provisional -1.
-__global__ void __launch_bounds__(PIB_THREADS, 4)
+__global__ void __launch_bounds__(PIB_THREADS, GLENET_PIB_CTAS)
 pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace ws, int* __restrict__ out_all,
                  int chunks_per_frame, int total_chunks) {
     extern __shared__ __align__(16) unsigned char pib_smem[];
@@ -379,23 +420,41 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
     const int c_end = (int)((long)(blockIdx.x + 1) * total_chunks / gridDim.x);
     const bool rec_in_smem = N <= PIB_SMEM_BOXES;
     int cur_frame = -1;
+#if GLENET_PIB_SMEM_HDR
+    __shared__ PibFrame s_h;
+    const volatile PibFrame& h = s_h;
+#else
     PibFrame h;
-    h.list_len = -1; h.exhaustive = 0; h.gx0 = h.gy0 = h.inv_x = h.inv_y = h.finv_x = h.finv_y = 0.f;
+    h.list_len = -1; h.exhaustive = 0; h.gx0 = h.gy0 = h.inv_x = h.inv_y = h.finv_x = h.finv_y = h.zc = h.zh = h.pad0 = h.pad1 = 0.f;
+#endif
 
-    for (int c = c_begin; c < c_end; ++c) {
+    for (int c = c_begin; c < c_end;) {
         const int f = c / chunks_per_frame;
         const int chunk = c - f * chunks_per_frame;
+#if GLENET_PIB_RUNS
+        // this CTA's chunks of one frame form ONE contiguous run of points: the register prefetch streams through
+        // it without a pipeline refill (and an integer division) at every chunk boundary
+        const int chunk_last = min(c_end - f * chunks_per_frame, chunks_per_frame);
+#else
+        const int chunk_last = chunk + 1;
+#endif
+        c = f * chunks_per_frame + chunk_last;
         const float* pts = pts_all + (size_t)f * M * 3;
         int* out = out_all + (size_t)f * M;
         const float* rec_g = ws.rec + (size_t)f * N * 8;
         const unsigned int* list = ws.list + (size_t)f * ws.cap;
         const float* rec = rec_in_smem ? s_rec : rec_g;
         const int p_begin = chunk * PIB_CHUNK;
-        const int p_end = min(M, p_begin + PIB_CHUNK);
+        const int p_end = (int)min((long)M, (long)chunk_last * PIB_CHUNK);
         const bool vec = ((((uintptr_t)pts) & 15) == 0) && ((((uintptr_t)out) & 15) == 0);
         if (f != cur_frame) {                                 // uniform over the CTA
             __syncthreads();                                  // everyone is done with the previous frame's tables
+#if GLENET_PIB_SMEM_HDR
+            if (tid == 0) s_h = ws.frames[f];
+            __syncthreads();
+#else
             h = ws.frames[f];
+#endif
             if (h.list_len >= 0) {
                 if (rec_in_smem) {
                     const float4* src = reinterpret_cast<const float4*>(rec_g);
@@ -435,7 +494,7 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
         }
 
         // ---- warp-autonomous streaming over this chunk: batch j of warp w covers 128 points
-        constexpr int NB = PIB_CHUNK / (PIB_THREADS * 4);     // batches per warp and chunk
+        const int NB = (p_end - p_begin + PIB_THREADS * 4 - 1) / (PIB_THREADS * 4);   // batches per warp in this run
         // candidate test of one queued point: coarse cell (two inline candidates in shared memory, longer
         // lists through global memory) -> exact predicate -> minimum index
         const unsigned long long* cells64 = ws.cells + (size_t)f * PIB_CELLS;
@@ -463,23 +522,24 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
             if (res != 0x7fffffff) out[__float_as_int(e.w)] = res;
         };
         int qn = 0;                                           // warp-uniform fill of the warp's queue
-        Pts4 cur, nxt;   // register prefetch two batches ahead: one batch of cold points is shorter than an L2 round trip
-        load_pts4(pts, p_begin + warp * PIB_WBATCH + lane * 4, p_end, vec, cur);
-        if (NB > 1) load_pts4(pts, p_begin + ((PIB_THREADS / 32) + warp) * PIB_WBATCH + lane * 4, p_end, vec, nxt);
-#pragma unroll 1
-        for (int j = 0; j < NB; ++j) {
+        // one batch (4 points per lane) of this warp: lookup, provisional -1, queue append, drain
+        auto batch = [&](const Pts4& cur, const int j) {
             const int p0 = p_begin + (j * (PIB_THREADS / 32) + warp) * PIB_WBATCH + lane * 4;
             const int nvalid = max(0, min(4, p_end - p0));
-            Pts4 nxt2;
-            if (j + 2 < NB) load_pts4(pts, p0 + 2 * (PIB_THREADS / 32) * PIB_WBATCH, p_end, vec, nxt2);
             // branch-free fine-bitmap lookup: floor -> one unsigned range test for both axes -> one LDS.
             // NaN maps to cell 0 (harmless: the exact predicate rejects it), out-of-grid to "cold".
             unsigned int hot = 0;
+            const float gx0 = h.gx0, gy0 = h.gy0, finv_x = h.finv_x, finv_y = h.finv_y, zc = h.zc, zh = h.zh;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int ix = __float2int_rd((cur.x[i] - h.gx0) * h.finv_x), iy = __float2int_rd((cur.y[i] - h.gy0) * h.finv_y);
+                const int ix = __float2int_rd((cur.x[i] - gx0) * finv_x), iy = __float2int_rd((cur.y[i] - gy0) * finv_y);
                 const unsigned int word = s_bits[((iy << 3) + (ix >> 5)) & (PIB_FWORDS - 1)];
+#if GLENET_PIB_ZWINDOW
+                // also cold: points above / below every box (NaN z is not culled here; the exact predicate rejects it)
+                const unsigned int in_grid = (((unsigned int)(ix | iy) < (unsigned int)PIB_FG) && !(fabsf(cur.z[i] - zc) > zh)) ? 1u : 0u;
+#else
                 const unsigned int in_grid = ((unsigned int)(ix | iy) < (unsigned int)PIB_FG) ? 1u : 0u;
+#endif
                 hot |= ((word >> (ix & 31)) & in_grid) << i;
             }
             hot &= (1u << nvalid) - 1u;                        // never queue a point beyond the chunk
@@ -496,6 +556,9 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
                 for (int i = 0; i < 4; ++i) {
                     const bool hi = (hot >> i) & 1u;
                     const unsigned int m = __ballot_sync(0xffffffffu, hi);
+#if GLENET_PIB_SLOTSKIP
+                    if (m == 0u) continue;                    // uniform: nobody queues its i-th point
+#endif
                     if (hi) wq[qn + __popc(m & lt)] = make_float4(cur.x[i], cur.y[i], cur.z[i], __int_as_float(p0 + i));
                     qn += __popc(m);
                 }
@@ -513,10 +576,42 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
                     __syncwarp();
                 }
             }
+        };
+        auto fetch = [&](Pts4& dst, const int j) {
+            load_pts4(pts, p_begin + (j * (PIB_THREADS / 32) + warp) * PIB_WBATCH + lane * 4, p_end, vec, dst);
+        };
+        // register prefetch two batches ahead: one batch of cold points is shorter than a DRAM round trip
+#if GLENET_PIB_UNROLL3
+        Pts4 b0, b1, b2;   // three buffers in a loop unrolled by three: no buffer is ever copied
+        fetch(b0, 0);
+        if (NB > 1) fetch(b1, 1);
+#pragma unroll 1
+        for (int j = 0; j < NB; j += 3) {
+            if (j + 2 < NB) fetch(b2, j + 2);
+            batch(b0, j);
+            if (j + 1 < NB) {
+                if (j + 3 < NB) fetch(b0, j + 3);
+                batch(b1, j + 1);
+                if (j + 2 < NB) {
+                    if (j + 4 < NB) fetch(b1, j + 4);
+                    batch(b2, j + 2);
+                }
+            }
+        }
+#else
+        Pts4 cur, nxt;
+        fetch(cur, 0);
+        if (NB > 1) fetch(nxt, 1);
+#pragma unroll 1
+        for (int j = 0; j < NB; ++j) {
+            Pts4 nxt2;
+            if (j + 2 < NB) fetch(nxt2, j + 2);
+            batch(cur, j);
             cur = nxt;
             nxt = nxt2;
         }
-        if (qn) {                                              // leftovers of the chunk
+#endif
+        if (qn) {                                              // leftovers of the run
             if (lane < qn) resolve(wq[lane]);
             __syncwarp();
         }
@@ -633,6 +728,7 @@ int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int 
     pib_build_kernel<<<B, PIB_BUILD_THREADS, 0, st>>>(boxes, N, w);
     int rc = check_launch(what);
     if (rc) return rc;
+    if (GLENET_PIB_DBG & 16) return GLENET_OK;
     const int chunks = (M + PIB_CHUNK - 1) / PIB_CHUNK;
     const long total = (long)chunks * B;
     if (total > 0x7fffffffL) return fail(GLENET_EINVAL, "%s: too many chunks", what);
@@ -644,7 +740,7 @@ int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int 
         if (rc) return rc;
         attr_done = true;
     }
-    const long resident = 4L * 148;   // persistent: 4 CTAs per SM
+    const long resident = (long)GLENET_PIB_CTAS * 148;   // persistent: GLENET_PIB_CTAS CTAs per SM
     const unsigned grid = (unsigned)(total < resident ? total : resident);
     // programmatic dependent launch: the query grid is scheduled while the build kernel drains and waits
     // (griddepcontrol.wait) before it touches the workspace -- hides the launch gap between the two kernels
