@@ -53,6 +53,9 @@ constexpr int PIB_WQ = PIB_WBATCH + 32;         // warp queue: one batch of hot 
 #ifndef GLENET_PIB_ZWINDOW       // 1: points outside the z window of all boxes of the frame are cold without a table lookup result
 #define GLENET_PIB_ZWINDOW 1
 #endif
+#ifndef GLENET_PIB_L2PF          // > 0: L2 prefetch of the points this many batches ahead of the register prefetch
+#define GLENET_PIB_L2PF 3
+#endif
 #ifndef GLENET_PIB_CTAS          // resident CTAs per SM the query kernel is compiled and launched for
 #define GLENET_PIB_CTAS 3
 #endif
@@ -61,8 +64,12 @@ constexpr int PIB_THREADS = 256;
 constexpr int PIB_DIRECT_BOXES = 32;            // at most this many boxes => single-launch direct kernel for small calls
 constexpr int PIB_DIRECT_PTS = 4096;            // points per CTA of the direct kernel
 constexpr long PIB_DIRECT_MAX_POINTS = 1 << 20; // ... when the whole call has at most this many points
-constexpr int PIB_BUILD_THREADS = 512;
-constexpr int PIB_SMEM_BOXES = 512;             // box records cached in shared memory by the query kernel
+#ifndef GLENET_PIB_BUILD_THREADS
+#define GLENET_PIB_BUILD_THREADS 1024
+#endif
+constexpr int PIB_BUILD_THREADS = GLENET_PIB_BUILD_THREADS;
+constexpr size_t PIB_BUILD_SMEM = (size_t)PIB_CELLS * (8 + 4 + 4) + (size_t)PIB_FWORDS * 4;   // dynamic shared memory of the build kernel
+constexpr int PIB_SMEM_BOXES = 256;             // box records cached in shared memory by the query kernel
 
 struct PibFrame {          // 48 B header per frame
     float gx0, gy0, inv_x, inv_y;   // coarse mapping: cell = floor((x - gx0) * inv_x)
@@ -81,7 +88,7 @@ struct PibWorkspace {
     unsigned int* start;   // [B][PIB_CELLS + 1]
     unsigned int* list;    // [B][cap]
     unsigned int* bits;    // [B][PIB_FWORDS] fine occupancy bitmap
-    unsigned long long* cells;   // [B][PIB_CELLS] packed coarse cell: id0:16 | id1:16 | list start:24 | count:8
+    unsigned long long* cells;   // [B][PIB_CELLS] packed coarse cell: four candidate ids, 16 bits each (0xffff none, last = 0xfffe: walk the list)
     size_t cap;
     size_t bytes;
 };
@@ -218,12 +225,15 @@ __device__ __forceinline__ void for_cells(const Footprint& f, float gx0, float g
 
 __global__ void __launch_bounds__(PIB_BUILD_THREADS)
 pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
-    __shared__ unsigned int cnt[PIB_CELLS];
-    __shared__ unsigned int s_bits[PIB_FWORDS];
-    __shared__ unsigned int scan_tmp[PIB_BUILD_THREADS];
+    extern __shared__ __align__(16) unsigned char pib_build_smem[];   // PIB_BUILD_SMEM bytes
+    unsigned long long* s_inl = reinterpret_cast<unsigned long long*>(pib_build_smem);   // [PIB_CELLS] first four candidates, 16 bits each
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(s_inl + PIB_CELLS);              // [PIB_CELLS] count, then fill cursor
+    unsigned int* s_start = cnt + PIB_CELLS;                                             // [PIB_CELLS] final count of the cell (frames with lists only)
+    unsigned int* s_bits = s_start + PIB_CELLS;                                          // [PIB_FWORDS]
+    __shared__ unsigned int scan_tmp[PIB_BUILD_THREADS / 32];
     __shared__ float red[6][PIB_BUILD_THREADS / 32];
     __shared__ float s_bounds[6];
-    __shared__ int s_bad, s_zwide;
+    __shared__ int s_bad, s_zwide, s_over;
     __shared__ unsigned int s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = blockIdx.x;
@@ -234,9 +244,9 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
     unsigned int* list = ws.list + (size_t)f * ws.cap;
     unsigned int* bits = ws.bits + (size_t)f * PIB_FWORDS;
 
-    for (int i = tid; i < PIB_CELLS; i += PIB_BUILD_THREADS) cnt[i] = 0;
+    for (int i = tid; i < PIB_CELLS; i += PIB_BUILD_THREADS) { cnt[i] = 0; s_inl[i] = ~0ull; }
     for (int i = tid; i < PIB_FWORDS; i += PIB_BUILD_THREADS) s_bits[i] = 0;
-    if (tid == 0) { s_bad = 0; s_zwide = 0; }
+    if (tid == 0) { s_bad = 0; s_zwide = 0; s_over = 0; }
     __syncthreads();
 
     // pass 1: records + frame bounds
@@ -298,7 +308,7 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
         finv_x = ((float)PIB_FG - 0.01f) / ex; finv_y = ((float)PIB_FG - 0.01f) / ey;
         if (!(inv_x > 0.f) || !(inv_y > 0.f) || !(finv_x <= FLT_MAX) || !(finv_y <= FLT_MAX)) exhaustive = true;
     }
-    if (N > 65535) exhaustive = true;
+    if (N > 65534) exhaustive = true;   // 0xffff = no candidate, 0xfffe = more than four
 
     unsigned int total = 0;
     if (!exhaustive && !empty) {
@@ -319,29 +329,47 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
                 if (part > 0 || (GLENET_PIB_DBG & 2)) continue;
                 for_cells<PIB_G>(fp, bx0, by0, inv_x, inv_y, [&](int cell) {
                     const unsigned int pos = atomicAdd(&cnt[cell], 1u);
-                    if (pass == 1) list[pos] = (unsigned int)k;
+                    if (pass == 0) {     // the first four candidates of a cell go inline; a fifth makes the frame need lists
+                        if (pos < 4u) reinterpret_cast<unsigned short*>(s_inl)[cell * 4 + pos] = (unsigned short)k;
+                        else s_over = 1;
+                    } else {
+                        list[pos] = (unsigned int)k;
+                    }
                 });
             }
             __syncthreads();
+            if (pass == 0 && !s_over) break;   // uniform: every cell is complete inline -- no scan, no lists, no second pass
             if (pass == 0) {
-                // exclusive scan of cnt[PIB_CELLS] -> start[], cnt becomes the fill cursor
+                // exclusive scan of cnt[PIB_CELLS] -> start[], cnt becomes the fill cursor (warp shuffles, two barriers)
                 constexpr int PER = PIB_CELLS / PIB_BUILD_THREADS;
                 unsigned int local[PER], sum = 0;
 #pragma unroll
                 for (int i = 0; i < PER; ++i) { local[i] = cnt[tid * PER + i]; sum += local[i]; }
-                scan_tmp[tid] = sum;
-                __syncthreads();
-                for (int o = 1; o < ((GLENET_PIB_DBG & 4) ? 0 : PIB_BUILD_THREADS); o <<= 1) {
-                    unsigned int v = (tid >= o) ? scan_tmp[tid - o] : 0u;
-                    __syncthreads();
-                    scan_tmp[tid] += v;
-                    __syncthreads();
+                unsigned int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
                 }
-                unsigned int run = scan_tmp[tid] - sum;
-                if (tid == PIB_BUILD_THREADS - 1) s_total = scan_tmp[tid];
+                if (lane == 31) scan_tmp[warp] = incl;
+                __syncthreads();
+                if (warp == 0) {
+                    constexpr int NW = PIB_BUILD_THREADS / 32;
+                    unsigned int w = lane < NW ? scan_tmp[lane] : 0u;
+#pragma unroll
+                    for (int o = 1; o < NW; o <<= 1) {
+                        const unsigned int t = __shfl_up_sync(0xffffffffu, w, o);
+                        if (lane >= o) w += t;
+                    }
+                    if (lane < NW) scan_tmp[lane] = w;
+                    if (lane == NW - 1) s_total = w;
+                }
+                __syncthreads();
+                unsigned int run = incl - sum + (warp ? scan_tmp[warp - 1] : 0u);
 #pragma unroll
                 for (int i = 0; i < PER; ++i) {
                     start[tid * PER + i] = run;
+                    s_start[tid * PER + i] = local[i];   // the cell's count (the pack below flags cells with more than four)
                     cnt[tid * PER + i] = run;
                     run += local[i];
                 }
@@ -353,18 +381,14 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
         }
         for (int i = tid; i < PIB_FWORDS; i += PIB_BUILD_THREADS) bits[i] = s_bits[i];
         if (!exhaustive && !(GLENET_PIB_DBG & 8)) {
-            // packed coarse cells: the first two candidates inline (most cells hold <= 2), the rest via the list
+            // packed coarse cells: up to four candidates inline, 16 bits each (0xffff = none); a cell with more gets
+            // 0xfffe in its last slot and is resolved through start[] / list[]
             unsigned long long* cells = ws.cells + (size_t)f * PIB_CELLS;
-            bool too_many = false;
             for (int c = tid; c < PIB_CELLS; c += PIB_BUILD_THREADS) {
-                const unsigned int s0 = start[c], n = start[c + 1] - s0;
-                const unsigned long long id0 = n > 0 ? list[s0] : 0xffffull, id1 = n > 1 ? list[s0 + 1] : 0xffffull;
-                too_many |= n > 255u;
-                cells[c] = id0 | (id1 << 16) | ((unsigned long long)(s0 & 0xffffffu) << 32) | ((unsigned long long)min(n, 255u) << 56);
+                unsigned long long v = s_inl[c];
+                if (s_over && s_start[c] > 4u) v = (v & 0x0000ffffffffffffull) | (0xfffeull << 48);
+                cells[c] = v;
             }
-            if (too_many || total > 0xffffffu) s_bad = 2;
-            __syncthreads();
-            if (s_bad == 2) exhaustive = true;
         }
     }
     if (tid == 0) {
@@ -411,8 +435,8 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
     extern __shared__ __align__(16) unsigned char pib_smem[];
     asm volatile("griddepcontrol.wait;" ::: "memory");   // the build kernel (previous in the stream) has completed and flushed
     float4* s_q = reinterpret_cast<float4*>(pib_smem);                                        // [warps][PIB_WQ] {x, y, z, index}
-    unsigned int* s_cells = reinterpret_cast<unsigned int*>(s_q + (PIB_THREADS / 32) * PIB_WQ); // [PIB_CELLS] id0:16 | id1:16
-    unsigned int* s_bits = s_cells + PIB_CELLS;                                               // [PIB_FWORDS]
+    unsigned long long* s_cells = reinterpret_cast<unsigned long long*>(s_q + (PIB_THREADS / 32) * PIB_WQ); // [PIB_CELLS] four ids
+    unsigned int* s_bits = reinterpret_cast<unsigned int*>(s_cells + PIB_CELLS);              // [PIB_FWORDS]
     float* s_rec = reinterpret_cast<float*>(s_bits + PIB_FWORDS);                             // [min(N, PIB_SMEM_BOXES) * 8]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float4* wq = s_q + warp * PIB_WQ;
@@ -464,14 +488,8 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
                 if (!h.exhaustive) {
                     const uint4* b = reinterpret_cast<const uint4*>(ws.bits + (size_t)f * PIB_FWORDS);
                     for (int i = tid; i < PIB_FWORDS / 4; i += PIB_THREADS) reinterpret_cast<uint4*>(s_bits)[i] = __ldg(b + i);
-                    // shared copy keeps the two inline candidates; id1 = 0xFFFE flags "more in the list"
-                    const unsigned long long* cl = ws.cells + (size_t)f * PIB_CELLS;
-                    for (int i = tid; i < PIB_CELLS; i += PIB_THREADS) {
-                        const unsigned long long c64 = __ldg(cl + i);
-                        unsigned int c32 = (unsigned int)c64;
-                        if ((unsigned int)(c64 >> 56) > 2u) c32 = (c32 & 0xffffu) | 0xfffe0000u;
-                        s_cells[i] = c32;
-                    }
+                    const uint4* cl = reinterpret_cast<const uint4*>(ws.cells + (size_t)f * PIB_CELLS);
+                    for (int i = tid; i < PIB_CELLS / 2; i += PIB_THREADS) reinterpret_cast<uint4*>(s_cells)[i] = __ldg(cl + i);
                 }
             }
             __syncthreads();
@@ -497,16 +515,17 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
         const int NB = (p_end - p_begin + PIB_THREADS * 4 - 1) / (PIB_THREADS * 4);   // batches per warp in this run
         // candidate test of one queued point: coarse cell (two inline candidates in shared memory, longer
         // lists through global memory) -> exact predicate -> minimum index
-        const unsigned long long* cells64 = ws.cells + (size_t)f * PIB_CELLS;
         auto resolve = [&](const float4 e) {
             const int cx = (int)((e.x - h.gx0) * h.inv_x), cy = (int)((e.y - h.gy0) * h.inv_y);
             const int ci = min(cy, PIB_G - 1) * PIB_G + min(cx, PIB_G - 1);
-            const unsigned int cell = s_cells[ci];
-            const int k0 = (int)(cell & 0xffffu), k1 = (int)(cell >> 16);
+            const unsigned long long cell = s_cells[ci];
+            const unsigned int lo = (unsigned int)cell, hi = (unsigned int)(cell >> 32);
+            const int k0 = (int)(lo & 0xffffu), k1 = (int)(lo >> 16), k2 = (int)(hi & 0xffffu), k3 = (int)(hi >> 16);
             int res = 0x7fffffff;
-            if (k1 == 0xfffe) {          // > 2 candidates: walk the whole list
-                const unsigned long long c64 = __ldg(cells64 + ci);
-                const unsigned int s0 = (unsigned int)(c64 >> 32) & 0xffffffu, n = (unsigned int)(c64 >> 56);
+            if (k3 == 0xfffe) {          // > 4 candidates (rare): walk the whole list; pointers rebuilt here
+                const unsigned int* st = ws.start + (size_t)f * (PIB_CELLS + 1) + ci;
+                const unsigned int s0 = __ldg(st), n = __ldg(st + 1) - s0;
+                const unsigned int* list = ws.list + (size_t)f * ws.cap;
                 for (unsigned int i = 0; i < n; i += 4) {   // four independent list loads per round trip to L2
                     int kk[4];
 #pragma unroll
@@ -515,9 +534,11 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
                     for (int u = 0; u < 4; ++u)
                         if (kk[u] < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)kk[u] * 8)) res = kk[u];
                 }
-            } else {
+            } else {                     // candidates are in no particular order: keep the minimum
                 if (k0 != 0xffff && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k0 * 8)) res = k0;
                 if (k1 != 0xffff && k1 < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k1 * 8)) res = k1;
+                if (k2 != 0xffff && k2 < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k2 * 8)) res = k2;
+                if (k3 != 0xffff && k3 < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k3 * 8)) res = k3;
             }
             if (res != 0x7fffffff) out[__float_as_int(e.w)] = res;
         };
@@ -606,6 +627,17 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
         for (int j = 0; j < NB; ++j) {
             Pts4 nxt2;
             if (j + 2 < NB) fetch(nxt2, j + 2);
+#if GLENET_PIB_L2PF
+            // The register rotation below (cur = nxt; nxt = nxt2) has to wait for nxt2, so the register prefetch is
+            // effectively ONE batch deep.  An L2 prefetch further ahead turns that wait into an L2 hit: the 1536 bytes
+            // of a batch are at most 13 lines, one `prefetch.global.L2` per lane.
+            if (j + GLENET_PIB_L2PF < NB) {
+                const char* b0 = reinterpret_cast<const char*>(pts + (size_t)(p_begin + ((j + GLENET_PIB_L2PF) * (PIB_THREADS / 32) + warp) * PIB_WBATCH) * 3);
+                const char* line = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(b0) & ~(uintptr_t)127) + lane * 128;
+                if (line < b0 + PIB_WBATCH * 12 && line < reinterpret_cast<const char*>(pts + (size_t)p_end * 3))
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(line));
+            }
+#endif
             batch(cur, j);
             cur = nxt;
             nxt = nxt2;
@@ -725,14 +757,21 @@ int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int 
         return check_launch(what);
     }
     PibWorkspace w = pib_layout(ws, B, N);
-    pib_build_kernel<<<B, PIB_BUILD_THREADS, 0, st>>>(boxes, N, w);
-    int rc = check_launch(what);
+    static bool build_attr_done = false;
+    int rc = GLENET_OK;
+    if (!build_attr_done) {
+        rc = set_smem(pib_build_kernel, PIB_BUILD_SMEM, what);
+        if (rc) return rc;
+        build_attr_done = true;
+    }
+    pib_build_kernel<<<B, PIB_BUILD_THREADS, PIB_BUILD_SMEM, st>>>(boxes, N, w);
+    rc = check_launch(what);
     if (rc) return rc;
     if (GLENET_PIB_DBG & 16) return GLENET_OK;
     const int chunks = (M + PIB_CHUNK - 1) / PIB_CHUNK;
     const long total = (long)chunks * B;
     if (total > 0x7fffffffL) return fail(GLENET_EINVAL, "%s: too many chunks", what);
-    const size_t smem_fixed = sizeof(float4) * (PIB_THREADS / 32) * PIB_WQ + sizeof(unsigned int) * (PIB_CELLS + PIB_FWORDS);
+    const size_t smem_fixed = sizeof(float4) * (PIB_THREADS / 32) * PIB_WQ + sizeof(unsigned long long) * PIB_CELLS + sizeof(unsigned int) * PIB_FWORDS;
     const size_t smem = smem_fixed + sizeof(float) * 8 * (size_t)(N <= PIB_SMEM_BOXES ? N : 0);
     static bool attr_done = false;
     if (!attr_done) {
