@@ -38,8 +38,8 @@ constexpr int PIB_WQ = PIB_WBATCH + 32;         // warp queue: one batch of hot 
 #ifndef GLENET_PIB_RUNS          // 1: a CTA's chunks of one frame are streamed as one run (no pipeline refill per chunk)
 #define GLENET_PIB_RUNS 1
 #endif
-#ifndef GLENET_PIB_UNROLL3       // 1: three prefetch buffers in a loop unrolled by three (no register copies)
-#define GLENET_PIB_UNROLL3 0
+#ifndef GLENET_PIB_UNROLL2       // 1: two prefetch buffers used alternately in a loop unrolled by two (no register copies)
+#define GLENET_PIB_UNROLL2 0
 #endif
 #ifndef GLENET_PIB_SMEM_HDR      // 1: frame header re-read from shared memory instead of living in registers
 #define GLENET_PIB_SMEM_HDR 0
@@ -602,22 +602,29 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
             load_pts4(pts, p_begin + (j * (PIB_THREADS / 32) + warp) * PIB_WBATCH + lane * 4, p_end, vec, dst);
         };
         // register prefetch two batches ahead: one batch of cold points is shorter than a DRAM round trip
-#if GLENET_PIB_UNROLL3
-        Pts4 b0, b1, b2;   // three buffers in a loop unrolled by three: no buffer is ever copied
-        fetch(b0, 0);
-        if (NB > 1) fetch(b1, 1);
-#pragma unroll 1
-        for (int j = 0; j < NB; j += 3) {
-            if (j + 2 < NB) fetch(b2, j + 2);
-            batch(b0, j);
-            if (j + 1 < NB) {
-                if (j + 3 < NB) fetch(b0, j + 3);
-                batch(b1, j + 1);
-                if (j + 2 < NB) {
-                    if (j + 4 < NB) fetch(b1, j + 4);
-                    batch(b2, j + 2);
-                }
+#if GLENET_PIB_UNROLL2
+        // Two buffers used alternately in a loop unrolled by two: nothing is copied, a buffer is refilled right after
+        // its batch and has the other buffer's batch to arrive (an L2 hit thanks to the prefetch further ahead).
+        auto l2_prefetch = [&](const int j) {
+#if GLENET_PIB_L2PF
+            if (j + GLENET_PIB_L2PF < NB) {
+                const char* b0 = reinterpret_cast<const char*>(pts + (size_t)(p_begin + ((j + GLENET_PIB_L2PF) * (PIB_THREADS / 32) + warp) * PIB_WBATCH) * 3);
+                const char* line = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(b0) & ~(uintptr_t)127) + lane * 128;
+                if (line < b0 + PIB_WBATCH * 12 && line < reinterpret_cast<const char*>(pts + (size_t)p_end * 3))
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(line));
             }
+#endif
+        };
+        Pts4 b0, b1;
+        fetch(b0, 0);
+#pragma unroll 1
+        for (int j = 0; j < NB; j += 2) {
+            if (j + 1 < NB) fetch(b1, j + 1);
+            l2_prefetch(j);
+            batch(b0, j);
+            if (j + 2 < NB) fetch(b0, j + 2);
+            l2_prefetch(j + 1);
+            if (j + 1 < NB) batch(b1, j + 1);
         }
 #else
         Pts4 cur, nxt;
@@ -757,12 +764,15 @@ int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int 
         return check_launch(what);
     }
     PibWorkspace w = pib_layout(ws, B, N);
-    static bool build_attr_done = false;
+    // the opt-in shared-memory sizes are per device: remember where they have been set
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool need_attr = dev < 0 || dev >= 64 || !attr_done[dev];
     int rc = GLENET_OK;
-    if (!build_attr_done) {
+    if (need_attr) {
         rc = set_smem(pib_build_kernel, PIB_BUILD_SMEM, what);
         if (rc) return rc;
-        build_attr_done = true;
     }
     pib_build_kernel<<<B, PIB_BUILD_THREADS, PIB_BUILD_SMEM, st>>>(boxes, N, w);
     rc = check_launch(what);
@@ -773,11 +783,10 @@ int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int 
     if (total > 0x7fffffffL) return fail(GLENET_EINVAL, "%s: too many chunks", what);
     const size_t smem_fixed = sizeof(float4) * (PIB_THREADS / 32) * PIB_WQ + sizeof(unsigned long long) * PIB_CELLS + sizeof(unsigned int) * PIB_FWORDS;
     const size_t smem = smem_fixed + sizeof(float) * 8 * (size_t)(N <= PIB_SMEM_BOXES ? N : 0);
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (need_attr) {
         rc = set_smem(pib_query_kernel, smem_fixed + sizeof(float) * 8 * PIB_SMEM_BOXES, what);
         if (rc) return rc;
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     const long resident = (long)GLENET_PIB_CTAS * 148;   // persistent: GLENET_PIB_CTAS CTAs per SM
     const unsigned grid = (unsigned)(total < resident ? total : resident);
