@@ -410,6 +410,41 @@ def test_points_in_boxes_properties_full_size(cuda):
     assert bool((R.points_in_boxes_gpu(pts_nan, boxes[None].to(cuda))[0, :7] == -1).all())
 
 
+def test_points_in_boxes_z_window_and_crowded_cells_vs_reference(cuda, ref_so):
+    """The z window of all boxes (points above / below every box skip the tables), cells with more than four candidates
+    and degenerate heights must not change a single assignment: bit-equal to the reference kernel."""
+    g = torch.Generator().manual_seed(11)
+    base = synth.waymo_boxes(120, 21)
+    # a crowd: 9 boxes stacked on one centre (more than four candidates per coarse cell), then copies shifted in z only
+    crowd = base[:1].repeat(9, 1) + torch.randn((9, 7), generator=g) * torch.tensor([0.2, 0.2, 0.05, 0.1, 0.1, 0.05, 0.3])
+    tower = base[1:2].repeat(6, 1); tower[:, 2] += torch.arange(6) * 1.5
+    boxes = torch.cat([crowd, tower, base[2:]])
+    pts = synth.points(150000, boxes, synth.WAYMO_RANGE, 0.4, seed=12)
+    # points exactly on the z faces of box 0 and of the lowest / highest box, and far above / below everything
+    k = torch.randint(0, boxes.shape[0], (3000,), generator=g)
+    on_face = boxes[k, :3].clone(); on_face[:, 2] += boxes[k, 5] * 0.5 * (torch.randint(0, 2, (3000,), generator=g) * 2 - 1)
+    lo, hi = (boxes[:, 2] - boxes[:, 5] / 2).min(), (boxes[:, 2] + boxes[:, 5] / 2).max()
+    edge = boxes[k, :3].clone(); edge[:, 2] = torch.where(torch.rand(3000, generator=g) < 0.5, lo, hi) + (torch.rand(3000, generator=g) - 0.5) * 4e-3
+    far = boxes[k, :3].clone(); far[:, 2] += 50.0 * (torch.randint(0, 2, (3000,), generator=g) * 2 - 1)
+    nanz = boxes[k[:50], :3].clone(); nanz[:, 2] = float("nan")
+    pts = torch.cat([pts, on_face, edge, far, nanz])[None].contiguous().to(cuda)
+    variants = {"plain": boxes}
+    for name, (col, val) in {"nan_cz": (2, float("nan")), "inf_cz": (2, float("inf")), "nan_dz": (5, float("nan")), "inf_dz": (5, float("inf")),
+                             "neg_dz": (5, -1.0), "zero_dz": (5, 0.0), "huge_cz": (2, 3e38)}.items():
+        b = boxes.clone(); b[3, col] = val; b[40, col] = val
+        variants[name] = b
+    for name, b in variants.items():
+        b = b[None].contiguous().to(cuda)
+        got, want = R.points_in_boxes_gpu(pts, b), ref_so.points_in_boxes_gpu(pts, b)
+        assert torch.equal(got, want), name
+    assert int((want >= 0).sum()) > 20000
+    # many frames in one call, each with its own z window; frame 2 has only padding (zero) boxes
+    bx = torch.stack([synth.waymo_boxes(64, 40 + f) for f in range(5)]); bx[:, :, 2] += torch.arange(5)[:, None] * 3.0; bx[2] = 0
+    pp = torch.stack([synth.points(30011, bx[f], synth.WAYMO_RANGE, 0.3, seed=50 + f) for f in range(5)]); pp[:, :, 2] += (torch.rand(5, 30011, generator=g) - 0.5) * 6
+    bx, pp = bx.to(cuda), pp.contiguous().to(cuda)
+    assert torch.equal(R.points_in_boxes_gpu(pp, bx), ref_so.points_in_boxes_gpu(pp, bx))
+
+
 def test_glenet_variance_voting_nms_on_gpu(cuda, cpu_golden):
     """NMS_TYPE new_nms_gpu (every shipped GLENet config) through the GPU IoU matrix vs the reference's Python + CPU IoU."""
     boxes, scores, var = (torch.from_numpy(cpu_golden[k]).to(cuda) for k in ("vnms_boxes", "vnms_scores", "vnms_var"))
