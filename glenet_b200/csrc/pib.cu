@@ -56,6 +56,15 @@ constexpr int PIB_WQ = PIB_WBATCH + 32;         // warp queue: one batch of hot 
 #ifndef GLENET_PIB_L2PF          // > 0: L2 prefetch of the points this many batches ahead of the register prefetch
 #define GLENET_PIB_L2PF 3
 #endif
+#ifndef GLENET_PIB_PFPTR         // 1: the L2 prefetch address advances incrementally instead of being rebuilt per batch
+#define GLENET_PIB_PFPTR 1
+#endif
+#ifndef GLENET_PIB_WARPRED       // 1: the build reduces the per-warp frame bounds with warp 0 instead of a serial loop of thread 0
+#define GLENET_PIB_WARPRED 1
+#endif
+#ifndef GLENET_PIB_REGPF         // register prefetch depth in batches (2: three buffers rotated, 1: two buffers)
+#define GLENET_PIB_REGPF 2
+#endif
 #ifndef GLENET_PIB_CTAS          // resident CTAs per SM the query kernel is compiled and launched for
 #define GLENET_PIB_CTAS 3
 #endif
@@ -283,12 +292,28 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
     }
     if (lane == 0) { red[0][warp] = bx0; red[1][warp] = by0; red[2][warp] = bx1; red[3][warp] = by1; red[4][warp] = zlo; red[5][warp] = zhi; }
     __syncthreads();
+#if GLENET_PIB_WARPRED
+    if (warp == 0) {
+        constexpr int NW = PIB_BUILD_THREADS / 32;
+        bx0 = lane < NW ? red[0][lane] : FLT_MAX;  by0 = lane < NW ? red[1][lane] : FLT_MAX;
+        bx1 = lane < NW ? red[2][lane] : -FLT_MAX; by1 = lane < NW ? red[3][lane] : -FLT_MAX;
+        zlo = lane < NW ? red[4][lane] : FLT_MAX;  zhi = lane < NW ? red[5][lane] : -FLT_MAX;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+            bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+            zlo = fminf(zlo, __shfl_xor_sync(0xffffffffu, zlo, o)); zhi = fmaxf(zhi, __shfl_xor_sync(0xffffffffu, zhi, o));
+        }
+    }
+    if (tid == 0) {
+#else
     if (tid == 0) {
         for (int w = 1; w < PIB_BUILD_THREADS / 32; ++w) {
             bx0 = fminf(bx0, red[0][w]); by0 = fminf(by0, red[1][w]);
             bx1 = fmaxf(bx1, red[2][w]); by1 = fmaxf(by1, red[3][w]);
             zlo = fminf(zlo, red[4][w]); zhi = fmaxf(zhi, red[5][w]);
         }
+#endif
         s_bounds[0] = bx0; s_bounds[1] = by0; s_bounds[2] = bx1; s_bounds[3] = by1;
         // conservative window: the slack (1e-3 + 1e-5 of the width + 1e-6 of the magnitude) is far above the rounding
         // of `z - cz`, `cz -+ tz` and `z - zc`; anything non-finite => no window
@@ -629,12 +654,34 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
 #else
         Pts4 cur, nxt;
         fetch(cur, 0);
+#if GLENET_PIB_REGPF >= 2
         if (NB > 1) fetch(nxt, 1);
+#endif
+#if GLENET_PIB_L2PF && GLENET_PIB_PFPTR
+        // this lane's line of the batch GLENET_PIB_L2PF ahead; a batch is 1536 bytes = at most 13 lines, and the stride
+        // from batch to batch (12288 bytes) keeps the alignment, so the pointer simply advances
+        const char* pf_line;
+        {
+            const char* b0 = reinterpret_cast<const char*>(pts + (size_t)(p_begin + (GLENET_PIB_L2PF * (PIB_THREADS / 32) + warp) * PIB_WBATCH) * 3);
+            pf_line = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(b0) & ~(uintptr_t)127) + lane * 128;
+            if (!(pf_line < b0 + PIB_WBATCH * 12)) pf_line = reinterpret_cast<const char*>(~(uintptr_t)0);   // lane has no line
+        }
+        const char* const pf_end = reinterpret_cast<const char*>(pts + (size_t)p_end * 3);
+#endif
 #pragma unroll 1
         for (int j = 0; j < NB; ++j) {
+#if GLENET_PIB_REGPF >= 2
             Pts4 nxt2;
             if (j + 2 < NB) fetch(nxt2, j + 2);
-#if GLENET_PIB_L2PF
+#else
+            if (j + 1 < NB) fetch(nxt, j + 1);
+#endif
+#if GLENET_PIB_L2PF && GLENET_PIB_PFPTR
+            // The register rotation below (cur = nxt; nxt = nxt2) has to wait for nxt2, so the register prefetch is
+            // effectively ONE batch deep.  An L2 prefetch further ahead turns that wait into an L2 hit.
+            if (pf_line < pf_end) asm volatile("prefetch.global.L2 [%0];" :: "l"(pf_line));
+            pf_line += (pf_line < pf_end) ? (size_t)PIB_THREADS * 4 * 12 : 0;
+#elif GLENET_PIB_L2PF
             // The register rotation below (cur = nxt; nxt = nxt2) has to wait for nxt2, so the register prefetch is
             // effectively ONE batch deep.  An L2 prefetch further ahead turns that wait into an L2 hit: the 1536 bytes
             // of a batch are at most 13 lines, one `prefetch.global.L2` per lane.
@@ -647,7 +694,9 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
 #endif
             batch(cur, j);
             cur = nxt;
+#if GLENET_PIB_REGPF >= 2
             nxt = nxt2;
+#endif
         }
 #endif
         if (qn) {                                              // leftovers of the run
