@@ -38,15 +38,6 @@ constexpr int PIB_WQ = PIB_WBATCH + 32;         // warp queue: one batch of hot 
 #ifndef GLENET_PIB_RUNS          // 1: a CTA's chunks of one frame are streamed as one run (no pipeline refill per chunk)
 #define GLENET_PIB_RUNS 1
 #endif
-#ifndef GLENET_PIB_UNROLL2       // 1: two prefetch buffers used alternately in a loop unrolled by two (no register copies)
-#define GLENET_PIB_UNROLL2 0
-#endif
-#ifndef GLENET_PIB_SMEM_HDR      // 1: frame header re-read from shared memory instead of living in registers
-#define GLENET_PIB_SMEM_HDR 0
-#endif
-#ifndef GLENET_PIB_SLOTSKIP      // 1: skip the queue-append code of a point slot in which no lane is hot
-#define GLENET_PIB_SLOTSKIP 0
-#endif
 #ifndef GLENET_PIB_DBG           // timing experiments only (results invalid): 1 no raster, 2 no coarse cells, 4 no scan, 8 no cell pack, 16 no query launch
 #define GLENET_PIB_DBG 0
 #endif
@@ -55,15 +46,6 @@ constexpr int PIB_WQ = PIB_WBATCH + 32;         // warp queue: one batch of hot 
 #endif
 #ifndef GLENET_PIB_L2PF          // > 0: L2 prefetch of the points this many batches ahead of the register prefetch
 #define GLENET_PIB_L2PF 3
-#endif
-#ifndef GLENET_PIB_PFPTR         // 1: the L2 prefetch address advances incrementally instead of being rebuilt per batch
-#define GLENET_PIB_PFPTR 1
-#endif
-#ifndef GLENET_PIB_WARPRED       // 1: the build reduces the per-warp frame bounds with warp 0 instead of a serial loop of thread 0
-#define GLENET_PIB_WARPRED 1
-#endif
-#ifndef GLENET_PIB_REGPF         // register prefetch depth in batches (2: three buffers rotated, 1: two buffers)
-#define GLENET_PIB_REGPF 2
 #endif
 #ifndef GLENET_PIB_CTAS          // resident CTAs per SM the query kernel is compiled and launched for
 #define GLENET_PIB_CTAS 3
@@ -292,7 +274,6 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
     }
     if (lane == 0) { red[0][warp] = bx0; red[1][warp] = by0; red[2][warp] = bx1; red[3][warp] = by1; red[4][warp] = zlo; red[5][warp] = zhi; }
     __syncthreads();
-#if GLENET_PIB_WARPRED
     if (warp == 0) {
         constexpr int NW = PIB_BUILD_THREADS / 32;
         bx0 = lane < NW ? red[0][lane] : FLT_MAX;  by0 = lane < NW ? red[1][lane] : FLT_MAX;
@@ -306,14 +287,6 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
         }
     }
     if (tid == 0) {
-#else
-    if (tid == 0) {
-        for (int w = 1; w < PIB_BUILD_THREADS / 32; ++w) {
-            bx0 = fminf(bx0, red[0][w]); by0 = fminf(by0, red[1][w]);
-            bx1 = fmaxf(bx1, red[2][w]); by1 = fmaxf(by1, red[3][w]);
-            zlo = fminf(zlo, red[4][w]); zhi = fmaxf(zhi, red[5][w]);
-        }
-#endif
         s_bounds[0] = bx0; s_bounds[1] = by0; s_bounds[2] = bx1; s_bounds[3] = by1;
         // conservative window: the slack (1e-3 + 1e-5 of the width + 1e-6 of the magnitude) is far above the rounding
         // of `z - cz`, `cz -+ tz` and `z - zc`; anything non-finite => no window
@@ -469,13 +442,8 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
     const int c_end = (int)((long)(blockIdx.x + 1) * total_chunks / gridDim.x);
     const bool rec_in_smem = N <= PIB_SMEM_BOXES;
     int cur_frame = -1;
-#if GLENET_PIB_SMEM_HDR
-    __shared__ PibFrame s_h;
-    const volatile PibFrame& h = s_h;
-#else
     PibFrame h;
     h.list_len = -1; h.exhaustive = 0; h.gx0 = h.gy0 = h.inv_x = h.inv_y = h.finv_x = h.finv_y = h.zc = h.zh = h.pad0 = h.pad1 = 0.f;
-#endif
 
     for (int c = c_begin; c < c_end;) {
         const int f = c / chunks_per_frame;
@@ -491,19 +459,13 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
         const float* pts = pts_all + (size_t)f * M * 3;
         int* out = out_all + (size_t)f * M;
         const float* rec_g = ws.rec + (size_t)f * N * 8;
-        const unsigned int* list = ws.list + (size_t)f * ws.cap;
         const float* rec = rec_in_smem ? s_rec : rec_g;
         const int p_begin = chunk * PIB_CHUNK;
         const int p_end = (int)min((long)M, (long)chunk_last * PIB_CHUNK);
         const bool vec = ((((uintptr_t)pts) & 15) == 0) && ((((uintptr_t)out) & 15) == 0);
         if (f != cur_frame) {                                 // uniform over the CTA
             __syncthreads();                                  // everyone is done with the previous frame's tables
-#if GLENET_PIB_SMEM_HDR
-            if (tid == 0) s_h = ws.frames[f];
-            __syncthreads();
-#else
             h = ws.frames[f];
-#endif
             if (h.list_len >= 0) {
                 if (rec_in_smem) {
                     const float4* src = reinterpret_cast<const float4*>(rec_g);
@@ -602,9 +564,6 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
                 for (int i = 0; i < 4; ++i) {
                     const bool hi = (hot >> i) & 1u;
                     const unsigned int m = __ballot_sync(0xffffffffu, hi);
-#if GLENET_PIB_SLOTSKIP
-                    if (m == 0u) continue;                    // uniform: nobody queues its i-th point
-#endif
                     if (hi) wq[qn + __popc(m & lt)] = make_float4(cur.x[i], cur.y[i], cur.z[i], __int_as_float(p0 + i));
                     qn += __popc(m);
                 }
@@ -627,37 +586,10 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
             load_pts4(pts, p_begin + (j * (PIB_THREADS / 32) + warp) * PIB_WBATCH + lane * 4, p_end, vec, dst);
         };
         // register prefetch two batches ahead: one batch of cold points is shorter than a DRAM round trip
-#if GLENET_PIB_UNROLL2
-        // Two buffers used alternately in a loop unrolled by two: nothing is copied, a buffer is refilled right after
-        // its batch and has the other buffer's batch to arrive (an L2 hit thanks to the prefetch further ahead).
-        auto l2_prefetch = [&](const int j) {
-#if GLENET_PIB_L2PF
-            if (j + GLENET_PIB_L2PF < NB) {
-                const char* b0 = reinterpret_cast<const char*>(pts + (size_t)(p_begin + ((j + GLENET_PIB_L2PF) * (PIB_THREADS / 32) + warp) * PIB_WBATCH) * 3);
-                const char* line = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(b0) & ~(uintptr_t)127) + lane * 128;
-                if (line < b0 + PIB_WBATCH * 12 && line < reinterpret_cast<const char*>(pts + (size_t)p_end * 3))
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(line));
-            }
-#endif
-        };
-        Pts4 b0, b1;
-        fetch(b0, 0);
-#pragma unroll 1
-        for (int j = 0; j < NB; j += 2) {
-            if (j + 1 < NB) fetch(b1, j + 1);
-            l2_prefetch(j);
-            batch(b0, j);
-            if (j + 2 < NB) fetch(b0, j + 2);
-            l2_prefetch(j + 1);
-            if (j + 1 < NB) batch(b1, j + 1);
-        }
-#else
         Pts4 cur, nxt;
         fetch(cur, 0);
-#if GLENET_PIB_REGPF >= 2
         if (NB > 1) fetch(nxt, 1);
-#endif
-#if GLENET_PIB_L2PF && GLENET_PIB_PFPTR
+#if GLENET_PIB_L2PF
         // this lane's line of the batch GLENET_PIB_L2PF ahead; a batch is 1536 bytes = at most 13 lines, and the stride
         // from batch to batch (12288 bytes) keeps the alignment, so the pointer simply advances
         const char* pf_line;
@@ -670,35 +602,18 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
 #endif
 #pragma unroll 1
         for (int j = 0; j < NB; ++j) {
-#if GLENET_PIB_REGPF >= 2
             Pts4 nxt2;
             if (j + 2 < NB) fetch(nxt2, j + 2);
-#else
-            if (j + 1 < NB) fetch(nxt, j + 1);
-#endif
-#if GLENET_PIB_L2PF && GLENET_PIB_PFPTR
+#if GLENET_PIB_L2PF
             // The register rotation below (cur = nxt; nxt = nxt2) has to wait for nxt2, so the register prefetch is
             // effectively ONE batch deep.  An L2 prefetch further ahead turns that wait into an L2 hit.
             if (pf_line < pf_end) asm volatile("prefetch.global.L2 [%0];" :: "l"(pf_line));
             pf_line += (pf_line < pf_end) ? (size_t)PIB_THREADS * 4 * 12 : 0;
-#elif GLENET_PIB_L2PF
-            // The register rotation below (cur = nxt; nxt = nxt2) has to wait for nxt2, so the register prefetch is
-            // effectively ONE batch deep.  An L2 prefetch further ahead turns that wait into an L2 hit: the 1536 bytes
-            // of a batch are at most 13 lines, one `prefetch.global.L2` per lane.
-            if (j + GLENET_PIB_L2PF < NB) {
-                const char* b0 = reinterpret_cast<const char*>(pts + (size_t)(p_begin + ((j + GLENET_PIB_L2PF) * (PIB_THREADS / 32) + warp) * PIB_WBATCH) * 3);
-                const char* line = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(b0) & ~(uintptr_t)127) + lane * 128;
-                if (line < b0 + PIB_WBATCH * 12 && line < reinterpret_cast<const char*>(pts + (size_t)p_end * 3))
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(line));
-            }
 #endif
             batch(cur, j);
             cur = nxt;
-#if GLENET_PIB_REGPF >= 2
             nxt = nxt2;
-#endif
         }
-#endif
         if (qn) {                                              // leftovers of the run
             if (lane < qn) resolve(wq[lane]);
             __syncwarp();
