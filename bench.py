@@ -42,9 +42,10 @@ PAIRS_PER_FRAME = N_ANCHORS * N_GT
 BYTES_PER_PAIR = 4.0           # the culled sweep is bound by the float32 result write
 WORKLOAD = "cfg4 anchor sweep: 16 frames x boxes_iou_bev(211200 KITTI anchors x 100 GT) per GPU"
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch from the ncu --set full capture in profiles/ (None until measured)
-TRAFFIC_PER_LAUNCH = 1.506e9
-TRAFFIC_NOTE = ("profiles/r01_iou_frames_summary.txt: 1.377 GB written + 0.129 GB read per 16-frame launch vs 1.352 GB algorithmic "
-                "(the 5.9 MB of anchors are re-read per frame because 1.4 GB of result stores evict them from L2)")
+TRAFFIC_PER_LAUNCH = 1.442e9
+TRAFFIC_NOTE = ("profiles/r01_iou_frames_summary.txt: 1.381 GB written + 0.061 GB read per 16-frame launch vs 1.352 GB algorithmic "
+                "(2 % write overhead at tile edges; the box loads carry an L2 evict-last policy, which halved the re-reads of the "
+                "5.9 MB of anchors that 1.4 GB of result stores push out of L2)")
 
 
 def measured_peaks():

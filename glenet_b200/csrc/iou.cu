@@ -106,6 +106,9 @@ struct __align__(128) IouSmem {
 };
 static_assert(IOU_TR_MAX * IOU_TC_MAX <= 65536 && IOU_TC_MAX == 128, "queue entries are (row << 7) | col in 16 bits");
 
+#ifndef GLENET_IOU_LDHINT   // 1: box loads of the tile prologue carry an L2 evict-last policy
+#define GLENET_IOU_LDHINT 1
+#endif
 // ---- bulk-copy engine (TMA without a tensor map): shared -> global, tracked by bulk async-groups
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned int bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
@@ -333,8 +336,17 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
         const int k = is_row ? i : i - tr;
         const float* box = (is_row ? A + (size_t)(r0 + k) * 7 : B + (size_t)(c0 + k) * 7);
         float raw[7];
+#if GLENET_IOU_LDHINT
+        // the boxes are re-read by every frame / tile row while 1.4 GB of results stream through L2: keep them (evict-last)
+        unsigned long long pol;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#pragma unroll
+        for (int f = 0; f < 7; ++f)
+            asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(raw[f]) : "l"(box + f), "l"(pol));
+#else
 #pragma unroll
         for (int f = 0; f < 7; ++f) raw[f] = box[f];
+#endif
         float* rec = (is_row ? sm.rpre : sm.cpre) + k * BPS;
 #pragma unroll
         for (int f = 0; f < 7; ++f) rec[f] = raw[f];
