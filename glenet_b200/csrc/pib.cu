@@ -10,12 +10,14 @@
 //
 //   build kernel (1 CTA / frame): per-box record {cx, cy, cz, cos(-h), sin(-h), tx, ty, tz}
 //       with the reference's FP64 comparisons folded into directed-rounded FP32 thresholds
-//       (exactly equivalent, see box_record()), plus a G x G uniform grid over the frame's
-//       boxes in CSR form: cell -> list of boxes whose (padded) footprint touches the cell.
-//   query kernel: points stream through coalesced; a point looks up its cell in a
-//       shared-memory copy of the CSR offsets and runs the exact reference predicate only
-//       against that cell's candidates, keeping the minimum index (= first hit of the
-//       reference's ascending loop with `break`).
+//       (exactly equivalent, see box_thresholds()); the z window of all boxes together; a fine
+//       256 x 256 occupancy bitmap of the (padded) footprints; and a coarse G x G grid whose
+//       cells hold up to four candidate boxes inline (CSR lists only for cells with more).
+//   query kernel: points stream through coalesced; a point outside the z window or in an
+//       empty bitmap cell is background at once; the others look up their coarse cell in
+//       shared memory and run the exact reference predicate only against that cell's
+//       candidates, keeping the minimum index (= first hit of the reference's ascending
+//       loop with `break`).
 // Frames whose boxes cannot be binned (non-finite extents, list overflow) fall back, on the
 // device and per frame, to the exhaustive loop with the same predicate -- never to the host.
 #include "common.cuh"
@@ -419,14 +421,17 @@ __device__ __forceinline__ void load_pts4(const float* __restrict__ pts, int p0,
     }
 }
 
-// Query kernel.  Persistent CTAs walk a contiguous range of (frame, chunk) work items and re-stage
-// the frame tables (fine bitmap 8 KB, coarse CSR offsets 16 KB, box records) only when the frame
-// changes.  Inside a chunk every WARP is autonomous -- no CTA barrier on the streaming path:
-//   1. 4 consecutive points per lane (three float4 loads, next batch prefetched into registers);
-//   2. fine-bitmap lookup in shared memory, provisional -1 for all four points with one int4 store;
-//   3. the ~13 % of points whose fine cell is occupied go to the warp's private queue
-//      (warp prefix sum, no atomics), and the warp drains it at once: coarse cell -> candidate
-//      list -> exact predicate -> minimum index over the provisional -1.
+// Query kernel.  Persistent CTAs (GLENET_PIB_CTAS per SM) walk a contiguous range of (frame, chunk) work
+// items -- the chunks of one frame as ONE run of points -- and re-stage the frame tables (fine bitmap 8 KB,
+// coarse cells 32 KB, box records) only when the frame changes.  Inside a run every WARP is autonomous -- no
+// CTA barrier on the streaming path:
+//   1. 4 consecutive points per lane (three float4 loads, two batches prefetched into registers and the
+//      lines of the batch GLENET_PIB_L2PF further ahead prefetched into L2);
+//   2. fine-bitmap lookup in shared memory combined with the z window, provisional -1 for all four points
+//      with one int4 store;
+//   3. the ~9 % of points that stay hot go to the warp's private queue (ballot prefix, no atomics), and the
+//      warp drains it 32 entries at a time: coarse cell -> up to four inline candidates (a list through L2
+//      only for crowded cells) -> exact predicate -> minimum index over the provisional -1.
 __global__ void __launch_bounds__(PIB_THREADS, GLENET_PIB_CTAS)
 pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace ws, int* __restrict__ out_all,
                  int chunks_per_frame, int total_chunks) {
