@@ -1,0 +1,40 @@
+"""ctypes binding of ``oracle/librotate_iou_oracle.so`` -- TEST INFRASTRUCTURE ONLY.
+
+CPU restatement of ``rotate_iou_gpu_eval`` (pcdet/datasets/kitti/kitti_object_eval_python/rotate_iou.py:263-330), the
+rotated IoU of the KITTI evaluator.  It prepares the next row of the scope table; the product has
+no kernel for it yet."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "librotate_iou_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(HERE, "rotate_iou_oracle.c")
+    if force or not os.path.isfile(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", HERE, "-B", "librotate_iou_oracle.so"], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return LIB
+
+
+def rotate_iou_eval(boxes: np.ndarray, query_boxes: np.ndarray, criterion: int = -1) -> np.ndarray:
+    """(N, 5) x (K, 5) [x, y, x_d, y_d, angle] -> (N, K) float32; criterion -1: IoU, 0: / area(query), 1: / area(box)."""
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(LIB)
+        _lib.oracle_rotate_iou_eval.restype = None
+        _lib.oracle_rotate_iou_eval.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    b = np.ascontiguousarray(boxes, dtype=np.float32)
+    q = np.ascontiguousarray(query_boxes, dtype=np.float32)
+    assert b.ndim == 2 and b.shape[1] == 5 and q.ndim == 2 and q.shape[1] == 5
+    out = np.zeros((b.shape[0], q.shape[0]), dtype=np.float32)
+    if out.size:
+        _lib.oracle_rotate_iou_eval(b.ctypes.data, b.shape[0], q.ctypes.data, q.shape[0], int(criterion), out.ctypes.data)
+    return out

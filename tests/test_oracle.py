@@ -139,3 +139,26 @@ def test_v1_restated_python_wrapper_equals_reference_file(ref_iou3d):
     pred, _ = synth.head_pairs(50, 5)
     for mode in ("wlh", "lwh", "hwl"):
         assert torch.equal(u.boxes3d_to_bev_torch(pred, mode), ref_iou3d.boxes3d_to_bev_torch(pred, mode))
+
+
+# ------------------------------------------------------------------ next scope row: KITTI evaluator's rotated IoU
+def test_rotate_iou_eval_oracle_vs_reference_golden():
+    """oracle/rotate_iou_oracle.c against the reference's own numba kernel, run by numba's CUDA simulator
+    (tests/golden/make_golden_rotate_iou.py).  Tolerance 1e-5 absolute: the simulator and the restatement differ in
+    float32 / float64 promotion of a few intermediates; zeros must be the same zeros."""
+    import os
+    from conftest import ROOT
+    from oracle import rotate_iou
+    g = np.load(os.path.join(ROOT, "tests", "golden", "rotate_iou_golden.npz"))
+    for crit in (-1, 0, 1):
+        got, want = rotate_iou.rotate_iou_eval(g["boxes"], g["query"], crit), g[f"iou_{crit}"]
+        assert got.shape == want.shape == (70, 45) and got.dtype == np.float32
+        assert np.abs(got - want).max() <= 1e-5
+        np.testing.assert_array_equal(got == 0, want == 0)
+    assert (g["iou_-1"] > 0).sum() > 400
+    # criterion semantics (rotate_iou.py:249-261): the QUERY box is rbox1 of devRotateIoUEval (:281-283)
+    inter = rotate_iou.rotate_iou_eval(g["boxes"], g["query"], 2)
+    a_q, a_b = g["query"][:, 2] * g["query"][:, 3], g["boxes"][:, 2] * g["boxes"][:, 3]
+    np.testing.assert_allclose(rotate_iou.rotate_iou_eval(g["boxes"], g["query"], 0), inter / a_q[None, :], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(rotate_iou.rotate_iou_eval(g["boxes"], g["query"], 1), inter / a_b[:, None], rtol=0, atol=1e-6)
+    assert rotate_iou.rotate_iou_eval(g["boxes"][:0], g["query"]).shape == (0, 45)
