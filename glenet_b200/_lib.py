@@ -62,8 +62,13 @@ def load() -> ctypes.CDLL:
         if _lib is not None:
             return _lib
         path = _build.LIBPATH
-        if not os.path.isfile(path):
+        # (re)build when the .so is missing or older than any source; returns at once when nothing is stale.  On a box
+        # without nvcc an existing .so is used as it is.
+        try:
             _build.build_library()
+        except RuntimeError:
+            if not os.path.isfile(path):
+                raise
         lib = ctypes.CDLL(path)
         for name, (restype, argtypes) in _SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the ABI does not export it

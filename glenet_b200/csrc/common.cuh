@@ -42,6 +42,9 @@ inline int set_smem(K kernel, size_t bytes, const char* what, bool max_carveout 
     return GLENET_OK;
 }
 
+// per-device caches of "attribute already set" flags are indexed by the CUDA device ordinal
+#define GLENET_MAX_DEVICES 64
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace glenet

@@ -31,6 +31,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math_constants.h>
+#include <atomic>
 
 namespace glenet {
 
@@ -46,9 +47,6 @@ namespace glenet {
 #endif
 #ifndef GLENET_IOU_QCAP
 #define GLENET_IOU_QCAP 512
-#endif
-#ifndef GLENET_IOU_WARP_MIN_CTAS
-#define GLENET_IOU_WARP_MIN_CTAS 2000000000   // warp-autonomous kernel off by default until validated on the GPU (GLENET_IOU_KERNEL=warp forces it)
 #endif
 #ifndef GLENET_IOU_ZBYTES
 #define GLENET_IOU_ZBYTES 4096
@@ -488,8 +486,6 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
 #endif
 }
 
-#include "iou_warp.cuh"
-
 // out[i] = f(a[i], b[i / group]) -- every pair is "heavy" by construction (CVAE samples vs their GT)
 constexpr int ALIGNED_THREADS = 128;
 template <int MODE, bool FMA>
@@ -504,7 +500,11 @@ iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict_
     const float* bb = B + (size_t)(i / group) * 7;
     float out_v = 0.f;
     const float ddx = ba[0] - bb[0], ddy = ba[1] - bb[1];
-    const float rr = cull_radius(ba) + cull_radius(bb);
+    float rr = cull_radius(ba) + cull_radius(bb);
+    // 3D IoU: 0 * NaN = NaN in the reference's torch arithmetic, so a pair with a non-finite z term is never culled
+    // (same rule as the tile kernel's prologue)
+    if (MODE == MODE_IOU3D && (!z_terms_finite(z_terms(ba[2], ba[5], __fmul_rn(ba[3], ba[4]))) || !z_terms_finite(z_terms(bb[2], bb[5], __fmul_rn(bb[3], bb[4])))))
+        rr = CUDART_INF_F;
     if (!(ddx * ddx + ddy * ddy > rr * rr)) {
         box_prepare<FMA>(ba, device_trig_fused(ba[6]), a);
         box_prepare<FMA>(bb, device_trig_fused(bb[6]), b);
@@ -562,11 +562,16 @@ static int launch_tile(const float* A, const float* trigA, int na, const float* 
                        long long* sp_idx, float* sp_val, unsigned long long* sp_count, long long sp_cap,
                        unsigned long long* row_key, unsigned long long* col_key) {
     auto kernel = iou_tile_kernel<MODE, FMA, OUT>;
-    static int resident = 0;   // per template instantiation
+    // the opt-in shared-memory size and the occupancy are per-device settings: cached per (instantiation, device)
+    static std::atomic<int> resident_of[GLENET_MAX_DEVICES];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int resident = (dev >= 0 && dev < GLENET_MAX_DEVICES) ? resident_of[dev].load(std::memory_order_acquire) : 0;
     if (!resident) {
         int rc = set_smem(kernel, sizeof(IouSmem), what, true);
         if (rc) return rc;
         resident = resident_ctas(kernel);
+        if (dev >= 0 && dev < GLENET_MAX_DEVICES) resident_of[dev].store(resident, std::memory_order_release);
     }
     int TR, TC, row_tiles, col_tiles;
     pick_tiles(na, nb, frames, resident, TR, TC, row_tiles, col_tiles);
@@ -614,48 +619,6 @@ static int launch_iou(const float* A, const float* trigA, int na, const float* B
     if (na == 0 || nb == 0 || frames == 0) return GLENET_OK;
     if (!A || !B || (!out && !sp_count && !row_key)) return fail(GLENET_EINVAL, "%s: null pointer", what);
     if (!FMA && (!trigA || !trigB)) return fail(GLENET_EINVAL, "%s: CPU dialect needs host-evaluated trig tables", what);
-    // Large sweeps go to the warp-autonomous kernel (iou_warp.cuh); everything else to the tile kernel, whose
-    // small tiles spread a small problem over more SMs.  GLENET_IOU_KERNEL=tile|warp overrides (tests, tuning).
-    {
-        static int forced = -1;   // 0 = auto, 1 = tile, 2 = warp
-        if (forced < 0) {
-            const char* e = getenv("GLENET_IOU_KERNEL");
-            forced = !e ? 0 : (!strcmp(e, "tile") ? 1 : (!strcmp(e, "warp") ? 2 : 0));
-        }
-        const long long wk_ctas = (long long)((na + WK_TR - 1) / WK_TR) * ((nb + IOU_TC_MAX - 1) / IOU_TC_MAX) * frames;
-        const bool use_warp = forced == 2 || (forced == 0 && wk_ctas >= GLENET_IOU_WARP_MIN_CTAS);
-        if (use_warp) {
-            auto wk = iou_warp_kernel<MODE, FMA>;
-            static bool wk_ready = false;
-            if (!wk_ready) {
-                int rc = set_smem(wk, sizeof(WkSmem), what, true);
-                if (rc) return rc;
-                wk_ready = true;
-            }
-            const int col_tiles = (nb + IOU_TC_MAX - 1) / IOU_TC_MAX;
-            const int TC = ((nb + col_tiles - 1) / col_tiles + 3) / 4 * 4;
-            const int ct = (nb + TC - 1) / TC, rt = (na + WK_TR - 1) / WK_TR;
-            if (rt > 65535 || frames > 65535) return fail(GLENET_EINVAL, "%s: more than 65535 row tiles or frames", what);
-            IouFrames fr;
-            fr.stride_a = stride_a; fr.stride_b = stride_b; fr.stride_out = (sp_count || row_key) ? 0 : stride_out; fr.na = na;
-            fr.sp_idx = sp_idx; fr.sp_val = sp_val; fr.sp_count = sp_count; fr.sp_cap = sp_cap;
-            fr.row_key = row_key; fr.col_key = col_key;
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)ct, (unsigned)rt, (unsigned)frames); cfg.blockDim = dim3(WK_THREADS);
-            cfg.dynamicSmemBytes = sizeof(WkSmem); cfg.stream = stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, wk, A, na, B, nb, reinterpret_cast<const float4*>(trigA),
-                                               reinterpret_cast<const float4*>(trigB), out, TC, fr);
-            if (e != cudaSuccess) {
-                snprintf(last_error_buf(), 512, "%s: launch failed: %s", what, cudaGetErrorString(e));
-                return -(int)e;
-            }
-            return check_launch(what);
-        }
-    }
     if (sp_count || row_key)
         return launch_tile<MODE, FMA, OUT_REDUCED>(A, trigA, na, B, trigB, nb, out, stream, what, frames, stride_a, stride_b, stride_out, sp_idx, sp_val, sp_count, sp_cap, row_key, col_key);
     return launch_tile<MODE, FMA, OUT_DENSE>(A, trigA, na, B, trigB, nb, out, stream, what, frames, stride_a, stride_b, stride_out, sp_idx, sp_val, sp_count, sp_cap, row_key, col_key);

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "geom.cuh"
 #include "../../include/glenet_geom.h"
+#include <atomic>
 
 namespace glenet {
 
@@ -339,13 +340,18 @@ static int launch_nms(bool normal, const float* boxes, int frames, int n, float 
     const long tiles = (long)col_blocks * (col_blocks + 1) / 2;
     if (tiles * frames > 0x7fffffffL) return fail(GLENET_EINVAL, "%s: too many tiles", what);
     unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws);
-    static bool attr_done = false;
-    if (!attr_done) {
+    // opt-in shared-memory sizes are per-device settings: remember where they have been set
+    static std::atomic<unsigned char> attr_done[GLENET_MAX_DEVICES];   // bit 0: mask kernels, bit 1 / 2: sweep kernel <false> / <true>
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool cacheable = dev >= 0 && dev < GLENET_MAX_DEVICES;
+    unsigned char done = cacheable ? attr_done[dev].load(std::memory_order_acquire) : 0;
+    if (!(done & 1)) {
         int rc = set_smem(nms_mask_kernel<false>, sizeof(NmsSmem), what);
         if (rc) return rc;
         rc = set_smem(nms_mask_kernel<true>, sizeof(NmsSmem), what);
         if (rc) return rc;
-        attr_done = true;
+        if (cacheable) attr_done[dev].fetch_or(1, std::memory_order_release);
     }
     const unsigned grid = (unsigned)(tiles * frames);
     if (normal)
@@ -359,11 +365,11 @@ static int launch_nms(bool normal, const float* boxes, int frames, int n, float 
     if (remv_bytes > 200 * 1024) return fail(GLENET_EINVAL, "%s: n too large for the on-chip suppression words", what);
     const bool pre = pre_bytes <= 200 * 1024;   // n <= ~12 700 boxes
     const size_t sweep_smem = pre ? pre_bytes : remv_bytes;
-    static bool sweep_attr[2] = {false, false};
-    if (!sweep_attr[pre]) {
+    const unsigned char sweep_bit = pre ? 4 : 2;
+    if (!(done & sweep_bit)) {
         rc = pre ? set_smem(nms_sweep_kernel<true>, 200 * 1024, what) : set_smem(nms_sweep_kernel<false>, 200 * 1024, what);
         if (rc) return rc;
-        sweep_attr[pre] = true;
+        if (cacheable) attr_done[dev].fetch_or(sweep_bit, std::memory_order_release);
     }
     if (pre)
         nms_sweep_kernel<true><<<frames, SWEEP_THREADS, sweep_smem, stream>>>(mask, n, col_blocks, reinterpret_cast<long long*>(keep), num_keep);

@@ -24,6 +24,7 @@
 #include "../../include/glenet_geom.h"
 #include <float.h>
 #include <math.h>
+#include <atomic>
 
 namespace glenet {
 
@@ -734,10 +735,10 @@ int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int 
     }
     PibWorkspace w = pib_layout(ws, B, N);
     // the opt-in shared-memory sizes are per device: remember where they have been set
-    static bool attr_done[64] = {false};
+    static std::atomic<bool> attr_done[GLENET_MAX_DEVICES];
     int dev = 0;
     cudaGetDevice(&dev);
-    const bool need_attr = dev < 0 || dev >= 64 || !attr_done[dev];
+    const bool need_attr = dev < 0 || dev >= GLENET_MAX_DEVICES || !attr_done[dev].load(std::memory_order_acquire);
     int rc = GLENET_OK;
     if (need_attr) {
         rc = set_smem(pib_build_kernel, PIB_BUILD_SMEM, what);
@@ -755,7 +756,7 @@ int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int 
     if (need_attr) {
         rc = set_smem(pib_query_kernel, smem_fixed + sizeof(float) * 8 * PIB_SMEM_BOXES, what);
         if (rc) return rc;
-        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+        if (dev >= 0 && dev < GLENET_MAX_DEVICES) attr_done[dev].store(true, std::memory_order_release);
     }
     const long resident = (long)GLENET_PIB_CTAS * 148;   // persistent: GLENET_PIB_CTAS CTAs per SM
     const unsigned grid = (unsigned)(total < resident ? total : resident);

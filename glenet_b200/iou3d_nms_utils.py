@@ -45,6 +45,23 @@ def _stream(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def _device_for_host_call(what: str) -> torch.device:
+    """The GPU that executes a host-signature (``_cpu``) entry point.
+
+    The reference calls these from forked DataLoader workers (database_sampler.py:246-247, box_utils.py:86,
+    augmentor_utils.py:149).  CUDA cannot be initialised in a child forked after the parent touched it, and this
+    package has no host implementation to fall back to (by design) -- so fail loudly and say what to do."""
+    bad_fork = getattr(torch.cuda, "_is_in_bad_fork", None)
+    if bad_fork is not None and bad_fork():
+        raise RuntimeError(
+            f"glenet_b200.{what} executes on the GPU and was called in a process forked after CUDA was initialised "
+            "(a DataLoader worker?).  Use multiprocessing_context='spawn' for the workers, or keep the reference's host "
+            "function for this call site: glenet_b200.shim.install() does so by default (cpu_entry_points=False).")
+    if not torch.cuda.is_available():
+        raise RuntimeError(f"glenet_b200.{what} needs a CUDA device: there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def _check_cuda_f32(t: torch.Tensor, name: str) -> None:
     # the reference's CHECK_INPUT exits the process on a CPU tensor (iou3d_nms.cpp:14-26) and
     # .data<float>() throws on another dtype; raise instead
@@ -97,8 +114,8 @@ def boxes_bev_iou_cpu(boxes_a, boxes_b):
     na, nb = a.shape[0], b.shape[0]
     ans_iou = boxes_a.new_zeros(torch.Size((na, nb)))
     if na and nb:
+        dev = _device_for_host_call("boxes_bev_iou_cpu")
         lib = _lib.load()
-        dev = torch.device("cuda", torch.cuda.current_device())
         # one host buffer: [boxes_a | boxes_b | trig_a | trig_b] -> one H2D copy
         # (the trig tables are read as float4 => their offsets are padded to 16 bytes)
         o_b = na * 7

@@ -15,39 +15,28 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .iou3d_nms_utils import _check_cuda_f32, _stream
+from .iou3d_nms_utils import _check_cuda_f32, _device_for_host_call, _stream
 
 __all__ = ["boxes_aligned_iou3d_gpu", "boxes_aligned_overlap_bev_gpu", "boxes_aligned_overlap_bev_cpu", "boxes3d_to_bev_torch"]
 
 
 def boxes3d_to_bev_torch(boxes3d, box_mode='wlh', rect=False):
-    """
-    Input(torch):
-        boxes3d: (N, 7) [x, y, z, h, w, l, ry]
-        rect: True/False means boxes in camera/velodyne coord system.
-    Output:
-        boxes_bev: (N, 5) [x1, y1, x2, y2, ry/rz], left-bottom: (x1, y1), right-top: (x2, y2), ry/rz: clockwise rotation angle
+    """(N, 7) ``[x, y, z, d3, d4, d5, ry]`` (or (N, 5) ``[x, y, d2, d3, ry]``) -> (N, 5) ``[x1, y1, x2, y2, ry]``.
 
-    Reference: iou3d_utils.py:79-106 (plain torch there too; kept for callers that want the BEV rows).
-    """
-    boxes_bev = boxes3d.new(torch.Size((boxes3d.shape[0], 5)))
-    if boxes3d.shape[-1] == 5:
-        w_index, l_index = box_mode.index('w') + 2, box_mode.index('l') + 2
-    elif boxes3d.shape[-1] == 7:
-        w_index, l_index = box_mode.index('w') + 3, box_mode.index('l') + 3
-    else:
+    Same result as the reference helper (``pcdet/ops/iou3d/iou3d_utils.py:79-106``): ``box_mode`` names which of the three
+    extent columns is 'w' (the extent along the first BEV axis) and 'l' (along the second); ``rect=True`` selects the
+    camera convention (BEV plane = columns 0 and 2, 'l' along the first axis).  One fused ``stack`` instead of five
+    column assignments; the halves are computed as ``extent / 2`` and added / subtracted once each, as there.
+    :func:`boxes_aligned_iou3d_gpu` does NOT call this -- the kernel fuses the conversion -- it is kept for callers
+    that want the BEV rows (``boxes_aligned_overlap_bev_gpu``)."""
+    width = boxes3d.shape[-1]
+    if width not in (5, 7):
         raise NotImplementedError
-    half_w, half_l = boxes3d[:, w_index] / 2., boxes3d[:, l_index] / 2.
-    if rect:
-        cu, cv = boxes3d[:, 0], boxes3d[:, 2]
-        boxes_bev[:, 0], boxes_bev[:, 1] = cu - half_l, cv - half_w
-        boxes_bev[:, 2], boxes_bev[:, 3] = cu + half_l, cv + half_w
-    else:
-        cu, cv = boxes3d[:, 0], boxes3d[:, 1]
-        boxes_bev[:, 0], boxes_bev[:, 1] = cu - half_w, cv - half_l
-        boxes_bev[:, 2], boxes_bev[:, 3] = cu + half_w, cv + half_l
-    boxes_bev[:, 4] = boxes3d[:, -1]
-    return boxes_bev
+    first_extent = 2 if width == 5 else 3
+    half = {k: boxes3d[:, first_extent + box_mode.index(k)] / 2. for k in 'wl'}
+    u, v = boxes3d[:, 0], boxes3d[:, 2 if rect else 1]
+    hu, hv = (half['l'], half['w']) if rect else (half['w'], half['l'])
+    return torch.stack((u - hu, v - hv, u + hu, v + hv, boxes3d[:, -1]), dim=1)
 
 
 def boxes_aligned_overlap_bev_gpu(boxes_a_bev, boxes_b_bev):
@@ -112,8 +101,8 @@ def boxes_aligned_overlap_bev_cpu(boxes_a_bev, boxes_b_bev):
     n = a.shape[0]
     ans = a.new_zeros((n, 1))
     if n:
+        dev = _device_for_host_call("boxes_aligned_overlap_bev_cpu")
         lib = _lib.load()
-        dev = torch.device("cuda", torch.cuda.current_device())
         # one pinned host buffer [boxes_a | boxes_b | pad | trig_a | trig_b] -> one H2D copy; trig tables 16-byte aligned
         o_b, o_ta = n * 5, (2 * n * 5 + 3) // 4 * 4
         o_tb = o_ta + 4 * n

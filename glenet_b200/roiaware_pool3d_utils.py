@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .iou3d_nms_utils import _stream, check_numpy_to_torch
+from .iou3d_nms_utils import _device_for_host_call, _stream, check_numpy_to_torch
 
 __all__ = ["points_in_boxes_cpu", "points_in_boxes_cpu_lists", "points_in_boxes_gpu"]
 
@@ -45,8 +45,8 @@ def _cpu_dialect_mask_on_device(points: torch.Tensor, boxes: torch.Tensor) -> to
     p = points.float().contiguous()
     if b.is_cuda or p.is_cuda:
         raise RuntimeError("points_in_boxes_cpu expects CPU tensors / numpy arrays")
+    dev = _device_for_host_call("points_in_boxes_cpu")
     lib = _lib.load()
-    dev = torch.device("cuda", torch.cuda.current_device())
     host = torch.empty(n * 7 + n * 2 + m * 3, dtype=torch.float32).pin_memory()
     o_t, o_p = n * 7, n * 9
     host[:o_t].copy_(b.view(-1))

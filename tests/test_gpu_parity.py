@@ -294,36 +294,6 @@ def test_fuzz_extreme_scales_vs_reference_kernels(cuda, ref_so, centre_scale, di
     assert torch.equal(R.points_in_boxes_gpu(pts, b[None]), ref_so.points_in_boxes_gpu(pts, b[None]))
 
 
-def test_experimental_warp_kernel_matches_tile_kernel(cuda, tmp_path):
-    """csrc/iou_warp.cuh (off by default) must stay bit-identical to the tile kernel: run a few shapes
-    in a subprocess with GLENET_IOU_KERNEL=warp and compare with this process's (tile kernel) results."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    script = (
-        "import sys, torch; sys.path.insert(0, %r)\n"
-        "from glenet_b200 import iou3d_nms_utils as I, synth\n"
-        "dev = torch.device('cuda:0'); out = {}\n"
-        "a = synth.anchors_kitti3()[:20000].to(dev)\n"
-        "g = torch.stack([synth.kitti_boxes(100, 60 + f) for f in range(3)]).to(dev)\n"
-        "out['frames'] = I.boxes_iou_bev_frames(a, g).cpu(); out['f3d'] = I.boxes_iou3d_gpu_frames(a, g[:, :37].contiguous()).cpu()\n"
-        "p = synth.proposals(900, 8, 2)[0].to(dev)\n"
-        "out['dense'] = I.boxes_iou_bev(p, p).cpu(); out['wide'] = I.boxes_overlap_bev(p[:300], synth.kitti_boxes(301, 4).to(dev)).cpu()\n"
-        "out['max'] = torch.stack([t.float() for t in I.iou_max_overlaps_frames(a, g)[:2]]).cpu()\n"
-        "torch.save(out, %r)\n"
-    )
-    res = {}
-    for kernel in ("tile", "warp"):
-        path = str(tmp_path / (kernel + ".pt"))
-        env = dict(os.environ, GLENET_IOU_KERNEL=kernel)
-        subprocess.run([sys.executable, "-c", script % (root, path)], check=True, env=env, timeout=300)
-        res[kernel] = torch.load(path)
-    for k in res["tile"]:
-        assert torch.equal(res["tile"][k], res["warp"][k]), k
-    assert float(res["tile"]["frames"].max()) > 0.5
-
-
 def test_dense_matrix_many_queue_drains(cuda):
     """Dense tiles (thousands of clipped pairs per tile => several queue drains per CTA): the result must be
     reproducible run after run and equal to a row-slab evaluation, which tiles the matrix differently
@@ -687,3 +657,89 @@ def test_v1_api_behaviour(cuda):
     assert float((same - 1).abs().max()) < 1e-4
     wide = torch.cat([pred, pred], dim=1)[:, :14]           # non-contiguous views are accepted, as .contiguous() in the reference
     assert torch.equal(I1.boxes_aligned_iou3d_gpu(wide[:, :7], tgt), I1.boxes_aligned_iou3d_gpu(pred, tgt))
+
+
+# ------------------------------------------------------------------ round 2: the holes VERDICT r01 named
+def _block_diagonal(fn, samples, gt, group, rows_per_call=6000):
+    """The drop-in form of cfg3: blocked pairwise calls, block diagonal taken."""
+    out = []
+    for r0 in range(0, samples.shape[0], rows_per_call):
+        r1 = min(samples.shape[0], r0 + rows_per_call)
+        g0, g1 = r0 // group, (r1 - 1) // group + 1
+        full = fn(samples[r0:r1].contiguous(), gt[g0:g1].contiguous())
+        idx = torch.arange(r0, r1, device=samples.device)
+        out.append(full[idx - r0, idx // group - g0])
+    return torch.cat(out)
+
+
+def test_aligned_iou_cfg3_bit_exact_vs_reference_block_diagonals(cuda, ref_so):
+    """cfg3 (CVAE: 30 samples x 20 000 GT = 600 000 aligned pairs): boxes_iou3d_aligned / boxes_iou_bev_aligned /
+    overlap against the block diagonal of the REFERENCE's pairwise functions (iou3d_nms_utils.py:88-121), at the benched size,
+    including NaN / Inf rows (0 * NaN = NaN must propagate as in torch), a ragged last group and group = 1."""
+    smp, gt = synth.cvae_samples(20000, 30, 0)
+    smp, gt = smp.to(cuda), gt.to(cuda)
+    # non-finite z terms / headings / sizes on both sides; far-away samples (culled pairs) next to a NaN GT
+    smp[7, 2] = float("nan"); smp[31, 5] = float("inf"); smp[64, 6] = float("nan"); smp[95, 3] = float("nan")
+    gt[5, 2] = float("nan"); smp[5 * 30 + 3, 0] += 500.0
+    gt[6, 5] = float("inf"); gt[7, 4] = float("nan"); smp[200, 0] += 300.0; smp[201, 1] -= 300.0
+    for name, ours, theirs in (("iou3d", I.boxes_iou3d_aligned, ref_so.boxes_iou3d_gpu), ("bev", I.boxes_iou_bev_aligned, ref_so.boxes_iou_bev)):
+        got = ours(smp, gt, 30)
+        want = _block_diagonal(theirs, smp, gt, 30)
+        g, w = got.cpu().numpy(), want.cpu().numpy()
+        np.testing.assert_array_equal(np.isnan(g), np.isnan(w), err_msg=name)
+        ok = ~np.isnan(w)
+        assert np.abs(g[ok] - w[ok]).max() <= IOU_TOL, name
+        np.testing.assert_array_equal(g[ok] == 0, w[ok] == 0)
+        assert (g[ok] == w[ok]).mean() >= 0.999, (name, (g[ok] == w[ok]).mean())
+        assert float(np.nanmax(g)) > 0.8
+        if name == "iou3d":        # NaN z terms poison the 3D IoU (0 * NaN), the BEV IoU never sees them
+            assert int(np.isnan(g).sum()) >= 60
+    # ragged last group (na not a multiple of group) and group = 1 (plain row-aligned pairs)
+    n = 30 * 777 + 11
+    got = I.boxes_iou3d_aligned(smp[:n], gt[:778], 30)
+    want = _block_diagonal(ref_so.boxes_iou3d_gpu, smp[:n], gt[:778], 30)
+    assert got.shape == (n,) and torch.equal(torch.nan_to_num(got, nan=-1.0), torch.nan_to_num(want, nan=-1.0))
+    a1, b1 = synth.cvae_samples(5000, 1, 3)
+    a1, b1 = a1.to(cuda), b1.to(cuda)
+    want1 = ref_so.boxes_iou_bev(a1[:3000], b1[:3000]).diagonal()
+    assert torch.equal(I.boxes_iou_bev_aligned(a1[:3000], b1[:3000], 1), want1)
+    # the dense pairwise kernel agrees with the aligned one on the same pairs (two code paths, one arithmetic)
+    blk = I.boxes_iou3d_gpu(smp[3000:9000].contiguous(), gt[100:300].contiguous())
+    idx = torch.arange(6000, device=cuda)
+    assert torch.equal(blk[idx, idx // 30], I.boxes_iou3d_aligned(smp[3000:9000].contiguous(), gt[100:300].contiguous(), 30))
+
+
+def test_points_in_boxes_benched_call_bit_exact_vs_reference(cuda, ref_so):
+    """The call bench.py times for cfg2 -- ONE points_in_boxes_gpu over a batch of frames, every frame with its own 200
+    boxes and its own 180 000 points (5 % resampled inside that frame's boxes) -- against the reference kernel
+    (roiaware_pool3d_kernel.cu:313-359).  16 frames here (the reference kernel takes ~14 ms per 128 frames, no problem,
+    but the bench's 128-frame input generation is what takes time); the batch dimension only strides the same code."""
+    B, M, N = 16, 180000, 200
+    boxes = torch.stack([synth.waymo_boxes(N, 100 + f) for f in range(B)])
+    pts = torch.stack([synth.points(M, boxes[f], synth.WAYMO_RANGE, 0.05, seed=500 + f) for f in range(B)])
+    boxes, pts = boxes.to(cuda), pts.to(cuda)
+    got, want = R.points_in_boxes_gpu(pts, boxes), ref_so.points_in_boxes_gpu(pts, boxes)
+    assert torch.equal(got, want)
+    inside = (want >= 0).float().mean(dim=1)
+    assert float(inside.min()) > 0.04 and float(inside.max()) < 0.12, inside      # every frame has its own resampled points
+
+
+def test_second_device_iou_and_nms(ref_so):
+    """The opt-in shared-memory attributes are per-device settings: the first call on cuda:1 must work after
+    cuda:0 has been used, for the IoU tile kernel (52 KB) and the NMS sweep (> 48 KB once n >= ~3000)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    boxes, scores = synth.proposals(4096, 20, 7)
+    gt = synth.kitti_boxes(100, 3)
+    res = []
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        b, sc, g = boxes.to(dev), scores.to(dev), gt.to(dev)
+        iou = I.boxes_iou_bev(b, g)
+        keep = I.nms_gpu(b, sc, 0.7)[0]
+        keep_n = I.nms_normal_gpu(b, sc, 0.7)[0]
+        pib = R.points_in_boxes_gpu(synth.points(50000, gt, synth.KITTI_RANGE, 0.2, seed=3)[None].to(dev), g[None])
+        assert iou.device == dev and keep.device == dev
+        res.append((iou.cpu(), keep.cpu(), keep_n.cpu(), pib.cpu()))
+    for x, y in zip(*res):
+        assert torch.equal(x, y)

@@ -12,12 +12,21 @@ from glenet_b200 import roiaware_pool3d_utils as R
 from glenet_b200 import shim, synth
 
 
+def _drop_pcdet_modules():
+    for name in [k for k in sys.modules if k == "pcdet" or k.startswith("pcdet.")]:
+        del sys.modules[name]
+
+
 def test_shim_registers_reference_module_paths():
-    shim.install()
+    _drop_pcdet_modules()
+    patched = shim.install()
     m = importlib.import_module("pcdet.ops.iou3d_nms.iou3d_nms_utils")
-    assert m is I
+    assert m.nms_gpu is I.nms_gpu and m.boxes_iou3d_gpu is I.boxes_iou3d_gpu and m.new_nms_gpu is I.new_nms_gpu
     from pcdet.ops.roiaware_pool3d import roiaware_pool3d_utils as r2
-    assert r2 is R
+    assert r2.points_in_boxes_gpu is R.points_in_boxes_gpu
+    # without pcdet installed the host-signature functions are provided too
+    assert r2.points_in_boxes_cpu is R.points_in_boxes_cpu and m.boxes_bev_iou_cpu is I.boxes_bev_iou_cpu
+    assert "nms_gpu" in patched["pcdet.ops.iou3d_nms.iou3d_nms_utils"]
     # the plugin mechanism of the reference: lookup by config string (model_nms_utils.py:40-52)
     for name in ("nms_gpu", "nms_normal_gpu"):
         assert callable(getattr(sys.modules["pcdet.ops.iou3d_nms.iou3d_nms_utils"], name))
@@ -63,7 +72,57 @@ def test_additive_apis_reject_bad_input_before_any_launch():
     assert torch.equal(bev[:, 2] - bev[:, 0], (pred[:, 0] + pred[:, 4] / 2) - (pred[:, 0] - pred[:, 4] / 2))   # 'lwh': w = column 4
 
 
+def test_shim_patches_a_real_checkout_function_by_function(tmp_path, monkeypatch):
+    """Inside a real pcdet checkout the original modules stay and keep everything this package does not provide
+    (RoIAwarePool3d for pcdet/models/roi_heads/partA2_head.py, the other functions of pcdet.ops.iou3d.iou3d_utils);
+    the _cpu entry points keep the reference's host code unless asked for (forked DataLoader workers)."""
+    _drop_pcdet_modules()
+    root = tmp_path / "checkout"
+    for pkg in ("pcdet", "pcdet/ops", "pcdet/ops/iou3d_nms", "pcdet/ops/roiaware_pool3d", "pcdet/ops/iou3d"):
+        (root / pkg).mkdir(parents=True, exist_ok=True)
+        (root / pkg / "__init__.py").write_text("")
+    (root / "pcdet/ops/iou3d_nms/iou3d_nms_utils.py").write_text(
+        "def nms_gpu(*a, **k):\n    return 'ref'\ndef boxes_bev_iou_cpu(*a):\n    return 'ref-cpu'\ndef some_other_helper():\n    return 7\n")
+    (root / "pcdet/ops/roiaware_pool3d/roiaware_pool3d_utils.py").write_text(
+        "class RoIAwarePool3d:\n    pass\ndef points_in_boxes_cpu(*a):\n    return 'ref-cpu'\ndef points_in_boxes_gpu(*a):\n    return 'ref'\n")
+    (root / "pcdet/ops/iou3d/iou3d_utils.py").write_text(
+        "def nms_gpu(*a):\n    return 'ref-v1'\ndef boxes_iou3d_gpu(*a):\n    return 'ref-v1'\ndef boxes_aligned_iou3d_gpu(*a):\n    return 'ref'\n")
+    monkeypatch.syspath_prepend(str(root))
+    importlib.invalidate_caches()
+    try:
+        shim.install()
+        m = importlib.import_module("pcdet.ops.iou3d_nms.iou3d_nms_utils")
+        r = importlib.import_module("pcdet.ops.roiaware_pool3d.roiaware_pool3d_utils")
+        v1 = importlib.import_module("pcdet.ops.iou3d.iou3d_utils")
+        assert m.__file__.startswith(str(root)) and m.nms_gpu is I.nms_gpu and m.some_other_helper() == 7
+        assert m.boxes_bev_iou_cpu() == "ref-cpu" and r.points_in_boxes_cpu() == "ref-cpu"        # left alone by default
+        assert hasattr(r, "RoIAwarePool3d") and r.points_in_boxes_gpu is R.points_in_boxes_gpu
+        assert v1.boxes_aligned_iou3d_gpu is I1.boxes_aligned_iou3d_gpu and v1.nms_gpu() == "ref-v1" and v1.boxes_iou3d_gpu() == "ref-v1"
+        shim.install(cpu_entry_points=True)
+        assert m.boxes_bev_iou_cpu is I.boxes_bev_iou_cpu and r.points_in_boxes_cpu is R.points_in_boxes_cpu
+    finally:
+        _drop_pcdet_modules()
+
+
+def test_cpu_entry_points_fail_loudly_without_a_usable_gpu(monkeypatch):
+    """No host implementation exists (by design): without a GPU, or in a child forked after CUDA initialisation,
+    the _cpu-named functions raise with an actionable message instead of computing on the CPU."""
+    a = synth.kitti_boxes(3, 0).numpy()
+    p = synth.points(10, synth.kitti_boxes(3, 0), seed=0).numpy()
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            I.boxes_bev_iou_cpu(a, a)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            R.points_in_boxes_cpu(p, a)
+    monkeypatch.setattr(torch.cuda, "_is_in_bad_fork", lambda: True)
+    with pytest.raises(RuntimeError, match="forked after CUDA was initialised"):
+        I.boxes_bev_iou_cpu(a, a)
+    with pytest.raises(RuntimeError, match="spawn"):
+        R.points_in_boxes_cpu(p, a)
+
+
 def test_shim_registers_the_aligned_iou_module():
+    _drop_pcdet_modules()
     shim.install()
     from pcdet.ops.iou3d.iou3d_utils import boxes_aligned_iou3d_gpu
     assert boxes_aligned_iou3d_gpu is I1.boxes_aligned_iou3d_gpu
