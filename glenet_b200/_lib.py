@@ -28,6 +28,22 @@ _SIGNATURES = {
                                                           ctypes.c_int, ctypes.c_int, ctypes.c_void_p, c_float_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p]),
     "glenet_boxes_iou_frames_max_gpu": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_longlong, ctypes.c_int, c_float_p, ctypes.c_longlong,
                                                        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "glenet_iou_keys_decode_gpu": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong,
+                                                  c_float_p, ctypes.c_void_p, c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "glenet_symm_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
+    "glenet_symm_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "glenet_symm_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
+    "glenet_symm_import": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "glenet_symm_unmap": (ctypes.c_int, [ctypes.c_void_p]),
+    "glenet_exchange_window_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_longlong]),
+    "glenet_exchange_status": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint)]),
+    "glenet_boxes_iou_frames_assign_gpu": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_longlong, ctypes.c_int, c_float_p, ctypes.c_longlong,
+                                                          ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p,
+                                                          c_float_p, ctypes.c_void_p, c_float_p, ctypes.c_void_p,
+                                                          ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_longlong, ctypes.c_uint, ctypes.c_void_p]),
+    "glenet_boxes_iou_frames_gather_gpu": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_longlong, ctypes.c_int, c_float_p, ctypes.c_longlong,
+                                                          ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_longlong,
+                                                          ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_longlong, ctypes.c_uint, ctypes.c_void_p]),
     "glenet_iou3d_v1_boxes_aligned_gpu": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                          c_float_p, c_float_p, c_float_p, ctypes.c_void_p]),
     "glenet_iou3d_v1_aligned_overlap_bev_gpu": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
@@ -46,7 +62,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 def lib_path() -> str:

@@ -44,6 +44,7 @@ inline int set_smem(K kernel, size_t bytes, const char* what, bool max_carveout 
 
 // per-device caches of "attribute already set" flags are indexed by the CUDA device ordinal
 #define GLENET_MAX_DEVICES 64
+#define GLENET_MAX_PEERS 8      // GPUs of one NVLink / NVSwitch box that can take part in an exchange
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

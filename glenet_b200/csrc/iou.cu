@@ -26,6 +26,7 @@
 // every pair in a 16x16 thread block with 208 B of local-memory stack per thread.
 #include "common.cuh"
 #include "geom.cuh"
+#include "exchange.cuh"
 #include "../../include/glenet_geom.h"
 #include <float.h>
 #include <stdlib.h>
@@ -62,7 +63,7 @@ constexpr int IOU_CTAS_PER_SM = GLENET_IOU_CTAS;  // register budget the kernel 
 constexpr int IOU_ZBYTES = GLENET_IOU_ZBYTES;     // block of zeros in shared memory = largest bulk store of the zero fill
 constexpr int BPS = BP_STRIDE_BEV;         // BoxPre stride in shared memory (the z terms of 3D IoU are read per clipped pair)
 
-enum { OUT_DENSE = 0, OUT_REDUCED = 1 };   // kernel output: the (na, nb) matrix, or the coordinate list / row-column maxima
+enum { OUT_DENSE = 0, OUT_REDUCED = 1, OUT_BOTH = 2 };   // kernel output: the (na, nb) matrix; the coordinate list / row-column maxima; matrix + maxima
 enum { MODE_OVERLAP = 0, MODE_IOU_BEV = 1, MODE_IOU3D = 2 };
 
 #ifdef GLENET_PHASE_TIMING   // developer instrumentation: accumulated clock64() per phase, thread 0 of every CTA
@@ -79,12 +80,16 @@ __device__ int g_dbg_flags;   // bit 0: skip the clip pass, bit 1: skip the zero
 struct IouFrames {
     long long stride_a, stride_b, stride_out;   // per-frame strides in floats
     int na;
+    // multi-GPU row slabs: this launch computes rows [row_offset, row_offset + na) of a matrix with na_total rows; the
+    // coordinate list and the column keys carry GLOBAL row indices (both are what crosses NVLink)
+    int row_offset; long long na_total;
     // sparse output (sp_count != nullptr): instead of the dense matrix, the non-zero elements are appended as
     // (flat index frame * na * nb + row * nb + col, value) in no particular order; sp_count keeps counting past sp_cap
     long long* sp_idx; float* sp_val; unsigned long long* sp_count; long long sp_cap;
     // reduced output (row_key != nullptr): per row / per column  max over the other axis of
     // (value bits << 32) | (0xffffffff - index), i.e. the maximum and the FIRST index attaining it; 0 = no non-zero element
     unsigned long long* row_key; unsigned long long* col_key;
+    IouPeers ex;   // ex.world <= 1: single GPU, nothing below the struct's first member is read
 };
 __device__ __forceinline__ bool iou_no_matrix(const IouFrames& fr) { return fr.sp_count != nullptr || fr.row_key != nullptr; }
 
@@ -252,10 +257,10 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
     unsigned short carry = 0;
     const int rem = n2 - nclip;   // < IOU_CHAIN unless the clip pass is disabled for a timing experiment
     if (tid < rem) carry = sm.queue2[nclip + tid];
-    if (OUT == OUT_DENSE && fill_pending && (nclip > 0 || last)) { fill_wait(); fill_pending = false; }   // also a barrier among the chain warps
+    if (OUT != OUT_REDUCED && fill_pending && (nclip > 0 || last)) { fill_wait(); fill_pending = false; }   // also a barrier among the chain warps
     else chain_sync();
     PHASE_MARK(6);
-    if (OUT == OUT_REDUCED && fr.row_key) {
+    if (OUT != OUT_DENSE && fr.row_key) {
         const int frame = blockIdx.z;
         for (int q = tid; q < nclip; q += IOU_CHAIN) {
             const unsigned int e = sm.queue2[q];
@@ -264,7 +269,7 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
                 const unsigned int r = r0 + (e >> 7), c = c0 + (e & 127);
                 const unsigned long long hi = (unsigned long long)__float_as_uint(v) << 32;
                 atomicMax(fr.row_key + (size_t)frame * fr.na + r, hi | (0xffffffffu - c));
-                atomicMax(fr.col_key + (size_t)frame * nb + c, hi | (0xffffffffu - r));
+                atomicMax(fr.col_key + (size_t)frame * nb + c, hi | (0xffffffffu - (r + (unsigned int)fr.row_offset)));
             }
         }
     }
@@ -281,13 +286,17 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
                 if (lane == 0) base = atomicAdd(fr.sp_count, (unsigned long long)__popc(m));
                 base = __shfl_sync(0xffffffffu, base, 0) + __popc(m & ((1u << lane) - 1));
                 if (nz && (long long)base < fr.sp_cap) {
-                    fr.sp_idx[base] = frame_base + (long long)(r0 + (e >> 7)) * nb + (c0 + (e & 127));
+                    const long long gi = frame_base + (long long)(r0 + (e >> 7)) * nb + (c0 + (e & 127));
+                    fr.sp_idx[base] = gi;
                     fr.sp_val[base] = v;
+                    // multi-GPU gather: the same entry goes into our segment of every peer's window (plain stores over NVLink)
+                    for (int p = 0; p < fr.ex.world; ++p)
+                        if (p != fr.ex.rank) { fr.ex.idx[p][base] = gi; fr.ex.val[p][base] = v; }
                 }
             }
         }
     }
-    if (OUT == OUT_DENSE) {
+    if (OUT != OUT_REDUCED) {
         for (int q = tid; q < nclip; q += IOU_CHAIN) {
             const unsigned int e = sm.queue2[q];
             out[(size_t)(r0 + (e >> 7)) * nb + (c0 + (e & 127))] = sm.qres[q];
@@ -300,11 +309,47 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
     PHASE_MARK(5);
 }
 
+// Multi-GPU epilogue of the tile kernel (chain warps; every CTA of the grid reaches it exactly once).
+//   keys : every CTA has folded its results into the LOCAL column keys; the last CTA to finish pushes the non-empty keys into
+//          every peer's window with system-scope atomic max over NVLink (a few KB) -- the cross-rank "max + first index"
+//          all-reduce of the target assigner, fused into the kernel that produced the values;
+//   list : every CTA has already stored its entries into every peer's window (drain_queue); the last CTA publishes the length.
+// Then it raises this rank's flag in every window (its own included); consumers (exchange.cu) wait on the flags.
+__device__ __noinline__ void exchange_epilogue(IouSmem& sm, const IouFrames& fr, int nb) {
+    const int tid = threadIdx.x;
+    if (fr.sp_count) __threadfence_system();   // this thread's list entries in the peers' windows are visible before the CTA counts as done
+    else __threadfence();
+    chain_sync();
+    if (tid == 0) {
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        sm.nact = (atomicAdd(fr.ex.done, 1u) == total - 1u) ? 1 : 0;
+    }
+    chain_sync();
+    if (!sm.nact) return;
+    __threadfence();
+    const int world = fr.ex.world, rank = fr.ex.rank;
+    if (fr.sp_count) {
+        const unsigned long long n = *reinterpret_cast<volatile unsigned long long*>(fr.sp_count);
+        if (tid < world) *reinterpret_cast<volatile unsigned long long*>(fr.ex.cnt[tid]) = n;
+    } else {
+        const int nkeys = (int)gridDim.z * nb;
+        const unsigned long long* mine = fr.ex.col_key[rank];
+        for (int i = tid; i < nkeys; i += IOU_CHAIN) {
+            const unsigned long long k = __ldcg(mine + i);
+            if (k) for (int p = 0; p < world; ++p) if (p != rank) atomicMax_system(fr.ex.col_key[p] + i, k);
+        }
+    }
+    __threadfence_system();
+    chain_sync();
+    if (tid == 0) *fr.ex.done = 0u;   // ready for the next launch
+    if (tid < world) *reinterpret_cast<volatile unsigned int*>(fr.ex.flag[tid] + rank) = fr.ex.step;
+}
+
 template <int MODE, bool FMA, int OUT>
 __global__ void __launch_bounds__(IOU_THREADS, IOU_CTAS_PER_SM)
 iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int nb,
                 const float4* __restrict__ trigA, const float4* __restrict__ trigB,
-                float* __restrict__ out, int TR, int TC, IouFrames fr) {
+                float* __restrict__ out, int TR, int TC, const __grid_constant__ IouFrames fr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     IouSmem& sm = *reinterpret_cast<IouSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -312,7 +357,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     // grid = (column tiles, row tiles, frames): no integer division to find the tile
     const int frame = blockIdx.z, tile_r = blockIdx.y, tile_c = blockIdx.x;
     A += (size_t)frame * fr.stride_a; B += (size_t)frame * fr.stride_b; out += (size_t)frame * fr.stride_out;
-    const long long frame_base = (long long)frame * na * nb;
+    const long long frame_base = ((long long)frame * fr.na_total + fr.row_offset) * nb;   // flat index of this launch's row 0 in frame `frame`
     // Programmatic dependent launch: this grid may have been made resident while the previous kernel of the
     // stream was still draining; everything below reads or writes global memory, so wait for it here.  The
     // launch latency and the CTA scheduling of back-to-back calls is what gets hidden.
@@ -366,7 +411,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel of the stream may be scheduled as SMs free up
 
     if (warp == IOU_CHAIN / 32) {   // ---- the fill warp
-        if (OUT != OUT_DENSE) return;   // no matrix, nothing to fill, and nobody waits for this warp
+        if (OUT == OUT_REDUCED) return;   // no matrix, nothing to fill, and nobody waits for this warp
         const bool vec = ((nb & 3) == 0) && ((c0 & 3) == 0) && ((tc & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
         if (vec) {   // the block of zeros the bulk copies read: written and fenced by the warp that issues them
 #pragma unroll
@@ -481,6 +526,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     }
     PHASE_MARK(2);
     // (a tile without active columns has nothing to write: its chain warps leave, the fill warp finishes on its own)
+    if (OUT != OUT_DENSE && fr.ex.world > 1) exchange_epilogue(sm, fr, nb);
 #ifdef GLENET_PHASE_TIMING
     if (tid == 0 && cta_lin < 4096) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_cta_log[cta_lin * 4 + 1] = t; }
 #endif
@@ -556,11 +602,21 @@ static void pick_tiles(int na, int nb, int frames, int resident, int& TR, int& T
     row_tiles = (na + TR - 1) / TR;
 }
 
+// Everything a launch can ask for beyond the dense single-frame matrix.
+struct IouLaunch {
+    int frames = 1;
+    long long stride_a = 0, stride_b = 0, stride_out = 0;
+    long long* sp_idx = nullptr; float* sp_val = nullptr; unsigned long long* sp_count = nullptr; long long sp_cap = 0;
+    unsigned long long* row_key = nullptr; unsigned long long* col_key = nullptr;
+    bool keys_prezeroed = false;   // the caller guarantees zeroed key buffers (the exchange's decode kernel re-zeroes them after use)
+    bool dense_and_keys = false;   // write the matrix AND fold the maxima (OUT_BOTH)
+    int row_offset = 0; long long na_total = 0;
+    IouPeers ex = {};              // ex.world <= 1: single GPU
+};
+
 template <int MODE, bool FMA, int OUT>
 static int launch_tile(const float* A, const float* trigA, int na, const float* B, const float* trigB, int nb, float* out, cudaStream_t stream,
-                       const char* what, int frames, long long stride_a, long long stride_b, long long stride_out,
-                       long long* sp_idx, float* sp_val, unsigned long long* sp_count, long long sp_cap,
-                       unsigned long long* row_key, unsigned long long* col_key) {
+                       const char* what, const IouLaunch& L) {
     auto kernel = iou_tile_kernel<MODE, FMA, OUT>;
     // the opt-in shared-memory size and the occupancy are per-device settings: cached per (instantiation, device)
     static std::atomic<int> resident_of[GLENET_MAX_DEVICES];
@@ -573,14 +629,17 @@ static int launch_tile(const float* A, const float* trigA, int na, const float* 
         resident = resident_ctas(kernel);
         if (dev >= 0 && dev < GLENET_MAX_DEVICES) resident_of[dev].store(resident, std::memory_order_release);
     }
+    const int frames = L.frames;
     int TR, TC, row_tiles, col_tiles;
     pick_tiles(na, nb, frames, resident, TR, TC, row_tiles, col_tiles);
     const long long tiles = (long long)row_tiles * col_tiles;
     if (tiles * frames > 0x7fffffffLL) return fail(GLENET_EINVAL, "%s: too many tiles", what);
     IouFrames fr;
-    fr.stride_a = stride_a; fr.stride_b = stride_b; fr.stride_out = (sp_count || row_key) ? 0 : stride_out; fr.na = na;
-    fr.row_key = row_key; fr.col_key = col_key;
-    fr.sp_idx = sp_idx; fr.sp_val = sp_val; fr.sp_count = sp_count; fr.sp_cap = sp_cap;
+    fr.stride_a = L.stride_a; fr.stride_b = L.stride_b; fr.stride_out = OUT == OUT_REDUCED ? 0 : L.stride_out; fr.na = na;
+    fr.row_offset = L.row_offset; fr.na_total = L.na_total > 0 ? L.na_total : na;
+    fr.row_key = L.row_key; fr.col_key = L.col_key;
+    fr.sp_idx = L.sp_idx; fr.sp_val = L.sp_val; fr.sp_count = L.sp_count; fr.sp_cap = L.sp_cap;
+    fr.ex = L.ex;
     cudaLaunchConfig_t cfg = {};
     if (row_tiles > 65535 || frames > 65535) return fail(GLENET_EINVAL, "%s: more than 65535 row tiles or frames", what);
     cfg.gridDim = dim3((unsigned)col_tiles, (unsigned)row_tiles, (unsigned)frames); cfg.blockDim = dim3(IOU_THREADS);
@@ -600,28 +659,39 @@ static int launch_tile(const float* A, const float* trigA, int na, const float* 
 
 template <int MODE, bool FMA>
 static int launch_iou(const float* A, const float* trigA, int na, const float* B, const float* trigB, int nb,
-                      float* out, cudaStream_t stream, const char* what,
-                      int frames = 1, long long stride_a = 0, long long stride_b = 0, long long stride_out = 0,
-                      long long* sp_idx = nullptr, float* sp_val = nullptr, unsigned long long* sp_count = nullptr, long long sp_cap = 0,
-                      unsigned long long* row_key = nullptr, unsigned long long* col_key = nullptr) {
+                      float* out, cudaStream_t stream, const char* what, const IouLaunch& L = IouLaunch()) {
+    const int frames = L.frames;
     if (na < 0 || nb < 0 || frames < 0) return fail(GLENET_EINVAL, "%s: negative count", what);
-    if (sp_count) {
-        if (sp_cap < 0 || (sp_cap > 0 && (!sp_idx || !sp_val))) return fail(GLENET_EINVAL, "%s: bad sparse buffers", what);
-        cudaError_t e = cudaMemsetAsync(sp_count, 0, sizeof(unsigned long long), stream);
+    if (L.sp_count) {
+        if (L.sp_cap < 0 || (L.sp_cap > 0 && (!L.sp_idx || !L.sp_val))) return fail(GLENET_EINVAL, "%s: bad sparse buffers", what);
+        cudaError_t e = cudaMemsetAsync(L.sp_count, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return fail(-(int)e, "%s: cudaMemsetAsync failed", what);
     }
-    if (row_key || col_key) {
-        if (!row_key || !col_key) return fail(GLENET_EINVAL, "%s: row and column keys go together", what);
-        cudaError_t e = cudaMemsetAsync(row_key, 0, sizeof(unsigned long long) * (size_t)frames * na, stream);
-        if (e == cudaSuccess) e = cudaMemsetAsync(col_key, 0, sizeof(unsigned long long) * (size_t)frames * nb, stream);
-        if (e != cudaSuccess) return fail(-(int)e, "%s: cudaMemsetAsync failed", what);
+    if (L.row_key || L.col_key) {
+        if (!L.row_key || !L.col_key) return fail(GLENET_EINVAL, "%s: row and column keys go together", what);
+        if (!L.keys_prezeroed) {
+            cudaError_t e = cudaMemsetAsync(L.row_key, 0, sizeof(unsigned long long) * (size_t)frames * na, stream);
+            if (e == cudaSuccess) e = cudaMemsetAsync(L.col_key, 0, sizeof(unsigned long long) * (size_t)frames * nb, stream);
+            if (e != cudaSuccess) return fail(-(int)e, "%s: cudaMemsetAsync failed", what);
+        }
     }
+    const bool reduced_only = (L.sp_count || L.row_key) && !L.dense_and_keys;
+    // An empty slab still has to take part in a multi-GPU exchange (its flag is what the peers wait for): the exchange entry
+    // points handle that case themselves; here nothing is launched.
     if (na == 0 || nb == 0 || frames == 0) return GLENET_OK;
-    if (!A || !B || (!out && !sp_count && !row_key)) return fail(GLENET_EINVAL, "%s: null pointer", what);
+    if (!A || !B || (!out && !reduced_only)) return fail(GLENET_EINVAL, "%s: null pointer", what);
     if (!FMA && (!trigA || !trigB)) return fail(GLENET_EINVAL, "%s: CPU dialect needs host-evaluated trig tables", what);
-    if (sp_count || row_key)
-        return launch_tile<MODE, FMA, OUT_REDUCED>(A, trigA, na, B, trigB, nb, out, stream, what, frames, stride_a, stride_b, stride_out, sp_idx, sp_val, sp_count, sp_cap, row_key, col_key);
-    return launch_tile<MODE, FMA, OUT_DENSE>(A, trigA, na, B, trigB, nb, out, stream, what, frames, stride_a, stride_b, stride_out, sp_idx, sp_val, sp_count, sp_cap, row_key, col_key);
+    if (reduced_only) return launch_tile<MODE, FMA, OUT_REDUCED>(A, trigA, na, B, trigB, nb, out, stream, what, L);
+    if (L.dense_and_keys) return launch_tile<MODE, FMA, OUT_BOTH>(A, trigA, na, B, trigB, nb, out, stream, what, L);
+    return launch_tile<MODE, FMA, OUT_DENSE>(A, trigA, na, B, trigB, nb, out, stream, what, L);
+}
+
+template <bool FMA = true>
+static int launch_iou_mode(int mode, const float* A, int na, const float* B, int nb, float* out, cudaStream_t stream, const char* what, const IouLaunch& L) {
+    if (mode == 0) return launch_iou<MODE_OVERLAP, FMA>(A, nullptr, na, B, nullptr, nb, out, stream, what, L);
+    if (mode == 1) return launch_iou<MODE_IOU_BEV, FMA>(A, nullptr, na, B, nullptr, nb, out, stream, what, L);
+    if (mode == 2) return launch_iou<MODE_IOU3D, FMA>(A, nullptr, na, B, nullptr, nb, out, stream, what, L);
+    return fail(GLENET_EINVAL, "%s: mode must be 0 (overlap), 1 (BEV IoU) or 2 (3D IoU)", what);
 }
 
 }  // namespace glenet
@@ -666,12 +736,9 @@ int glenet_boxes_iou_frames_gpu(int mode, const float* a, long long a_frame_stri
                                 int nb, float* out, int frames, glenet_stream_t s) {
     const char* what = "glenet_boxes_iou_frames_gpu";
     if (a_frame_stride < 0 || b_frame_stride < 0) return fail(GLENET_EINVAL, "%s: negative stride", what);
-    const long long so = (long long)na * nb;
-    cudaStream_t st = (cudaStream_t)s;
-    if (mode == 0) return launch_iou<MODE_OVERLAP, true>(a, nullptr, na, b, nullptr, nb, out, st, what, frames, a_frame_stride, b_frame_stride, so);
-    if (mode == 1) return launch_iou<MODE_IOU_BEV, true>(a, nullptr, na, b, nullptr, nb, out, st, what, frames, a_frame_stride, b_frame_stride, so);
-    if (mode == 2) return launch_iou<MODE_IOU3D, true>(a, nullptr, na, b, nullptr, nb, out, st, what, frames, a_frame_stride, b_frame_stride, so);
-    return fail(GLENET_EINVAL, "%s: mode must be 0 (overlap), 1 (BEV IoU) or 2 (3D IoU)", what);
+    IouLaunch L;
+    L.frames = frames; L.stride_a = a_frame_stride; L.stride_b = b_frame_stride; L.stride_out = (long long)na * nb;
+    return launch_iou_mode(mode, a, na, b, nb, out, (cudaStream_t)s, what, L);
 }
 int glenet_boxes_iou_frames_sparse_gpu(int mode, const float* a, long long a_frame_stride, int na, const float* b, long long b_frame_stride,
                                        int nb, int frames, long long* idx, float* val, long long cap, unsigned long long* count,
@@ -679,23 +746,189 @@ int glenet_boxes_iou_frames_sparse_gpu(int mode, const float* a, long long a_fra
     const char* what = "glenet_boxes_iou_frames_sparse_gpu";
     if (a_frame_stride < 0 || b_frame_stride < 0) return fail(GLENET_EINVAL, "%s: negative stride", what);
     if (!count) return fail(GLENET_EINVAL, "%s: null count pointer", what);
-    cudaStream_t st = (cudaStream_t)s;
-    if (mode == 0) return launch_iou<MODE_OVERLAP, true>(a, nullptr, na, b, nullptr, nb, nullptr, st, what, frames, a_frame_stride, b_frame_stride, 0, idx, val, count, cap);
-    if (mode == 1) return launch_iou<MODE_IOU_BEV, true>(a, nullptr, na, b, nullptr, nb, nullptr, st, what, frames, a_frame_stride, b_frame_stride, 0, idx, val, count, cap);
-    if (mode == 2) return launch_iou<MODE_IOU3D, true>(a, nullptr, na, b, nullptr, nb, nullptr, st, what, frames, a_frame_stride, b_frame_stride, 0, idx, val, count, cap);
-    return fail(GLENET_EINVAL, "%s: mode must be 0 (overlap), 1 (BEV IoU) or 2 (3D IoU)", what);
+    IouLaunch L;
+    L.frames = frames; L.stride_a = a_frame_stride; L.stride_b = b_frame_stride;
+    L.sp_idx = idx; L.sp_val = val; L.sp_cap = cap; L.sp_count = count;
+    return launch_iou_mode(mode, a, na, b, nb, nullptr, (cudaStream_t)s, what, L);
 }
 int glenet_boxes_iou_frames_max_gpu(int mode, const float* a, long long a_frame_stride, int na, const float* b, long long b_frame_stride,
                                     int nb, int frames, unsigned long long* row_key, unsigned long long* col_key, glenet_stream_t s) {
     const char* what = "glenet_boxes_iou_frames_max_gpu";
     if (a_frame_stride < 0 || b_frame_stride < 0) return fail(GLENET_EINVAL, "%s: negative stride", what);
     if (!row_key || !col_key) return fail(GLENET_EINVAL, "%s: null key pointer", what);
-    cudaStream_t st = (cudaStream_t)s;
-    if (mode == 0) return launch_iou<MODE_OVERLAP, true>(a, nullptr, na, b, nullptr, nb, nullptr, st, what, frames, a_frame_stride, b_frame_stride, 0, nullptr, nullptr, nullptr, 0, row_key, col_key);
-    if (mode == 1) return launch_iou<MODE_IOU_BEV, true>(a, nullptr, na, b, nullptr, nb, nullptr, st, what, frames, a_frame_stride, b_frame_stride, 0, nullptr, nullptr, nullptr, 0, row_key, col_key);
-    if (mode == 2) return launch_iou<MODE_IOU3D, true>(a, nullptr, na, b, nullptr, nb, nullptr, st, what, frames, a_frame_stride, b_frame_stride, 0, nullptr, nullptr, nullptr, 0, row_key, col_key);
-    return fail(GLENET_EINVAL, "%s: mode must be 0 (overlap), 1 (BEV IoU) or 2 (3D IoU)", what);
+    IouLaunch L;
+    L.frames = frames; L.stride_a = a_frame_stride; L.stride_b = b_frame_stride; L.row_key = row_key; L.col_key = col_key;
+    return launch_iou_mode(mode, a, na, b, nb, nullptr, (cudaStream_t)s, what, L);
 }
+// ---------------------------------------------------------------- multi-GPU exchange (row-sharded sweep)
+size_t glenet_exchange_window_bytes(int frames, int nb, long long list_cap) {
+    if (frames < 0 || nb < 0 || list_cap < 0) return 0;
+    return exchange_layout(frames, nb, list_cap).bytes;
+}
+int glenet_symm_alloc(size_t bytes, void** dev_ptr) {
+    if (!dev_ptr || bytes == 0) return fail(GLENET_EINVAL, "%s: bad argument", "glenet_symm_alloc");
+    cudaError_t e = cudaMalloc(dev_ptr, bytes);   // a whole allocation of its own: CUDA IPC exports allocations, not sub-blocks of a pool
+    if (e == cudaSuccess) e = cudaMemset(*dev_ptr, 0, bytes);
+    return e == cudaSuccess ? GLENET_OK : fail(-(int)e, "%s: cudaMalloc failed", "glenet_symm_alloc");
+}
+int glenet_symm_free(void* dev_ptr) {
+    cudaError_t e = cudaFree(dev_ptr);
+    return e == cudaSuccess ? GLENET_OK : fail(-(int)e, "%s: cudaFree failed", "glenet_symm_free");
+}
+int glenet_symm_export(const void* dev_ptr, unsigned char* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!dev_ptr || !handle64) return fail(GLENET_EINVAL, "%s: null pointer", "glenet_symm_export");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr));
+    if (e != cudaSuccess) { snprintf(last_error_buf(), 512, "glenet_symm_export: %s", cudaGetErrorString(e)); return -(int)e; }
+    memcpy(handle64, &h, 64);
+    return GLENET_OK;
+}
+int glenet_symm_import(const unsigned char* handle64, void** peer_ptr) {
+    if (!peer_ptr || !handle64) return fail(GLENET_EINVAL, "%s: null pointer", "glenet_symm_import");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { snprintf(last_error_buf(), 512, "glenet_symm_import: %s", cudaGetErrorString(e)); return -(int)e; }
+    return GLENET_OK;
+}
+int glenet_symm_unmap(void* peer_ptr) {
+    cudaError_t e = cudaIpcCloseMemHandle(peer_ptr);
+    return e == cudaSuccess ? GLENET_OK : fail(-(int)e, "%s: cudaIpcCloseMemHandle failed", "glenet_symm_unmap");
+}
+
+/* diagnostic: the error bits a consumer kernel left in the local window (1 = timed out waiting for a peer's flag,
+ * 2 = a coordinate list overflowed its capacity).  Synchronises the device. */
+int glenet_exchange_status(const void* window_local, unsigned int* status_host) {
+    if (!window_local || !status_host) return fail(GLENET_EINVAL, "%s: null pointer", "glenet_exchange_status");
+    const ExchangeLayout lay = exchange_layout(0, 0, 0);
+    cudaError_t e = cudaMemcpy(status_host, reinterpret_cast<const unsigned char*>(window_local) + lay.off_status, sizeof(unsigned int), cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? GLENET_OK : fail(-(int)e, "%s: cudaMemcpy failed", "glenet_exchange_status");
+}
+
+static int exchange_args_ok(const char* what, int world, int rank, void* const* windows, int frames, int nb, long long na_total, int row_offset, int na) {
+    if (world < 1 || world > GLENET_MAX_PEERS || rank < 0 || rank >= world) return fail(GLENET_EINVAL, "%s: bad world / rank", what);
+    if (!windows) return fail(GLENET_EINVAL, "%s: null window table", what);
+    for (int p = 0; p < world; ++p) if (!windows[p] || ((uintptr_t)windows[p] & 255)) return fail(GLENET_EALIGN, "%s: exchange windows must be non-null and 256-byte aligned", what);
+    if (frames < 0 || nb < 0 || na < 0 || row_offset < 0 || na_total < (long long)row_offset + na) return fail(GLENET_EINVAL, "%s: slab outside the matrix", what);
+    return GLENET_OK;
+}
+
+int glenet_boxes_iou_frames_assign_gpu(int mode, const float* a, long long a_frame_stride, int na, const float* b, long long b_frame_stride,
+                                       int nb, int frames, float* out, int row_offset, long long na_total, unsigned long long* row_key,
+                                       float* row_max, long long* row_arg, float* col_max, long long* col_arg,
+                                       int world, int rank, void* const* windows, long long list_cap, unsigned int step, glenet_stream_t s) {
+    const char* what = "glenet_boxes_iou_frames_assign_gpu";
+    cudaStream_t st = (cudaStream_t)s;
+    int rc = exchange_args_ok(what, world, rank, windows, frames, nb, na_total, row_offset, na);
+    if (rc) return rc;
+    if (a_frame_stride < 0 || b_frame_stride < 0) return fail(GLENET_EINVAL, "%s: negative stride", what);
+    if (!row_max || !row_arg || !col_max || !col_arg || (!row_key && na > 0)) return fail(GLENET_EINVAL, "%s: null output pointer", what);
+    const ExchangeLayout lay = exchange_layout(frames, nb, list_cap);
+    const int par = (int)(step & 1u);
+    auto at = [&](int p, size_t off) { return reinterpret_cast<unsigned char*>(windows[p]) + off; };
+    IouLaunch L;
+    L.frames = frames; L.stride_a = a_frame_stride; L.stride_b = b_frame_stride; L.stride_out = (long long)na * nb;
+    L.row_key = row_key; L.col_key = reinterpret_cast<unsigned long long*>(at(rank, lay.off_col_key[par]));
+    L.keys_prezeroed = true; L.dense_and_keys = out != nullptr;
+    L.row_offset = row_offset; L.na_total = na_total;
+    L.ex.world = world; L.ex.rank = rank; L.ex.step = step;
+    L.ex.done = reinterpret_cast<unsigned int*>(at(rank, lay.off_done));
+    for (int p = 0; p < world; ++p) {
+        L.ex.col_key[p] = reinterpret_cast<unsigned long long*>(at(p, lay.off_col_key[par]));
+        L.ex.flag[p] = reinterpret_cast<unsigned int*>(at(p, lay.off_flags_assign));
+    }
+    if (na > 0 && nb > 0 && frames > 0) {
+        rc = launch_iou_mode(mode, a, na, b, nb, out, st, what, L);
+        if (rc) return rc;
+    } else if (world > 1) {
+        exchange_signal_kernel<<<1, 32, 0, st>>>(L.ex, false);
+        rc = check_launch(what);
+        if (rc) return rc;
+    }
+    const long long n_row = (long long)frames * na, n_col = (long long)frames * nb;
+    if (n_row + n_col == 0) return GLENET_OK;
+    long long blocks = (n_row + n_col + 255) / 256;
+    if (blocks > 296) blocks = 296;
+    exchange_decode_kernel<<<(unsigned)blocks, 256, 0, st>>>(row_key, n_row, L.col_key, n_col, row_max, row_arg, col_max, col_arg,
+                                                             reinterpret_cast<const unsigned int*>(at(rank, lay.off_flags_assign)), world, step,
+                                                             reinterpret_cast<unsigned int*>(at(rank, lay.off_status)));
+    return check_launch(what);
+}
+
+int glenet_boxes_iou_frames_gather_gpu(int mode, const float* a, long long a_frame_stride, int na, const float* b, long long b_frame_stride,
+                                       int nb, int frames, float* out_full, int zero_fill, int row_offset, long long na_total,
+                                       int world, int rank, void* const* windows, long long list_cap, unsigned int step, glenet_stream_t s) {
+    const char* what = "glenet_boxes_iou_frames_gather_gpu";
+    cudaStream_t st = (cudaStream_t)s;
+    int rc = exchange_args_ok(what, world, rank, windows, frames, nb, na_total, row_offset, na);
+    if (rc) return rc;
+    if (a_frame_stride < 0 || b_frame_stride < 0) return fail(GLENET_EINVAL, "%s: negative stride", what);
+    if (list_cap <= 0) return fail(GLENET_EINVAL, "%s: the coordinate lists need a capacity", what);
+    const long long out_elems = (long long)frames * na_total * nb;
+    if (out_elems == 0) return GLENET_OK;
+    if (!out_full) return fail(GLENET_EINVAL, "%s: null output pointer", what);
+    const ExchangeLayout lay = exchange_layout(frames, nb, list_cap);
+    const int par = (int)(step & 1u);
+    auto at = [&](int p, size_t off) { return reinterpret_cast<unsigned char*>(windows[p]) + off; };
+    if (zero_fill < 0 || zero_fill > 3) return fail(GLENET_EINVAL, "%s: zero_fill must be 0..3", what);
+    const bool phase_kernel = zero_fill != 3, phase_scatter = zero_fill != 2;
+    if (zero_fill == 1) {
+        cudaError_t e = cudaMemsetAsync(out_full, 0, sizeof(float) * (size_t)out_elems, st);
+        if (e != cudaSuccess) return fail(-(int)e, "%s: cudaMemsetAsync failed", what);
+    }
+    IouLaunch L;
+    L.frames = frames; L.stride_a = a_frame_stride; L.stride_b = b_frame_stride;
+    L.row_offset = row_offset; L.na_total = na_total;
+    L.sp_cap = list_cap;
+    L.sp_count = reinterpret_cast<unsigned long long*>(at(rank, lay.off_count));
+    L.sp_idx = reinterpret_cast<long long*>(at(rank, lay.off_idx[par])) + (size_t)rank * list_cap;
+    L.sp_val = reinterpret_cast<float*>(at(rank, lay.off_val[par])) + (size_t)rank * list_cap;
+    L.ex.world = world; L.ex.rank = rank; L.ex.step = step;
+    L.ex.done = reinterpret_cast<unsigned int*>(at(rank, lay.off_done)) + 1;
+    for (int p = 0; p < world; ++p) {
+        L.ex.idx[p] = reinterpret_cast<long long*>(at(p, lay.off_idx[par])) + (size_t)rank * list_cap;
+        L.ex.val[p] = reinterpret_cast<float*>(at(p, lay.off_val[par])) + (size_t)rank * list_cap;
+        L.ex.cnt[p] = reinterpret_cast<unsigned long long*>(at(p, lay.off_cnt[par])) + rank;
+        L.ex.flag[p] = reinterpret_cast<unsigned int*>(at(p, lay.off_flags_gather));
+    }
+    if (!phase_kernel) {
+    } else if (na > 0 && nb > 0 && frames > 0) {
+        rc = launch_iou_mode(mode, a, na, b, nb, nullptr, st, what, L);
+        if (rc) return rc;
+    } else {
+        cudaError_t e = cudaMemsetAsync(L.sp_count, 0, sizeof(unsigned long long), st);
+        if (e != cudaSuccess) return fail(-(int)e, "%s: cudaMemsetAsync failed", what);
+        if (world > 1) {
+            exchange_signal_kernel<<<1, 32, 0, st>>>(L.ex, true);
+            rc = check_launch(what);
+            if (rc) return rc;
+        }
+    }
+    if (!phase_scatter) return GLENET_OK;
+    // one rank: the kernel's own counter is the list length; several: the per-source lengths the peers' last CTAs published
+    const unsigned long long* cnt = world > 1 ? reinterpret_cast<const unsigned long long*>(at(rank, lay.off_cnt[par])) : L.sp_count;
+    const long long* idx = reinterpret_cast<const long long*>(at(rank, lay.off_idx[par])) + (world > 1 ? 0 : (size_t)rank * list_cap);
+    const float* val = reinterpret_cast<const float*>(at(rank, lay.off_val[par])) + (world > 1 ? 0 : (size_t)rank * list_cap);
+    exchange_scatter_kernel<<<296, 256, 0, st>>>(out_full, idx, val, cnt, list_cap, out_elems,
+                                                 reinterpret_cast<const unsigned int*>(at(rank, lay.off_flags_gather)), world, step,
+                                                 reinterpret_cast<unsigned int*>(at(rank, lay.off_status)));
+    return check_launch(what);
+}
+
+// keys of glenet_boxes_iou_frames_max_gpu -> (max, argmax) vectors in one launch (and the key buffers are left zeroed)
+int glenet_iou_keys_decode_gpu(unsigned long long* row_key, long long n_row, unsigned long long* col_key, long long n_col,
+                               float* row_max, long long* row_arg, float* col_max, long long* col_arg, glenet_stream_t s) {
+    const char* what = "glenet_iou_keys_decode_gpu";
+    if (n_row < 0 || n_col < 0) return fail(GLENET_EINVAL, "%s: negative count", what);
+    if (n_row + n_col == 0) return GLENET_OK;
+    if ((n_row && (!row_key || !row_max || !row_arg)) || (n_col && (!col_key || !col_max || !col_arg))) return fail(GLENET_EINVAL, "%s: null pointer", what);
+    long long blocks = (n_row + n_col + 255) / 256;
+    if (blocks > 296) blocks = 296;
+    exchange_decode_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(row_key, n_row, col_key, n_col, row_max, row_arg, col_max, col_arg, nullptr, 1, 0u, nullptr);
+    return check_launch(what);
+}
+
 int glenet_boxes_iou_bev_cpu_dialect(const float* a, const float* trig_a, int na, const float* b, const float* trig_b,
                                      int nb, float* out, glenet_stream_t s) {
     if (((uintptr_t)trig_a | (uintptr_t)trig_b) & 15) return fail(GLENET_EALIGN, "%s: trig tables must be 16-byte aligned", "glenet_boxes_iou_bev_cpu_dialect");

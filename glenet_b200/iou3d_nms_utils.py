@@ -282,8 +282,8 @@ def iou_max_overlaps_frames(boxes_a, boxes_b, mode="bev"):
     numpy, axis_aligned_target_assigner.py:141-150), ``iou.max(dim=1)``, ``iou.argmax(dim=1)`` of
     ``iou = boxes_iou_*_frames(boxes_a, boxes_b)``.  Rows / columns without any overlap report max 0, argmax 0.
     These four vectors are what the anchor assignment and the RoI sampler consume
-    (axis_aligned_target_assigner.py:141-165, proposal_target_layer.py:113-114).  One kernel launch (atomic max on
-    packed (value, index) keys) plus the decode; no host sync."""
+    (axis_aligned_target_assigner.py:141-165, proposal_target_layer.py:113-114).  Two launches -- the IoU kernel (atomic max
+    on packed (value, index) keys) and one decode kernel -- and no host sync."""
     _check_cuda_f32(boxes_a, "boxes_a")
     _check_cuda_f32(boxes_b, "boxes_b")
     if boxes_b.dim() == 2:
@@ -299,21 +299,20 @@ def iou_max_overlaps_frames(boxes_a, boxes_b, mode="bev"):
     dev = a.device
     row_key = torch.empty((frames, na), dtype=torch.int64, device=dev)
     col_key = torch.empty((frames, nb), dtype=torch.int64, device=dev)
+    a_max = torch.empty((frames, na), dtype=torch.float32, device=dev)
+    a_arg = torch.empty((frames, na), dtype=torch.int64, device=dev)
+    b_max = torch.empty((frames, nb), dtype=torch.float32, device=dev)
+    b_arg = torch.empty((frames, nb), dtype=torch.int64, device=dev)
     if frames:
         lib = _lib.load()
         with torch.cuda.device(dev):
             rc = lib.glenet_boxes_iou_frames_max_gpu(_MODES[mode], a.data_ptr(), stride_a, na, b.data_ptr(), nb * 7, nb, frames,
                                                      row_key.data_ptr(), col_key.data_ptr(), _stream(dev))
-        _lib.check(rc, "glenet_boxes_iou_frames_max_gpu")
-
-    def decode(key):
-        # key = (float bits << 32) | (0xffffffff - index); key == 0 <=> nothing non-zero on that row / column
-        val = (key >> 32).to(torch.int32).view(torch.float32)
-        arg = torch.where(key == 0, torch.zeros_like(key), 0xffffffff - (key & 0xffffffff))
-        return val, arg
-
-    a_max, a_arg = decode(row_key)
-    b_max, b_arg = decode(col_key)
+            _lib.check(rc, "glenet_boxes_iou_frames_max_gpu")
+            # key = (float bits << 32) | (0xffffffff - index); key == 0 <=> nothing non-zero on that row / column
+            rc = lib.glenet_iou_keys_decode_gpu(row_key.data_ptr(), frames * na, col_key.data_ptr(), frames * nb,
+                                                a_max.data_ptr(), a_arg.data_ptr(), b_max.data_ptr(), b_arg.data_ptr(), _stream(dev))
+        _lib.check(rc, "glenet_iou_keys_decode_gpu")
     return a_max, a_arg, b_max, b_arg
 
 

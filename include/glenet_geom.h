@@ -10,7 +10,8 @@
  *   - boxes are float32 rows [x, y, z, dx, dy, dz, heading], row-major, contiguous;
  *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
  *   - the caller owns inputs, outputs and workspaces; the library never allocates,
- *     frees or synchronises (all work is enqueued on `stream`);
+ *     frees or synchronises (all work is enqueued on `stream`) -- the one exception is the
+ *     explicit glenet_symm_* allocator of the multi-GPU exchange windows;
  *   - return value: 0 on success, a negative code on failure (-(cudaError_t) for CUDA
  *     errors, <= -1000 for argument errors); glenet_last_error() gives the text;
  *   - n == 0 is legal everywhere and launches nothing (the reference prints a launch
@@ -84,6 +85,61 @@ int glenet_boxes_iou_frames_sparse_gpu(int mode, const float* boxes_a, long long
 int glenet_boxes_iou_frames_max_gpu(int mode, const float* boxes_a, long long a_frame_stride, int na,
                                     const float* boxes_b, long long b_frame_stride, int nb, int frames,
                                     unsigned long long* row_key, unsigned long long* col_key, glenet_stream_t stream);
+
+/* The two key arrays of glenet_boxes_iou_frames_max_gpu turned into (max, argmax) vectors by ONE launch: n_row = frames * na,
+ * n_col = frames * nb; max float32, argmax int64 (first index among equal maxima; 0 where nothing overlaps).  The key
+ * arrays are left zeroed. */
+int glenet_iou_keys_decode_gpu(unsigned long long* row_key, long long n_row, unsigned long long* col_key, long long n_col,
+                               float* row_max, long long* row_arg, float* col_max, long long* col_arg, glenet_stream_t stream);
+
+/* ---------------------------------------------------------------- multi-GPU: the row-sharded sweep (additive)
+ * The reference never shards its geometry ops; its consumer of the big matrices is the target assigner
+ * (pcdet/models/dense_heads/target_assigner/axis_aligned_target_assigner.py:132-165), which needs per frame the row maxima of
+ * the anchors and the column maxima + first row over ALL anchors.  Here rank r of `world` (one process per GPU of one NVLink /
+ * NVSwitch box) computes rows [row_offset, row_offset + na) of the (na_total, nb) matrix of every frame; results move between
+ * GPUs inside the IoU kernel -- peer stores / system-scope atomics into "exchange windows" mapped through CUDA IPC -- not
+ * through NCCL.
+ *
+ * Symmetric memory.  glenet_symm_alloc is the ONE place where the library allocates (CUDA IPC exports whole allocations);
+ * the block is zeroed.  export/import move the 64-byte IPC handle between the processes (any transport, e.g.
+ * torch.distributed); import maps a peer's block into this process.  These five calls synchronise like cudaMalloc does. */
+int glenet_symm_alloc(size_t bytes, void** dev_ptr);
+int glenet_symm_free(void* dev_ptr);
+int glenet_symm_export(const void* dev_ptr, unsigned char* handle64);
+int glenet_symm_import(const unsigned char* handle64, void** peer_ptr);
+int glenet_symm_unmap(void* peer_ptr);
+/* Size of one rank's exchange window for problems of up to `frames` x `nb` column keys and coordinate lists of `list_cap`
+ * entries per source rank (0: no gather).  All ranks must use the same three numbers. */
+size_t glenet_exchange_window_bytes(int frames, int nb, long long list_cap);
+/* Diagnostic (synchronises the device): error bits left in the LOCAL window by the consumer kernels -- 1 = gave up waiting
+ * for a peer's flag (~4 s), 2 = a coordinate list overflowed list_cap. */
+int glenet_exchange_status(const void* window_local, unsigned int* status_host);
+
+/* assign: this rank's slab of the IoU matrix (out: (frames, na, nb), or NULL to skip the matrix) plus the assigner's
+ * reductions -- row_max / row_arg (frames, na): max over the columns and first column attaining it; col_max / col_arg
+ * (frames, nb): max over the rows OF ALL RANKS and the first GLOBAL row attaining it (identical on every rank).
+ * windows: host array of `world` device pointers, windows[rank] = the local window, the others IPC-mapped.
+ * row_key: (frames, na) u64 scratch, zeroed before the first call (the call leaves it zeroed).
+ * step: 1, 2, 3, ... -- the same number on every rank for the same collective call.  The call enqueues the IoU kernel
+ * (which pushes its column keys into the peers' windows and raises a flag) and a decode kernel that waits for all flags. */
+int glenet_boxes_iou_frames_assign_gpu(int mode, const float* boxes_a, long long a_frame_stride, int na,
+                                       const float* boxes_b, long long b_frame_stride, int nb, int frames,
+                                       float* out, int row_offset, long long na_total, unsigned long long* row_key,
+                                       float* row_max, long long* row_arg, float* col_max, long long* col_arg,
+                                       int world, int rank, void* const* windows, long long list_cap, unsigned int step,
+                                       glenet_stream_t stream);
+/* gather: the WHOLE (frames, na_total, nb) matrix on every rank.  Each rank zero-fills its own copy and the kernel ships
+ * only the non-zero elements of its slab -- (flat index, value) entries stored into every peer's window from the clip
+ * epilogue; a scatter kernel applies all ranks' lists once their flags are up.  An anchor sweep is > 99 % zeros: ~14 MB
+ * travel instead of the 1.2 GB of an all-gather.
+ * zero_fill: 1 = memset out_full, IoU kernel, scatter, all on `stream`; 0 = the same without the memset (the caller has
+ * zeroed out_full); 2 = IoU kernel only and 3 = scatter only -- the two halves of one step (same `step`), so that a caller
+ * can run the fill on a second stream under the IoU kernel and make only the scatter wait for it. */
+int glenet_boxes_iou_frames_gather_gpu(int mode, const float* boxes_a, long long a_frame_stride, int na,
+                                       const float* boxes_b, long long b_frame_stride, int nb, int frames,
+                                       float* out_full, int zero_fill, int row_offset, long long na_total,
+                                       int world, int rank, void* const* windows, long long list_cap, unsigned int step,
+                                       glenet_stream_t stream);
 
 /* Row-aligned variants: out[i] = f(boxes_a[i], boxes_b[i / group]) for i < na, where boxes_b
  * holds ceil(na / group) rows.  Additive API for the CVAE label-uncertainty workload
