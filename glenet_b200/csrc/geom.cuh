@@ -20,8 +20,10 @@
 // polygon is the only per-thread array left, and the angular sort
 // evaluates one atan2f per vertex instead of two per comparison.
 #pragma once
+#ifndef GLENET_HOST_EMUL   // tests/emul compiles this header with g++ against host stand-ins for the built-ins
 #include <math_constants.h>
 #include <cuda_runtime.h>
+#endif
 #include <math.h>
 #include <stdint.h>
 
@@ -53,7 +55,7 @@ enum {
     BP_PY = 11,                // 4 rotated corner y
     BP_ZMIN = 15, BP_ZMAX = 16, BP_VOL = 17,   // boxes_iou3d_gpu terms (iou3d_nms_utils.py:100-117)
     BP_STRIDE = 21,            // record stride with the z terms (3D IoU)
-    BP_STRIDE_BEV = 17         // BEV-only kernels drop them: 20 % less shared memory => one more CTA per SM
+    BP_STRIDE_BEV = 15         // BEV-only kernels drop them (odd stride: consecutive records start on different banks)
 };
 
 // trig4 = {cos(h), sin(h), cos(-h), sin(-h)}

@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "geom.cuh"
 #include "exchange.cuh"
+#include "clip.cuh"
 #include "../../include/glenet_geom.h"
 #include <float.h>
 #include <stdlib.h>
@@ -41,10 +42,13 @@ namespace glenet {
 #define GLENET_IOU_THREADS 256
 #endif
 #ifndef GLENET_IOU_TR_MAX
-#define GLENET_IOU_TR_MAX 384
+#define GLENET_IOU_TR_MAX 480
 #endif
 #ifndef GLENET_IOU_CTAS
-#define GLENET_IOU_CTAS 4
+#define GLENET_IOU_CTAS 3
+#endif
+#ifndef GLENET_IOU_CLIP_PAIRS   // pairs per pass of the phased clip: one per lane of the first CLIP_PAIRS / 32 chain warps
+#define GLENET_IOU_CLIP_PAIRS (GLENET_IOU_THREADS - 32)
 #endif
 #ifndef GLENET_IOU_QCAP
 #define GLENET_IOU_QCAP 512
@@ -61,6 +65,8 @@ constexpr int IOU_QCAP = GLENET_IOU_QCAP;         // circle-test survivors per d
 constexpr int IOU_Q2CAP = IOU_QCAP + IOU_CHAIN;   // + the partial clip pass carried over from the previous drain
 constexpr int IOU_CTAS_PER_SM = GLENET_IOU_CTAS;  // register budget the kernel is compiled for
 constexpr int IOU_ZBYTES = GLENET_IOU_ZBYTES;     // block of zeros in shared memory = largest bulk store of the zero fill
+constexpr int IOU_CLIP_PAIRS = GLENET_IOU_CLIP_PAIRS;
+static_assert(IOU_CLIP_PAIRS % 32 == 0 && IOU_CLIP_PAIRS >= 32 && IOU_CLIP_PAIRS <= IOU_CHAIN, "whole warps of the chain clip");
 constexpr int BPS = BP_STRIDE_BEV;         // BoxPre stride in shared memory (the z terms of 3D IoU are read per clipped pair)
 
 enum { OUT_DENSE = 0, OUT_REDUCED = 1, OUT_BOTH = 2 };   // kernel output: the (na, nb) matrix; the coordinate list / row-column maxima; matrix + maxima
@@ -95,9 +101,10 @@ __device__ __forceinline__ bool iou_no_matrix(const IouFrames& fr) { return fr.s
 
 struct __align__(128) IouSmem {
     float4 zero[IOU_ZBYTES / 16];          // source of the bulk zero fill
-    float4 row[IOU_TR_MAX];                // {cx, cy, cull radius, -}
-    float ccx[IOU_TC_MAX], ccy[IOU_TC_MAX], crad[IOU_TC_MAX];
-    float rpre[IOU_TR_MAX * BPS];
+    float2 verts[IOU_CLIP_PAIRS * CLIP_SLOTS];              // vertex slots of the phased clip (clip.cuh), one pair per lane
+    unsigned int wl[IOU_CLIP_PAIRS / 32][32 * CLIP_SLOTS];  // per-warp work lists of its phase B
+    float rrad[IOU_TR_MAX], crad[IOU_TC_MAX];               // cull radii; the centres are slots 0 / 1 of the records below
+    float rpre[IOU_TR_MAX * BPS];          // rows: raw box in the first 7 slots until a pair needs it, then the BoxPre record (same centre slots)
     float cpre[IOU_TC_MAX * BPS];
     float qres[IOU_Q2CAP];                 // clipped results, parked until the zero fill has landed
     unsigned short queue[IOU_QCAP];        // (row << 7) | col  (row < 384, col < 128): survivors of the circle test
@@ -247,11 +254,29 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
     if (tid == 0) { atomicAdd(&g_phase_cycles[8], (unsigned long long)n); atomicAdd(&g_phase_cycles[9], (unsigned long long)nclip);
                     atomicAdd(&g_phase_cycles[10], (unsigned long long)nprep); atomicAdd(&g_phase_cycles[11], 1ull); }
 #endif
-    for (int q = tid; q < nclip; q += IOU_CHAIN) {
-        const unsigned int e = sm.queue2[q];
-        const float* a = sm.rpre + (e >> 7) * BPS;
-        const float* b = sm.cpre + (e & 127) * BPS;
-        sm.qres[q] = finish_pair<MODE>(a, b, box_overlap<FMA>(a, b), A + (size_t)(r0 + (e >> 7)) * 7, B + (size_t)(c0 + (e & 127)) * 7);
+    // ---- the phased clip of clip.cuh over queue2[0, nclip): one pair per lane, A (24 result bits, corners to their slots),
+    //      B (the warp's crossings pooled, one per lane) and C (sort + fan) are warp-local -- no CTA barrier in here
+    if (tid < IOU_CLIP_PAIRS) {
+        const int cw = tid >> 5;
+#pragma unroll 1
+        for (int q = tid; q - (tid & 31) < nclip; q += IOU_CLIP_PAIRS) {   // warp-uniform trip count
+            const bool live = q < nclip;
+            const unsigned int e = live ? sm.queue2[q] : 0u;
+            const float* a = sm.rpre + (e >> 7) * BPS;
+            const float* b = sm.cpre + (e & 127) * BPS;
+            float2* slots = sm.verts + tid * CLIP_SLOTS;
+            const unsigned int w = live ? clip_pair_tests<FMA>(a, b) : 0u;
+            const unsigned int hits = clip_hits16(w);
+            const int cnt = __popc(hits) + __popc(clip_corners8(w));
+            const bool fast = cnt >= 3 && cnt <= CLIP_SLOTS, slow = cnt > CLIP_SLOTS;
+            if (fast) clip_write_corners(a, b, w, slots);
+            clip_warp_points<FMA>(fast ? hits : 0u, e >> 7, e & 127u, sm.wl[cw], sm.rpre, sm.cpre, BPS, sm.verts + (cw * 32) * CLIP_SLOTS);
+            const float ov_slow = clip_warp_slow<FMA>(slow, w, e >> 7, e & 127u, sm.rpre, sm.cpre, BPS, reinterpret_cast<float2*>(sm.wl[cw]));
+            if (live) {
+                const float ov = slow ? ov_slow : (fast ? clip_area8<FMA>(slots, cnt) : 0.f);
+                sm.qres[q] = finish_pair<MODE>(a, b, ov, A + (size_t)(r0 + (e >> 7)) * 7, B + (size_t)(c0 + (e & 127)) * 7);
+            }
+        }
     }
     PHASE_MARK(4);
     unsigned short carry = 0;
@@ -399,10 +424,10 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
         // non-finite z term must reach finish_pair for every pair
         if (MODE == MODE_IOU3D && !z_terms_finite(z_terms(raw[2], raw[5], __fmul_rn(raw[3], raw[4])))) rad = CUDART_INF_F;
         if (is_row) {
-            sm.row[k] = make_float4(cx, cy, rad, 0.f); sm.rflag[k] = 0;
+            sm.rrad[k] = rad; sm.rflag[k] = 0;
             minx = fminf(minx, cx); maxx = fmaxf(maxx, cx); miny = fminf(miny, cy); maxy = fmaxf(maxy, cy);
             maxr = (rad != rad) ? CUDART_INF_F : fmaxf(maxr, rad);   // a NaN radius must not be dropped by fmaxf
-        } else { sm.ccx[k] = cx; sm.ccy[k] = cy; sm.crad[k] = rad; sm.cflag[k] = 0; }
+        } else { sm.crad[k] = rad; sm.cflag[k] = 0; }
     }
     minx = warp_min(minx); maxx = warp_max(maxx); miny = warp_min(miny); maxy = warp_max(maxy); maxr = warp_max(maxr);
     if (lane == 0) { sm.red[warp][0] = minx; sm.red[warp][1] = maxx; sm.red[warp][2] = miny; sm.red[warp][3] = maxy; sm.red[warp][4] = maxr; }
@@ -439,7 +464,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     //      whole tile with ONE test (rows with a NaN centre produce no polygon vertex in the reference
     //      either, so leaving them out of the bounding box is exact).  NaN in the column => stays active.
     for (int c = tid; c < tc; c += IOU_CHAIN) {
-        const float cx = sm.ccx[c], cy = sm.ccy[c];
+        const float cx = sm.cpre[c * BPS + BP_CX], cy = sm.cpre[c * BPS + BP_CY];
         const float ddx = fmaxf(fmaxf(minx - cx, cx - maxx), 0.f), ddy = fmaxf(fmaxf(miny - cy, cy - maxy), 0.f);
         const float rr = maxr + sm.crad[c];
         const bool far = (cx == cx) && (cy == cy) && (ddx * ddx + ddy * ddy > rr * rr);
@@ -460,12 +485,12 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     const int grp = tall ? 0 : warp / rwarps;
     const bool idle = !tall && grp >= groups;
     int rows[IOU_RPT];
-    float4 rw[IOU_RPT];
+    float3 rw[IOU_RPT];   // {cx, cy, cull radius}
 #pragma unroll
     for (int j = 0; j < IOU_RPT; ++j) {
         rows[j] = tall ? tid + j * IOU_CHAIN : (j == 0 ? (warp - grp * rwarps) * 32 + lane : IOU_TR_MAX);
         if (idle || rows[j] >= tr) rows[j] = -1;
-        rw[j] = rows[j] >= 0 ? sm.row[rows[j]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        rw[j] = rows[j] >= 0 ? make_float3(sm.rpre[rows[j] * BPS + BP_CX], sm.rpre[rows[j] * BPS + BP_CY], sm.rrad[rows[j]]) : make_float3(0.f, 0.f, 0.f);
     }
     bool fill_pending = true;
     for (int cb = 0; cb < nact;) {
@@ -478,7 +503,7 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
 #pragma unroll 4
         for (int k = k0; k < k1; ++k) {
             const int c = sm.act[k];
-            const float cx = sm.ccx[c], cy = sm.ccy[c], cr = sm.crad[c];
+            const float cx = sm.cpre[c * BPS + BP_CX], cy = sm.cpre[c * BPS + BP_CY], cr = sm.crad[c];
 #pragma unroll
             for (int j = 0; j < IOU_RPT; ++j) {
                 const float dx = rw[j].x - cx, dy = rw[j].y - cy, rr = rw[j].z + cr;
@@ -532,32 +557,83 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
 #endif
 }
 
-// out[i] = f(a[i], b[i / group]) -- every pair is "heavy" by construction (CVAE samples vs their GT)
-constexpr int ALIGNED_THREADS = 128;
+// out[i] = f(a[i], b[i / group]) -- every pair is "heavy" by construction (CVAE samples vs their GT), so this is the
+// FP32-bound workload of the path.  Persistent CTAs walk batches of AL_PAIRS pairs through the phased clip of clip.cuh:
+//   prepare (one lane per box, BoxPre records in shared memory) | barrier |
+//   A (one lane per pair: 24 result bits, corners to their slots) -> B (the warp's crossings pooled, one per lane)
+//   -> C (one lane per pair: sort + fan) -- A, B and C are warp-local, no CTA barrier between them.
+// Pairs with more than eight vertices (~1 %) are finished by their warp, all 32 lanes on one pair (clip_warp_slow).
+constexpr int AL_THREADS = 256;
+constexpr int AL_PAIRS = AL_THREADS;        // one pair per lane and batch
+#ifndef GLENET_AL_CTAS
+#define GLENET_AL_CTAS 4
+#endif
+constexpr int AL_CTAS_PER_SM = GLENET_AL_CTAS;
+struct AlignedSmem {
+    float2 verts[AL_PAIRS * CLIP_SLOTS];
+    unsigned int wl[AL_THREADS / 32][32 * CLIP_SLOTS];   // per-warp work lists of phase B (then the scratch of clip_warp_slow)
+    float arec[AL_PAIRS * BPS];
+    float brec[1];                          // [nb_max * (BPS + 1)], sized by the launcher: the b boxes one batch can meet (+ cull radius)
+};
+
 template <int MODE, bool FMA>
-__global__ void __launch_bounds__(ALIGNED_THREADS, 8)
-iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int group,
-                   float* __restrict__ out) {
-    const int tid = threadIdx.x;
-    const int i = blockIdx.x * ALIGNED_THREADS + tid;
-    if (i >= na) return;
-    float a[BP_STRIDE], b[BP_STRIDE];   // statically indexed => registers
-    const float* ba = A + (size_t)i * 7;
-    const float* bb = B + (size_t)(i / group) * 7;
-    float out_v = 0.f;
-    const float ddx = ba[0] - bb[0], ddy = ba[1] - bb[1];
-    float rr = cull_radius(ba) + cull_radius(bb);
-    // 3D IoU: 0 * NaN = NaN in the reference's torch arithmetic, so a pair with a non-finite z term is never culled
-    // (same rule as the tile kernel's prologue)
-    if (MODE == MODE_IOU3D && (!z_terms_finite(z_terms(ba[2], ba[5], __fmul_rn(ba[3], ba[4]))) || !z_terms_finite(z_terms(bb[2], bb[5], __fmul_rn(bb[3], bb[4])))))
-        rr = CUDART_INF_F;
-    if (!(ddx * ddx + ddy * ddy > rr * rr)) {
-        box_prepare<FMA>(ba, device_trig_fused(ba[6]), a);
-        box_prepare<FMA>(bb, device_trig_fused(bb[6]), b);
-        const float ov = box_overlap_unrolled<FMA>(a, b);
-        out_v = (MODE == MODE_OVERLAP) ? ov : (MODE == MODE_IOU_BEV) ? iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) : iou3d_from_overlap(a, b, ov);
+__global__ void __launch_bounds__(AL_THREADS, AL_CTAS_PER_SM)
+iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int group, float* __restrict__ out, int nbatches, int nb_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    AlignedSmem& sm = *reinterpret_cast<AlignedSmem*>(smem_raw);
+    float* brad = sm.brec + nb_max * BPS;   // cull radius of the staged b boxes (+inf: never cull, the 3D IoU of a non-finite height)
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int bt = blockIdx.x; bt < nbatches; bt += gridDim.x) {
+        const int p0 = bt * AL_PAIRS, np = min(AL_PAIRS, na - p0);
+        const int b0 = p0 / group, nbx = (p0 + np - 1) / group - b0 + 1;
+        __syncthreads();   // the previous batch is done with the b records
+        for (int k = tid; k < nbx; k += AL_THREADS) {
+            const float* bb = B + (size_t)(b0 + k) * 7;
+            float raw[7];
+#pragma unroll
+            for (int f = 0; f < 7; ++f) raw[f] = bb[f];
+            box_prepare<FMA, false>(raw, device_trig_fused(raw[6]), sm.brec + k * BPS);
+            float rad = cull_radius(raw);
+            // 3D IoU: 0 * NaN = NaN in the reference's torch arithmetic, so a pair with a non-finite z term is never culled
+            if (MODE == MODE_IOU3D && !z_terms_finite(z_terms(raw[2], raw[5], __fmul_rn(raw[3], raw[4])))) rad = CUDART_INF_F;
+            brad[k] = rad;
+        }
+        // this lane's pair: its b box is (p0 + tid) / group; consecutive lanes step through the groups without a division each
+        const int gi = p0 + tid;
+        const int bsel = tid < np ? gi / group - b0 : 0;
+        float raw[7];
+        const float* ba = A + (size_t)(tid < np ? gi : p0) * 7;
+#pragma unroll
+        for (int f = 0; f < 7; ++f) raw[f] = ba[f];
+        float* a = sm.arec + tid * BPS;
+        float arad = cull_radius(raw);
+        if (MODE == MODE_IOU3D && !z_terms_finite(z_terms(raw[2], raw[5], __fmul_rn(raw[3], raw[4])))) arad = CUDART_INF_F;
+        __syncthreads();
+        const float* b = sm.brec + bsel * BPS;
+        bool active = false;
+        if (tid < np) {
+            const float ddx = raw[0] - b[BP_CX], ddy = raw[1] - b[BP_CY], rr = arad + brad[bsel];
+            active = !(ddx * ddx + ddy * ddy > rr * rr);
+            if (active) box_prepare<FMA, false>(raw, device_trig_fused(raw[6]), a);
+            else out[gi] = 0.f;
+        }
+        // ---- A: result bits, corners to their slots
+        float2* slots = sm.verts + tid * CLIP_SLOTS;
+        const unsigned int w = active ? clip_pair_tests<FMA>(a, b) : 0u;
+        const unsigned int hits = clip_hits16(w);
+        const int cnt = __popc(hits) + __popc(clip_corners8(w));
+        const bool fast = cnt >= 3 && cnt <= CLIP_SLOTS;
+        if (fast) clip_write_corners(a, b, w, slots);
+        // ---- B: the warp's crossings, one per lane
+        clip_warp_points<FMA>(fast ? hits : 0u, (unsigned int)tid, (unsigned int)bsel, sm.wl[warp], sm.arec, sm.brec, BPS, sm.verts + (warp * 32) * CLIP_SLOTS);
+        // ---- C: sort + fan (more than eight vertices: the whole warp, one pair at a time)
+        const bool slow = cnt > CLIP_SLOTS;
+        const float ov_slow = clip_warp_slow<FMA>(slow, w, (unsigned int)tid, (unsigned int)bsel, sm.arec, sm.brec, BPS, reinterpret_cast<float2*>(sm.wl[warp]));
+        if (active) {
+            const float ov = slow ? ov_slow : (fast ? clip_area8<FMA>(slots, cnt) : 0.f);
+            out[gi] = finish_pair<MODE>(a, b, ov, ba, B + (size_t)(b0 + bsel) * 7);
+        }
     }
-    out[i] = out_v;
 }
 
 #ifdef GLENET_PHASE_TIMING
@@ -941,11 +1017,19 @@ int glenet_boxes_iou_aligned_gpu(int mode, const float* a, int na, const float* 
     if (na < 0 || group <= 0 || mode < 0 || mode > 2) return fail(GLENET_EINVAL, "%s: bad argument", what);
     if (na == 0) return GLENET_OK;
     if (!a || !b || !out) return fail(GLENET_EINVAL, "%s: null pointer", what);
-    const unsigned grid = (na + ALIGNED_THREADS - 1) / ALIGNED_THREADS;
+    const int nbatches = (na + AL_PAIRS - 1) / AL_PAIRS;
+    const int nb_max = (AL_PAIRS - 1) / group + 2;   // b boxes a batch of AL_PAIRS consecutive pairs can meet
+    const size_t smem = sizeof(AlignedSmem) + sizeof(float) * (size_t)nb_max * (BPS + 1);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = nbatches < sms * AL_CTAS_PER_SM ? nbatches : sms * AL_CTAS_PER_SM;
     cudaStream_t st = (cudaStream_t)s;
-    if (mode == 0) iou_aligned_kernel<MODE_OVERLAP, true><<<grid, ALIGNED_THREADS, 0, st>>>(a, na, b, group, out);
-    else if (mode == 1) iou_aligned_kernel<MODE_IOU_BEV, true><<<grid, ALIGNED_THREADS, 0, st>>>(a, na, b, group, out);
-    else iou_aligned_kernel<MODE_IOU3D, true><<<grid, ALIGNED_THREADS, 0, st>>>(a, na, b, group, out);
+    int rc;
+    // (the opt-in shared-memory size is a per-device attribute and cheap to set: no cache)
+    if (mode == 0) { auto k = iou_aligned_kernel<MODE_OVERLAP, true>; rc = set_smem(k, smem, what); if (rc) return rc; k<<<grid, AL_THREADS, smem, st>>>(a, na, b, group, out, nbatches, nb_max); }
+    else if (mode == 1) { auto k = iou_aligned_kernel<MODE_IOU_BEV, true>; rc = set_smem(k, smem, what); if (rc) return rc; k<<<grid, AL_THREADS, smem, st>>>(a, na, b, group, out, nbatches, nb_max); }
+    else { auto k = iou_aligned_kernel<MODE_IOU3D, true>; rc = set_smem(k, smem, what); if (rc) return rc; k<<<grid, AL_THREADS, smem, st>>>(a, na, b, group, out, nbatches, nb_max); }
     return check_launch(what);
 }
 

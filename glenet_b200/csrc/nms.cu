@@ -17,6 +17,7 @@
 //                 on the device.
 #include "common.cuh"
 #include "geom.cuh"
+#include "clip.cuh"
 #include "../../include/glenet_geom.h"
 #include <atomic>
 
@@ -26,21 +27,29 @@ namespace glenet {
 __device__ unsigned long long g_sweep_cycles[4];   // [0] warp 0 busy, [1] whole loop, [2] job warps busy (warp 1), [3] steps
 #endif
 
+#ifndef GLENET_NMS_CTAS   // resident CTAs per SM the mask kernel is compiled for (register budget: 4 -> 64, 5 -> 48 registers)
+#define GLENET_NMS_CTAS 4
+#endif
 constexpr int NMS_THREADS = 256;
 constexpr int NMS_TILE = 64;
 constexpr int SWEEP_THREADS = 512;
 
+constexpr int NMS_PASS = NMS_THREADS;       // pairs per pass of the phased clip: one per lane
+constexpr int NBS = BP_STRIDE_BEV;          // BoxPre stride (no z terms in NMS)
 struct NmsSmem {
+    // vertex slots of the phased clip (clip.cuh); the circle-test queue aliases their first half: it is dead once queue2 exists
+    union { float2 verts[NMS_PASS * CLIP_SLOTS]; unsigned short queue[NMS_TILE * NMS_TILE]; };
     float rcx[NMS_TILE], rcy[NMS_TILE], rrad[NMS_TILE];
     float ccx[NMS_TILE], ccy[NMS_TILE], crad[NMS_TILE];
-    float rpre[NMS_TILE * BP_STRIDE];
-    float cpre[NMS_TILE * BP_STRIDE];
+    float rpre[NMS_TILE * NBS];
+    float cpre[NMS_TILE * NBS];
     unsigned long long bits[NMS_TILE];
-    unsigned short queue[NMS_TILE * NMS_TILE];    // survivors of the circle test
+    unsigned int wl[NMS_THREADS / 32][32 * CLIP_SLOTS];   // per-warp work lists of the clip's phase B
     unsigned short queue2[NMS_TILE * NMS_TILE];   // pairs whose IoU could exceed the threshold: the ones that are clipped
     unsigned char rflag[NMS_TILE], cflag[NMS_TILE];
     int qcount, q2count;
 };
+static_assert(sizeof(unsigned short) * NMS_TILE * NMS_TILE <= sizeof(float2) * NMS_PASS * CLIP_SLOTS, "queue aliases verts");
 
 // iou_normal (iou3d_nms_kernel.cu:314-325) as compiled in nms_normal_kernel: a = row box, b = column box,
 // Sa + Sb is contracted to fma(b.dx, b.dy, Sa).
@@ -69,12 +78,12 @@ __device__ __forceinline__ void tri_decode(int t, int nblk, int& rb, int& cb) {
 }
 
 template <bool NORMAL>
-__global__ void __launch_bounds__(NMS_THREADS, 5)
+__global__ void __launch_bounds__(NMS_THREADS, GLENET_NMS_CTAS)
 nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsigned long long* __restrict__ mask_all,
                 int col_blocks, int tiles_per_frame) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem& sm = *reinterpret_cast<NmsSmem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.x / tiles_per_frame;
     const int t = blockIdx.x - frame * tiles_per_frame;
     const float* boxes = boxes_all + (size_t)frame * n * 7;
@@ -163,7 +172,7 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
         const int k = is_row ? i : i - tr;
         if ((is_row ? sm.rflag[k] : sm.cflag[k]) == 1) {
             const float* box = boxes + (size_t)((is_row ? r0 : c0) + k) * 7;
-            box_prepare<true>(box, device_trig(box[6]), (is_row ? sm.rpre : sm.cpre) + k * BP_STRIDE);
+            box_prepare<true, false>(box, device_trig(box[6]), (is_row ? sm.rpre : sm.cpre) + k * NBS);
         }
     }
     __syncthreads();
@@ -178,8 +187,8 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
         bool need = false;
         if (q < nq) {
             p = sm.queue[q];
-            const float* a = sm.rpre + (p >> 6) * BP_STRIDE;
-            const float* b = sm.cpre + (p & 63) * BP_STRIDE;
+            const float* a = sm.rpre + (p >> 6) * NBS;
+            const float* b = sm.cpre + (p & 63) * NBS;
             const float ub = overlap_upper_bound(a, b);
             const float iou_ub = ub / fmaxf(a[BP_AREA] + b[BP_AREA] - ub, 1e-8f);
             need = all_pairs || (!(ub <= 0.f) && !(iou_ub <= thr_lo)) || !(a[BP_AREA] + b[BP_AREA] > ub);   // degenerate areas: let the clip decide
@@ -193,14 +202,29 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
         }
     }
     __syncthreads();
+    // ---- phased clip (clip.cuh) over queue2, NMS_PASS pairs at a time
     const int nq2 = sm.q2count;
-    for (int q = tid; q < nq2; q += NMS_THREADS) {
-        const int p = sm.queue2[q];
-        const float* a = sm.rpre + (p >> 6) * BP_STRIDE;
-        const float* b = sm.cpre + (p & 63) * BP_STRIDE;
-        const float ov = box_overlap<true>(a, b);
+    auto set_bit = [&](int p, float ov, const float* a, const float* b) {
         if (iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) > thresh)   // 32-bit halves: a native shared-memory atomic instead of a 64-bit CAS loop
             atomicOr(reinterpret_cast<unsigned int*>(&sm.bits[p >> 6]) + ((p >> 5) & 1), 1u << (p & 31));
+    };
+    for (int base = 0; base < nq2; base += NMS_PASS) {
+        // one pair per lane; A (result bits, corners), B (the warp's crossings pooled) and C (sort + fan) are warp-local
+        const bool live = base + tid < nq2;
+        const int p = live ? sm.queue2[base + tid] : 0;
+        const float* a = sm.rpre + (p >> 6) * NBS;
+        const float* b = sm.cpre + (p & 63) * NBS;
+        float2* slots = sm.verts + tid * CLIP_SLOTS;
+        const unsigned int w = live ? clip_pair_tests<true>(a, b) : 0u;
+        const unsigned int hits = clip_hits16(w);
+        const int cnt = __popc(hits) + __popc(clip_corners8(w));
+        const bool fast = cnt >= 3 && cnt <= CLIP_SLOTS;
+        if (fast) clip_write_corners(a, b, w, slots);
+        clip_warp_points<true>(fast ? hits : 0u, (unsigned int)(p >> 6), (unsigned int)(p & 63), sm.wl[warp], sm.rpre, sm.cpre, NBS, sm.verts + (warp * 32) * CLIP_SLOTS);
+        // more than eight vertices (corners admitted by the margin next to a crossing): the whole warp, one pair at a time
+        const bool slow = cnt > CLIP_SLOTS;
+        const float ov_slow = clip_warp_slow<true>(slow, w, (unsigned int)(p >> 6), (unsigned int)(p & 63), sm.rpre, sm.cpre, NBS, reinterpret_cast<float2*>(sm.wl[warp]));
+        if (live) set_bit(p, slow ? ov_slow : (fast ? clip_area8<true>(slots, cnt) : 0.f), a, b);
     }
     __syncthreads();
     if (tid < tr) mask[(size_t)(r0 + tid) * col_blocks + cb] = sm.bits[tid];

@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from glenet_b200 import iou3d_nms_utils as I, iou3d_utils as I1, synth
 dev = torch.device('cuda:0')
 s, g = synth.cvae_samples(20000, 30, 0); s, g = s.to(dev), g.to(dev)

@@ -44,6 +44,19 @@ elif what == "nms":
         fb.append(b); fs.append(s)
     fb, fs = torch.stack(fb).to(dev), torch.stack(fs).to(dev)
     fn = lambda: I.nms_gpu_batch(fb, fs, 0.7)
+elif what == "assign":      # the bench's multi-GPU step on one rank: dense slab + assigner reductions (OUT_BOTH) + decode
+    from glenet_b200 import sharded
+    a = synth.anchors_kitti3().to(dev)
+    b = torch.stack([synth.kitti_boxes(100, 100 + f + 1) for f in range(16)]).to(dev)
+    out = torch.empty((16, a.shape[0], 100), device=dev)
+    win = sharded.ExchangeWindow(frames=16, nb=100, list_cap=0)
+    fn = lambda: sharded.anchor_assign_sharded(a, b, win, out=out)
+elif what == "pib16":       # per-frame points (SURVEY 8d generator), 16 frames
+    B = 16
+    boxes = torch.stack([synth.waymo_boxes(200, 100 + f) for f in range(B)])
+    pts = torch.stack([synth.points(180000, boxes[f], synth.WAYMO_RANGE, 0.05, seed=500 + f) for f in range(B)]).to(dev)
+    boxes = boxes.to(dev)
+    fn = lambda: R.points_in_boxes_gpu(pts, boxes)
 else:
     raise SystemExit("unknown workload")
 
