@@ -38,8 +38,10 @@ constexpr int CLIP_SLOW_SLOTS = 16;    // cross_points[16] of the reference (:15
 // ---------------------------------------------------------------- phase A
 // Result bits of quad lane i: bit j (0..3) = edge i of a crosses edge j of b (intersection() would return 1),
 // bit 4 = corner i of b is inside a, bit 5 = corner i of a is inside b (check_in_box2d, MARGIN).
-template <bool FMA, bool V1 = false>
-__device__ __forceinline__ unsigned int clip_edge_tests(const float* __restrict__ a, const float* __restrict__ b, int i) {
+// WARP_SKIP: all 32 lanes call with their own pair (live = false for lanes without one) and an edge pair whose bounding
+// boxes are disjoint in EVERY lane of the warp -- typically the opposite sides of two similar boxes -- is skipped.
+template <bool FMA, bool V1 = false, bool WARP_SKIP = false>
+__device__ __forceinline__ unsigned int clip_edge_tests(const float* __restrict__ a, const float* __restrict__ b, int i, bool live = true) {
     const int i1 = (i + 1) & 3;
     const float p0x = a[BP_PX + i], p0y = a[BP_PY + i], p1x = a[BP_PX + i1], p1y = a[BP_PY + i1];
     float bx[4], by[4];
@@ -53,7 +55,10 @@ __device__ __forceinline__ unsigned int clip_edge_tests(const float* __restrict_
         const int j1 = (j + 1) & 3;
         const float q0x = bx[j], q0y = by[j], q1x = bx[j1], q1y = by[j1];
         // check_rect_cross (:43-48)
-        const bool rc = (pminx <= fmaxf(q0x, q1x)) & (fminf(q0x, q1x) <= pmaxx) & (pminy <= fmaxf(q0y, q1y)) & (fminf(q0y, q1y) <= pmaxy);
+        const bool rc = live & (pminx <= fmaxf(q0x, q1x)) & (fminf(q0x, q1x) <= pmaxx) & (pminy <= fmaxf(q0y, q1y)) & (fminf(q0y, q1y) <= pmaxy);
+#ifndef GLENET_HOST_EMUL
+        if (WARP_SKIP && !__any_sync(0xffffffffu, rc)) continue;
+#endif
         const float qdx = __fsub_rn(q1x, q0x), qdy = __fsub_rn(q1y, q0y);
         const float s1 = mul_sub<FMA>(__fsub_rn(q0x, p0x), pdy, pdx, __fsub_rn(q0y, p0y));
         const float s2 = __fsub_rn(__fmul_rn(pdx, __fsub_rn(q1y, p0y)), __fmul_rn(pdy, __fsub_rn(q1x, p0x)));
@@ -62,8 +67,8 @@ __device__ __forceinline__ unsigned int clip_edge_tests(const float* __restrict_
         if (rc & (__fmul_rn(s1, s2) > 0.f) & (__fmul_rn(s3, s4) > 0.f)) bits |= 1u << j;
     }
     // corner i of b against a (re-read with the dynamic index from shared memory: bx[i] would force the array out of registers)
-    if (corner_test<FMA, V1>(a, b[BP_PX + i], b[BP_PY + i])) bits |= 16u;
-    if (corner_test<FMA, V1>(b, p0x, p0y)) bits |= 32u;
+    if (live & corner_test<FMA, V1>(a, b[BP_PX + i], b[BP_PY + i])) bits |= 16u;
+    if (live & corner_test<FMA, V1>(b, p0x, p0y)) bits |= 32u;
     return bits;
 }
 
@@ -87,11 +92,12 @@ __device__ __forceinline__ unsigned int clip_corners8(unsigned int w) { // bit 2
 }
 
 // All 24 result bits of a pair by ONE lane (phase A of the throughput-oriented kernels); byte i = clip_edge_tests(a, b, i).
+// All 32 lanes of the warp must call (lanes without a pair pass live = false and any valid records).
 template <bool FMA, bool V1 = false>
-__device__ __forceinline__ unsigned int clip_pair_tests(const float* __restrict__ a, const float* __restrict__ b) {
+__device__ __forceinline__ unsigned int clip_pair_tests(const float* __restrict__ a, const float* __restrict__ b, bool live = true) {
     unsigned int w = 0u;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) w |= clip_edge_tests<FMA, V1>(a, b, i) << (8 * i);
+    for (int i = 0; i < 4; ++i) w |= clip_edge_tests<FMA, V1, true>(a, b, i, live) << (8 * i);
     return w;
 }
 
@@ -234,9 +240,12 @@ __device__ __forceinline__ void clip_write_vertices(const float* __restrict__ a,
 }
 
 // ---------------------------------------------------------------- phase C
-__device__ __forceinline__ unsigned int clip_sort_key(float k) {   // order-preserving float -> uint
-    const unsigned int u = __float_as_uint(k);
-    return u ^ ((unsigned int)((int)u >> 31) | 0x80000000u);
+// Sort key of a vertex direction: pseudo-angle shifted from [-2, 2] to [2, 6].  Positive floats order like their bit
+// patterns, and in [2, 8) one ulp is 2.4e-7 .. 4.8e-7 ABSOLUTE, so "keys within 64 ulps" below means "directions within
+// ~1.5e-5 .. 3e-5 of pseudo-angle", uniformly -- far more than the rounding of pseudo_angle (~5e-7), far less than the
+// angle between two genuinely different vertices.
+__device__ __forceinline__ unsigned int clip_sort_key(float dy, float dx) {
+    return __float_as_uint(__fadd_rn(pseudo_angle(dy, dx), 4.0f));
 }
 
 // Area of the polygon in `slots` (3 <= cnt <= 8 vertices in discovery order): the reference's centroid / angular order /
@@ -257,7 +266,7 @@ __device__ __forceinline__ float clip_area8(const float2* __restrict__ slots, in
     unsigned int P[CLIP_SLOTS];
 #pragma unroll
     for (int k = 0; k < CLIP_SLOTS; ++k) {
-        const unsigned int key = clip_sort_key(pseudo_angle(__fsub_rn(Y[k], ccy), __fsub_rn(X[k], ccx)));
+        const unsigned int key = clip_sort_key(__fsub_rn(Y[k], ccy), __fsub_rn(X[k], ccx));
         P[k] = k < cnt ? ((key & ~7u) | (unsigned int)k) : 0xffffffffu;
     }
 #define GLENET_CE(i, j) { const unsigned int lo_ = min(P[i], P[j]), hi_ = max(P[i], P[j]); P[i] = lo_; P[j] = hi_; }
@@ -269,10 +278,11 @@ __device__ __forceinline__ float clip_area8(const float2* __restrict__ slots, in
     GLENET_CE(2, 4) GLENET_CE(3, 5)
     GLENET_CE(3, 4)
 #undef GLENET_CE
-    // Neighbours whose keys are within ~64 ulps are NOT interchangeable: a corner admitted by the margin and a crossing 1 cm
-    // from it can lie on one ray from the centroid, and their order decides ~1e-3 of IoU.  The packed keys lost three bits
-    // to the slot number and the pseudo-angle is only monotone up to its own rounding, so such polygons (~1e-5 of the pairs)
-    // are sorted again exactly as the reference does it: atan2f keys, ties to the discovery order (stable sort, :199-209).
+    // Neighbours whose keys are within 64 ulps (see clip_sort_key) are NOT interchangeable: a corner admitted by the margin
+    // and a crossing 1 cm from it can lie on one ray from the centroid, and their order decides ~1e-3 of IoU.  The packed
+    // keys lost three bits to the slot number and the pseudo-angle is only monotone up to its own rounding, so such polygons
+    // (~1e-4 of the pairs) are sorted again exactly as the reference does it: atan2f keys, ties to the discovery order
+    // (stable sort, :199-209).
     bool tie = false;
 #pragma unroll
     for (int k = 0; k + 1 < CLIP_SLOTS; ++k) tie |= (k + 1 < cnt) & (P[k + 1] - P[k] < 512u);

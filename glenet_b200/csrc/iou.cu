@@ -42,7 +42,7 @@ namespace glenet {
 #define GLENET_IOU_THREADS 256
 #endif
 #ifndef GLENET_IOU_TR_MAX
-#define GLENET_IOU_TR_MAX 480
+#define GLENET_IOU_TR_MAX 384
 #endif
 #ifndef GLENET_IOU_CTAS
 #define GLENET_IOU_CTAS 3
@@ -95,6 +95,9 @@ struct IouFrames {
     // reduced output (row_key != nullptr): per row / per column  max over the other axis of
     // (value bits << 32) | (0xffffffff - index), i.e. the maximum and the FIRST index attaining it; 0 = no non-zero element
     unsigned long long* row_key; unsigned long long* col_key;
+    // with ONE column tile every row's maximum is final inside its tile: the tile writes the decoded (max, first argmax) itself
+    // and no row key ever reaches global memory (row_key is then only a non-null marker)
+    float* row_max; long long* row_arg;
     IouPeers ex;   // ex.world <= 1: single GPU, nothing below the struct's first member is read
 };
 __device__ __forceinline__ bool iou_no_matrix(const IouFrames& fr) { return fr.sp_count != nullptr || fr.row_key != nullptr; }
@@ -103,6 +106,7 @@ struct __align__(128) IouSmem {
     float4 zero[IOU_ZBYTES / 16];          // source of the bulk zero fill
     float2 verts[IOU_CLIP_PAIRS * CLIP_SLOTS];              // vertex slots of the phased clip (clip.cuh), one pair per lane
     unsigned int wl[IOU_CLIP_PAIRS / 32][32 * CLIP_SLOTS];  // per-warp work lists of its phase B
+    unsigned long long rkey[IOU_TR_MAX], ckey[IOU_TC_MAX];  // the tile's row / column maxima (key output modes), flushed to global memory once
     float rrad[IOU_TR_MAX], crad[IOU_TC_MAX];               // cull radii; the centres are slots 0 / 1 of the records below
     float rpre[IOU_TR_MAX * BPS];          // rows: raw box in the first 7 slots until a pair needs it, then the BoxPre record (same centre slots)
     float cpre[IOU_TC_MAX * BPS];
@@ -265,7 +269,7 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
             const float* a = sm.rpre + (e >> 7) * BPS;
             const float* b = sm.cpre + (e & 127) * BPS;
             float2* slots = sm.verts + tid * CLIP_SLOTS;
-            const unsigned int w = live ? clip_pair_tests<FMA>(a, b) : 0u;
+            const unsigned int w = clip_pair_tests<FMA>(a, b, live);
             const unsigned int hits = clip_hits16(w);
             const int cnt = __popc(hits) + __popc(clip_corners8(w));
             const bool fast = cnt >= 3 && cnt <= CLIP_SLOTS, slow = cnt > CLIP_SLOTS;
@@ -291,12 +295,14 @@ __device__ __forceinline__ void drain_queue(IouSmem& sm, const float* __restrict
             const unsigned int e = sm.queue2[q];
             const float v = sm.qres[q];
             if (!(v == 0.f)) {
-                const unsigned int r = r0 + (e >> 7), c = c0 + (e & 127);
+                // Folded in SHARED memory and flushed once per tile: global atomics issued here, between the tile's barriers, wait
+                // for their acknowledgement from an L2 that is busy with a wave of zero fills (measured: + 80 % on the dense + keys launch).
                 const unsigned long long hi = (unsigned long long)__float_as_uint(v) << 32;
-                atomicMax(fr.row_key + (size_t)frame * fr.na + r, hi | (0xffffffffu - c));
-                atomicMax(fr.col_key + (size_t)frame * nb + c, hi | (0xffffffffu - (r + (unsigned int)fr.row_offset)));
+                atomicMax(&sm.rkey[e >> 7], hi | (0xffffffffu - (c0 + (e & 127))));
+                atomicMax(&sm.ckey[e & 127], hi | (0xffffffffu - (unsigned int)(r0 + (e >> 7) + fr.row_offset)));
             }
         }
+        (void)frame;
     }
     if (OUT == OUT_REDUCED && fr.sp_count) {
         for (int q0 = 0; q0 < nclip; q0 += IOU_CHAIN) {
@@ -425,9 +431,10 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
         if (MODE == MODE_IOU3D && !z_terms_finite(z_terms(raw[2], raw[5], __fmul_rn(raw[3], raw[4])))) rad = CUDART_INF_F;
         if (is_row) {
             sm.rrad[k] = rad; sm.rflag[k] = 0;
+            if (OUT != OUT_DENSE) sm.rkey[k] = 0ull;
             minx = fminf(minx, cx); maxx = fmaxf(maxx, cx); miny = fminf(miny, cy); maxy = fmaxf(maxy, cy);
             maxr = (rad != rad) ? CUDART_INF_F : fmaxf(maxr, rad);   // a NaN radius must not be dropped by fmaxf
-        } else { sm.crad[k] = rad; sm.cflag[k] = 0; }
+        } else { sm.crad[k] = rad; sm.cflag[k] = 0; if (OUT != OUT_DENSE) sm.ckey[k] = 0ull; }
     }
     minx = warp_min(minx); maxx = warp_max(maxx); miny = warp_min(miny); maxy = warp_max(maxy); maxr = warp_max(maxr);
     if (lane == 0) { sm.red[warp][0] = minx; sm.red[warp][1] = maxx; sm.red[warp][2] = miny; sm.red[warp][3] = maxy; sm.red[warp][4] = maxr; }
@@ -551,6 +558,19 @@ iou_tile_kernel(const float* __restrict__ A, int na, const float* __restrict__ B
     }
     PHASE_MARK(2);
     // (a tile without active columns has nothing to write: its chain warps leave, the fill warp finishes on its own)
+    if (OUT != OUT_DENSE && fr.row_key) {   // the tile's maxima -> global keys; nothing in this CTA waits for these atomics
+        chain_sync();
+        unsigned long long* gcol = fr.col_key + (size_t)frame * nb + c0;
+        const size_t row0 = (size_t)frame * fr.na + r0;
+        for (int i = tid; i < tr + tc; i += IOU_CHAIN) {
+            const unsigned long long k = i < tr ? sm.rkey[i] : sm.ckey[i - tr];
+            if (i >= tr) { if (k) atomicMax(gcol + (i - tr), k); }
+            else if (fr.row_max) {   // decoded in place (the launcher only passes row_max with a single column tile)
+                fr.row_max[row0 + i] = __uint_as_float((unsigned int)(k >> 32));
+                fr.row_arg[row0 + i] = k ? (long long)(0xffffffffu - (unsigned int)k) : 0;
+            } else if (k) atomicMax(fr.row_key + row0 + i, k);
+        }
+    }
     if (OUT != OUT_DENSE && fr.ex.world > 1) exchange_epilogue(sm, fr, nb);
 #ifdef GLENET_PHASE_TIMING
     if (tid == 0 && cta_lin < 4096) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_cta_log[cta_lin * 4 + 1] = t; }
@@ -573,34 +593,73 @@ struct AlignedSmem {
     float2 verts[AL_PAIRS * CLIP_SLOTS];
     unsigned int wl[AL_THREADS / 32][32 * CLIP_SLOTS];   // per-warp work lists of phase B (then the scratch of clip_warp_slow)
     float arec[AL_PAIRS * BPS];
-    float brec[1];                          // [nb_max * (BPS + 1)], sized by the launcher: the b boxes one batch can meet (+ cull radius)
+    float brec[1];                          // [2][nb_max * (BPS + 1)], sized by the launcher: the b boxes one batch can meet (+ cull radii), double-buffered
 };
+
+// n / d for n < 2^31 by multiply-shift (Granlund-Montgomery); the launcher precomputes {m, s} for the runtime `group`
+struct FastDiv { unsigned int m, s, d; };
+static FastDiv fastdiv_make(unsigned int d) {
+    FastDiv f; f.d = d; f.s = 0; f.m = 0;
+    if (d <= 1) return f;
+    while ((1u << f.s) < d) ++f.s;                                   // s = ceil(log2 d)
+    f.m = (unsigned int)((((unsigned long long)1 << 32) * ((1ull << f.s) - d)) / d + 1);
+    return f;
+}
+__device__ __forceinline__ unsigned int fastdiv(unsigned int n, const FastDiv& f) {
+    if (f.d <= 1) return n;
+    const unsigned int t = __umulhi(f.m, n);
+    return (t + ((n - t) >> 1)) >> (f.s - 1);
+}
+
+template <int MODE, bool FMA>
+__device__ __forceinline__ void aligned_stage_b(const float* __restrict__ B, int b0, int nbx, float* __restrict__ brec, float* __restrict__ brad, int tid) {
+    for (int k = tid; k < nbx; k += AL_THREADS) {
+        const float* bb = B + (size_t)(b0 + k) * 7;
+        float raw[7];
+#pragma unroll
+        for (int f = 0; f < 7; ++f) raw[f] = bb[f];
+        box_prepare<FMA, false>(raw, device_trig_fused(raw[6]), brec + k * BPS);
+        float rad = cull_radius(raw);
+        // 3D IoU: 0 * NaN = NaN in the reference's torch arithmetic, so a pair with a non-finite z term is never culled
+        if (MODE == MODE_IOU3D && !z_terms_finite(z_terms(raw[2], raw[5], __fmul_rn(raw[3], raw[4])))) rad = CUDART_INF_F;
+        brad[k] = rad;
+    }
+}
 
 template <int MODE, bool FMA>
 __global__ void __launch_bounds__(AL_THREADS, AL_CTAS_PER_SM)
-iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int group, float* __restrict__ out, int nbatches, int nb_max) {
+iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, const FastDiv group, float* __restrict__ out, int nbatches, int nb_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AlignedSmem& sm = *reinterpret_cast<AlignedSmem*>(smem_raw);
-    float* brad = sm.brec + nb_max * BPS;   // cull radius of the staged b boxes (+inf: never cull, the 3D IoU of a non-finite height)
+    // two sets of b records (+ cull radii; +inf = never cull): the first lanes stage the NEXT batch's while the current one is clipped
+    const int bset = nb_max * (BPS + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int bt = blockIdx.x; bt < nbatches; bt += gridDim.x) {
+    auto batch_b = [&](int bt, int& b0, int& nbx) {
         const int p0 = bt * AL_PAIRS, np = min(AL_PAIRS, na - p0);
-        const int b0 = p0 / group, nbx = (p0 + np - 1) / group - b0 + 1;
-        __syncthreads();   // the previous batch is done with the b records
-        for (int k = tid; k < nbx; k += AL_THREADS) {
-            const float* bb = B + (size_t)(b0 + k) * 7;
-            float raw[7];
-#pragma unroll
-            for (int f = 0; f < 7; ++f) raw[f] = bb[f];
-            box_prepare<FMA, false>(raw, device_trig_fused(raw[6]), sm.brec + k * BPS);
-            float rad = cull_radius(raw);
-            // 3D IoU: 0 * NaN = NaN in the reference's torch arithmetic, so a pair with a non-finite z term is never culled
-            if (MODE == MODE_IOU3D && !z_terms_finite(z_terms(raw[2], raw[5], __fmul_rn(raw[3], raw[4])))) rad = CUDART_INF_F;
-            brad[k] = rad;
+        b0 = (int)fastdiv((unsigned int)p0, group);
+        nbx = (int)fastdiv((unsigned int)(p0 + np - 1), group) - b0 + 1;
+    };
+    int b0, nbx;
+    if ((int)blockIdx.x < nbatches) {
+        batch_b(blockIdx.x, b0, nbx);
+        aligned_stage_b<MODE, FMA>(B, b0, nbx, sm.brec, sm.brec + nb_max * BPS, tid);
+    }
+    int cur = 0;
+    for (int bt = blockIdx.x; bt < nbatches; bt += gridDim.x, cur ^= 1) {
+        const int p0 = bt * AL_PAIRS, np = min(AL_PAIRS, na - p0);
+        batch_b(bt, b0, nbx);
+        const float* brec = sm.brec + cur * bset;
+        const float* brad = brec + nb_max * BPS;
+        __syncthreads();   // this batch's b records are staged; everybody is done with the other set
+        if (bt + (int)gridDim.x < nbatches) {
+            int nb0, nnbx;
+            batch_b(bt + gridDim.x, nb0, nnbx);
+            float* nrec = sm.brec + (cur ^ 1) * bset;
+            aligned_stage_b<MODE, FMA>(B, nb0, nnbx, nrec, nrec + nb_max * BPS, tid);
         }
-        // this lane's pair: its b box is (p0 + tid) / group; consecutive lanes step through the groups without a division each
+        // this lane's pair
         const int gi = p0 + tid;
-        const int bsel = tid < np ? gi / group - b0 : 0;
+        const int bsel = tid < np ? (int)fastdiv((unsigned int)gi, group) - b0 : 0;
         float raw[7];
         const float* ba = A + (size_t)(tid < np ? gi : p0) * 7;
 #pragma unroll
@@ -608,8 +667,7 @@ iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict_
         float* a = sm.arec + tid * BPS;
         float arad = cull_radius(raw);
         if (MODE == MODE_IOU3D && !z_terms_finite(z_terms(raw[2], raw[5], __fmul_rn(raw[3], raw[4])))) arad = CUDART_INF_F;
-        __syncthreads();
-        const float* b = sm.brec + bsel * BPS;
+        const float* b = brec + bsel * BPS;
         bool active = false;
         if (tid < np) {
             const float ddx = raw[0] - b[BP_CX], ddy = raw[1] - b[BP_CY], rr = arad + brad[bsel];
@@ -617,18 +675,19 @@ iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict_
             if (active) box_prepare<FMA, false>(raw, device_trig_fused(raw[6]), a);
             else out[gi] = 0.f;
         }
+        __syncwarp();
         // ---- A: result bits, corners to their slots
         float2* slots = sm.verts + tid * CLIP_SLOTS;
-        const unsigned int w = active ? clip_pair_tests<FMA>(a, b) : 0u;
+        const unsigned int w = clip_pair_tests<FMA>(a, b, active);
         const unsigned int hits = clip_hits16(w);
         const int cnt = __popc(hits) + __popc(clip_corners8(w));
         const bool fast = cnt >= 3 && cnt <= CLIP_SLOTS;
         if (fast) clip_write_corners(a, b, w, slots);
         // ---- B: the warp's crossings, one per lane
-        clip_warp_points<FMA>(fast ? hits : 0u, (unsigned int)tid, (unsigned int)bsel, sm.wl[warp], sm.arec, sm.brec, BPS, sm.verts + (warp * 32) * CLIP_SLOTS);
+        clip_warp_points<FMA>(fast ? hits : 0u, (unsigned int)tid, (unsigned int)bsel, sm.wl[warp], sm.arec, brec, BPS, sm.verts + (warp * 32) * CLIP_SLOTS);
         // ---- C: sort + fan (more than eight vertices: the whole warp, one pair at a time)
         const bool slow = cnt > CLIP_SLOTS;
-        const float ov_slow = clip_warp_slow<FMA>(slow, w, (unsigned int)tid, (unsigned int)bsel, sm.arec, sm.brec, BPS, reinterpret_cast<float2*>(sm.wl[warp]));
+        const float ov_slow = clip_warp_slow<FMA>(slow, w, (unsigned int)tid, (unsigned int)bsel, sm.arec, brec, BPS, reinterpret_cast<float2*>(sm.wl[warp]));
         if (active) {
             const float ov = slow ? ov_slow : (fast ? clip_area8<FMA>(slots, cnt) : 0.f);
             out[gi] = finish_pair<MODE>(a, b, ov, ba, B + (size_t)(b0 + bsel) * 7);
@@ -651,13 +710,13 @@ static int resident_ctas(K kernel) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, IOU_THREADS, sizeof(IouSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
     return sms * per_sm;
 }
-static void pick_tiles(int na, int nb, int frames, int resident, int& TR, int& TC, int& row_tiles, int& col_tiles) {
+static void pick_tiles(int na, int nb, int frames, int resident, int& TR, int& TC, int& row_tiles, int& col_tiles, bool allow_col_split = true) {
     col_tiles = (nb + IOU_TC_MAX - 1) / IOU_TC_MAX;
     {   // very small problems (< 1/4 wave): split the columns further -- a small dense matrix
         // is bound by the clip passes of its few tiles, and more CTAs are more clip lanes
         const long rt32 = (long)((na + 31) / 32) * frames;
         const long want = resident / rt32, most = (nb + 31) / 32;
-        if (g_col_split && rt32 * col_tiles * 4 < resident && want > col_tiles) col_tiles = (int)(want < most ? want : most);
+        if (allow_col_split && g_col_split && rt32 * col_tiles * 4 < resident && want > col_tiles) col_tiles = (int)(want < most ? want : most);
     }
     TC = ((nb + col_tiles - 1) / col_tiles + 3) / 4 * 4;   // multiple of 4 keeps every tile on the 16-byte store path
     col_tiles = (nb + TC - 1) / TC;
@@ -675,6 +734,10 @@ static void pick_tiles(int na, int nb, int frames, int resident, int& TR, int& T
 #ifdef GLENET_PHASE_TIMING
     if (g_debug_tile_rows) TR = g_debug_tile_rows;
 #endif
+    {   // tuning aid: GLENET_IOU_TILE_ROWS=<multiple of 32> overrides the choice (read once per process)
+        static const int forced_rows = [] { const char* e = getenv("GLENET_IOU_TILE_ROWS"); return e ? atoi(e) : 0; }();
+        if (forced_rows >= 32 && forced_rows <= IOU_TR_MAX) TR = forced_rows / 32 * 32;
+    }
     row_tiles = (na + TR - 1) / TR;
 }
 
@@ -684,6 +747,7 @@ struct IouLaunch {
     long long stride_a = 0, stride_b = 0, stride_out = 0;
     long long* sp_idx = nullptr; float* sp_val = nullptr; unsigned long long* sp_count = nullptr; long long sp_cap = 0;
     unsigned long long* row_key = nullptr; unsigned long long* col_key = nullptr;
+    float* row_max = nullptr; long long* row_arg = nullptr;   // direct row outputs, honoured when the launch has one column tile
     bool keys_prezeroed = false;   // the caller guarantees zeroed key buffers (the exchange's decode kernel re-zeroes them after use)
     bool dense_and_keys = false;   // write the matrix AND fold the maxima (OUT_BOTH)
     int row_offset = 0; long long na_total = 0;
@@ -707,13 +771,14 @@ static int launch_tile(const float* A, const float* trigA, int na, const float* 
     }
     const int frames = L.frames;
     int TR, TC, row_tiles, col_tiles;
-    pick_tiles(na, nb, frames, resident, TR, TC, row_tiles, col_tiles);
+    pick_tiles(na, nb, frames, resident, TR, TC, row_tiles, col_tiles, L.row_max == nullptr);   // direct row outputs need whole rows in one tile
     const long long tiles = (long long)row_tiles * col_tiles;
     if (tiles * frames > 0x7fffffffLL) return fail(GLENET_EINVAL, "%s: too many tiles", what);
     IouFrames fr;
     fr.stride_a = L.stride_a; fr.stride_b = L.stride_b; fr.stride_out = OUT == OUT_REDUCED ? 0 : L.stride_out; fr.na = na;
     fr.row_offset = L.row_offset; fr.na_total = L.na_total > 0 ? L.na_total : na;
     fr.row_key = L.row_key; fr.col_key = L.col_key;
+    fr.row_max = col_tiles == 1 ? L.row_max : nullptr; fr.row_arg = col_tiles == 1 ? L.row_arg : nullptr;
     fr.sp_idx = L.sp_idx; fr.sp_val = L.sp_val; fr.sp_count = L.sp_count; fr.sp_cap = L.sp_cap;
     fr.ex = L.ex;
     cudaLaunchConfig_t cfg = {};
@@ -906,6 +971,8 @@ int glenet_boxes_iou_frames_assign_gpu(int mode, const float* a, long long a_fra
     IouLaunch L;
     L.frames = frames; L.stride_a = a_frame_stride; L.stride_b = b_frame_stride; L.stride_out = (long long)na * nb;
     L.row_key = row_key; L.col_key = reinterpret_cast<unsigned long long*>(at(rank, lay.off_col_key[par]));
+    L.row_max = row_max; L.row_arg = row_arg;
+    const bool rows_direct = nb <= IOU_TC_MAX;   // one column tile (pick_tiles never splits columns of a problem this tall)
     L.keys_prezeroed = true; L.dense_and_keys = out != nullptr;
     L.row_offset = row_offset; L.na_total = na_total;
     L.ex.world = world; L.ex.rank = rank; L.ex.step = step;
@@ -922,7 +989,7 @@ int glenet_boxes_iou_frames_assign_gpu(int mode, const float* a, long long a_fra
         rc = check_launch(what);
         if (rc) return rc;
     }
-    const long long n_row = (long long)frames * na, n_col = (long long)frames * nb;
+    const long long n_row = rows_direct ? 0 : (long long)frames * na, n_col = (long long)frames * nb;
     if (n_row + n_col == 0) return GLENET_OK;
     long long blocks = (n_row + n_col + 255) / 256;
     if (blocks > 296) blocks = 296;
@@ -1019,7 +1086,8 @@ int glenet_boxes_iou_aligned_gpu(int mode, const float* a, int na, const float* 
     if (!a || !b || !out) return fail(GLENET_EINVAL, "%s: null pointer", what);
     const int nbatches = (na + AL_PAIRS - 1) / AL_PAIRS;
     const int nb_max = (AL_PAIRS - 1) / group + 2;   // b boxes a batch of AL_PAIRS consecutive pairs can meet
-    const size_t smem = sizeof(AlignedSmem) + sizeof(float) * (size_t)nb_max * (BPS + 1);
+    const size_t smem = sizeof(AlignedSmem) + sizeof(float) * 2 * (size_t)nb_max * (BPS + 1);
+    const FastDiv gdiv = fastdiv_make((unsigned int)group);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1027,9 +1095,9 @@ int glenet_boxes_iou_aligned_gpu(int mode, const float* a, int na, const float* 
     cudaStream_t st = (cudaStream_t)s;
     int rc;
     // (the opt-in shared-memory size is a per-device attribute and cheap to set: no cache)
-    if (mode == 0) { auto k = iou_aligned_kernel<MODE_OVERLAP, true>; rc = set_smem(k, smem, what); if (rc) return rc; k<<<grid, AL_THREADS, smem, st>>>(a, na, b, group, out, nbatches, nb_max); }
-    else if (mode == 1) { auto k = iou_aligned_kernel<MODE_IOU_BEV, true>; rc = set_smem(k, smem, what); if (rc) return rc; k<<<grid, AL_THREADS, smem, st>>>(a, na, b, group, out, nbatches, nb_max); }
-    else { auto k = iou_aligned_kernel<MODE_IOU3D, true>; rc = set_smem(k, smem, what); if (rc) return rc; k<<<grid, AL_THREADS, smem, st>>>(a, na, b, group, out, nbatches, nb_max); }
+    if (mode == 0) { auto k = iou_aligned_kernel<MODE_OVERLAP, true>; rc = set_smem(k, smem, what); if (rc) return rc; k<<<grid, AL_THREADS, smem, st>>>(a, na, b, gdiv, out, nbatches, nb_max); }
+    else if (mode == 1) { auto k = iou_aligned_kernel<MODE_IOU_BEV, true>; rc = set_smem(k, smem, what); if (rc) return rc; k<<<grid, AL_THREADS, smem, st>>>(a, na, b, gdiv, out, nbatches, nb_max); }
+    else { auto k = iou_aligned_kernel<MODE_IOU3D, true>; rc = set_smem(k, smem, what); if (rc) return rc; k<<<grid, AL_THREADS, smem, st>>>(a, na, b, gdiv, out, nbatches, nb_max); }
     return check_launch(what);
 }
 

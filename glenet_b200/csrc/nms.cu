@@ -215,7 +215,7 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
         const float* a = sm.rpre + (p >> 6) * NBS;
         const float* b = sm.cpre + (p & 63) * NBS;
         float2* slots = sm.verts + tid * CLIP_SLOTS;
-        const unsigned int w = live ? clip_pair_tests<true>(a, b) : 0u;
+        const unsigned int w = clip_pair_tests<true>(a, b, live);
         const unsigned int hits = clip_hits16(w);
         const int cnt = __popc(hits) + __popc(clip_corners8(w));
         const bool fast = cnt >= 3 && cnt <= CLIP_SLOTS;
