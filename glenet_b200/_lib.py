@@ -56,13 +56,15 @@ _SIGNATURES = {
     "glenet_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "glenet_nms_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "glenet_nms_normal_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "glenet_variance_nms_gpu": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_float, ctypes.c_void_p]),
     "glenet_points_in_boxes_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "glenet_points_in_boxes_gpu": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "glenet_points_in_boxes_cpu_dialect": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 def lib_path() -> str:

@@ -93,11 +93,13 @@ __device__ __forceinline__ unsigned int clip_corners8(unsigned int w) { // bit 2
 
 // All 24 result bits of a pair by ONE lane (phase A of the throughput-oriented kernels); byte i = clip_edge_tests(a, b, i).
 // All 32 lanes of the warp must call (lanes without a pair pass live = false and any valid records).
-template <bool FMA, bool V1 = false>
+// WARP_SKIP pays where the boxes of a warp's pairs resemble each other (aligned samples vs their GT: the opposite sides
+// never meet, 25 % of the tests go away; measured - 3 %); on mixed pairs (tile / NMS kernels) the votes only cost (+ 10 %).
+template <bool FMA, bool V1 = false, bool WARP_SKIP = false>
 __device__ __forceinline__ unsigned int clip_pair_tests(const float* __restrict__ a, const float* __restrict__ b, bool live = true) {
     unsigned int w = 0u;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) w |= clip_edge_tests<FMA, V1, true>(a, b, i, live) << (8 * i);
+    for (int i = 0; i < 4; ++i) w |= clip_edge_tests<FMA, V1, WARP_SKIP>(a, b, i, live) << (8 * i);
     return w;
 }
 
@@ -241,9 +243,11 @@ __device__ __forceinline__ void clip_write_vertices(const float* __restrict__ a,
 
 // ---------------------------------------------------------------- phase C
 // Sort key of a vertex direction: pseudo-angle shifted from [-2, 2] to [2, 6].  Positive floats order like their bit
-// patterns, and in [2, 8) one ulp is 2.4e-7 .. 4.8e-7 ABSOLUTE, so "keys within 64 ulps" below means "directions within
-// ~1.5e-5 .. 3e-5 of pseudo-angle", uniformly -- far more than the rounding of pseudo_angle (~5e-7), far less than the
-// angle between two genuinely different vertices.
+// patterns, and in [2, 8) one ulp is 2.4e-7 .. 4.8e-7 ABSOLUTE, so "keys within CLIP_TIE_ULPS" below means "directions
+// within ~4e-6 .. 8e-6 of pseudo-angle", uniformly.  The rounding of pseudo_angle + 4 is below 1e-6 (approximate
+// division 3e-7, the two additions 6e-8 + 2.4e-7 .. 4.8e-7), so two keys further apart than that are in the order of their
+// true directions -- which is also atan2f's order.
+constexpr unsigned int CLIP_TIE_ULPS = 16u;
 __device__ __forceinline__ unsigned int clip_sort_key(float dy, float dx) {
     return __float_as_uint(__fadd_rn(pseudo_angle(dy, dx), 4.0f));
 }
@@ -278,14 +282,14 @@ __device__ __forceinline__ float clip_area8(const float2* __restrict__ slots, in
     GLENET_CE(2, 4) GLENET_CE(3, 5)
     GLENET_CE(3, 4)
 #undef GLENET_CE
-    // Neighbours whose keys are within 64 ulps (see clip_sort_key) are NOT interchangeable: a corner admitted by the margin
+    // Neighbours whose keys are within CLIP_TIE_ULPS (see clip_sort_key) are NOT interchangeable: a corner admitted by the margin
     // and a crossing 1 cm from it can lie on one ray from the centroid, and their order decides ~1e-3 of IoU.  The packed
     // keys lost three bits to the slot number and the pseudo-angle is only monotone up to its own rounding, so such polygons
     // (~1e-4 of the pairs) are sorted again exactly as the reference does it: atan2f keys, ties to the discovery order
     // (stable sort, :199-209).
     bool tie = false;
 #pragma unroll
-    for (int k = 0; k + 1 < CLIP_SLOTS; ++k) tie |= (k + 1 < cnt) & (P[k + 1] - P[k] < 512u);
+    for (int k = 0; k + 1 < CLIP_SLOTS; ++k) tie |= (k + 1 < cnt) & (P[k + 1] - P[k] < 8u * CLIP_TIE_ULPS);
     if (tie) {
         float K[CLIP_SLOTS];
 #pragma unroll

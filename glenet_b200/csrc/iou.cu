@@ -678,7 +678,7 @@ iou_aligned_kernel(const float* __restrict__ A, int na, const float* __restrict_
         __syncwarp();
         // ---- A: result bits, corners to their slots
         float2* slots = sm.verts + tid * CLIP_SLOTS;
-        const unsigned int w = clip_pair_tests<FMA>(a, b, active);
+        const unsigned int w = clip_pair_tests<FMA, false, true>(a, b, active);
         const unsigned int hits = clip_hits16(w);
         const int cnt = __popc(hits) + __popc(clip_corners8(w));
         const bool fast = cnt >= 3 && cnt <= CLIP_SLOTS;

@@ -89,6 +89,33 @@ def _pairwise(fn_name: str, boxes_a: torch.Tensor, boxes_b: torch.Tensor) -> tor
 
 
 # ---------------------------------------------------------------- IoU
+def _bev_iou_cpu_dialect_on_device(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """(N, M) BEV IoU of float32 CPU boxes in the CPU dialect, computed and LEFT on the GPU."""
+    na, nb = a.shape[0], b.shape[0]
+    dev = _device_for_host_call("boxes_bev_iou_cpu")
+    lib = _lib.load()
+    # one host buffer: [boxes_a | boxes_b | trig_a | trig_b] -> one H2D copy
+    # (the trig tables are read as float4 => their offsets are padded to 16 bytes)
+    o_b = na * 7
+    o_ta = (o_b + nb * 7 + 3) // 4 * 4
+    o_tb = o_ta + na * 4
+    host = torch.empty(o_tb + nb * 4, dtype=torch.float32).pin_memory()
+    host[:o_b].copy_(a.reshape(-1))
+    host[o_b:o_b + nb * 7].copy_(b.reshape(-1))
+    base = host.data_ptr()
+    lib.glenet_host_trig4(a.data_ptr(), na, base + 4 * o_ta)
+    lib.glenet_host_trig4(b.data_ptr(), nb, base + 4 * o_tb)
+    d = host.to(dev, non_blocking=True)
+    out = torch.empty((na, nb), dtype=torch.float32, device=dev)
+    p = d.data_ptr()
+    with torch.cuda.device(dev):
+        rc = lib.glenet_boxes_iou_bev_cpu_dialect(p, p + 4 * o_ta, na, p + 4 * o_b, p + 4 * o_tb, nb,
+                                                  out.data_ptr(), _stream(dev))
+    _lib.check(rc, "glenet_boxes_iou_bev_cpu_dialect")
+    out.record_stream(torch.cuda.current_stream(dev))
+    return out
+
+
 def boxes_bev_iou_cpu(boxes_a, boxes_b):
     """
     Args:
@@ -114,27 +141,7 @@ def boxes_bev_iou_cpu(boxes_a, boxes_b):
     na, nb = a.shape[0], b.shape[0]
     ans_iou = boxes_a.new_zeros(torch.Size((na, nb)))
     if na and nb:
-        dev = _device_for_host_call("boxes_bev_iou_cpu")
-        lib = _lib.load()
-        # one host buffer: [boxes_a | boxes_b | trig_a | trig_b] -> one H2D copy
-        # (the trig tables are read as float4 => their offsets are padded to 16 bytes)
-        o_b = na * 7
-        o_ta = (o_b + nb * 7 + 3) // 4 * 4
-        o_tb = o_ta + na * 4
-        host = torch.empty(o_tb + nb * 4, dtype=torch.float32).pin_memory()
-        host[:o_b].copy_(a.view(-1))
-        host[o_b:o_b + nb * 7].copy_(b.view(-1))
-        base = host.data_ptr()
-        lib.glenet_host_trig4(a.data_ptr(), na, base + 4 * o_ta)
-        lib.glenet_host_trig4(b.data_ptr(), nb, base + 4 * o_tb)
-        d = host.to(dev, non_blocking=True)
-        out = torch.empty((na, nb), dtype=torch.float32, device=dev)
-        p = d.data_ptr()
-        with torch.cuda.device(dev):
-            rc = lib.glenet_boxes_iou_bev_cpu_dialect(p, p + 4 * o_ta, na, p + 4 * o_b, p + 4 * o_tb, nb,
-                                                      out.data_ptr(), _stream(dev))
-        _lib.check(rc, "glenet_boxes_iou_bev_cpu_dialect")
-        ans_iou.copy_(out)   # D2H, synchronising
+        ans_iou.copy_(_bev_iou_cpu_dialect_on_device(a, b))   # D2H, synchronising
     return ans_iou.numpy() if is_numpy else ans_iou
 
 

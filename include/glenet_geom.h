@@ -196,6 +196,17 @@ int glenet_nms_normal_gpu(const float* boxes, int frames, int n, float nms_overl
                           int64_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes,
                           glenet_stream_t stream);
 
+/* GLENet's variance-voting NMS and soft-NMS: the Python loops of nms_func (pcdet/ops/iou3d_nms/iou3d_nms_utils.py:227-273, the
+ * body of new_nms_gpu :200-224, NMS_TYPE of every shipped GLENet config) and softnms (:312-356) as one kernel per call, one
+ * CTA per frame.  boxes (frames, n, 7) and scores (frames, n) are updated IN PLACE: a retired box is replaced by the
+ * variance-weighted average of the boxes that overlap it by more than iou_threshold (variance: (frames, n, var_cols) or NULL
+ * for no voting; var_cols >= 7 for mode 0, >= 6 otherwise), scores are zeroed (mode 0), decayed by exp(-iou^2 / soft_sigma)
+ * (mode 1) or by 1 - iou where iou >= soft_sigma (mode 2).  iou: (frames, n, n), element [j][i] = IoU(box j as a, box i as b)
+ * of the ORIGINAL boxes (glenet_boxes_iou_bev_cpu_dialect for new_nms_gpu, glenet_boxes_iou_bev_gpu for softnms), resident on
+ * the device.  The float32 sums of the vote run in index order, as numpy's do.  n <= 12288. */
+int glenet_variance_nms_gpu(float* boxes, float* scores, const float* variance, int var_cols, const float* iou, int frames, int n,
+                            float iou_threshold, float score_threshold, int mode, float soft_sigma, glenet_stream_t stream);
+
 /* ---------------------------------------------------------------- points in boxes
  * points_in_boxes_gpu(boxes, pts, box_idx_of_points)  pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:98-118
  * boxes (B, N, 7), pts (B, M, 3), box_idx_of_points (B, M) int32: index of the first box

@@ -211,3 +211,72 @@ def iou3d_v1_overlap_bev_cpu(boxes_a_bev, boxes_b_bev):
     ans = torch.zeros((boxes_a_bev.shape[0], boxes_b_bev.shape[0]), dtype=torch.float32)
     iou3d_cuda().boxes_overlap_bev_cpu(boxes_a_bev.contiguous(), boxes_b_bev.contiguous(), ans)
     return ans
+
+
+# ---------------------------------------------------------------- GLENet's variance-voting NMS / soft-NMS (Python loops of the reference)
+def nms_func_reference(boxes, scores, iou_threshold, score_threshold=0, variance=None, ious_all=None):
+    """iou3d_nms_utils.py:227-273 restated on numpy float32 arrays (updated in place, like the reference).  ``ious_all`` is the
+    (N, N) matrix the reference gets from boxes_bev_iou_cpu(boxes, boxes); pass it in to check a device loop against the same
+    matrix, or leave it None to compute it with the compiled reference.  The loop stops once only zero scores are left
+    (those iterations change nothing the caller reads)."""
+    if ious_all is None:
+        ious_all = boxes_bev_iou_cpu(boxes, boxes)
+    undone_mask = scores >= score_threshold
+    while undone_mask.sum() > 0:
+        idx = scores[undone_mask].argmax()
+        idx = undone_mask.nonzero()[0][idx]
+        if score_threshold <= 0 and not scores[idx] > 0:
+            break
+        top_box = boxes[idx:idx + 1]
+        _boxes = boxes[undone_mask]
+        ious = ious_all[undone_mask, idx]
+        if variance is not None:
+            _variance = variance[undone_mask, :7]
+            ioumask = ious > iou_threshold
+            klbox = _boxes[ioumask]
+            if top_box[:, 6] > 0:
+                klbox[np.abs(klbox[:, 6] - top_box[:, 6]) >= np.pi * 3 / 2, 6] += np.pi * 2
+            else:
+                klbox[np.abs(klbox[:, 6] - top_box[:, 6]) >= np.pi * 3 / 2, 6] -= np.pi * 2
+            kliou = ious[ioumask]
+            klvar = _variance[ioumask]
+            pi = (np.exp(-1 * (1 - kliou) ** 2 / 0.05)).reshape(-1, 1)
+            pi = pi / klvar
+            pi[np.abs(klbox[:, 6] - top_box[:, 6]) >= np.pi / 4, 6] = 0
+            pi = pi / pi.sum(0)
+            boxes[idx, :7] = (pi * klbox[:, :7]).sum(0)
+        undone_mask[idx] = False
+        scores[undone_mask] *= (ious_all[undone_mask, idx] < iou_threshold)
+        undone_mask[scores < score_threshold] = False
+    return scores, boxes
+
+
+def softnms_reference(boxes, scores, iou_threshold, soft_sigma, score_threshold, soft_mode="gaussian", variance=None):
+    """iou3d_nms_utils.py:312-356 restated (CUDA tensors, in place): one reference boxes_iou_bev launch per iteration."""
+    undone_mask = scores >= score_threshold
+    while undone_mask.sum() > 1:
+        idx = scores[undone_mask].argmax()
+        idx = undone_mask.nonzero(as_tuple=False)[idx].item()
+        top_box = boxes[idx:idx + 1]
+        undone_mask[idx] = False
+        _boxes = boxes[undone_mask]
+        ious = boxes_iou_bev(_boxes, top_box).flatten()
+        if variance is not None:
+            _variance = variance[undone_mask, :6]
+            ioumask = ious > iou_threshold
+            klbox = torch.cat((_boxes[ioumask], top_box), 0)
+            kliou = ious[ioumask]
+            klvar = torch.cat((_variance[ioumask], variance[idx:idx + 1, :6]), 0)
+            pi = torch.exp(-1 * torch.pow((1 - kliou), 2) / 0.05)
+            pi = torch.cat((pi, torch.ones(1, device=pi.device)), 0).unsqueeze(1)
+            pi = pi / klvar
+            pi = pi / pi.sum(0)
+            boxes[idx, :6] = (pi * klbox[:, :6]).sum(0)
+        if soft_mode == "linear":
+            scales = ious.new_ones(ious.size())
+            scales[ious >= soft_sigma] = 1 - ious[ious >= soft_sigma]
+        else:
+            scales = torch.exp(-ious ** 2 / soft_sigma)
+        scores[undone_mask] *= scales.flatten()
+        undone_mask[scores < score_threshold] = False
+    return scores, boxes

@@ -743,3 +743,41 @@ def test_second_device_iou_and_nms(ref_so):
         res.append((iou.cpu(), keep.cpu(), keep_n.cpu(), pib.cpu()))
     for x, y in zip(*res):
         assert torch.equal(x, y)
+
+
+def test_variance_voting_and_soft_nms_device_loops_vs_reference_loops(cuda, ref_so):
+    """csrc/vnms.cu against the reference's Python loops (restated in oracle/ref.py around the compiled reference):
+    nms_func on 1500 proposals from the SAME CPU-dialect IoU matrix (the voting sums run in the reference's order, so the
+    voted boxes agree to expf's last bits), and softnms_gpu (gaussian / linear, with and without variances) against the
+    reference's per-iteration boxes_iou_bev launches."""
+    g = torch.Generator().manual_seed(23)
+    boxes, scores = synth.proposals(1500, 14, 5)
+    var = torch.rand((1500, 7), generator=g) * 0.5 + 0.05
+    bn, sn, vn = boxes.numpy().copy(), scores.numpy().copy(), var.numpy().copy()
+    ious = I.boxes_bev_iou_cpu(bn, bn)                                   # the matrix new_nms_gpu's device loop sees (CPU dialect, bit-exact vs the reference CPU code)
+    assert np.abs(ious - ref_so.boxes_bev_iou_cpu(bn, bn)).max() <= IOU_TOL
+    for variance in (vn, None):
+        for thr, sthr in ((0.25, 0), (0.5, 0.3)):
+            s_ref, b_ref = ref_so.nms_func_reference(bn.copy(), sn.copy(), thr, sthr, variance=None if variance is None else variance.copy(), ious_all=ious)
+            s_got, b_got = I.nms_func(bn.copy(), sn.copy(), thr, sthr, variance=None if variance is None else variance.copy())
+            np.testing.assert_array_equal(s_got, s_ref)
+            keep = s_ref > 0
+            assert keep.sum() > 10
+            np.testing.assert_allclose(b_got[keep], b_ref[keep], rtol=0, atol=2e-5)
+    # new_nms_gpu: tensors in, numpy out, keep sorted by descending score
+    keep, none, nb = I.new_nms_gpu(boxes.to(cuda), scores.to(cuda), 0.25, variance=var.to(cuda), NMS_TYPE="new_nms_gpu")
+    assert none is None and isinstance(keep, np.ndarray) and nb.shape == (1500, 7) and np.all(np.diff(scores.numpy()[keep]) <= 0)
+    # soft-NMS
+    bs, ss = synth.proposals(400, 6, 9)
+    vs = (torch.rand((400, 7), generator=g) * 0.5 + 0.05)
+    for mode in ("gaussian", "linear"):
+        for variance in (vs, None):
+            kw = dict(score_threshold=0.1, soft_mode=mode, soft_sigma=0.3, variance=None if variance is None else variance.to(cuda))
+            k_got, _, b_got = I.softnms_gpu(bs.to(cuda), ss.to(cuda), 0.25, **kw)
+            b_r, s_r = bs.to(cuda), ss.to(cuda)
+            s_r, b_r = ref_so.softnms_reference(b_r, s_r, 0.25, 0.3, 0.1, mode, variance=kw["variance"])
+            k_ref = (s_r > 0.1).nonzero(as_tuple=False).view(-1)
+            k_ref = k_ref[s_r[k_ref].argsort(descending=True)]
+            assert k_got.is_cuda and sorted(k_got.tolist()) == sorted(k_ref.tolist()), (mode, variance is None)
+            assert torch.allclose(b_got[k_ref], b_r[k_ref], rtol=0, atol=1e-4)
+            assert k_ref.numel() > 5
