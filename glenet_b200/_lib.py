@@ -61,10 +61,16 @@ _SIGNATURES = {
     "glenet_points_in_boxes_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "glenet_points_in_boxes_gpu": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "glenet_points_in_boxes_cpu_dialect": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "glenet_gt_crop_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_longlong]),
+    "glenet_gt_crop_gpu": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, c_float_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                          ctypes.c_longlong, ctypes.c_void_p, c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "glenet_rotate_iou_eval_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "glenet_rotate_iou_eval_blocks_gpu": (ctypes.c_int, [c_float_p, ctypes.c_void_p, c_float_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 def lib_path() -> str:

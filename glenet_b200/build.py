@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libglenet_geom.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["iou.cu", "iou3d_v1.cu", "nms.cu", "pib.cu", "vnms.cu", "host.cpp"]
+SOURCES = ["iou.cu", "iou3d_v1.cu", "nms.cu", "pib.cu", "vnms.cu", "rotate_iou.cu", "crop.cu", "host.cpp"]
 HEADERS = ["common.cuh", "geom.cuh", "exchange.cuh", "clip.cuh", os.path.join(INCLUDE, "glenet_geom.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

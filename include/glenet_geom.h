@@ -225,6 +225,41 @@ int glenet_points_in_boxes_cpu_dialect(const float* boxes, const float* trig, in
                                        const float* pts, int pts_num, int32_t* pts_indices,
                                        glenet_stream_t stream);
 
+/* ---------------------------------------------------------------- GT-database crops (next scope row)
+ * The per-object selection + centring loop of the GT-database builders,
+ *   pcdet/datasets/kitti/kitti_dataset.py:248-259    gt_points = points[point_indices[i] > 0]; gt_points[:, :3] -= gt_boxes[i, :3]
+ *   pcdet/datasets/waymo/waymo_dataset.py:369-380    gt_points = points[box_idxs_of_pts == i];  gt_points[:, :3] -= gt_boxes[i, :3]
+ * as stream compaction on the device.  selection: GLENET_CROP_MASK -> (n_boxes, n_points) int32 mask of
+ * glenet_points_in_boxes_cpu_dialect (object i takes the points with mask > 0); GLENET_CROP_INDEX -> (n_points) int32 of
+ * glenet_points_in_boxes_gpu for one frame (object i takes the points with index == i).  points: (n_points, features) float32,
+ * features >= 3, xyz first; centres: (n_boxes, 3) FLOAT64 (numpy subtracts in the boxes' precision and rounds to float32).
+ * Output: offsets (n_boxes + 1) int64, crops (capacity, features) float32 -- rows offsets[i] .. offsets[i + 1] are object i's
+ * points in ascending point order, xyz relative to its centre: the bytes ndarray.tofile writes to the object's .bin
+ * (cvae_uncertainty/dataset.py:313 reads them back).  Rows beyond `capacity` are dropped (offsets stay exact, so the caller
+ * can retry); capacity == 0 is a sizing call.  workspace: glenet_gt_crop_workspace_bytes() bytes, 16-byte aligned. */
+enum { GLENET_CROP_MASK = 0, GLENET_CROP_INDEX = 1 };
+size_t glenet_gt_crop_workspace_bytes(int n_boxes, long long n_points);
+int glenet_gt_crop_gpu(int mode, const int32_t* selection, const float* points, long long n_points, int features,
+                       const double* centres, int n_boxes, long long capacity, long long* offsets, float* crops,
+                       void* workspace, size_t workspace_bytes, glenet_stream_t stream);
+
+/* ---------------------------------------------------------------- KITTI evaluator's rotated IoU (next scope row)
+ * rotate_iou_gpu_eval(boxes, query_boxes, criterion)   pcdet/datasets/kitti/kitti_object_eval_python/rotate_iou.py:263-330
+ * (a numba-CUDA kernel in the reference; its callers: kitti_object_eval_python/eval.py:115-151).
+ * boxes (n, 5), query_boxes (k, 5): rows [x, y, x_d, y_d, angle], angle clockwise when positive; iou (n, k) float32, every
+ * element written: iou[i][j] = devRotateIoUEval(query_boxes[j], boxes[i]): criterion -1 intersection / union,
+ * 0 intersection / area(query box), 1 intersection / area(box), anything else the intersection area.
+ * Same float32 / float64 typing and the same FMA contraction as the kernel numba compiles for sm_100a. */
+int glenet_rotate_iou_eval_gpu(const float* boxes, int n, const float* query_boxes, int k, int criterion, float* iou,
+                               glenet_stream_t stream);
+/* Block-diagonal form (additive): group g pairs boxes[box_offsets[g] .. box_offsets[g+1]) with
+ * query_boxes[query_offsets[g] .. query_offsets[g+1]) and writes its dense (nb_g, nq_g) block at iou + out_offsets[g] --
+ * the per-frame blocks calculate_iou_partly (eval.py:383-397) slices out of the dense matrix of one evaluation part.
+ * Offsets are device arrays (groups + 1 entries; int32, int32, int64); max_boxes / max_queries bound the group sizes. */
+int glenet_rotate_iou_eval_blocks_gpu(const float* boxes, const int* box_offsets, const float* query_boxes, const int* query_offsets,
+                                      const long long* out_offsets, int groups, int max_boxes, int max_queries, int criterion,
+                                      float* iou, glenet_stream_t stream);
+
 /* ---------------------------------------------------------------- host helpers (CPU dialect)
  * Per-box trigonometry evaluated by the HOST's libm, exactly the calls the reference's CPU
  * code makes (iou3d_cpu.cpp:74-84,146-151; roiaware_pool3d.cpp:121-125).  boxes_host: (n, 7)

@@ -13,6 +13,11 @@ Compiles the *unmodified* reference sources where they lie under
 into the repository: only build products land in ``oracle/_ref`` which is
 git-ignored (but travels to the GPU box with ``gpurun``).
 
+* ``oracle/_ref/rotate_iou_numba.py`` <- pcdet/datasets/kitti/kitti_object_eval_python/rotate_iou.py, staged
+  unmodified: a numba-CUDA module has no build step other than the JIT at import, which needs the GPU, so the "build
+  product" that can travel to the GPU box is the file itself (reference sources for the box are staged in
+  a git-ignored directory).  ``oracle/ref.py:rotate_iou_numba()`` imports it there.
+
 Host code MUST be compiled with ``-O2``: ``iou3d_nms_kernel.cu:43`` declares
 ``check_rect_cross`` as a non-inline ``__device__`` function, for which nvcc emits
 a strong host stub that calls ``exit(1)``; at ``-O0`` the CPU path in
@@ -53,6 +58,17 @@ EXTS = {
 }
 
 
+STAGED = {"rotate_iou_numba.py": "pcdet/datasets/kitti/kitti_object_eval_python/rotate_iou.py"}
+
+
+def stage_python() -> None:
+    os.makedirs(OUT, exist_ok=True)
+    for name, src in STAGED.items():
+        path = os.path.join(REF, src)
+        if os.path.isfile(path):
+            shutil.copy2(path, os.path.join(OUT, name))
+
+
 def have_reference() -> bool:
     return all(os.path.isfile(os.path.join(REF, s)) for srcs in EXTS.values() for s in srcs)
 
@@ -63,6 +79,8 @@ def built() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> bool:
     """Build both extensions into oracle/_ref.  Returns True when they exist afterwards."""
+    if have_reference():
+        stage_python()
     if built() and not force:
         return True
     if not have_reference():

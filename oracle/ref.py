@@ -65,6 +65,23 @@ def iou3d_cuda():
     return _load("iou3d_cuda")
 
 
+def rotate_iou_numba():
+    """The reference's numba-CUDA module (kitti_object_eval_python/rotate_iou.py), staged unmodified by build_ref.py.
+    Importing it JIT-compiles the kernel for the current device: GPU box only.  None when unavailable."""
+    path = os.path.join(REF_DIR, "rotate_iou_numba.py")
+    if "rotate_iou_numba" not in _mods:
+        mod = None
+        if os.path.isfile(path):
+            try:
+                spec = importlib.util.spec_from_file_location("rotate_iou_numba", path)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+            except Exception:   # no GPU / numba without CUDA support
+                mod = None
+        _mods["rotate_iou_numba"] = mod
+    return _mods["rotate_iou_numba"]
+
+
 def _np2t(x):
     # common_utils.py:15-18
     if isinstance(x, np.ndarray):
@@ -280,3 +297,17 @@ def softnms_reference(boxes, scores, iou_threshold, soft_sigma, score_threshold,
         scores[undone_mask] *= scales.flatten()
         undone_mask[scores < score_threshold] = False
     return scores, boxes
+
+
+# ---------------------------------------------------------------- GT-database crops (kitti_dataset.py:248-254, waymo_dataset.py:369-372)
+def gt_crops_reference(points: np.ndarray, gt_boxes: np.ndarray, selection: np.ndarray, rule: str):
+    """The reference's per-object selection + centring, statement for statement: ``selection`` is the (N, M) mask of
+    points_in_boxes_cpu (rule "kitti": ``points[point_indices[i] > 0]``) or the (M,) index vector of points_in_boxes_gpu
+    (rule "waymo": ``points[box_idxs_of_pts == i]``); then ``gt_points[:, :3] -= gt_boxes[i, :3]`` in place on the float32
+    rows (numpy subtracts in the boxes' dtype and casts back).  Returns the list of per-object arrays."""
+    out = []
+    for i in range(gt_boxes.shape[0]):
+        gt_points = points[selection[i] > 0] if rule == "kitti" else points[selection == i]
+        gt_points[:, :3] -= gt_boxes[i, :3]
+        out.append(gt_points)
+    return out

@@ -177,3 +177,19 @@ def test_scale_by_iou_modes():
     lin = V.scale_by_iou(iou, 0.3, "linear")
     assert torch.allclose(lin, torch.tensor([1.0, 1.0, 0.5, 0.1]))
     assert torch.allclose(V.scale_by_iou(iou, 0.3, "gaussian"), torch.exp(-iou ** 2 / 0.3))
+
+
+def test_rotate_iou_and_crop_wrappers_host_side():
+    """Argument handling that needs no device: empty problems return without touching CUDA (rotate_iou.py:303-305)."""
+    import numpy as np
+    from glenet_b200 import gt_database as G, rotate_iou as RI
+    b = np.zeros((0, 5), dtype=np.float64)
+    q = np.ones((4, 5), dtype=np.float32)
+    out = RI.rotate_iou_gpu_eval(b, q)
+    assert out.shape == (0, 4) and out.dtype == np.float32        # the reference returns the float32 zeros before the dtype cast
+    assert RI.rotate_iou_gpu_eval(q, b).shape == (4, 0)
+    assert RI.rotate_iou_gpu_eval_blocks(b, b, [0, 0], [0, 0]) [0].shape == (0, 0)
+    o, c = G.crop_gt_objects(np.zeros((10, 4), dtype=np.float32), np.zeros((0, 7), dtype=np.float32), "kitti")
+    assert o.tolist() == [0] and c.shape == (0, 4)
+    o, c = G.crop_gt_objects(np.zeros((0, 5), dtype=np.float32), np.zeros((3, 7)), "waymo")
+    assert o.tolist() == [0, 0, 0, 0] and c.shape == (0, 5)

@@ -162,3 +162,24 @@ def test_rotate_iou_eval_oracle_vs_reference_golden():
     np.testing.assert_allclose(rotate_iou.rotate_iou_eval(g["boxes"], g["query"], 0), inter / a_q[None, :], rtol=0, atol=1e-6)
     np.testing.assert_allclose(rotate_iou.rotate_iou_eval(g["boxes"], g["query"], 1), inter / a_b[:, None], rtol=0, atol=1e-6)
     assert rotate_iou.rotate_iou_eval(g["boxes"][:0], g["query"]).shape == (0, 45)
+
+
+def test_rotate_iou_eval_oracle_contraction_dialect():
+    """Dialect 1 (the FMA pattern of the kernel numba compiles for sm_100a) stays within 1e-5 of the simulator goldens, and
+    -- with the cos / sin tables libdevice produced -- reproduces the goldens the reference kernel wrote on a B200 bit for bit."""
+    import os
+    from conftest import ROOT
+    from oracle import rotate_iou
+    g = np.load(os.path.join(ROOT, "tests", "golden", "rotate_iou_golden.npz"))
+    for crit in (-1, 0, 1):
+        got = rotate_iou.rotate_iou_eval(g["boxes"], g["query"], crit, contract=True)
+        assert np.abs(got - g[f"iou_{crit}"]).max() <= 1e-5
+    path = os.path.join(ROOT, "tests", "golden", "rotate_iou_gpu_golden.npz")
+    if not os.path.isfile(path):
+        pytest.skip("tests/golden/rotate_iou_gpu_golden.npz missing (make_golden_rotate_iou.py gpu on a B200)")
+    h = np.load(path)
+    for crit in (-1, 0, 1, 2):
+        got = rotate_iou.rotate_iou_eval(h["boxes"], h["query"], crit, contract=True, trig_boxes=h["trig_boxes"], trig_query=h["trig_query"])
+        want = h[f"iou_{crit}"]
+        same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+        assert same.all(), (crit, int((~same).sum()), float(np.nanmax(np.abs(got - want))))

@@ -1,0 +1,183 @@
+"""Next scope rows on the GPU: ``pytest -m gpu``.
+
+* ``glenet_b200.rotate_iou.rotate_iou_gpu_eval`` (csrc/rotate_iou.cu) against (a) the goldens the reference's numba kernel
+  produced on a B200 (tests/golden/rotate_iou_gpu_golden.npz, bit-exact), (b) the goldens the same file produced under
+  numba's CUDA simulator (1e-5), (c) the C oracle in its contraction dialect fed with this device's cos / sin (bit-exact on
+  larger seeded problems), (d) the reference kernel itself, JIT-compiled on this box, when oracle/_ref carries it;
+* ``glenet_b200.gt_database`` (csrc/crop.cu) against the reference's per-object numpy statements.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR
+from glenet_b200 import _lib, gt_database as G, roiaware_pool3d_utils as R, rotate_iou as RI, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _bev_boxes(rng, n, centres, spread=0.8):
+    c = centres[rng.integers(0, len(centres), n)]
+    xy = c + rng.normal(0, spread, (n, 2))
+    dims = np.stack([rng.uniform(3.5, 4.3, n), rng.uniform(1.45, 1.75, n)], 1)
+    ang = rng.uniform(-np.pi, np.pi, (n, 1))
+    return np.concatenate([xy, dims, ang], 1).astype(np.float32)
+
+
+def _device_trig(arr, dev):
+    a = torch.from_numpy(arr[:, 4].copy()).to(dev)
+    return torch.stack([torch.cos(a), torch.sin(a)], 1).cpu().numpy()
+
+
+def _same_bits(a, b):
+    a, b = np.ascontiguousarray(a, dtype=np.float32), np.ascontiguousarray(b, dtype=np.float32)
+    return np.array_equal(a.view(np.uint32), b.view(np.uint32)) or np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)]) and np.array_equal(np.isnan(a), np.isnan(b))
+
+
+def test_rotate_iou_vs_simulator_golden(cuda):
+    g = np.load(os.path.join(GOLDEN_DIR, "rotate_iou_golden.npz"))
+    # pairs of IDENTICAL boxes (the script plants five) sit on the discontinuities of the reference's >= / > tests: the
+    # simulator (no FMA) returns 0 for them, the kernel numba compiles (FMA-contracted) 1/3 -- see the B200 goldens below
+    generic = np.ones((70, 45), dtype=bool)
+    generic[np.arange(5), np.arange(5)] = False
+    for crit in (-1, 0, 1):
+        got, want = RI.rotate_iou_gpu_eval(g["boxes"], g["query"], crit), g[f"iou_{crit}"]
+        assert got.shape == want.shape == (70, 45) and got.dtype == np.float32
+        assert np.abs(got - want)[generic].max() <= 1e-5
+    # dtype follows the boxes (rotate_iou.py:330), empty inputs return zeros without a launch (:303-305)
+    assert RI.rotate_iou_gpu_eval(g["boxes"].astype(np.float64), g["query"]).dtype == np.float64
+    assert RI.rotate_iou_gpu_eval(g["boxes"][:0], g["query"]).shape == (0, 45)
+    assert RI.rotate_iou_gpu_eval(g["boxes"], g["query"][:0]).shape == (70, 0)
+
+
+def test_rotate_iou_vs_b200_golden_bit_exact(cuda):
+    path = os.path.join(GOLDEN_DIR, "rotate_iou_gpu_golden.npz")
+    if not os.path.isfile(path):
+        pytest.skip("tests/golden/rotate_iou_gpu_golden.npz missing (make_golden_rotate_iou.py gpu on a B200)")
+    g = np.load(path)
+    for crit in (-1, 0, 1, 2):
+        got, want = RI.rotate_iou_gpu_eval(g["boxes"], g["query"], crit), g[f"iou_{crit}"]
+        assert _same_bits(got, want), (crit, np.nanmax(np.abs(got - want)), int((got != want).sum()))
+
+
+def test_rotate_iou_vs_oracle_contraction_dialect(cuda):
+    from oracle import rotate_iou as O
+    rng = np.random.default_rng(5)
+    centres = rng.uniform(-40, 40, (25, 2))
+    boxes, query = _bev_boxes(rng, 333, centres), _bev_boxes(rng, 257, centres)     # ragged tiles: 333 = 5 * 64 + 13, 257 = 4 * 64 + 1
+    boxes[:9] = query[:9]
+    boxes[9:12, 4] = 0.0; query[9:12] = boxes[9:12]; query[9:12, 1] += 0.5
+    tb, tq = _device_trig(boxes, cuda), _device_trig(query, cuda)
+    for crit in (-1, 0, 1, 7):
+        got = RI.rotate_iou_gpu_eval(boxes, query, crit)
+        want = O.rotate_iou_eval(boxes, query, crit, contract=True, trig_boxes=tb, trig_query=tq)
+        assert _same_bits(got, want), (crit, np.nanmax(np.abs(got - want)), int((got != want).sum()))
+    assert (RI.rotate_iou_gpu_eval(boxes, query) > 0).mean() > 0.01
+    # non-finite and degenerate rows propagate as in the reference's arithmetic (0 / 0 -> NaN; NaN coordinates never culled)
+    boxes[20, 2:4] = 0.0
+    query[20, 2:4] = 0.0
+    boxes[21, 0] = np.nan
+    tb, tq = _device_trig(boxes, cuda), _device_trig(query, cuda)
+    got = RI.rotate_iou_gpu_eval(boxes, query, -1)
+    want = O.rotate_iou_eval(boxes, query, -1, contract=True, trig_boxes=tb, trig_query=tq)
+    assert _same_bits(got, want), (np.nanmax(np.abs(got - want)), int((got != want).sum()))
+    assert np.isinf(got[20]).sum() > 200          # a zero-size box "contains" every corner: intersection = the query's area, union 0
+
+
+def test_rotate_iou_blocks_equal_dense_diagonal_blocks(cuda):
+    rng = np.random.default_rng(9)
+    centres = rng.uniform(0, 50, (8, 2))
+    bc = np.array([5, 0, 70, 3, 130, 1], dtype=np.int64)          # per-frame GT counts (a frame without GT; blocks wider than a tile)
+    qc = np.array([9, 4, 66, 0, 40, 200], dtype=np.int64)         # per-frame detection counts
+    boxes, query = _bev_boxes(rng, int(bc.sum()), centres), _bev_boxes(rng, int(qc.sum()), centres)
+    dense = RI.rotate_iou_gpu_eval(boxes, query, -1)
+    blocks = RI.rotate_iou_gpu_eval_blocks(boxes, query, bc, qc, -1)
+    bo, qo = np.concatenate([[0], np.cumsum(bc)]), np.concatenate([[0], np.cumsum(qc)])
+    for g, blk in enumerate(blocks):
+        assert blk.shape == (bc[g], qc[g])
+        assert np.array_equal(blk, dense[bo[g]:bo[g + 1], qo[g]:qo[g + 1]])
+
+
+def test_rotate_iou_vs_reference_numba_kernel_on_this_gpu(cuda):
+    from oracle import ref
+    mod = ref.rotate_iou_numba()
+    if mod is None:
+        pytest.skip("oracle/_ref/rotate_iou_numba.py not staged or numba.cuda unusable on this box")
+    rng = np.random.default_rng(21)
+    centres = rng.uniform(0, 70, (30, 2))
+    boxes, query = _bev_boxes(rng, 500, centres), _bev_boxes(rng, 700, centres)
+    for crit in (-1, 0, 1, 2):
+        want = mod.rotate_iou_gpu_eval(boxes, query, crit)
+        got = RI.rotate_iou_gpu_eval(boxes, query, crit)
+        assert _same_bits(got, want), (crit, np.nanmax(np.abs(got - want)), int((got != want).sum()))
+    # the evaluator's two callers (eval.py:115-151) on camera-frame boxes [x, y, z, l, h, w, ry]
+    b7 = np.concatenate([boxes[:60, :1], rng.uniform(1, 2, (60, 1)).astype(np.float32), boxes[:60, 1:2], boxes[:60, 2:3], rng.uniform(1.4, 1.7, (60, 1)).astype(np.float32), boxes[:60, 3:5]], 1).astype(np.float64)
+    q7 = b7 + rng.normal(0, 0.1, b7.shape)
+    rinc = mod.rotate_iou_gpu_eval(b7[:, [0, 2, 3, 5, 6]], q7[:, [0, 2, 3, 5, 6]], 2)
+    assert np.array_equal(RI.bev_box_overlap(b7[:, [0, 2, 3, 5, 6]], q7[:, [0, 2, 3, 5, 6]], 2), rinc)
+    d3 = RI.d3_box_overlap(b7, q7)
+    assert d3.shape == (60, 60) and np.all(np.diag(d3) > 0.3) and np.all(d3 <= 1.0 + 1e-9)
+
+
+# ------------------------------------------------------------------ GT-database crops
+def _frame(rule, n_obj, n_pts, seed, feats):
+    rngs = synth.KITTI_RANGE if rule == "kitti" else synth.WAYMO_RANGE
+    boxes = (synth.kitti_boxes if rule == "kitti" else synth.waymo_boxes)(n_obj, seed)
+    xyz = synth.points(n_pts, boxes, rngs, 0.2, seed=seed + 1)
+    extra = torch.rand((n_pts, feats - 3), generator=torch.Generator().manual_seed(seed + 2))
+    return torch.cat([xyz, extra], 1).numpy().copy(), boxes.numpy().copy()
+
+
+@pytest.mark.parametrize("rule,feats,box_dtype", [("kitti", 4, np.float64), ("kitti", 4, np.float32), ("waymo", 5, np.float32), ("waymo", 6, np.float64)])
+def test_gt_crops_equal_reference_statements(cuda, rule, feats, box_dtype):
+    from oracle import ref
+    points, boxes = _frame(rule, 17, 60000, 40, feats)
+    boxes[3, :3] = boxes[2, :3] + 0.3                      # two overlapping objects: a point may be selected twice under the KITTI rule
+    gt = boxes.astype(box_dtype)
+    if box_dtype == np.float64:
+        gt[:, :3] += 1e-9 * np.arange(17)[:, None]         # centres that are not float32 numbers (calib arithmetic in float64)
+    if rule == "kitti":
+        sel = R.points_in_boxes_cpu(points[:, :3], gt)     # numpy in -> (N, M) int32 numpy, as kitti_dataset.py:248-250
+    else:
+        sel = R.points_in_boxes_gpu(torch.from_numpy(points[:, 0:3]).unsqueeze(0).float().cuda(),
+                                    torch.from_numpy(gt[:, 0:7]).unsqueeze(0).float().cuda()).long().squeeze(0).cpu().numpy()
+    want = ref.gt_crops_reference(points, gt, sel, rule)
+    offsets, crops = G.crop_gt_objects(points, gt, rule)
+    assert offsets.dtype == np.int64 and crops.dtype == np.float32 and offsets[0] == 0 and offsets[-1] == crops.shape[0]
+    assert sum(len(w) for w in want) > 1000
+    for i, w in enumerate(want):
+        got = crops[offsets[i]:offsets[i + 1]]
+        assert got.shape == w.shape and np.array_equal(got.view(np.uint32), w.astype(np.float32).view(np.uint32)), i
+
+
+def test_gt_crops_files_and_edge_cases(cuda, tmp_path):
+    points, boxes = _frame("kitti", 6, 30000, 7, 4)
+    offsets, crops = G.crop_gt_objects(points, boxes, "kitti")
+    names = ["%s_%s_%d.bin" % ("000123", "Car", i) for i in range(6)]
+    counts = G.write_gt_crops(tmp_path, names, offsets, crops, write=[True, True, False, True, True, True])
+    assert counts == list(np.diff(offsets))
+    assert not (tmp_path / names[2]).exists()
+    for i in (0, 1, 3, 4, 5):
+        back = np.fromfile(tmp_path / names[i], dtype=np.float32).reshape(-1, 4)     # cvae_uncertainty/dataset.py:313
+        assert np.array_equal(back, crops[offsets[i]:offsets[i + 1]])
+    # no objects / no points
+    o, c = G.crop_gt_objects(points, boxes[:0], "waymo")
+    assert o.tolist() == [0] and c.shape == (0, 4)
+    o, c = G.crop_gt_objects(points[:0], boxes, "kitti")
+    assert o.tolist() == [0] * 7 and c.shape == (0, 4)
+    # a mask that selects more rows than there are points (every box identical): the sizing retry path
+    same = np.repeat(boxes[:1], 5, 0)
+    o, c = G.crop_gt_objects(points, same, "kitti")
+    assert o[-1] == 5 * o[1] and np.array_equal(c[: o[1]], c[o[1]: o[2]])
+    # C ABI: sizing call (capacity 0) leaves the offsets exact
+    lib = _lib.load()
+    sel = R.points_in_boxes_gpu(torch.from_numpy(points[None, :, :3]).cuda(), torch.from_numpy(boxes[None]).cuda())[0]
+    ctr = torch.from_numpy(boxes[:, :3].astype(np.float64)).cuda()
+    off = torch.empty(7, dtype=torch.int64, device="cuda")
+    wsb = lib.glenet_gt_crop_workspace_bytes(6, 30000)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    rc = lib.glenet_gt_crop_gpu(1, sel.data_ptr(), torch.from_numpy(points).cuda().data_ptr(), 30000, 4, ctr.data_ptr(), 6, 0, off.data_ptr(), None,
+                                ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0 and off.cpu().tolist() == G.crop_gt_objects(points, boxes, "waymo")[0].tolist()
