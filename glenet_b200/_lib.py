@@ -65,12 +65,13 @@ _SIGNATURES = {
     "glenet_gt_crop_gpu": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, c_float_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                           ctypes.c_longlong, ctypes.c_void_p, c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "glenet_rotate_iou_eval_gpu": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "glenet_cvae_iou3d_gpu": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "glenet_rotate_iou_eval_blocks_gpu": (ctypes.c_int, [c_float_p, ctypes.c_void_p, c_float_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 
 def lib_path() -> str:

@@ -217,6 +217,142 @@ rotate_iou_eval_kernel(const float* __restrict__ boxes, int N, const float* __re
     }
 }
 
+
+// ---------------------------------------------------------------- CVAE recall IoU (aligned pairs, numpy float32 dialect)
+// iou3d(gboxes, qboxes) of cvae_uncertainty/eval_utils/eval_utils.py:14-65: the recall of the CVAE's predicted boxes against
+// their ground truth (:219-229).  The reference clamps the boxes to +-200, builds corners with torch elementwise ops
+// (pcdet/utils/loss_utils.py:721-759) and then runs the same RRPN overlap as above as PYTHON loops over numpy float32
+// scalars on the host (compute_vertex :276-411, sort_vertex :551-593, area_polygon :615-635) -- one pair at a time; its
+// authors suggest commenting the call out (:197).  One thread per pair here.  Dialect: every float32 operation rounded
+// separately (numpy scalars do not contract), corners of g tested against q first (with the extra abab > 0 && adad > 0),
+// then corners of q against g, then the edge pairs with a cap of 8 vertices; vertices ordered by DESCENDING float32 angle
+// (atan2 in float64 of the float32 unit vector, + 2 * 3.1415926 when negative) with numpy's argsort over all 8 slots
+// (unused slots carry angle 0, NaN sorts last); float32 fan sum.  cos / sin come from this device's libdevice, as they do
+// for the reference's CUDA tensors.
+__device__ __forceinline__ float np_msub(float x, float y, float z, float w) { return __fsub_rn(__fmul_rn(x, y), __fmul_rn(z, w)); }
+__device__ __forceinline__ float np_madd(float x, float y, float z, float w) { return __fadd_rn(__fmul_rn(x, y), __fmul_rn(z, w)); }
+__device__ __forceinline__ float torch_clamp(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }   // NaN stays NaN
+__device__ __forceinline__ float torch_min(float a, float b) { return (a < b || a != a) ? a : b; }                       // NaN propagates
+__device__ __forceinline__ float torch_max(float a, float b) { return (a > b || a != a) ? a : b; }
+
+// rbbox_to_corners (loss_utils.py:728-759) on [x, y, w, l, angle]
+__device__ __forceinline__ void cv_corners(float x, float y, float w, float l, float ang, float* c) {
+    const float cs = cosf(ang), sn = sinf(ang);
+    const float dxcos = __fmul_rn(__fmul_rn(w, cs), 0.5f), dxsin = __fmul_rn(__fmul_rn(w, sn), 0.5f);
+    const float dycos = __fmul_rn(__fmul_rn(l, cs), 0.5f), dysin = __fmul_rn(__fmul_rn(l, sn), 0.5f);
+    c[0] = __fadd_rn(__fsub_rn(-dxcos, dysin), x); c[1] = __fadd_rn(__fsub_rn(dxsin, dycos), y);
+    c[2] = __fadd_rn(__fadd_rn(-dxcos, dysin), x); c[3] = __fadd_rn(__fadd_rn(dxsin, dycos), y);
+    c[4] = __fadd_rn(__fadd_rn(dxcos, dysin), x);  c[5] = __fadd_rn(__fadd_rn(-dxsin, dycos), y);
+    c[6] = __fadd_rn(__fsub_rn(dxcos, dysin), x);  c[7] = __fadd_rn(__fsub_rn(-dxsin, dycos), y);
+}
+
+// corners of `p` inside quadrilateral `q` (compute_vertex steps 1 and 2)
+__device__ __forceinline__ bool cv_in_quad(float px, float py, const float* q, bool need_positive) {
+    const float ab0 = __fsub_rn(q[2], q[0]), ab1 = __fsub_rn(q[3], q[1]), ad0 = __fsub_rn(q[6], q[0]), ad1 = __fsub_rn(q[7], q[1]);
+    const float ap0 = __fsub_rn(px, q[0]), ap1 = __fsub_rn(py, q[1]);
+    const float abab = np_madd(ab0, ab0, ab1, ab1), abap = np_madd(ab0, ap0, ab1, ap1);
+    const float adad = np_madd(ad0, ad0, ad1, ad1), adap = np_madd(ad0, ap0, ad1, ap1);
+    const bool in = abab >= abap && abap >= 0.f && adad >= adap && adap >= 0.f;
+    return need_positive ? (in && adad > 0.f && abab > 0.f) : in;
+}
+
+constexpr int CV_THREADS = 128;
+
+__global__ void __launch_bounds__(CV_THREADS)
+cvae_iou3d_kernel(const float* __restrict__ gboxes, const float* __restrict__ qboxes, int n, float* __restrict__ ious) {
+    __shared__ float s_vx[8 * CV_THREADS], s_vy[8 * CV_THREADS], s_ang[8 * CV_THREADS];
+    const int tid = threadIdx.x, i = blockIdx.x * CV_THREADS + tid;
+    if (i >= n) return;
+    float* vx = s_vx + tid; float* vy = s_vy + tid; float* ang = s_ang + tid;
+    constexpr int S = CV_THREADS;
+    float g[7], q[7];
+#pragma unroll
+    for (int f = 0; f < 7; ++f) { g[f] = torch_clamp(gboxes[(size_t)i * 7 + f], -200.f, 200.f); q[f] = torch_clamp(qboxes[(size_t)i * 7 + f], -200.f, 200.f); }
+    float cg[8], cq[8];
+    cv_corners(g[0], g[1], g[3], g[4], g[6], cg);
+    cv_corners(q[0], q[1], q[3], q[4], q[6], cq);
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { vx[k * S] = 0.f; vy[k * S] = 0.f; }       // intersections = np.zeros((N, 16)): unused slots are read by the argsort gather
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (cv_in_quad(cg[2 * k], cg[2 * k + 1], cq, true)) { vx[cnt * S] = cg[2 * k]; vy[cnt * S] = cg[2 * k + 1]; ++cnt; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (cv_in_quad(cq[2 * k], cq[2 * k + 1], cg, false)) { vx[cnt * S] = cq[2 * k]; vy[cnt * S] = cq[2 * k + 1]; ++cnt; }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const float A0 = cg[2 * a], A1 = cg[2 * a + 1], B0 = cg[2 * ((a + 1) & 3)], B1 = cg[2 * ((a + 1) & 3) + 1];
+            const float C0 = cq[2 * b], C1 = cq[2 * b + 1], D0 = cq[2 * ((b + 1) & 3)], D1 = cq[2 * ((b + 1) & 3) + 1];
+            const float BA0 = __fsub_rn(B0, A0), BA1 = __fsub_rn(B1, A1), CA0 = __fsub_rn(C0, A0), CA1 = __fsub_rn(C1, A1);
+            const float DA0 = __fsub_rn(D0, A0), DA1 = __fsub_rn(D1, A1);
+            const bool acd = __fmul_rn(DA1, CA0) > __fmul_rn(CA1, DA0);
+            const bool bcd = __fmul_rn(__fsub_rn(D1, B1), __fsub_rn(C0, B0)) > __fmul_rn(__fsub_rn(C1, B1), __fsub_rn(D0, B0));
+            if (acd == bcd) continue;
+            const bool abc = __fmul_rn(CA1, BA0) > __fmul_rn(BA1, CA0);
+            const bool abd = __fmul_rn(DA1, BA0) > __fmul_rn(BA1, DA0);
+            if (abc == abd) continue;
+            if (cnt > 7) continue;                                        // loss_utils.py:383-397
+            const float DC0 = __fsub_rn(D0, C0), DC1 = __fsub_rn(D1, C1);
+            const float ABBA = np_msub(A0, B1, B0, A1), CDDC = np_msub(C0, D1, D0, C1);
+            const float DH = np_msub(BA1, DC0, BA0, DC1);
+            vx[cnt * S] = __fdiv_rn(np_msub(ABBA, DC0, BA0, CDDC), DH);
+            vy[cnt * S] = __fdiv_rn(np_msub(ABBA, DC1, BA1, CDDC), DH);
+            ++cnt;
+        }
+    }
+    float area = 0.f;
+    if (cnt > 2) {
+        // sort_vertex: float32 centroid, float64 atan2 of the float32 unit vector, angles stored as float32
+        float c0 = 0.f, c1 = 0.f;
+        for (int k = 0; k < cnt; ++k) { c0 = __fadd_rn(c0, vx[k * S]); c1 = __fadd_rn(c1, vy[k * S]); }
+        c0 = __fdiv_rn(c0, (float)cnt); c1 = __fdiv_rn(c1, (float)cnt);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ang[k * S] = 0.f;
+        for (int k = 0; k < cnt; ++k) {
+            float v0 = __fsub_rn(vx[k * S], c0), v1 = __fsub_rn(vy[k * S], c1);
+            const float d = (float)sqrt((double)np_madd(v0, v0, v1, v1));   // math.sqrt in float64; numpy 2 divides float32 by the float32 value of it
+            v0 = __fdiv_rn(v0, d); v1 = __fdiv_rn(v1, d);
+            const double a = atan2((double)v1, (double)v0);
+            ang[k * S] = a < 0.0 ? (float)(a + 2 * 3.1415926) : (float)a;
+        }
+        // np.argsort(-angle) over the 8 slots (stable for 8 elements, NaN last): rank of slot k = slots that sort before it
+        float px[8], py[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float ak = ang[k * S];
+            int rank = 0;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const float am = ang[m * S];
+                const bool m_nan = am != am, k_nan = ak != ak;
+                const bool before = k_nan ? (!m_nan || m < k) : (!m_nan && (am > ak || (am == ak && m < k)));
+                rank += (m != k && before) ? 1 : 0;
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) if (rank == r) { px[r] = vx[k * S]; py[r] = vy[k * S]; }
+        }
+        // area_polygon: float32 fan from the first sorted vertex
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            if (k < cnt - 2) {
+                const float t = np_msub(__fsub_rn(px[0], px[k + 2]), __fsub_rn(py[k + 1], py[k + 2]), __fsub_rn(py[0], py[k + 2]), __fsub_rn(px[k + 1], px[k + 2]));
+                area = __fadd_rn(area, fabsf(__fmul_rn(t, 0.5f)));
+            }
+        }
+    }
+    // eval_utils.py:48-64
+    const float top = torch_min(__fadd_rn(g[2], __fmul_rn(0.5f, g[5])), __fadd_rn(q[2], __fmul_rn(0.5f, q[5])));
+    const float bot = torch_max(__fsub_rn(g[2], __fmul_rn(0.5f, g[5])), __fsub_rn(q[2], __fmul_rn(0.5f, q[5])));
+    float inter_h = __fsub_rn(top, bot);
+    if (inter_h < 0.f) inter_h = 0.f;
+    const float vg = __fmul_rn(__fmul_rn(g[3], g[4]), g[5]), vq = __fmul_rn(__fmul_rn(q[3], q[4]), q[5]);
+    const float inc = __fmul_rn(inter_h, area);
+    ious[i] = __fdiv_rn(inc, __fsub_rn(__fadd_rn(vg, vq), inc));
+}
+
 }  // namespace glenet
 
 using namespace glenet;
@@ -245,6 +381,15 @@ int glenet_rotate_iou_eval_blocks_gpu(const float* boxes, const int* box_offsets
     const dim3 grid((max_queries + RI_TILE - 1) / RI_TILE, (max_boxes + RI_TILE - 1) / RI_TILE, groups);
     if (grid.y > 65535u) return fail(GLENET_EINVAL, "%s: group too large", what);
     rotate_iou_eval_kernel<<<grid, RI_THREADS, 0, (cudaStream_t)s>>>(boxes, 0, query_boxes, 0, criterion, iou, box_offsets, query_offsets, out_offsets);
+    return check_launch(what);
+}
+
+int glenet_cvae_iou3d_gpu(const float* gboxes, const float* qboxes, int n, float* ious, glenet_stream_t s) {
+    const char* what = "glenet_cvae_iou3d_gpu";
+    if (n < 0) return fail(GLENET_EINVAL, "%s: negative box count", what);
+    if (n == 0) return GLENET_OK;
+    if (!gboxes || !qboxes || !ious) return fail(GLENET_EINVAL, "%s: null pointer", what);
+    cvae_iou3d_kernel<<<(n + CV_THREADS - 1) / CV_THREADS, CV_THREADS, 0, (cudaStream_t)s>>>(gboxes, qboxes, n, ious);
     return check_launch(what);
 }
 

@@ -260,6 +260,13 @@ int glenet_rotate_iou_eval_blocks_gpu(const float* boxes, const int* box_offsets
                                       const long long* out_offsets, int groups, int max_boxes, int max_queries, int criterion,
                                       float* iou, glenet_stream_t stream);
 
+/* iou3d(gboxes, qboxes)                                cvae_uncertainty/eval_utils/eval_utils.py:14-65
+ * The recall IoU of the CVAE evaluation (:219-229): row-aligned 3D IoU of n (ground truth, prediction) pairs, boxes
+ * [x, y, z, w, l, h, ry] float32, clamped to +-200 as the reference does.  The reference evaluates the BEV overlap with
+ * Python loops over numpy float32 scalars on the host (pcdet/utils/loss_utils.py:276-411,551-635); this is one kernel in
+ * that dialect (no FMA contraction, descending-angle vertex order, float32 fan sum).  ious: (n) float32. */
+int glenet_cvae_iou3d_gpu(const float* gboxes, const float* qboxes, int n, float* ious, glenet_stream_t stream);
+
 /* ---------------------------------------------------------------- host helpers (CPU dialect)
  * Per-box trigonometry evaluated by the HOST's libm, exactly the calls the reference's CPU
  * code makes (iou3d_cpu.cpp:74-84,146-151; roiaware_pool3d.cpp:121-125).  boxes_host: (n, 7)

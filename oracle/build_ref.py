@@ -13,6 +13,9 @@ Compiles the *unmodified* reference sources where they lie under
 into the repository: only build products land in ``oracle/_ref`` which is
 git-ignored (but travels to the GPU box with ``gpurun``).
 
+* ``oracle/_ref/loss_utils_ref.py``, ``oracle/_ref/cvae_eval_utils_ref.py`` <- pcdet/utils/loss_utils.py,
+  cvae_uncertainty/eval_utils/eval_utils.py, staged unmodified for the same reason as the next item (their torch
+  cos / sin must run on the GPU to reproduce what the reference computes there).
 * ``oracle/_ref/rotate_iou_numba.py`` <- pcdet/datasets/kitti/kitti_object_eval_python/rotate_iou.py, staged
   unmodified: a numba-CUDA module has no build step other than the JIT at import, which needs the GPU, so the "build
   product" that can travel to the GPU box is the file itself (reference sources for the box are staged in
@@ -58,7 +61,14 @@ EXTS = {
 }
 
 
-STAGED = {"rotate_iou_numba.py": "pcdet/datasets/kitti/kitti_object_eval_python/rotate_iou.py"}
+STAGED = {
+    "rotate_iou_numba.py": "pcdet/datasets/kitti/kitti_object_eval_python/rotate_iou.py",
+    # the CVAE recall IoU: Python loops over numpy scalars behind torch cos / sin -- with CUDA tensors (as eval_utils.py:217-219
+    # passes them) the trigonometry is libdevice's, and the ill-conditioned intersection formula amplifies a 1-ulp difference
+    # in it to ~1e-4 of IoU, so the goldens that pin the kernel have to be made on the GPU box (make_golden_cvae_iou3d.py gpu)
+    "loss_utils_ref.py": "pcdet/utils/loss_utils.py",
+    "cvae_eval_utils_ref.py": "cvae_uncertainty/eval_utils/eval_utils.py",
+}
 
 
 def stage_python() -> None:

@@ -32,7 +32,7 @@ def test_library_builds_loads_and_exports_everything():
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"
     # and the binding table covers exactly the header
     assert sorted(glenet_b200.EXPORTS) == declared_symbols()
-    assert lib.glenet_abi_version() == 10
+    assert lib.glenet_abi_version() == 11
     assert lib.glenet_nms_workspace_bytes(1, 4096) == 4096 * 64 * 8
     assert lib.glenet_points_in_boxes_workspace_bytes(2, 200) > 2 * 200 * 32
     # workspace layout of csrc/pib.cu (pib_layout): per frame a 48-byte header, 8 floats per box, 4097 list starts,

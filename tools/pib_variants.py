@@ -7,9 +7,10 @@ sys.path.insert(0, ROOT)
 from glenet_b200 import synth
 dev = torch.device("cuda:0")
 B, M, N = 128, 180000, 200
-boxes = torch.stack([synth.waymo_boxes(N, 100 + f) for f in range(B)]).to(dev)
-base = synth.points(M, boxes[0].cpu(), synth.WAYMO_RANGE, 0.05, seed=5).to(dev)
-pts = (base.unsqueeze(0).repeat(B, 1, 1) + torch.randn(B, M, 3, device=dev) * 0.01).contiguous()
+# the bench's input: every frame its own boxes and its own points, 5 % resampled inside that frame's boxes
+boxes_h = torch.stack([synth.waymo_boxes(N, 100 + f) for f in range(B)])
+pts = torch.stack([synth.points(M, boxes_h[f], synth.WAYMO_RANGE, 0.05, seed=500 + f) for f in range(B)]).to(dev).contiguous()
+boxes = boxes_h.to(dev)
 # second problem: ragged sizes (M not a multiple of anything, 3 frames, 77 boxes)
 B2, M2, N2 = 3, 123457, 77
 boxes2 = torch.stack([synth.waymo_boxes(N2, 7 + f) for f in range(B2)]).to(dev)
