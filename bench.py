@@ -450,7 +450,11 @@ def run_ours(args, rank, world, local_rank):
                 torch.empty((world, FRAMES, per, N_GT), dtype=torch.float32, device=dev)
 
             def step_gather_nccl():
-                I.boxes_iou_bev_frames(slab_anchors, gts, out=padded[:, :rows])
+                if rows == per:
+                    I.boxes_iou_bev_frames(slab_anchors, gts, out=padded)
+                else:   # the last rank's slab is shorter than the 64-row-aligned slab size: its rows go into the padded block
+                    I.boxes_iou_bev_frames(slab_anchors, gts, out=out_slab)
+                    padded[:, :rows].copy_(out_slab)
                 dist.all_gather_into_tensor(gathered, padded)
             shard["full_gather_nccl_ms"] = timed(step_gather_nccl, 3, 1) / 3
             recv = (world - 1) / world * pairs_step * 4

@@ -363,11 +363,18 @@ __device__ __noinline__ void exchange_epilogue(IouSmem& sm, const IouFrames& fr,
         const unsigned long long n = *reinterpret_cast<volatile unsigned long long*>(fr.sp_count);
         if (tid < world) *reinterpret_cast<volatile unsigned long long*>(fr.ex.cnt[tid]) = n;
     } else {
+        // the finished local keys go into our slot of every peer's window: plain 16-byte stores (the consumer zeroes the
+        // slot after reading it, so zeros need not travel -- but a 16-byte store of two keys is cheaper than a test)
         const int nkeys = (int)gridDim.z * nb;
         const unsigned long long* mine = fr.ex.col_key[rank];
-        for (int i = tid; i < nkeys; i += IOU_CHAIN) {
-            const unsigned long long k = __ldcg(mine + i);
-            if (k) for (int p = 0; p < world; ++p) if (p != rank) atomicMax_system(fr.ex.col_key[p] + i, k);
+        const int pairs = nkeys >> 1;
+        for (int i = tid; i < pairs; i += IOU_CHAIN) {
+            const ulonglong2 k = __ldcg(reinterpret_cast<const ulonglong2*>(mine) + i);
+            for (int p = 0; p < world; ++p) if (p != rank) reinterpret_cast<ulonglong2*>(fr.ex.col_key[p])[i] = k;
+        }
+        if ((nkeys & 1) && tid == 0) {
+            const unsigned long long k = __ldcg(mine + nkeys - 1);
+            for (int p = 0; p < world; ++p) if (p != rank) fr.ex.col_key[p][nkeys - 1] = k;
         }
     }
     __threadfence_system();
@@ -970,7 +977,8 @@ int glenet_boxes_iou_frames_assign_gpu(int mode, const float* a, long long a_fra
     auto at = [&](int p, size_t off) { return reinterpret_cast<unsigned char*>(windows[p]) + off; };
     IouLaunch L;
     L.frames = frames; L.stride_a = a_frame_stride; L.stride_b = b_frame_stride; L.stride_out = (long long)na * nb;
-    L.row_key = row_key; L.col_key = reinterpret_cast<unsigned long long*>(at(rank, lay.off_col_key[par]));
+    // key slots of this parity: [source rank][frames * nb]; ours (slot `rank`) is the local accumulator of the tile kernel
+    L.row_key = row_key; L.col_key = reinterpret_cast<unsigned long long*>(at(rank, lay.off_col_key[par] + (size_t)rank * lay.key_slot));
     L.row_max = row_max; L.row_arg = row_arg;
     const bool rows_direct = nb <= IOU_TC_MAX;   // one column tile (pick_tiles never splits columns of a problem this tall)
     L.keys_prezeroed = true; L.dense_and_keys = out != nullptr;
@@ -978,25 +986,46 @@ int glenet_boxes_iou_frames_assign_gpu(int mode, const float* a, long long a_fra
     L.ex.world = world; L.ex.rank = rank; L.ex.step = step;
     L.ex.done = reinterpret_cast<unsigned int*>(at(rank, lay.off_done));
     for (int p = 0; p < world; ++p) {
-        L.ex.col_key[p] = reinterpret_cast<unsigned long long*>(at(p, lay.off_col_key[par]));
+        L.ex.col_key[p] = reinterpret_cast<unsigned long long*>(at(p, lay.off_col_key[par] + (size_t)rank * lay.key_slot));
         L.ex.flag[p] = reinterpret_cast<unsigned int*>(at(p, lay.off_flags_assign));
     }
-    if (na > 0 && nb > 0 && frames > 0) {
+    const bool launches_tiles = na > 0 && nb > 0 && frames > 0;
+    L.ex.decode = 1;
+    L.ex.slot_stride = (long long)(lay.key_slot / 8);
+    L.ex.slots = reinterpret_cast<unsigned long long*>(at(rank, lay.off_col_key[par]));
+    L.ex.flags_local = reinterpret_cast<const unsigned int*>(at(rank, lay.off_flags_assign));
+    L.ex.status = reinterpret_cast<unsigned int*>(at(rank, lay.off_status));
+    L.ex.col_max = col_max; L.ex.col_arg = col_arg;
+    const IouPeers peers = L.ex;
+    if (launches_tiles) {
+        // the tile kernel only folds its maxima into the LOCAL keys (no epilogue, no fence); the exchange kernel behind it does the rest
+        L.ex = IouPeers();
         rc = launch_iou_mode(mode, a, na, b, nb, out, st, what, L);
         if (rc) return rc;
-    } else if (world > 1) {
-        exchange_signal_kernel<<<1, 32, 0, st>>>(L.ex, false);
+    }
+    const long long n_col = (long long)frames * nb;
+    if (n_col > 0) {
+        cudaLaunchConfig_t cfg = {};
+        long long ctas = (n_col + 2047) / 2048;
+        cfg.gridDim = dim3((unsigned)(ctas > 8 ? 8 : ctas)); cfg.blockDim = dim3(256); cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, exchange_assign_kernel, peers, (int)n_col);
+        if (e != cudaSuccess) { snprintf(last_error_buf(), 512, "%s: launch failed: %s", what, cudaGetErrorString(e)); return -(int)e; }
         rc = check_launch(what);
         if (rc) return rc;
     }
-    const long long n_row = rows_direct ? 0 : (long long)frames * na, n_col = (long long)frames * nb;
-    if (n_row + n_col == 0) return GLENET_OK;
-    long long blocks = (n_row + n_col + 255) / 256;
-    if (blocks > 296) blocks = 296;
-    exchange_decode_kernel<<<(unsigned)blocks, 256, 0, st>>>(row_key, n_row, L.col_key, n_col, row_max, row_arg, col_max, col_arg,
-                                                             reinterpret_cast<const unsigned int*>(at(rank, lay.off_flags_assign)), world, step,
-                                                             reinterpret_cast<unsigned int*>(at(rank, lay.off_status)));
-    return check_launch(what);
+    // row keys only exist when the columns are split over several tiles (nb > 128): decode them (the column part is done)
+    if (rows_direct || !launches_tiles) return GLENET_OK;
+    {
+        const long long n_row = (long long)frames * na;
+        long long blocks = (n_row + 255) / 256;
+        if (blocks > 296) blocks = 296;
+        exchange_decode_kernel<<<(unsigned)blocks, 256, 0, st>>>(row_key, n_row, nullptr, 0, row_max, row_arg, nullptr, nullptr, nullptr, 1, 0u, nullptr);
+        return check_launch(what);
+    }
 }
 
 int glenet_boxes_iou_frames_gather_gpu(int mode, const float* a, long long a_frame_stride, int na, const float* b, long long b_frame_stride,

@@ -27,14 +27,21 @@ import importlib
 import sys
 import types
 
-from . import iou3d_nms_utils, iou3d_utils, roiaware_pool3d_utils
+from . import cvae_eval_utils, iou3d_nms_utils, iou3d_utils, roiaware_pool3d_utils, rotate_iou
 
 _TARGETS = {
     "pcdet.ops.iou3d_nms.iou3d_nms_utils": iou3d_nms_utils,
     "pcdet.ops.roiaware_pool3d.roiaware_pool3d_utils": roiaware_pool3d_utils,
     # only boxes_aligned_iou3d_gpu (+ its helpers) of pcdet/ops/iou3d is provided: the one function GLENet imports from it
     "pcdet.ops.iou3d.iou3d_utils": iou3d_utils,
+    # the KITTI evaluator's rotated IoU (a numba-CUDA module in the reference) ...
+    "pcdet.datasets.kitti.kitti_object_eval_python.rotate_iou": rotate_iou,
+    # ... and the recall IoU of the CVAE evaluation (cvae_uncertainty/ is run from its own directory: `eval_utils.eval_utils`)
+    "eval_utils.eval_utils": cvae_eval_utils,
 }
+# modules that bind one of the patched functions with `from x import f` at import time (eval.py:5: from .rotate_iou import
+# rotate_iou_gpu_eval): the name is rebound there as well when the module is already loaded
+_REBIND = {"pcdet.datasets.kitti.kitti_object_eval_python.eval": ("rotate_iou_gpu_eval", "bev_box_overlap", "d3_box_overlap")}
 # host-signature functions that execute on the GPU here (see the module docstring)
 CPU_ENTRY_POINTS = ("boxes_bev_iou_cpu", "points_in_boxes_cpu", "boxes_aligned_overlap_bev_cpu")
 
@@ -83,6 +90,11 @@ def install(cpu_entry_points: bool | None = None) -> dict:
                 setattr(orig, name, getattr(ours, name))
                 done.append(name)
             patched[dotted] = done
+            for user, fnames in _REBIND.items():
+                mod = sys.modules.get(user)
+                for fname in fnames:
+                    if mod is not None and fname in names and hasattr(mod, fname):
+                        setattr(mod, fname, getattr(ours, fname))
             continue
         # stub mode: a fresh module that carries exactly the provided functions
         parent, _, leaf = dotted.rpartition(".")

@@ -51,6 +51,12 @@ elif what == "assign":      # the bench's multi-GPU step on one rank: dense slab
     out = torch.empty((16, a.shape[0], 100), device=dev)
     win = sharded.ExchangeWindow(frames=16, nb=100, list_cap=0)
     fn = lambda: sharded.anchor_assign_sharded(a, b, win, out=out)
+elif what == "pib128":      # the bench's points_in_boxes call: 128 frames, per-frame boxes and points (SURVEY 8d generator)
+    B = 128
+    boxes = torch.stack([synth.waymo_boxes(200, 100 + f) for f in range(B)])
+    pts = torch.stack([synth.points(180000, boxes[f], synth.WAYMO_RANGE, 0.05, seed=500 + f) for f in range(B)]).to(dev)
+    boxes = boxes.to(dev)
+    fn = lambda: R.points_in_boxes_gpu(pts, boxes)
 elif what == "pib16":       # per-frame points (SURVEY 8d generator), 16 frames
     B = 16
     boxes = torch.stack([synth.waymo_boxes(200, 100 + f) for f in range(B)])

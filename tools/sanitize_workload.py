@@ -21,5 +21,23 @@ bx = torch.stack([synth.waymo_boxes(40, 30 + f) for f in range(2)])
 pts = torch.stack([synth.points(9000, bx[f], synth.WAYMO_RANGE, 0.1, seed=f) for f in range(2)])
 R.points_in_boxes_gpu(pts.to(dev), bx.to(dev)); R.points_in_boxes_gpu(pts.to(dev), bx[:, :5].contiguous().to(dev))
 R.points_in_boxes_cpu(pts[0], bx[0]); I.boxes_bev_iou_cpu(p[:50].cpu(), p[:40].cpu())
+# variance-voting / soft NMS (vnms.cu), the single-rank exchange window (assign + gather + scatter + decode kernels)
+v = (torch.rand((700, 7), generator=torch.Generator().manual_seed(5)) * 0.5 + 0.05).to(dev)
+I.new_nms_gpu(p, s, 0.25, variance=v); I.softnms_gpu(p[:200], s[:200], 0.25, score_threshold=0.1, soft_mode="gaussian", soft_sigma=0.3, variance=v[:200])
+from glenet_b200 import sharded
+win = sharded.ExchangeWindow(frames=2, nb=100, list_cap=1 << 16)
+sharded.anchor_assign_sharded(a, g4, win); sharded.anchor_assign_sharded(a, g4, win, dense=False); sharded.boxes_iou_gather_sharded(a, g4, win)
+assert win.status() == 0
+win.close()
+# next scope rows: KITTI-evaluator rotated IoU (dense + blocks), GT-database crops (both rules), CVAE recall IoU
+import numpy as np
+from glenet_b200 import cvae_eval_utils as C, gt_database as G, rotate_iou as RI
+rng = np.random.default_rng(0)
+rb = np.concatenate([rng.uniform(0, 30, (150, 2)), rng.uniform(1.5, 4.3, (150, 2)), rng.uniform(-3.2, 3.2, (150, 1))], 1).astype(np.float32)
+RI.rotate_iou_gpu_eval(rb, rb[:131], -1); RI.rotate_iou_gpu_eval_blocks(rb, rb[:131], [70, 0, 80], [60, 1, 70], 2)
+G.crop_gt_objects(torch.cat([pts[0], torch.rand(9000, 1)], 1).numpy(), bx[0].numpy().astype(np.float64), "kitti")
+G.crop_gt_objects(torch.cat([pts[0], torch.rand(9000, 2)], 1).numpy(), bx[0].numpy(), "waymo")
+smp, gt = synth.cvae_samples(300, 1, 2)
+C.iou3d(gt.to(dev), smp.reshape(-1, 7).to(dev))
 torch.cuda.synchronize()
 print("sanitize workload done")
