@@ -21,6 +21,10 @@
 #include "../../include/glenet_geom.h"
 #include <atomic>
 
+#ifndef GLENET_NMS_APPROX     // 1: decide pairs far from the threshold from the approximate true overlap (no clip)
+#define GLENET_NMS_APPROX 1
+#endif
+
 namespace glenet {
 
 #ifdef GLENET_PHASE_TIMING   // developer instrumentation of the sweep (tools/nms_sweep_timing.py)
@@ -180,7 +184,7 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
     // the threshold (with a safety margin far above float rounding); the others cannot set a mask bit.  At
     // thresh = 0.7 this drops ~45 % of the circle-test survivors of a proposal cluster.  NaN anywhere => clipped.
     const int nq = sm.qcount;
-    const float thr_lo = thresh * (1.f - 1e-3f) - 1e-5f;
+    const float thr_lo = thresh * (1.f - 1e-3f) - 1e-5f, thr_hi = thresh * (1.f + 1e-3f) + 1e-5f;
     for (int q0 = 0; q0 < nq; q0 += NMS_THREADS) {
         const int q = q0 + tid;
         int p = 0;
@@ -192,6 +196,23 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
             const float ub = overlap_upper_bound(a, b);
             const float iou_ub = ub / fmaxf(a[BP_AREA] + b[BP_AREA] - ub, 1e-8f);
             need = all_pairs || (!(ub <= 0.f) && !(iou_ub <= thr_lo)) || !(a[BP_AREA] + b[BP_AREA] > ub);   // degenerate areas: let the clip decide
+#if GLENET_NMS_APPROX
+            // Second filter: the true intersection area, approximately (geom.cuh: overlap_approx, ~240 instructions).  The
+            // reference's overlap lies in [approx - slack, approx + band + slack]; a pair whose IoU is on one side of the
+            // threshold for that whole interval is decided here, only the rest (IoU within ~0.03 of the threshold) is clipped.
+            if (need && !all_pairs && overlap_approx_usable(a, b)) {
+                const float ova = overlap_approx(a, b);
+                float slack, band;
+                overlap_approx_band(a, b, slack, band);
+                const float s = a[BP_AREA] + b[BP_AREA];
+                const float hi = ova + band + slack, lo = ova - slack;
+                if (hi / fmaxf(s - hi, 1e-8f) <= thr_lo && s > hi) need = false;                    // cannot reach the threshold
+                else if (lo > 0.f && s > lo && lo / fmaxf(s - lo, 1e-8f) > thr_hi) {                // exceeds it for certain
+                    need = false;
+                    atomicOr(reinterpret_cast<unsigned int*>(&sm.bits[p >> 6]) + ((p >> 5) & 1), 1u << (p & 31));
+                }                                                                                   // NaN anywhere: both tests fail, the clip decides
+            }
+#endif
         }
         const unsigned int m = __ballot_sync(0xffffffffu, need);
         if (m) {

@@ -80,4 +80,19 @@ void emul_clip_reference_chain(const float* a, const float* trig_a, const float*
     }
 }
 
+// the approximate true overlap of geom.cuh (NMS decision filter) with its error bands
+void emul_overlap_approx(const float* a, const float* trig_a, const float* b, const float* trig_b, int n,
+                         float* out_approx, float* out_slack, float* out_band, int* out_usable) {
+    for (int p = 0; p < n; ++p) {
+        float ra[BP_STRIDE], rb[BP_STRIDE];
+        const float4 ta = make_float4(trig_a[4 * p], trig_a[4 * p + 1], trig_a[4 * p + 2], trig_a[4 * p + 3]);
+        const float4 tb = make_float4(trig_b[4 * p], trig_b[4 * p + 1], trig_b[4 * p + 2], trig_b[4 * p + 3]);
+        box_prepare<true>(a + 7 * p, ta, ra);
+        box_prepare<true>(b + 7 * p, tb, rb);
+        out_approx[p] = overlap_approx(ra, rb);
+        overlap_approx_band(ra, rb, out_slack[p], out_band[p]);
+        out_usable[p] = overlap_approx_usable(ra, rb) ? 1 : 0;
+    }
+}
+
 }  // extern "C"

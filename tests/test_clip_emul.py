@@ -30,6 +30,7 @@ def emul():
     lib.emul_clip_aligned.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_void_p] * 3
     lib.emul_clip_reference_chain.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p]
     lib.emul_clip_aligned_lane.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p]
+    lib.emul_overlap_approx.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_void_p] * 4
     return lib
 
 
@@ -114,3 +115,55 @@ def test_near_collinear_vertices_keep_their_exact_order(emul, capi):
     assert np.abs(iou - want_iou).max() <= 1e-6
     assert np.abs(iou - d["ref_gpu_iou_bev"]).max() <= 1e-6       # libdevice vs glibc trigonometry: last-bit differences only
     assert (ov == want_ov).mean() >= 0.7
+
+
+def test_nms_approximate_overlap_brackets_the_reference(emul, capi):
+    """geom.cuh: overlap_approx / overlap_approx_band -- the filter that lets nms_mask_kernel decide IoU > thresh without the
+    clip.  For every pair the filter accepts (overlap_approx_usable: positive sizes, relative heading not within 1e-3 rad of
+    a multiple of 90 degrees) the reference's overlap (oracle, GPU dialect) must lie in [approx - slack, approx + band + slack]: proposal clusters (cars, pedestrians-sized, mixed), far coordinates, the
+    adversarial set (identical boxes, shared edges, corners at MARGIN +- ulp, 90-degree turns)."""
+    import math
+    sets = []
+    for seed in range(3):
+        p, _ = synth.proposals(500, 8, seed)
+        sets.append(p.numpy())
+    small = synth.proposals(400, 6, 7)[0].numpy().copy()
+    small[:, 3:5] *= np.array([0.2, 0.4], dtype=np.float32)          # 0.8 x 0.6 m boxes: the MARGIN band is large relative to them
+    small[:, :2] = small[:, :2] * 0.25 + 30.0
+    sets.append(small)
+    far = synth.proposals(300, 5, 9)[0].numpy().copy(); far[:, :2] += 5000.0
+    sets.append(far)
+    base = np.array([10.0, 5.0, -1.0, 3.9, 1.6, 1.5, 0.3], dtype=np.float32)
+    rows = [base.copy()]
+    for dxy in (0.0, 1e-3, 0.00999, 0.01, 0.01001, 0.02, 0.5, 1.6, 1.61, 3.9, 3.91):
+        for ang in (0.0, 0.3, 0.3 + math.pi / 2, 0.3 + math.pi, 1.57, -2.8):
+            for sgn in (0, 1):
+                b = base.copy()
+                b[0] += (dxy * math.cos(0.3)) if sgn == 0 else (-dxy * math.sin(0.3))
+                b[1] += (dxy * math.sin(0.3)) if sgn == 0 else (dxy * math.cos(0.3))
+                b[6] = ang
+                rows.append(b)
+    sets.append(np.stack(rows).astype(np.float32))
+    checked = 0
+    for boxes in sets:
+        n = boxes.shape[0]
+        ref = capi.boxes_overlap_bev(boxes, boxes, dialect=capi.GPU)
+        i, j = np.nonzero(np.triu(np.ones((n, n), dtype=bool), 1))
+        a, b = np.ascontiguousarray(boxes[i]), np.ascontiguousarray(boxes[j])
+        ta, tb = trig4(a), trig4(b)
+        m = a.shape[0]
+        approx, slack, band = (np.empty(m, np.float32) for _ in range(3))
+        usable = np.empty(m, np.int32)
+        emul.emul_overlap_approx(a.ctypes.data, ta.ctypes.data, b.ctypes.data, tb.ctypes.data, m, approx.ctypes.data, slack.ctypes.data, band.ctypes.data, usable.ctypes.data)
+        u = usable == 1
+        a, b, approx, slack, band, r = a[u], b[u], approx[u], slack[u], band[u], ref[i, j][u]
+        m = int(u.sum())
+        assert np.isfinite(approx).all()
+        lo_ok, hi_ok = r >= approx - slack, r <= approx + band + slack
+        assert lo_ok.all() and hi_ok.all(), (int((~lo_ok).sum()), int((~hi_ok).sum()), float((approx - slack - r).max()), float((r - approx - band - slack).max()))
+        # and the filter is worth having: the interval is narrow next to the overlaps it has to classify
+        big = r > 0.3 * np.minimum(a[:, 3] * a[:, 4], b[:, 3] * b[:, 4])
+        if big.any():
+            assert np.median((band + 2 * slack)[big] / r[big]) < 0.2
+        checked += m
+    assert checked > 350000
