@@ -272,7 +272,7 @@ __device__ __forceinline__ float overlap_upper_bound(const float* __restrict__ a
 // reference's polygon also takes corners up to MARGIN outside the other box, so
 //     approx - slack  <=  reference overlap  <=  approx + MARGIN-band + slack        (overlap_approx_band)
 // which is what NMS needs to decide  IoU > thresh  for every pair that is not within that band of the threshold
-// (measured against the oracle, tests/test_clip_emul.py: reference - true in [-4e-5, +0.22 * band] on 2.5e5 proposal pairs).
+// (measured against the reference restated in C, tests/test_clip_emul.py: reference - true in [-4e-5, +0.22 * band] on 2.5e5 proposal pairs).
 // Requires positive extents; NaN / Inf propagate (callers treat a non-finite result as "run the exact clip").
 __device__ __forceinline__ float lb_weight(float px, float py, float dx, float dy, float hx, float hy) {
     const float ix = __fdividef(1.f, dx), iy = __fdividef(1.f, dy);            // d == 0: +-inf, the slab tests degenerate correctly (0 * inf = NaN is dropped by fminf / fmaxf)
