@@ -21,6 +21,9 @@
 #include "../../include/glenet_geom.h"
 #include <atomic>
 
+#ifndef GLENET_NMS_DEFER      // 1: the exact clips of a tile are appended to a global list and run as one dense kernel
+#define GLENET_NMS_DEFER 1
+#endif
 #ifndef GLENET_NMS_APPROX     // 1: decide pairs far from the threshold from the approximate true overlap (no clip)
 #define GLENET_NMS_APPROX 1
 #endif
@@ -38,6 +41,8 @@ constexpr int NMS_THREADS = 256;
 constexpr int NMS_TILE = 64;
 constexpr int SWEEP_THREADS = 512;
 
+// entries of the deferred-clip list (pairs within ~0.03 IoU of the threshold: ~6 n per frame on dense proposal clusters)
+static inline unsigned long long nms_list_cap(int frames, int n) { return (unsigned long long)frames * (unsigned long long)n * 32ull; }
 constexpr int NMS_PASS = NMS_THREADS;       // pairs per pass of the phased clip: one per lane
 constexpr int NBS = BP_STRIDE_BEV;          // BoxPre stride (no z terms in NMS)
 struct NmsSmem {
@@ -84,7 +89,8 @@ __device__ __forceinline__ void tri_decode(int t, int nblk, int& rb, int& cb) {
 template <bool NORMAL>
 __global__ void __launch_bounds__(NMS_THREADS, GLENET_NMS_CTAS)
 nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsigned long long* __restrict__ mask_all,
-                int col_blocks, int tiles_per_frame) {
+                int col_blocks, int tiles_per_frame, unsigned long long* __restrict__ list_count, unsigned long long* __restrict__ list,
+                unsigned long long list_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem& sm = *reinterpret_cast<NmsSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -223,8 +229,36 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
         }
     }
     __syncthreads();
-    // ---- phased clip (clip.cuh) over queue2, NMS_PASS pairs at a time
     const int nq2 = sm.q2count;
+#if GLENET_NMS_DEFER
+    // ---- the pairs that still need the exact clip leave the tile: they are appended to a global list and clipped by
+    //      nms_clip_list_kernel, one pair per lane of full warps.  (A tile keeps ~25 of its 4096 pairs; clipping them here
+    //      costs the latency of one whole clip per tile -- half of the tile's phase chain -- on a handful of lanes.)
+    //      A full list (or thresh < 0, where every pair is kept) falls back to the clip below.
+    if (list && nq2 > 0 && !all_pairs) {
+        if (tid == 0) {
+            const unsigned long long base = atomicAdd(list_count, (unsigned long long)nq2);
+            sm.qcount = (base + (unsigned long long)nq2 <= list_cap) ? 1 : 0;
+            reinterpret_cast<unsigned long long*>(sm.wl[0])[0] = base;
+        }
+        __syncthreads();
+        if (sm.qcount) {
+            const unsigned long long base = reinterpret_cast<unsigned long long*>(sm.wl[0])[0];
+            for (int q = tid; q < nq2; q += NMS_THREADS) {
+                const int p = sm.queue2[q];
+                list[base + q] = ((unsigned long long)frame << 40) | ((unsigned long long)(r0 + (p >> 6)) << 20) | (unsigned long long)(c0 + (p & 63));
+            }
+            if (tid < tr) mask[(size_t)(r0 + tid) * col_blocks + cb] = sm.bits[tid];
+            return;
+        }
+        // the list is full: what this tile reserved inside it is marked void (only the first overflowing tile reserves
+        // anything below the capacity), and the tile clips its pairs itself
+        const unsigned long long base = reinterpret_cast<unsigned long long*>(sm.wl[0])[0];
+        for (int q = tid; q < nq2; q += NMS_THREADS) if (base + q < list_cap) list[base + q] = ~0ull;
+        __syncthreads();   // wl[0] is about to be reused by the clip
+    }
+#endif
+    // ---- phased clip (clip.cuh) over queue2, NMS_PASS pairs at a time
     auto set_bit = [&](int p, float ov, const float* a, const float* b) {
         if (iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) > thresh)   // 32-bit halves: a native shared-memory atomic instead of a 64-bit CAS loop
             atomicOr(reinterpret_cast<unsigned int*>(&sm.bits[p >> 6]) + ((p >> 5) & 1), 1u << (p & 31));
@@ -249,6 +283,60 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
     }
     __syncthreads();
     if (tid < tr) mask[(size_t)(r0 + tid) * col_blocks + cb] = sm.bits[tid];
+}
+
+// Exact clip of the pairs the mask kernel could not decide (nms_mask_kernel, GLENET_NMS_DEFER): one pair per lane, both
+// BoxPre records in shared memory, the phased clip of clip.cuh, the mask bit set with a 32-bit atomicOr.  Persistent CTAs walk
+// the list; its length is read from device memory (no host synchronisation).  Row box = box_a, column box = box_b, prepared
+// with the same calls as in the tile (iou3d_nms_kernel.cu:267-311).
+constexpr int NCL_THREADS = 128;
+struct NclSmem {
+    float2 verts[NCL_THREADS * CLIP_SLOTS];
+    unsigned int wl[NCL_THREADS / 32][32 * CLIP_SLOTS];
+    float arec[NCL_THREADS * NBS], brec[NCL_THREADS * NBS];
+};
+__global__ void __launch_bounds__(NCL_THREADS, 4)
+nms_clip_list_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsigned long long* __restrict__ mask_all, int col_blocks,
+                     const unsigned long long* __restrict__ list_count, const unsigned long long* __restrict__ list, unsigned long long list_cap) {
+    __shared__ NclSmem sm;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    unsigned long long total = *list_count;
+    if (total > list_cap) total = list_cap;   // reservations beyond the capacity were refused (their tiles clipped locally); refused slots below it hold ~0
+    for (unsigned long long base = (unsigned long long)blockIdx.x * NCL_THREADS; base < total; base += (unsigned long long)gridDim.x * NCL_THREADS) {
+        bool live = base + tid < total;
+        int frame = 0, i = 0, j = 0;
+        if (live) {
+            const unsigned long long e = list[base + tid];
+            live = e != ~0ull;
+            frame = (int)(e >> 40); i = (int)((e >> 20) & 0xfffffu); j = (int)(e & 0xfffffu);
+        }
+        float* a = sm.arec + tid * NBS;
+        float* b = sm.brec + tid * NBS;
+        if (live) {
+            const float* ba = boxes_all + ((size_t)frame * n + i) * 7;
+            const float* bb = boxes_all + ((size_t)frame * n + j) * 7;
+            box_prepare<true, false>(ba, device_trig(ba[6]), a);
+            box_prepare<true, false>(bb, device_trig(bb[6]), b);
+        }
+        __syncwarp();
+        float2* slots = sm.verts + tid * CLIP_SLOTS;
+        const unsigned int w = clip_pair_tests<true>(a, b, live);
+        const unsigned int hits = clip_hits16(w);
+        const int cnt = __popc(hits) + __popc(clip_corners8(w));
+        const bool fast = cnt >= 3 && cnt <= CLIP_SLOTS;
+        if (fast) clip_write_corners(a, b, w, slots);
+        clip_warp_points<true>(fast ? hits : 0u, (unsigned int)tid, (unsigned int)tid, sm.wl[warp], sm.arec, sm.brec, NBS, sm.verts + (warp * 32) * CLIP_SLOTS);
+        const bool slow = cnt > CLIP_SLOTS;
+        const float ov_slow = clip_warp_slow<true>(slow, w, (unsigned int)tid, (unsigned int)tid, sm.arec, sm.brec, NBS, reinterpret_cast<float2*>(sm.wl[warp]));
+        if (live) {
+            const float ov = slow ? ov_slow : (fast ? clip_area8<true>(slots, cnt) : 0.f);
+            if (iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) > thresh) {
+                unsigned long long* word = mask_all + ((size_t)frame * n + i) * col_blocks + (j >> 6);
+                atomicOr(reinterpret_cast<unsigned int*>(word) + ((j >> 5) & 1), 1u << (j & 31));
+            }
+        }
+        __syncwarp();   // the records and slots of this batch are dead before the next one overwrites them
+    }
 }
 
 // Greedy sweep of iou3d_nms.cpp:116-132 on the device.  One CTA per frame, one barrier per 64-box chunk.
@@ -399,12 +487,30 @@ static int launch_nms(bool normal, const float* boxes, int frames, int n, float 
         if (cacheable) attr_done[dev].fetch_or(1, std::memory_order_release);
     }
     const unsigned grid = (unsigned)(tiles * frames);
+    // deferred exact clips: [count][list] behind the mask (glenet_nms_workspace_bytes)
+    const size_t mask_bytes = align_up((size_t)frames * n * col_blocks * sizeof(unsigned long long), 16);
+    unsigned long long* list_count = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(ws) + mask_bytes);
+    unsigned long long* list = list_count + 2;
+    const unsigned long long list_cap = nms_list_cap(frames, n);
+    const bool defer = GLENET_NMS_DEFER && !normal && n < (1 << 20) && frames < (1 << 23);
+    if (defer) {
+        cudaError_t e = cudaMemsetAsync(list_count, 0, 16, stream);
+        if (e != cudaSuccess) return fail(-(int)e, "%s: memset failed", what);
+    }
     if (normal)
-        nms_mask_kernel<true><<<grid, NMS_THREADS, sizeof(NmsSmem), stream>>>(boxes, n, thresh, mask, col_blocks, (int)tiles);
+        nms_mask_kernel<true><<<grid, NMS_THREADS, sizeof(NmsSmem), stream>>>(boxes, n, thresh, mask, col_blocks, (int)tiles, nullptr, nullptr, 0ull);
     else
-        nms_mask_kernel<false><<<grid, NMS_THREADS, sizeof(NmsSmem), stream>>>(boxes, n, thresh, mask, col_blocks, (int)tiles);
+        nms_mask_kernel<false><<<grid, NMS_THREADS, sizeof(NmsSmem), stream>>>(boxes, n, thresh, mask, col_blocks, (int)tiles,
+                                                                              defer ? list_count : nullptr, defer ? list : nullptr, list_cap);
     int rc = check_launch(what);
     if (rc) return rc;
+    if (defer) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        nms_clip_list_kernel<<<sms * 4, NCL_THREADS, 0, stream>>>(boxes, n, thresh, mask, col_blocks, list_count, list, list_cap);
+        rc = check_launch(what);
+        if (rc) return rc;
+    }
     const size_t remv_bytes = sizeof(unsigned long long) * col_blocks;
     const size_t pre_bytes = remv_bytes + 2 * sizeof(unsigned long long) * (size_t)n;
     if (remv_bytes > 200 * 1024) return fail(GLENET_EINVAL, "%s: n too large for the on-chip suppression words", what);
@@ -432,7 +538,8 @@ extern "C" {
 size_t glenet_nms_workspace_bytes(int frames, int n) {
     if (frames <= 0 || n <= 0) return 16;
     const size_t col_blocks = ((size_t)n + NMS_TILE - 1) / NMS_TILE;
-    return align_up((size_t)frames * n * col_blocks * sizeof(unsigned long long), 16);
+    // the suppression mask, then the list of pairs whose exact clip is deferred: a 16-byte counter + 32 n entries per frame
+    return align_up((size_t)frames * n * col_blocks * sizeof(unsigned long long), 16) + 16 + (size_t)nms_list_cap(frames, n) * sizeof(unsigned long long);
 }
 
 #ifdef GLENET_PHASE_TIMING

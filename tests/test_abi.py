@@ -33,7 +33,7 @@ def test_library_builds_loads_and_exports_everything():
     # and the binding table covers exactly the header
     assert sorted(glenet_b200.EXPORTS) == declared_symbols()
     assert lib.glenet_abi_version() == 11
-    assert lib.glenet_nms_workspace_bytes(1, 4096) == 4096 * 64 * 8
+    assert lib.glenet_nms_workspace_bytes(1, 4096) == 4096 * 64 * 8 + 16 + 32 * 4096 * 8   # mask + deferred-clip list
     assert lib.glenet_points_in_boxes_workspace_bytes(2, 200) > 2 * 200 * 32
     # workspace layout of csrc/pib.cu (pib_layout): per frame a 48-byte header, 8 floats per box, 4097 list starts,
     # 32 N + 8192 list slots, a 256 x 256 bit occupancy map and 4096 packed 8-byte cells; every section 16-byte aligned
