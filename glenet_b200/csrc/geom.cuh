@@ -274,8 +274,17 @@ __device__ __forceinline__ float overlap_upper_bound(const float* __restrict__ a
 // which is what NMS needs to decide  IoU > thresh  for every pair that is not within that band of the threshold
 // (measured against the reference restated in C, tests/test_clip_emul.py: reference - true in [-4e-5, +0.22 * band] on 2.5e5 proposal pairs).
 // Requires positive extents; NaN / Inf propagate (callers treat a non-finite result as "run the exact clip").
+__device__ __forceinline__ float rcp_approx(float x) {   // one MUFU.RCP (__fdividef(1, x) adds a range fix-up that the slab tests do not need)
+#ifdef GLENET_HOST_EMUL
+    return 1.0f / x;
+#else
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
 __device__ __forceinline__ float lb_weight(float px, float py, float dx, float dy, float hx, float hy) {
-    const float ix = __fdividef(1.f, dx), iy = __fdividef(1.f, dy);            // d == 0: +-inf, the slab tests degenerate correctly (0 * inf = NaN is dropped by fminf / fmaxf)
+    const float ix = rcp_approx(dx), iy = rcp_approx(dy);                      // d == 0: +-inf, the slab tests degenerate correctly (0 * inf = NaN is dropped by fminf / fmaxf)
     const float ta = (-hx - px) * ix, tb = (hx - px) * ix, tc = (-hy - py) * iy, td = (hy - py) * iy;
     const float t0 = fmaxf(fmaxf(fminf(ta, tb), fminf(tc, td)), 0.f);
     const float t1 = fminf(fminf(fmaxf(ta, tb), fmaxf(tc, td)), 1.f);

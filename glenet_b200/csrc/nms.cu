@@ -34,8 +34,8 @@ namespace glenet {
 __device__ unsigned long long g_sweep_cycles[4];   // [0] warp 0 busy, [1] whole loop, [2] job warps busy (warp 1), [3] steps
 #endif
 
-#ifndef GLENET_NMS_CTAS   // resident CTAs per SM the mask kernel is compiled for (register budget: 4 -> 64, 5 -> 48 registers)
-#define GLENET_NMS_CTAS 4
+#ifndef GLENET_NMS_CTAS   // resident CTAs per SM the mask kernel is compiled for (register budget: 4 -> 64, 5 -> 48 registers; measured 340.6 vs 326.8 us for 8 x 4096 once the fallback clip was out of line)
+#define GLENET_NMS_CTAS 5
 #endif
 constexpr int NMS_THREADS = 256;
 constexpr int NMS_TILE = 64;
@@ -84,6 +84,33 @@ __device__ __forceinline__ void tri_decode(int t, int nblk, int& rb, int& cb) {
     while ((r + 1) * nblk - (r + 1) * r / 2 <= t) ++r;
     rb = r;
     cb = r + (t - (r * nblk - r * (r - 1) / 2));
+}
+
+// The in-tile exact clip over queue2 (all pairs when thresh < 0, or when the deferred-clip list is full), NMS_PASS pairs at a time.
+__device__ __noinline__ void nms_tile_clip(NmsSmem& sm, int nq2, float thresh) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    auto set_bit = [&](int p, float ov, const float* a, const float* b) {
+        if (iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) > thresh)   // 32-bit halves: a native shared-memory atomic instead of a 64-bit CAS loop
+            atomicOr(reinterpret_cast<unsigned int*>(&sm.bits[p >> 6]) + ((p >> 5) & 1), 1u << (p & 31));
+    };
+    for (int base = 0; base < nq2; base += NMS_PASS) {
+        // one pair per lane; A (result bits, corners), B (the warp's crossings pooled) and C (sort + fan) are warp-local
+        const bool live = base + tid < nq2;
+        const int p = live ? sm.queue2[base + tid] : 0;
+        const float* a = sm.rpre + (p >> 6) * NBS;
+        const float* b = sm.cpre + (p & 63) * NBS;
+        float2* slots = sm.verts + tid * CLIP_SLOTS;
+        const unsigned int w = clip_pair_tests<true>(a, b, live);
+        const unsigned int hits = clip_hits16(w);
+        const int cnt = __popc(hits) + __popc(clip_corners8(w));
+        const bool fast = cnt >= 3 && cnt <= CLIP_SLOTS;
+        if (fast) clip_write_corners(a, b, w, slots);
+        clip_warp_points<true>(fast ? hits : 0u, (unsigned int)(p >> 6), (unsigned int)(p & 63), sm.wl[warp], sm.rpre, sm.cpre, NBS, sm.verts + (warp * 32) * CLIP_SLOTS);
+        // more than eight vertices (corners admitted by the margin next to a crossing): the whole warp, one pair at a time
+        const bool slow = cnt > CLIP_SLOTS;
+        const float ov_slow = clip_warp_slow<true>(slow, w, (unsigned int)(p >> 6), (unsigned int)(p & 63), sm.rpre, sm.cpre, NBS, reinterpret_cast<float2*>(sm.wl[warp]));
+        if (live) set_bit(p, slow ? ov_slow : (fast ? clip_area8<true>(slots, cnt) : 0.f), a, b);
+    }
 }
 
 template <bool NORMAL>
@@ -147,13 +174,21 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
     const int c = tid & (NMS_TILE - 1), rq = tid >> 6;
     unsigned int hits = 0u;
     if (c < tc) {
-        const float ccx = sm.ccx[c], ccy = sm.ccy[c], ccr = sm.crad[c];
+        // rows this thread may pair its column with: r = 4 k + rq below tr, and above the diagonal (r < c) on a diagonal tile --
+        // one mask instead of two tests per pair
+        const int lim = diag ? min(tr, c) : tr;
+        const int kmax = lim > rq ? (lim - rq + (NMS_THREADS / NMS_TILE) - 1) / (NMS_THREADS / NMS_TILE) : 0;
+        const unsigned int valid = kmax >= NMS_RPT ? (1u << NMS_RPT) - 1u : (1u << kmax) - 1u;
+        if (all_pairs) hits = valid;
+        else {
+            const float ccx = sm.ccx[c], ccy = sm.ccy[c], ccr = sm.crad[c];
 #pragma unroll
-        for (int k = 0; k < NMS_RPT; ++k) {
-            const int r = k * (NMS_THREADS / NMS_TILE) + rq;
-            const float ddx = sm.rcx[r] - ccx, ddy = sm.rcy[r] - ccy, rr = sm.rrad[r] + ccr;
-            const bool heavy = r < tr && !(diag && c <= r) && (all_pairs || !(ddx * ddx + ddy * ddy > rr * rr));
-            hits |= (heavy ? 1u : 0u) << k;
+            for (int k = 0; k < NMS_RPT; ++k) {
+                const int r = k * (NMS_THREADS / NMS_TILE) + rq;
+                const float ddx = sm.rcx[r] - ccx, ddy = sm.rcy[r] - ccy, rr = sm.rrad[r] + ccr;
+                hits |= (!(ddx * ddx + ddy * ddy > rr * rr) ? 1u : 0u) << k;     // NaN anywhere: not culled
+            }
+            hits &= valid;
         }
     }
     {
@@ -258,29 +293,9 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
         __syncthreads();   // wl[0] is about to be reused by the clip
     }
 #endif
-    // ---- phased clip (clip.cuh) over queue2, NMS_PASS pairs at a time
-    auto set_bit = [&](int p, float ov, const float* a, const float* b) {
-        if (iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) > thresh)   // 32-bit halves: a native shared-memory atomic instead of a 64-bit CAS loop
-            atomicOr(reinterpret_cast<unsigned int*>(&sm.bits[p >> 6]) + ((p >> 5) & 1), 1u << (p & 31));
-    };
-    for (int base = 0; base < nq2; base += NMS_PASS) {
-        // one pair per lane; A (result bits, corners), B (the warp's crossings pooled) and C (sort + fan) are warp-local
-        const bool live = base + tid < nq2;
-        const int p = live ? sm.queue2[base + tid] : 0;
-        const float* a = sm.rpre + (p >> 6) * NBS;
-        const float* b = sm.cpre + (p & 63) * NBS;
-        float2* slots = sm.verts + tid * CLIP_SLOTS;
-        const unsigned int w = clip_pair_tests<true>(a, b, live);
-        const unsigned int hits = clip_hits16(w);
-        const int cnt = __popc(hits) + __popc(clip_corners8(w));
-        const bool fast = cnt >= 3 && cnt <= CLIP_SLOTS;
-        if (fast) clip_write_corners(a, b, w, slots);
-        clip_warp_points<true>(fast ? hits : 0u, (unsigned int)(p >> 6), (unsigned int)(p & 63), sm.wl[warp], sm.rpre, sm.cpre, NBS, sm.verts + (warp * 32) * CLIP_SLOTS);
-        // more than eight vertices (corners admitted by the margin next to a crossing): the whole warp, one pair at a time
-        const bool slow = cnt > CLIP_SLOTS;
-        const float ov_slow = clip_warp_slow<true>(slow, w, (unsigned int)(p >> 6), (unsigned int)(p & 63), sm.rpre, sm.cpre, NBS, reinterpret_cast<float2*>(sm.wl[warp]));
-        if (live) set_bit(p, slow ? ov_slow : (fast ? clip_area8<true>(slots, cnt) : 0.f), a, b);
-    }
+    // ---- phased clip (clip.cuh) over queue2: only when the pairs could not be deferred (out of line: it must not set the
+    //      register budget of the phases every tile runs)
+    nms_tile_clip(sm, nq2, thresh);
     __syncthreads();
     if (tid < tr) mask[(size_t)(r0 + tid) * col_blocks + cb] = sm.bits[tid];
 }

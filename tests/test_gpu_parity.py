@@ -258,6 +258,42 @@ def test_nms_threshold_corner_cases_vs_reference(cuda, ref_so):
         assert torch.equal(I.nms_gpu(dup, sc, thr)[0], ref_so.nms_gpu(dup, sc, thr)[0]), thr
 
 
+def test_nms_deferred_clip_list_and_its_overflow_vs_reference(cuda, ref_so):
+    """nms_mask_kernel decides most pairs from the approximate true overlap and defers the exact clips to a global list
+    (32 n entries per frame).  (a) IoU values crowded around the threshold: many pairs inside the undecided band; (b) boxes with
+    identical headings in two groups 0.69 m apart (IoU ~ 0.7 across the groups, parallel edges => the approximate filter is not
+    used): ~1e6 exact clips, far more than the list holds, so the overflow path -- void entries, tiles clipping locally -- runs;
+    (c) small boxes, for which the MARGIN band is wide.  Keep indices must equal the reference kernel's in every case."""
+    g = torch.Generator().manual_seed(77)
+    base = torch.tensor([20.0, 3.0, -1.0, 3.9, 1.6, 1.5, 0.4])
+    # (a) one cluster, shifts chosen so that pairwise IoU spreads over 0.5 .. 0.9, headings jittered (approx filter in use)
+    a = base.repeat(1500, 1)
+    a[:, 0] += torch.rand(1500, generator=g) * 0.9
+    a[:, 1] += torch.rand(1500, generator=g) * 0.15
+    a[:, 6] += torch.randn(1500, generator=g) * 0.03
+    # (b) two groups with identical headings
+    b = base.repeat(2000, 1)
+    b[1000:, 0] += 0.69 * float(torch.cos(torch.tensor(0.4))); b[1000:, 1] += 0.69 * float(torch.sin(torch.tensor(0.4)))
+    b[:, :2] += torch.randn((2000, 2), generator=g) * 0.01
+    # (c) pedestrian-sized boxes
+    c = torch.tensor([5.0, -7.0, -0.6, 0.8, 0.6, 1.73, -1.1]).repeat(1200, 1)
+    c[:, :2] += torch.randn((1200, 2), generator=g) * 0.12
+    c[:, 6] += torch.randn(1200, generator=g) * 0.2
+    for boxes, thrs in ((a, (0.6, 0.7, 0.75)), (b, (0.7,)), (c, (0.5, 0.7))):
+        boxes = boxes.to(cuda)
+        scores = torch.rand(boxes.shape[0], generator=g).to(cuda)
+        for thr in thrs:
+            got, want = I.nms_gpu(boxes, scores, thr)[0], ref_so.nms_gpu(boxes, scores, thr)[0]
+            assert torch.equal(got, want), (boxes.shape[0], thr, got.numel(), want.numel())
+    # batched: the list is shared by the frames of a call
+    fb = torch.stack([a[:1200], b[:1200], c]).to(cuda)
+    fs = torch.rand((3, 1200), generator=g).to(cuda)
+    keep, num = I.nms_gpu_batch(fb, fs, 0.7)
+    for f in range(3):
+        want = ref_so.nms_gpu(fb[f], fs[f], 0.7)[0]
+        assert torch.equal(keep[f, : int(num[f])], want), f
+
+
 def _fuzz_boxes(n, g, centre_scale, dim_lo, dim_hi, heading_scale):
     c = (torch.rand((n, 3), generator=g) - 0.5) * 2 * centre_scale
     c[:, 2] *= 0.02

@@ -8,7 +8,7 @@ rm -f ../lib/libglenet_geom_var_*.so
 build() { # name flags...
   name=$1; shift
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I ../../include -shared "$@" \
-       iou.cu iou3d_v1.cu nms.cu pib.cu host.cpp -o ../lib/libglenet_geom_var_$name.so 2>&1 | grep -E "error" || true
+       iou.cu iou3d_v1.cu nms.cu pib.cu vnms.cu rotate_iou.cu crop.cu host.cpp -o ../lib/libglenet_geom_var_$name.so 2>&1 | grep -E "error" || true
   echo "built $name ($*)"
 }
 VARIANTS=${VARIANTS:-"base:"}
