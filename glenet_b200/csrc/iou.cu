@@ -1006,8 +1006,8 @@ int glenet_boxes_iou_frames_assign_gpu(int mode, const float* a, long long a_fra
     const long long n_col = (long long)frames * nb;
     if (n_col > 0) {
         cudaLaunchConfig_t cfg = {};
-        long long ctas = (n_col + 2047) / 2048;
-        cfg.gridDim = dim3((unsigned)(ctas > 8 ? 8 : ctas)); cfg.blockDim = dim3(256); cfg.stream = st;
+        long long ctas = (n_col + 255) / 256;          // one key per thread: the push and the decode are latency chains (NVLink / L2 round trips)
+        cfg.gridDim = dim3((unsigned)(ctas > 16 ? 16 : ctas)); cfg.blockDim = dim3(256); cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
