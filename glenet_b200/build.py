@@ -73,6 +73,28 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIBPATH
 
 
+TOOLS_CUDA = os.path.join(os.path.dirname(HERE), "tools", "cuda")
+TOOL_BINARIES = ["ffma_peak"]       # measurement microkernels bench.py runs beside the library (FP32 peak of this GPU)
+
+
+def build_tools(force: bool = False) -> list:
+    """Compile the measurement microkernels of tools/cuda into tools/cuda/bin (git-ignored, travels to the GPU box)."""
+    out = []
+    bindir = os.path.join(TOOLS_CUDA, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    for name in TOOL_BINARIES:
+        src, exe = os.path.join(TOOLS_CUDA, name + ".cu"), os.path.join(bindir, name)
+        if force or not os.path.isfile(exe) or os.path.getmtime(src) > os.path.getmtime(exe):
+            r = subprocess.run([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-o", exe, src],
+                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if r.returncode:
+                print(r.stdout)
+                raise RuntimeError(f"nvcc failed on {src}")
+        out.append(exe)
+    return out
+
+
 if __name__ == "__main__":
+    build_tools(force="--force" in sys.argv)
     path = build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)
