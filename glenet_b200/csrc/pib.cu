@@ -30,8 +30,24 @@ namespace glenet {
 
 constexpr int PIB_G = 64;                       // coarse grid (CSR candidate lists), cells per axis
 constexpr int PIB_CELLS = PIB_G * PIB_G;
+#ifndef GLENET_PIB_ZSLABS        // fine map: 16 / 8 = 128 x 128 cells x that many z-slab bits (a point is hot only if a box covers its
+#define GLENET_PIB_ZSLABS 16     // cell AND its z slab); -1 = 256 x 256 x 1 bit AND 64 x 64 x 16 z-slab bits; 0 = 256 x 256 x 1 bit + one z window
+#endif
+#define GLENET_PIB_HYBRID (GLENET_PIB_ZSLABS < 0)
+#if GLENET_PIB_ZSLABS > 0
+constexpr int PIB_FG = 128;                     // fine occupancy map, cells per axis
+constexpr int PIB_ZS = GLENET_PIB_ZSLABS;       // z slabs of the frame's z window = bits per cell
+constexpr int PIB_FWORDS = PIB_FG * PIB_FG * PIB_ZS / 32;
+#elif GLENET_PIB_HYBRID
+constexpr int PIB_FG = 256;                     // fine occupancy bitmap, cells per axis (1 bit per cell) ...
+constexpr int PIB_ZS = 16;                      // ... and 16 z-slab bits for every 4 x 4 cells
+constexpr int PIB_FBITWORDS = PIB_FG * PIB_FG / 32;
+constexpr int PIB_FWORDS = PIB_FBITWORDS + (PIB_FG / 4) * (PIB_FG / 4) / 2;
+#else
 constexpr int PIB_FG = 256;                     // fine occupancy bitmap, cells per axis (1 bit per cell)
+constexpr int PIB_ZS = 1;
 constexpr int PIB_FWORDS = PIB_FG * PIB_FG / 32;
+#endif
 constexpr int PIB_ROUND = 4 * 256;              // points per CTA round of the direct kernel (4 per thread)
 constexpr int PIB_WBATCH = 128;                 // points per warp batch (4 per lane)
 constexpr int PIB_WQ = PIB_WBATCH + 32;         // warp queue: one batch of hot points + a remainder of < 32
@@ -51,10 +67,22 @@ constexpr int PIB_WQ = PIB_WBATCH + 32;         // warp queue: one batch of hot 
 #define GLENET_PIB_L2PF 3
 #endif
 #ifndef GLENET_PIB_CTAS          // resident CTAs per SM the query kernel is compiled and launched for
-#define GLENET_PIB_CTAS 3
+#define GLENET_PIB_CTAS (GLENET_PIB_ZSLABS == 16 ? 2 : 3)
+#endif
+#ifndef GLENET_PIB_BUILD_SPLIT   // 1: the threads sharing a box split its coarse-cell rows as well as its fine rows
+#define GLENET_PIB_BUILD_SPLIT 1
+#endif
+#ifndef GLENET_PIB_PREFILL       // 1: the query grid writes the provisional -1 of its whole range while the build kernel still runs
+#define GLENET_PIB_PREFILL 0
+#endif
+#ifndef GLENET_PIB_PF            // register prefetch depth of the query's point stream: 2, 1 or 0 (L2 prefetch only)
+#define GLENET_PIB_PF 1
 #endif
 constexpr int PIB_CHUNK = GLENET_PIB_CHUNK;     // points per work item of the query kernel
-constexpr int PIB_THREADS = 256;
+#ifndef GLENET_PIB_THREADS
+#define GLENET_PIB_THREADS 256
+#endif
+constexpr int PIB_THREADS = GLENET_PIB_THREADS;
 constexpr int PIB_DIRECT_BOXES = 32;            // at most this many boxes => single-launch direct kernel for small calls
 constexpr int PIB_DIRECT_PTS = 4096;            // points per CTA of the direct kernel
 constexpr long PIB_DIRECT_MAX_POINTS = 1 << 20; // ... when the whole call has at most this many points
@@ -63,14 +91,19 @@ constexpr long PIB_DIRECT_MAX_POINTS = 1 << 20; // ... when the whole call has a
 #endif
 constexpr int PIB_BUILD_THREADS = GLENET_PIB_BUILD_THREADS;
 constexpr size_t PIB_BUILD_SMEM = (size_t)PIB_CELLS * (8 + 4 + 4) + (size_t)PIB_FWORDS * 4;   // dynamic shared memory of the build kernel
-constexpr int PIB_SMEM_BOXES = 256;             // box records cached in shared memory by the query kernel
+#ifndef GLENET_PIB_REC_STRIDE     // floats per box record in the query kernel's shared memory: 12 spreads random records over all banks
+#define GLENET_PIB_REC_STRIDE 12  // (8 = packed: records k and k + 4 share their banks)
+#endif
+constexpr int PIB_REC_STRIDE = GLENET_PIB_REC_STRIDE;
+constexpr int PIB_SMEM_BOXES = 224;             // box records cached in shared memory by the query kernel
 
 struct PibFrame {          // 48 B header per frame
     float gx0, gy0, inv_x, inv_y;   // coarse mapping: cell = floor((x - gx0) * inv_x)
     int exhaustive;        // 1 => query kernel loops over all boxes
     int list_len;          // < 0 => no box of the frame can contain any point
     float finv_x, finv_y;  // fine bitmap mapping
-    float zc, zh;          // z window of all boxes together: |z - zc| > zh => the point is in no box (zh = +inf: no window)
+    float zc, zh;          // z window of all boxes together: |z - zc| > zh => the point is in no box (zh = +inf: no window);
+                           // with z slabs: slab = floor(fma(z, zc, zh)) (zc = slabs per metre, 0 = no window: every point in slab 0)
     float foff_x, foff_y;  // fine bitmap mapping, fused form: cell = floor(fma(x, finv_x, foff_x)), foff = -gx0 * finv_x
 };
 
@@ -79,7 +112,6 @@ __host__ __device__ inline size_t pib_list_cap(int n) { return (size_t)32 * n + 
 struct PibWorkspace {
     PibFrame* frames;      // [B]
     float* rec;            // [B][N][8]
-    unsigned int* start;   // [B][PIB_CELLS + 1]
     unsigned int* list;    // [B][cap]
     unsigned int* bits;    // [B][PIB_FWORDS] fine occupancy bitmap
     unsigned long long* cells;   // [B][PIB_CELLS] packed coarse cell: four candidate ids, 16 bits each (0xffff none, last = 0xfffe: walk the list)
@@ -93,7 +125,6 @@ __host__ __device__ inline PibWorkspace pib_layout(void* base, int B, int N) {
     unsigned char* p = (unsigned char*)base;
     w.frames = (PibFrame*)(p + off); off += ((size_t)B * sizeof(PibFrame) + 15) / 16 * 16;
     w.rec = (float*)(p + off);       off += ((size_t)B * N * 8 * sizeof(float) + 15) / 16 * 16;
-    w.start = (unsigned int*)(p + off); off += ((size_t)B * (PIB_CELLS + 1) * sizeof(unsigned int) + 15) / 16 * 16;
     w.cap = pib_list_cap(N);
     w.list = (unsigned int*)(p + off);  off += ((size_t)B * w.cap * sizeof(unsigned int) + 15) / 16 * 16;
     w.bits = (unsigned int*)(p + off);  off += ((size_t)B * PIB_FWORDS * sizeof(unsigned int) + 15) / 16 * 16;
@@ -118,13 +149,14 @@ __device__ __forceinline__ void box_thresholds(float dx, float dy, float dz, flo
 }
 
 // lidar_to_local_coords (:16-20) as compiled for the GPU: lx = fma(sx, c, -(sy*s)), ly = fma(sy, c, sx*s)
+// The record is read as two 16-byte words (two LDS.128 / LDG.128, not eight scalar loads).
 __device__ __forceinline__ bool pt_in_box_gpu(float x, float y, float z, const float* __restrict__ r) {
-    if (fabsf(__fsub_rn(z, r[2])) > r[7]) return false;
-    const float sx = __fsub_rn(x, r[0]), sy = __fsub_rn(y, r[1]);
-    const float c = r[3], s = r[4];
+    const float4 r0 = *reinterpret_cast<const float4*>(r), r1 = *reinterpret_cast<const float4*>(r + 4);
+    const float sx = __fsub_rn(x, r0.x), sy = __fsub_rn(y, r0.y);
+    const float c = r0.w, s = r1.x;
     const float lx = __fmaf_rn(sx, c, -__fmul_rn(sy, s));
     const float ly = __fmaf_rn(sy, c, __fmul_rn(sx, s));
-    return (r[5] > fabsf(lx)) & (r[6] > fabsf(ly));
+    return !(fabsf(__fsub_rn(z, r0.z)) > r1.w) & (r1.y > fabsf(lx)) & (r1.z > fabsf(ly));
 }
 
 // Footprint of a box in world coordinates: padded AABB of the region where the predicate can hold.
@@ -153,7 +185,7 @@ __device__ __forceinline__ Footprint footprint(const float* __restrict__ r) {
 // -- O(rows) instead of O(cells) work -- and the row's bits are set word-wise.  Everything is padded
 // outwards (strip and span), so the bitmap is a superset of the cells any inside point can map to.
 __device__ __forceinline__ void raster_fine_rows(const Footprint& f, float gx0, float gy0, float finv_x, float finv_y,
-                                                 unsigned int* __restrict__ s_bits, int row_phase = 0, int row_stride = 1) {
+                                                 unsigned int* __restrict__ s_bits, unsigned int zmask, int row_phase = 0, int row_stride = 1) {
     const int iy0 = max(0, min(PIB_FG - 1, (int)floorf((f.y0 - gy0) * finv_y)));
     const int iy1 = max(0, min(PIB_FG - 1, (int)floorf((f.y1 - gy0) * finv_y)));
     const float ch = 1.f / finv_y, cw = 1.f / finv_x;
@@ -189,16 +221,50 @@ __device__ __forceinline__ void raster_fine_rows(const Footprint& f, float gx0, 
         if (!(xmax >= xmin)) continue;
         const int ix0 = max(0, min(PIB_FG - 1, (int)floorf((f.cx + xmin - eps_x - gx0) * finv_x)));
         const int ix1 = max(0, min(PIB_FG - 1, (int)floorf((f.cx + xmax + eps_x - gx0) * finv_x)));
+#if GLENET_PIB_ZSLABS > 0
+        constexpr int CPW = 32 / PIB_ZS;                    // cells per 32-bit word: OR the box's z slabs into the row's span
+        const unsigned int zrep = zmask * (PIB_ZS == 16 ? 0x00010001u : 0x01010101u);
+        for (int w = ix0 / CPW; w <= ix1 / CPW; ++w) {
+            const int lo = max(ix0 - w * CPW, 0) * PIB_ZS, hi = (min(ix1 - w * CPW, CPW - 1) + 1) * PIB_ZS;
+            const unsigned int mask = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+            atomicOr(&s_bits[iy * (PIB_FG / CPW) + w], zrep & mask);
+        }
+#else
+#if GLENET_PIB_HYBRID
+        for (int w = ix0 >> 3; w <= (ix1 >> 3); ++w) {     // z slabs of the 4 x 4 blocks the span touches (two 16-bit blocks per word)
+            const unsigned int mask = (8 * w + 3 >= ix0 ? zmask : 0u) | (8 * w + 4 <= ix1 ? zmask << 16 : 0u);
+            atomicOr(&s_bits[PIB_FBITWORDS + (iy >> 2) * (PIB_FG / 8) + w], mask);
+        }
+#endif
+        (void)zmask;
         for (int w = ix0 >> 5; w <= (ix1 >> 5); ++w) {
             const int lo = max(ix0 - (w << 5), 0), hi = min(ix1 - (w << 5), 31);
             const unsigned int mask = (hi >= 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
             atomicOr(&s_bits[iy * (PIB_FG / 32) + w], mask);
         }
+#endif
     }
 }
 
+// z slabs a box can accept points in (16-bit mask), by the frame's slab mapping.  The predicate keeps a point when
+// |fl(z - cz)| <= tz; the slack (1e-3 + 1e-5 of the extent + 1e-6 of the magnitude) is far above the rounding of that
+// subtraction and of cz -+ tz.  tz < 0: the predicate rejects everything => no slab.
+__device__ __forceinline__ unsigned int z_slab_mask(float cz, float tz, float zinv, float zoff) {
+#if GLENET_PIB_ZSLABS
+    if (tz < 0.f) return 0u;
+    if (zinv == 0.f) return 1u;                                   // no z window in this frame: every point maps to slab 0
+    const float sl = 1e-3f + 1e-5f * tz + 1e-6f * fabsf(cz);
+    const int lo = max(0, min(PIB_ZS - 1, __float2int_rd(__fmaf_rn(cz - tz - sl, zinv, zoff))));
+    const int hi = max(0, min(PIB_ZS - 1, __float2int_rd(__fmaf_rn(cz + tz + sl, zinv, zoff))));
+    return ((2u << hi) - 1u) & ~((1u << lo) - 1u);
+#else
+    (void)cz; (void)zinv; (void)zoff;
+    return tz < 0.f ? 0u : 1u;
+#endif
+}
+
 template <int G, typename F>
-__device__ __forceinline__ void for_cells(const Footprint& f, float gx0, float gy0, float inv_x, float inv_y, F visit) {
+__device__ __forceinline__ void for_cells(const Footprint& f, float gx0, float gy0, float inv_x, float inv_y, int row_phase, int row_stride, F visit) {
     const int ix0 = max(0, min(G - 1, (int)floorf((f.x0 - gx0) * inv_x)));
     const int ix1 = max(0, min(G - 1, (int)floorf((f.x1 - gx0) * inv_x)));
     const int iy0 = max(0, min(G - 1, (int)floorf((f.y0 - gy0) * inv_y)));
@@ -208,7 +274,7 @@ __device__ __forceinline__ void for_cells(const Footprint& f, float gx0, float g
     const float slack = f.pad + 1e-3f * (cwx + cwy);
     const int nx = ix1 - ix0 + 1, ncell = nx * (iy1 - iy0 + 1);
     (void)ncell;
-    for (int iy = iy0; iy <= iy1; ++iy)
+    for (int iy = iy0 + row_phase; iy <= iy1; iy += row_stride)
     for (int ix = ix0; ix <= ix1; ++ix) {
         const float mx = gx0 + ((float)ix + 0.5f) * cwx - f.cx, my = gy0 + ((float)iy + 0.5f) * cwy - f.cy;
         const float lx = mx * f.c - my * f.s, ly = mx * f.s + my * f.c;
@@ -222,9 +288,8 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
     extern __shared__ __align__(16) unsigned char pib_build_smem[];   // PIB_BUILD_SMEM bytes
     unsigned long long* s_inl = reinterpret_cast<unsigned long long*>(pib_build_smem);   // [PIB_CELLS] first four candidates, 16 bits each
     unsigned int* cnt = reinterpret_cast<unsigned int*>(s_inl + PIB_CELLS);              // [PIB_CELLS] count, then fill cursor
-    unsigned int* s_start = cnt + PIB_CELLS;                                             // [PIB_CELLS] final count of the cell (frames with lists only)
+    unsigned int* s_start = cnt + PIB_CELLS;                                             // [PIB_CELLS] crowded cells: offset of their slice of list[]
     unsigned int* s_bits = s_start + PIB_CELLS;                                          // [PIB_FWORDS]
-    __shared__ unsigned int scan_tmp[PIB_BUILD_THREADS / 32];
     __shared__ float red[6][PIB_BUILD_THREADS / 32];
     __shared__ float s_bounds[6];
     __shared__ int s_bad, s_zwide, s_over;
@@ -234,7 +299,6 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the query grid be scheduled behind this one
     const float* boxes = boxes_all + (size_t)f * N * 7;
     float* rec = ws.rec + (size_t)f * N * 8;
-    unsigned int* start = ws.start + (size_t)f * (PIB_CELLS + 1);
     unsigned int* list = ws.list + (size_t)f * ws.cap;
     unsigned int* bits = ws.bits + (size_t)f * PIB_FWORDS;
 
@@ -296,6 +360,13 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
         float zc = 0.5f * zlo + 0.5f * zhi;
         float zh = (0.5f * zhi - 0.5f * zlo) * 1.00001f + 1e-3f + 1e-6f * fmaxf(fabsf(zlo), fabsf(zhi));
         if (s_zwide || !(zhi >= zlo) || !(zh <= FLT_MAX) || !(fabsf(zc) <= FLT_MAX)) { zc = 0.f; zh = __int_as_float(0x7f800000); }
+#if GLENET_PIB_ZSLABS
+        // slab = floor(fma(z, zinv, zoff)): PIB_ZS slabs over [zc - zh, zc + zh]; the SAME monotone mapping gives every box its
+        // slab range (z_slab_mask), so a point the predicate can accept always finds its slab set.  No window: all in slab 0.
+        float zinv = ((float)PIB_ZS - 0.01f) / (2.f * zh), zoff = -(zc - zh) * zinv;
+        if (!(zh <= FLT_MAX) || !(zinv <= FLT_MAX) || !(fabsf(zoff) <= FLT_MAX)) { zinv = 0.f; zoff = 0.f; }
+        zc = zinv; zh = zoff;
+#endif
         s_bounds[4] = zc; s_bounds[5] = zh;
     }
     __syncthreads();   // also publishes the records written above to the whole CTA
@@ -325,69 +396,58 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
                 const int part = it / N, k = it - part * N;
                 const Footprint fp = footprint(rec + (size_t)k * 8);
                 if (fp.never) continue;
-                if (!(GLENET_PIB_DBG & 1) && pass == 0 && (parts == 1 || part > 0))
-                    raster_fine_rows(fp, bx0, by0, finv_x, finv_y, s_bits, parts == 1 ? 0 : part - 1, parts == 1 ? 1 : parts - 1);
+#if GLENET_PIB_BUILD_SPLIT
+                // the `parts` threads of a box take interleaved rows of BOTH grids (pass 1, the rare list fill, is one thread per box)
+                const int row_phase = pass == 0 ? part : 0, row_stride = pass == 0 ? parts : 1;
+                if (!(GLENET_PIB_DBG & 1) && pass == 0) {
+                    const unsigned int zmask = z_slab_mask(rec[(size_t)k * 8 + 2], rec[(size_t)k * 8 + 7], s_bounds[4], s_bounds[5]);
+                    if (zmask) raster_fine_rows(fp, bx0, by0, finv_x, finv_y, s_bits, zmask, row_phase, row_stride);
+                }
+                if (GLENET_PIB_DBG & 2) continue;
+#else
+                const int row_phase = 0, row_stride = 1;
+                if (!(GLENET_PIB_DBG & 1) && pass == 0 && (parts == 1 || part > 0)) {
+                    const unsigned int zmask = z_slab_mask(rec[(size_t)k * 8 + 2], rec[(size_t)k * 8 + 7], s_bounds[4], s_bounds[5]);
+                    if (zmask) raster_fine_rows(fp, bx0, by0, finv_x, finv_y, s_bits, zmask, parts == 1 ? 0 : part - 1, parts == 1 ? 1 : parts - 1);
+                }
                 if (part > 0 || (GLENET_PIB_DBG & 2)) continue;
-                for_cells<PIB_G>(fp, bx0, by0, inv_x, inv_y, [&](int cell) {
-                    const unsigned int pos = atomicAdd(&cnt[cell], 1u);
-                    if (pass == 0) {     // the first four candidates of a cell go inline; a fifth makes the frame need lists
+#endif
+                for_cells<PIB_G>(fp, bx0, by0, inv_x, inv_y, row_phase, row_stride, [&](int cell) {
+                    if (pass == 0) {     // the first four candidates of a cell go inline; a fifth makes it a crowded cell
+                        const unsigned int pos = atomicAdd(&cnt[cell], 1u);
                         if (pos < 4u) reinterpret_cast<unsigned short*>(s_inl)[cell * 4 + pos] = (unsigned short)k;
                         else s_over = 1;
-                    } else {
-                        list[pos] = (unsigned int)k;
+                    } else if (cnt[cell] > 4u) {
+                        const unsigned int pos = atomicAdd(&reinterpret_cast<unsigned int*>(s_inl)[2 * cell], 1u);
+                        list[s_start[cell] + pos] = (unsigned int)k;
                     }
                 });
             }
             __syncthreads();
-            if (pass == 0 && !s_over) break;   // uniform: every cell is complete inline -- no scan, no lists, no second pass
-            if (pass == 0) {
-                // exclusive scan of cnt[PIB_CELLS] -> start[], cnt becomes the fill cursor (warp shuffles, two barriers)
-                constexpr int PER = PIB_CELLS / PIB_BUILD_THREADS;
-                unsigned int local[PER], sum = 0;
-#pragma unroll
-                for (int i = 0; i < PER; ++i) { local[i] = cnt[tid * PER + i]; sum += local[i]; }
-                unsigned int incl = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
+            if (pass == 1 || !s_over || (GLENET_PIB_DBG & 4)) break;   // uniform: usually every cell is complete inline -- no lists, no second pass
+            // Crowded cells (a fifth candidate arrived): each gets a contiguous slice of list[] -- reserved in any order with one
+            // atomicAdd -- and the second pass re-visits the boxes' cells and fills only those slices.  The cell word then holds
+            // (slice offset, count, 0xfffe) instead of four inline ids, so the query needs no separate index.
+            if (tid == 0) s_total = 0;
+            __syncthreads();
+            for (int c = tid; c < PIB_CELLS; c += PIB_BUILD_THREADS) {
+                if (cnt[c] > 4u) {
+                    s_start[c] = atomicAdd(&s_total, cnt[c]);
+                    reinterpret_cast<unsigned int*>(s_inl)[2 * c] = 0u;      // fill cursor (the inline ids are no longer needed)
                 }
-                if (lane == 31) scan_tmp[warp] = incl;
-                __syncthreads();
-                if (warp == 0) {
-                    constexpr int NW = PIB_BUILD_THREADS / 32;
-                    unsigned int w = lane < NW ? scan_tmp[lane] : 0u;
-#pragma unroll
-                    for (int o = 1; o < NW; o <<= 1) {
-                        const unsigned int t = __shfl_up_sync(0xffffffffu, w, o);
-                        if (lane >= o) w += t;
-                    }
-                    if (lane < NW) scan_tmp[lane] = w;
-                    if (lane == NW - 1) s_total = w;
-                }
-                __syncthreads();
-                unsigned int run = incl - sum + (warp ? scan_tmp[warp - 1] : 0u);
-#pragma unroll
-                for (int i = 0; i < PER; ++i) {
-                    start[tid * PER + i] = run;
-                    s_start[tid * PER + i] = local[i];   // the cell's count (the pack below flags cells with more than four)
-                    cnt[tid * PER + i] = run;
-                    run += local[i];
-                }
-                __syncthreads();
-                total = s_total;
-                if (tid == 0) start[PIB_CELLS] = total;
-                if (total > ws.cap) { exhaustive = true; break; }   // uniform
             }
+            __syncthreads();
+            total = s_total;
+            if (total > ws.cap) { exhaustive = true; break; }   // uniform
         }
         for (int i = tid; i < PIB_FWORDS; i += PIB_BUILD_THREADS) bits[i] = s_bits[i];
         if (!exhaustive && !(GLENET_PIB_DBG & 8)) {
-            // packed coarse cells: up to four candidates inline, 16 bits each (0xffff = none); a cell with more gets
-            // 0xfffe in its last slot and is resolved through start[] / list[]
+            // packed coarse cells: up to four candidates inline, 16 bits each (0xffff = none); a crowded cell holds
+            // {offset into list[] : 32, count : 16, 0xfffe : 16}
             unsigned long long* cells = ws.cells + (size_t)f * PIB_CELLS;
             for (int c = tid; c < PIB_CELLS; c += PIB_BUILD_THREADS) {
                 unsigned long long v = s_inl[c];
-                if (s_over && s_start[c] > 4u) v = (v & 0x0000ffffffffffffull) | (0xfffeull << 48);
+                if (s_over && cnt[c] > 4u) v = (unsigned long long)s_start[c] | ((unsigned long long)cnt[c] << 32) | (0xfffeull << 48);
                 cells[c] = v;
             }
         }
@@ -433,20 +493,44 @@ __device__ __forceinline__ void load_pts4(const float* __restrict__ pts, int p0,
 //   3. the ~9 % of points that stay hot go to the warp's private queue (ballot prefix, no atomics), and the
 //      warp drains it 32 entries at a time: coarse cell -> up to four inline candidates (a list through L2
 //      only for crowded cells) -> exact predicate -> minimum index over the provisional -1.
+template <bool REC_SMEM>   // box records staged in shared memory (N <= PIB_SMEM_BOXES) or read through L1 / L2
 __global__ void __launch_bounds__(PIB_THREADS, GLENET_PIB_CTAS)
 pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace ws, int* __restrict__ out_all,
                  int chunks_per_frame, int total_chunks) {
     extern __shared__ __align__(16) unsigned char pib_smem[];
+#if GLENET_PIB_PREFILL
+    // Provisional -1 for this CTA's whole range, written while the build kernel (which never touches `out`) still runs:
+    // that is HBM time nobody else is using, and the streaming loop below then only stores the hits.  Everything older
+    // than the build kernel has completed (only this grid is a programmatic dependent), and every later result store
+    // to these addresses comes from this CTA after at least one __syncthreads.
+    {
+        const int cb = (int)((long)blockIdx.x * total_chunks / gridDim.x), ce = (int)((long)(blockIdx.x + 1) * total_chunks / gridDim.x);
+        for (int c = cb; c < ce;) {
+            const int f = c / chunks_per_frame, chunk = c - f * chunks_per_frame;
+            const int chunk_last = min(ce - f * chunks_per_frame, chunks_per_frame);
+            c = f * chunks_per_frame + chunk_last;
+            int* o = out_all + (size_t)f * M;
+            const int pb = chunk * PIB_CHUNK, pe = (int)min((long)M, (long)chunk_last * PIB_CHUNK);
+            const int head = min(pe, pb + (int)((4 - (((uintptr_t)(o + pb) >> 2) & 3)) & 3));   // first 16-byte aligned element
+            if ((int)threadIdx.x < head - pb) o[pb + threadIdx.x] = -1;
+            const int nv = (pe - head) >> 2;
+            int4* o4 = reinterpret_cast<int4*>(o + head);
+            for (int i = threadIdx.x; i < nv; i += PIB_THREADS) o4[i] = make_int4(-1, -1, -1, -1);
+            const int tail = head + (nv << 2);
+            if ((int)threadIdx.x < pe - tail) o[tail + threadIdx.x] = -1;
+        }
+    }
+#endif
     asm volatile("griddepcontrol.wait;" ::: "memory");   // the build kernel (previous in the stream) has completed and flushed
     float4* s_q = reinterpret_cast<float4*>(pib_smem);                                        // [warps][PIB_WQ] {x, y, z, index}
     unsigned long long* s_cells = reinterpret_cast<unsigned long long*>(s_q + (PIB_THREADS / 32) * PIB_WQ); // [PIB_CELLS] four ids
     unsigned int* s_bits = reinterpret_cast<unsigned int*>(s_cells + PIB_CELLS);              // [PIB_FWORDS]
-    float* s_rec = reinterpret_cast<float*>(s_bits + PIB_FWORDS);                             // [min(N, PIB_SMEM_BOXES) * 8]
+    float* s_rec = reinterpret_cast<float*>(s_bits + PIB_FWORDS);                             // [N * PIB_REC_STRIDE] (REC_SMEM)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float4* wq = s_q + warp * PIB_WQ;
     const int c_begin = (int)((long)blockIdx.x * total_chunks / gridDim.x);
     const int c_end = (int)((long)(blockIdx.x + 1) * total_chunks / gridDim.x);
-    const bool rec_in_smem = N <= PIB_SMEM_BOXES;
+    constexpr int RS = REC_SMEM ? PIB_REC_STRIDE : 8;       // floats from one record to the next
     int cur_frame = -1;
     PibFrame h;
     h.list_len = -1; h.exhaustive = 0; h.gx0 = h.gy0 = h.inv_x = h.inv_y = h.finv_x = h.finv_y = h.zc = h.zh = h.foff_x = h.foff_y = 0.f;
@@ -465,7 +549,7 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
         const float* pts = pts_all + (size_t)f * M * 3;
         int* out = out_all + (size_t)f * M;
         const float* rec_g = ws.rec + (size_t)f * N * 8;
-        const float* rec = rec_in_smem ? s_rec : rec_g;
+        const float* rec = REC_SMEM ? s_rec : rec_g;          // resolved at compile time: LDS or LDG, never a generic load
         const int p_begin = chunk * PIB_CHUNK;
         const int p_end = (int)min((long)M, (long)chunk_last * PIB_CHUNK);
         const bool vec = ((((uintptr_t)pts) & 15) == 0) && ((((uintptr_t)out) & 15) == 0);
@@ -473,10 +557,10 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
             __syncthreads();                                  // everyone is done with the previous frame's tables
             h = ws.frames[f];
             if (h.list_len >= 0) {
-                if (rec_in_smem) {
+                if (REC_SMEM) {
                     const float4* src = reinterpret_cast<const float4*>(rec_g);
                     float4* dst = reinterpret_cast<float4*>(s_rec);
-                    for (int i = tid; i < N * 2; i += PIB_THREADS) dst[i] = __ldg(src + i);
+                    for (int i = tid; i < N * 2; i += PIB_THREADS) dst[(i >> 1) * (PIB_REC_STRIDE / 4) + (i & 1)] = __ldg(src + i);
                 }
                 if (!h.exhaustive) {
                     const uint4* b = reinterpret_cast<const uint4*>(ws.bits + (size_t)f * PIB_FWORDS);
@@ -497,7 +581,7 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
                 const float x = pts[(size_t)p * 3], y = pts[(size_t)p * 3 + 1], z = pts[(size_t)p * 3 + 2];
                 int res = -1;
                 for (int k = 0; k < N; ++k) {
-                    if (pt_in_box_gpu(x, y, z, rec + (size_t)k * 8)) { res = k; break; }
+                    if (pt_in_box_gpu(x, y, z, rec + (size_t)k * RS)) { res = k; break; }
                 }
                 out[p] = res;
             }
@@ -515,9 +599,8 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
             const unsigned int lo = (unsigned int)cell, hi = (unsigned int)(cell >> 32);
             const int k0 = (int)(lo & 0xffffu), k1 = (int)(lo >> 16), k2 = (int)(hi & 0xffffu), k3 = (int)(hi >> 16);
             int res = 0x7fffffff;
-            if (k3 == 0xfffe) {          // > 4 candidates (rare): walk the whole list; pointers rebuilt here
-                const unsigned int* st = ws.start + (size_t)f * (PIB_CELLS + 1) + ci;
-                const unsigned int s0 = __ldg(st), n = __ldg(st + 1) - s0;
+            if (k3 == 0xfffe) {          // crowded cell (rare): {offset, count} of its slice of the frame's list; pointer rebuilt here
+                const unsigned int s0 = lo, n = hi & 0xffffu;
                 const unsigned int* list = ws.list + (size_t)f * ws.cap;
                 for (unsigned int i = 0; i < n; i += 4) {   // four independent list loads per round trip to L2
                     int kk[4];
@@ -525,13 +608,13 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
                     for (int u = 0; u < 4; ++u) kk[u] = (i + u < n) ? (int)__ldg(list + s0 + i + u) : 0x7fffffff;
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (kk[u] < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)kk[u] * 8)) res = kk[u];
+                        if (kk[u] < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)kk[u] * RS)) res = kk[u];
                 }
             } else {                     // candidates are in no particular order: keep the minimum
-                if (k0 != 0xffff && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k0 * 8)) res = k0;
-                if (k1 != 0xffff && k1 < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k1 * 8)) res = k1;
-                if (k2 != 0xffff && k2 < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k2 * 8)) res = k2;
-                if (k3 != 0xffff && k3 < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k3 * 8)) res = k3;
+                if (k0 != 0xffff && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k0 * RS)) res = k0;
+                if (k1 != 0xffff && k1 < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k1 * RS)) res = k1;
+                if (k2 != 0xffff && k2 < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k2 * RS)) res = k2;
+                if (k3 != 0xffff && k3 < res && pt_in_box_gpu(e.x, e.y, e.z, rec + (size_t)k3 * RS)) res = k3;
             }
             if (res != 0x7fffffff) out[__float_as_int(e.w)] = res;
         };
@@ -549,6 +632,24 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int ix = __float2int_rd(__fmaf_rn(cur.x[i], finv_x, foff_x)), iy = __float2int_rd(__fmaf_rn(cur.y[i], finv_y, foff_y));
+#if GLENET_PIB_ZSLABS > 0
+                // cell = z-slab bits; slabs outside [0, PIB_ZS) shift the bits out (PTX shr clamps the amount: negative slab
+                // numbers are huge unsigned amounts).  NaN z -> slab 0; corrected below.
+                const int zs = __float2int_rd(__fmaf_rn(cur.z[i], zc, zh));
+                const int ci = ((iy << 7) + ix) & (PIB_FG * PIB_FG - 1);
+                const unsigned int cell = PIB_ZS == 16 ? (unsigned int)reinterpret_cast<const unsigned short*>(s_bits)[ci]
+                                                       : (unsigned int)reinterpret_cast<const unsigned char*>(s_bits)[ci];
+                unsigned int bit;
+                asm("shr.u32 %0, %1, %2;" : "=r"(bit) : "r"(cell), "r"(zs));
+                hot |= ((unsigned int)(ix | iy) < (unsigned int)PIB_FG) ? ((bit & 1u) << i) : 0u;
+#elif GLENET_PIB_HYBRID
+                const int zs = __float2int_rd(__fmaf_rn(cur.z[i], zc, zh));
+                const unsigned int word = s_bits[((iy << 3) + (ix >> 5)) & (PIB_FBITWORDS - 1)];
+                const unsigned int cell = reinterpret_cast<const unsigned short*>(s_bits + PIB_FBITWORDS)[(((iy >> 2) << 6) + (ix >> 2)) & 4095];
+                unsigned int bit;
+                asm("shr.u32 %0, %1, %2;" : "=r"(bit) : "r"(cell), "r"(zs));
+                hot |= ((unsigned int)(ix | iy) < (unsigned int)PIB_FG) ? ((bit & (word >> (ix & 31)) & 1u) << i) : 0u;
+#else
                 const unsigned int word = s_bits[((iy << 3) + (ix >> 5)) & (PIB_FWORDS - 1)];
 #if GLENET_PIB_ZWINDOW
                 // also cold: points above / below every box (NaN z is not culled here; the exact predicate rejects it)
@@ -557,13 +658,40 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
                 const bool in_grid = (unsigned int)(ix | iy) < (unsigned int)PIB_FG;
 #endif
                 hot |= in_grid ? (((word >> (ix & 31)) & 1u) << i) : 0u;
+#endif
             }
+#if GLENET_PIB_ZSLABS
+            // A NaN z passes the reference's z test (`|z - cz| > dz/2` is false), so such a point belongs to the first box whose
+            // footprint holds it, whatever the slab: one sum test per lane, the fix-up itself practically never runs.
+            const float zsum = (cur.z[0] + cur.z[1]) + (cur.z[2] + cur.z[3]);
+            if (zsum != zsum) {
+#pragma unroll 1
+                for (int i = 0; i < 4; ++i) {
+                    const float zi = i == 0 ? cur.z[0] : i == 1 ? cur.z[1] : i == 2 ? cur.z[2] : cur.z[3];
+                    if (zi == zi) continue;
+                    const float xi = i == 0 ? cur.x[0] : i == 1 ? cur.x[1] : i == 2 ? cur.x[2] : cur.x[3];
+                    const float yi = i == 0 ? cur.y[0] : i == 1 ? cur.y[1] : i == 2 ? cur.y[2] : cur.y[3];
+                    const int ix = __float2int_rd(__fmaf_rn(xi, finv_x, foff_x)), iy = __float2int_rd(__fmaf_rn(yi, finv_y, foff_y));
+                    if ((unsigned int)(ix | iy) >= (unsigned int)PIB_FG) continue;
+#if GLENET_PIB_HYBRID
+                    const unsigned int any = (s_bits[((iy << 3) + (ix >> 5)) & (PIB_FBITWORDS - 1)] >> (ix & 31)) & 1u;
+#else
+                    const int ci = (iy << 7) + ix;
+                    const unsigned int any = PIB_ZS == 16 ? (unsigned int)reinterpret_cast<const unsigned short*>(s_bits)[ci]
+                                                          : (unsigned int)reinterpret_cast<const unsigned char*>(s_bits)[ci];
+#endif
+                    if (any) hot |= 1u << i;
+                }
+            }
+#endif
             hot &= (1u << nvalid) - 1u;                        // never queue a point beyond the chunk
+#if !GLENET_PIB_PREFILL
             if (vec && nvalid == 4) *reinterpret_cast<int4*>(out + p0) = make_int4(-1, -1, -1, -1);
             else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) if (i < nvalid) out[p0 + i] = -1;
             }
+#endif
             if (__any_sync(0xffffffffu, hot != 0)) {
                 // append the hot points: one ballot per point slot gives every lane its queue position (the order of the
                 // queue is irrelevant) -- cheaper than a 5-step prefix sum followed by per-lane sequential writes
@@ -593,10 +721,12 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
         auto fetch = [&](Pts4& dst, const int j) {
             load_pts4(pts, p_begin + (j * (PIB_THREADS / 32) + warp) * PIB_WBATCH + lane * 4, p_end, vec, dst);
         };
-        // register prefetch two batches ahead: one batch of cold points is shorter than a DRAM round trip
+        // register prefetch GLENET_PIB_PF batches ahead (2: one batch of cold points is shorter than a DRAM round trip)
         Pts4 cur, nxt;
         fetch(cur, 0);
+#if GLENET_PIB_PF >= 2
         if (NB > 1) fetch(nxt, 1);
+#endif
 #if GLENET_PIB_L2PF
         // this lane's line of the batch GLENET_PIB_L2PF ahead; a batch is 1536 bytes = at most 13 lines, and the stride
         // from batch to batch (12288 bytes) keeps the alignment, so the pointer simply advances
@@ -610,8 +740,12 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
 #endif
 #pragma unroll 1
         for (int j = 0; j < NB; ++j) {
+#if GLENET_PIB_PF >= 2
             Pts4 nxt2;
             if (j + 2 < NB) fetch(nxt2, j + 2);
+#elif GLENET_PIB_PF == 1
+            if (j + 1 < NB) fetch(nxt, j + 1);
+#endif
 #if GLENET_PIB_L2PF
             // The register rotation below (cur = nxt; nxt = nxt2) has to wait for nxt2, so the register prefetch is
             // effectively ONE batch deep.  An L2 prefetch further ahead turns that wait into an L2 hit.
@@ -619,8 +753,14 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
             pf_line += (pf_line < pf_end) ? (size_t)PIB_THREADS * 4 * 12 : 0;
 #endif
             batch(cur, j);
+#if GLENET_PIB_PF >= 2
             cur = nxt;
             nxt = nxt2;
+#elif GLENET_PIB_PF == 1
+            cur = nxt;
+#else
+            if (j + 1 < NB) fetch(cur, j + 1);
+#endif
         }
         if (qn) {                                              // leftovers of the run
             if (lane < qn) resolve(wq[lane]);
@@ -631,7 +771,7 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
 
 // Small problems (N <= PIB_DIRECT_BOXES, few points): one launch, no grid.  Every CTA rebuilds the
 // N box records in shared memory and runs the reference's ascending loop with early exit.
-__global__ void __launch_bounds__(PIB_THREADS)
+__global__ void __launch_bounds__(PIB_ROUND / 4)
 pib_direct_kernel(const float* __restrict__ boxes_all, const float* __restrict__ pts_all, int N, int M,
                   int* __restrict__ out_all, int chunks_per_frame) {
     __shared__ __align__(16) float s_rec[PIB_DIRECT_BOXES * 8];
@@ -732,7 +872,7 @@ int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int 
     if ((uintptr_t)ws & 15) return fail(GLENET_EALIGN, "%s: workspace must be 16-byte aligned", what);
     if (N <= PIB_DIRECT_BOXES && (long)B * M <= PIB_DIRECT_MAX_POINTS) {
         const int chunks = (M + PIB_DIRECT_PTS - 1) / PIB_DIRECT_PTS;
-        pib_direct_kernel<<<(unsigned)(chunks * B), PIB_THREADS, 0, st>>>(boxes, pts, N, M, out, chunks);
+        pib_direct_kernel<<<(unsigned)(chunks * B), PIB_ROUND / 4, 0, st>>>(boxes, pts, N, M, out, chunks);
         return check_launch(what);
     }
     PibWorkspace w = pib_layout(ws, B, N);
@@ -754,9 +894,12 @@ int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int 
     const long total = (long)chunks * B;
     if (total > 0x7fffffffL) return fail(GLENET_EINVAL, "%s: too many chunks", what);
     const size_t smem_fixed = sizeof(float4) * (PIB_THREADS / 32) * PIB_WQ + sizeof(unsigned long long) * PIB_CELLS + sizeof(unsigned int) * PIB_FWORDS;
-    const size_t smem = smem_fixed + sizeof(float) * 8 * (size_t)(N <= PIB_SMEM_BOXES ? N : 0);
+    const bool rec_smem = N <= PIB_SMEM_BOXES;
+    const size_t smem = smem_fixed + sizeof(float) * PIB_REC_STRIDE * (size_t)(rec_smem ? N : 0);
     if (need_attr) {
-        rc = set_smem(pib_query_kernel, smem_fixed + sizeof(float) * 8 * PIB_SMEM_BOXES, what);
+        rc = set_smem(pib_query_kernel<true>, smem_fixed + sizeof(float) * PIB_REC_STRIDE * PIB_SMEM_BOXES, what);
+        if (rc) return rc;
+        rc = set_smem(pib_query_kernel<false>, smem_fixed, what);
         if (rc) return rc;
         if (dev >= 0 && dev < GLENET_MAX_DEVICES) attr_done[dev].store(true, std::memory_order_release);
     }
@@ -771,7 +914,8 @@ int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     const int total_i = (int)total;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, pib_query_kernel, pts, N, M, w, out, chunks, total_i);
+    cudaError_t le = rec_smem ? cudaLaunchKernelEx(&cfg, pib_query_kernel<true>, pts, N, M, w, out, chunks, total_i)
+                              : cudaLaunchKernelEx(&cfg, pib_query_kernel<false>, pts, N, M, w, out, chunks, total_i);
     if (le != cudaSuccess) {
         snprintf(last_error_buf(), 512, "%s: launch failed: %s", what, cudaGetErrorString(le));
         return -(int)le;
@@ -792,7 +936,7 @@ int glenet_points_in_boxes_cpu_dialect(const float* boxes, const float* trig, in
     return check_launch(what);
 }
 
-int glenet_abi_version(void) { return 11; }
+int glenet_abi_version(void) { return 12; }
 const char* glenet_last_error(void) { return last_error_buf(); }
 
 }  // extern "C"

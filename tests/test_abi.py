@@ -32,14 +32,15 @@ def test_library_builds_loads_and_exports_everything():
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"
     # and the binding table covers exactly the header
     assert sorted(glenet_b200.EXPORTS) == declared_symbols()
-    assert lib.glenet_abi_version() == 11
+    assert lib.glenet_abi_version() == 12
     assert lib.glenet_nms_workspace_bytes(1, 4096) == 4096 * 64 * 8 + 16 + 32 * 4096 * 8   # mask + deferred-clip list
     assert lib.glenet_points_in_boxes_workspace_bytes(2, 200) > 2 * 200 * 32
-    # workspace layout of csrc/pib.cu (pib_layout): per frame a 48-byte header, 8 floats per box, 4097 list starts,
-    # 32 N + 8192 list slots, a 256 x 256 bit occupancy map and 4096 packed 8-byte cells; every section 16-byte aligned
+    # workspace layout of csrc/pib.cu (pib_layout): per frame a 48-byte header, 8 floats per box, 32 N + 8192 list slots
+    # (slices of crowded coarse cells), a 128 x 128 fine map of 16 z-slab bits and 4096 packed 8-byte coarse cells; every
+    # section 16-byte aligned
     up = lambda v: (v + 15) // 16 * 16
     for b, n in ((1, 1), (2, 200), (128, 200), (3, 77), (5, 4096)):
-        want = up(b * 48) + up(b * n * 32) + up(b * 4097 * 4) + up(b * (32 * n + 8192) * 4) + up(b * 2048 * 4) + up(b * 4096 * 8)
+        want = up(b * 48) + up(b * n * 32) + up(b * (32 * n + 8192) * 4) + up(b * 128 * 128 * 2) + up(b * 4096 * 8)
         assert lib.glenet_points_in_boxes_workspace_bytes(b, n) == want, (b, n)
     assert lib.glenet_points_in_boxes_workspace_bytes(0, 5) == 16 and lib.glenet_points_in_boxes_workspace_bytes(4, 0) == 16
 
