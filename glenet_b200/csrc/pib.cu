@@ -305,6 +305,10 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
     for (int i = tid; i < PIB_CELLS; i += PIB_BUILD_THREADS) { cnt[i] = 0; s_inl[i] = ~0ull; }
     for (int i = tid; i < PIB_FWORDS; i += PIB_BUILD_THREADS) s_bits[i] = 0;
     if (tid == 0) { s_bad = 0; s_zwide = 0; s_over = 0; }
+    // The build is launched as a programmatic dependent of whatever precedes it in the stream: the launch and the clearing of
+    // 100 KB of shared memory overlap that kernel's tail.  Nothing global is touched before this wait (the previous call's
+    // query may still be reading the workspace, a producer may still be writing the boxes).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
 
     // pass 1: records + frame bounds
@@ -391,14 +395,14 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
         // coarse cells, the others rasterise interleaved fine rows -- laid out so that a warp holds one part only.
         const int parts = N * 4 <= PIB_BUILD_THREADS ? 4 : (N * 2 <= PIB_BUILD_THREADS ? 2 : 1);
         for (int pass = 0; pass < 2; ++pass) {
-            const int items = pass == 0 ? N * parts : N;
+            const int items = N * parts;
             for (int it = tid; it < items; it += PIB_BUILD_THREADS) {
                 const int part = it / N, k = it - part * N;
                 const Footprint fp = footprint(rec + (size_t)k * 8);
                 if (fp.never) continue;
 #if GLENET_PIB_BUILD_SPLIT
-                // the `parts` threads of a box take interleaved rows of BOTH grids (pass 1, the rare list fill, is one thread per box)
-                const int row_phase = pass == 0 ? part : 0, row_stride = pass == 0 ? parts : 1;
+                // the `parts` threads of a box take interleaved rows of BOTH grids, in both passes
+                const int row_phase = part, row_stride = parts;
                 if (!(GLENET_PIB_DBG & 1) && pass == 0) {
                     const unsigned int zmask = z_slab_mask(rec[(size_t)k * 8 + 2], rec[(size_t)k * 8 + 7], s_bounds[4], s_bounds[5]);
                     if (zmask) raster_fine_rows(fp, bx0, by0, finv_x, finv_y, s_bits, zmask, row_phase, row_stride);
@@ -522,6 +526,7 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
     }
 #endif
     asm volatile("griddepcontrol.wait;" ::: "memory");   // the build kernel (previous in the stream) has completed and flushed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a programmatic dependent (e.g. the next call's build) may be scheduled as SMs free up
     float4* s_q = reinterpret_cast<float4*>(pib_smem);                                        // [warps][PIB_WQ] {x, y, z, index}
     unsigned long long* s_cells = reinterpret_cast<unsigned long long*>(s_q + (PIB_THREADS / 32) * PIB_WQ); // [PIB_CELLS] four ids
     unsigned int* s_bits = reinterpret_cast<unsigned int*>(s_cells + PIB_CELLS);              // [PIB_FWORDS]
@@ -886,7 +891,19 @@ int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int 
         rc = set_smem(pib_build_kernel, PIB_BUILD_SMEM, what);
         if (rc) return rc;
     }
-    pib_build_kernel<<<B, PIB_BUILD_THREADS, PIB_BUILD_SMEM, st>>>(boxes, N, w);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    {
+        cudaLaunchConfig_t bcfg = {};
+        bcfg.gridDim = dim3((unsigned)B); bcfg.blockDim = dim3(PIB_BUILD_THREADS); bcfg.dynamicSmemBytes = PIB_BUILD_SMEM; bcfg.stream = st;
+        bcfg.attrs = attr; bcfg.numAttrs = 1;
+        cudaError_t be = cudaLaunchKernelEx(&bcfg, pib_build_kernel, boxes, N, w);
+        if (be != cudaSuccess) {
+            snprintf(last_error_buf(), 512, "%s: launch failed: %s", what, cudaGetErrorString(be));
+            return -(int)be;
+        }
+    }
     rc = check_launch(what);
     if (rc) return rc;
     if (GLENET_PIB_DBG & 16) return GLENET_OK;
@@ -909,9 +926,6 @@ int glenet_points_in_boxes_gpu(const float* boxes, const float* pts, int B, int 
     // (griddepcontrol.wait) before it touches the workspace -- hides the launch gap between the two kernels
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PIB_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     const int total_i = (int)total;
     cudaError_t le = rec_smem ? cudaLaunchKernelEx(&cfg, pib_query_kernel<true>, pts, N, M, w, out, chunks, total_i)

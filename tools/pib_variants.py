@@ -15,6 +15,8 @@ boxes = boxes_h.to(dev)
 B2, M2, N2 = 3, 123457, 77
 boxes2 = torch.stack([synth.waymo_boxes(N2, 7 + f) for f in range(B2)]).to(dev)
 pts2 = torch.stack([synth.points(M2, boxes2[f].cpu(), synth.WAYMO_RANGE, 0.2, seed=11 + f) for f in range(B2)]).to(dev).contiguous()
+# third problem: the reference's own call, one frame (launch / latency bound)
+boxes3, pts3 = boxes[:1].contiguous(), pts[:1].contiguous()
 ref = {}
 for path in sorted(glob.glob(os.path.join(ROOT, "glenet_b200/lib/variants/libpib_*.so"))):
     lib = ctypes.CDLL(path)
@@ -24,7 +26,7 @@ for path in sorted(glob.glob(os.path.join(ROOT, "glenet_b200/lib/variants/libpib
     fn.restype = ctypes.c_int
     fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     line = f"{os.path.basename(path):32s}"
-    for tag, (bx, pt, b, n, m) in {"cfg2": (boxes, pts, B, N, M), "ragged": (boxes2, pts2, B2, N2, M2)}.items():
+    for tag, (bx, pt, b, n, m) in {"cfg2": (boxes, pts, B, N, M), "ragged": (boxes2, pts2, B2, N2, M2), "frame1": (boxes3, pts3, 1, N, M)}.items():
         nbytes = wsb(b, n)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         out = torch.full((b, m), -7, dtype=torch.int32, device=dev)
