@@ -10,14 +10,14 @@
 //
 //   build kernel (1 CTA / frame): per-box record {cx, cy, cz, cos(-h), sin(-h), tx, ty, tz}
 //       with the reference's FP64 comparisons folded into directed-rounded FP32 thresholds
-//       (exactly equivalent, see box_thresholds()); the z window of all boxes together; a fine
-//       256 x 256 occupancy bitmap of the (padded) footprints; and a coarse G x G grid whose
-//       cells hold up to four candidate boxes inline (CSR lists only for cells with more).
-//   query kernel: points stream through coalesced; a point outside the z window or in an
-//       empty bitmap cell is background at once; the others look up their coarse cell in
-//       shared memory and run the exact reference predicate only against that cell's
-//       candidates, keeping the minimum index (= first hit of the reference's ascending
-//       loop with `break`).
+//       (exactly equivalent, see box_thresholds()); a fine map of 128 x 128 cells x 16 z slabs
+//       (one bit per cell and slab of the frame's z window that a padded footprint touches); and
+//       a coarse G x G grid whose cells hold up to four candidate boxes inline (a crowded cell
+//       holds the offset and length of its slice of a candidate list instead).
+//   query kernel: points stream through coalesced; a point whose (cell, z slab) bit is clear is
+//       background at once; the others look up their coarse cell in shared memory and run the
+//       exact reference predicate only against that cell's candidates, keeping the minimum
+//       index (= first hit of the reference's ascending loop with `break`).
 // Frames whose boxes cannot be binned (non-finite extents, list overflow) fall back, on the
 // device and per frame, to the exhaustive loop with the same predicate -- never to the host.
 #include "common.cuh"
@@ -30,22 +30,16 @@ namespace glenet {
 
 constexpr int PIB_G = 64;                       // coarse grid (CSR candidate lists), cells per axis
 constexpr int PIB_CELLS = PIB_G * PIB_G;
-#ifndef GLENET_PIB_ZSLABS        // fine map: 16 / 8 = 128 x 128 cells x that many z-slab bits (a point is hot only if a box covers its
-#define GLENET_PIB_ZSLABS 16     // cell AND its z slab); -1 = 256 x 256 x 1 bit AND 64 x 64 x 16 z-slab bits; 0 = 256 x 256 x 1 bit + one z window
+#ifndef GLENET_PIB_ZSLABS        // 16: fine map = 128 x 128 cells x 16 z-slab bits (a point is hot only if a box covers its cell AND its
+#define GLENET_PIB_ZSLABS 16     // z slab); 0: 256 x 256 cells x 1 bit + one z window for the whole frame (the round-1 layout, kept for A/B timing)
 #endif
-#define GLENET_PIB_HYBRID (GLENET_PIB_ZSLABS < 0)
-#if GLENET_PIB_ZSLABS > 0
+#if GLENET_PIB_ZSLABS
 constexpr int PIB_FG = 128;                     // fine occupancy map, cells per axis
-constexpr int PIB_ZS = GLENET_PIB_ZSLABS;       // z slabs of the frame's z window = bits per cell
+constexpr int PIB_ZS = 16;                      // z slabs of the frame's z window = bits per cell
 constexpr int PIB_FWORDS = PIB_FG * PIB_FG * PIB_ZS / 32;
-#elif GLENET_PIB_HYBRID
-constexpr int PIB_FG = 256;                     // fine occupancy bitmap, cells per axis (1 bit per cell) ...
-constexpr int PIB_ZS = 16;                      // ... and 16 z-slab bits for every 4 x 4 cells
-constexpr int PIB_FBITWORDS = PIB_FG * PIB_FG / 32;
-constexpr int PIB_FWORDS = PIB_FBITWORDS + (PIB_FG / 4) * (PIB_FG / 4) / 2;
+static_assert(GLENET_PIB_ZSLABS == 16, "the fine map holds 16-bit cells");
 #else
 constexpr int PIB_FG = 256;                     // fine occupancy bitmap, cells per axis (1 bit per cell)
-constexpr int PIB_ZS = 1;
 constexpr int PIB_FWORDS = PIB_FG * PIB_FG / 32;
 #endif
 constexpr int PIB_ROUND = 4 * 256;              // points per CTA round of the direct kernel (4 per thread)
@@ -67,15 +61,9 @@ constexpr int PIB_WQ = PIB_WBATCH + 32;         // warp queue: one batch of hot 
 #define GLENET_PIB_L2PF 3
 #endif
 #ifndef GLENET_PIB_CTAS          // resident CTAs per SM the query kernel is compiled and launched for
-#define GLENET_PIB_CTAS (GLENET_PIB_ZSLABS == 16 ? 2 : 3)
+#define GLENET_PIB_CTAS (GLENET_PIB_ZSLABS ? 2 : 3)
 #endif
-#ifndef GLENET_PIB_BUILD_SPLIT   // 1: the threads sharing a box split its coarse-cell rows as well as its fine rows
-#define GLENET_PIB_BUILD_SPLIT 1
-#endif
-#ifndef GLENET_PIB_PREFILL       // 1: the query grid writes the provisional -1 of its whole range while the build kernel still runs
-#define GLENET_PIB_PREFILL 0
-#endif
-#ifndef GLENET_PIB_PF            // register prefetch depth of the query's point stream: 2, 1 or 0 (L2 prefetch only)
+#ifndef GLENET_PIB_PF            // register prefetch depth of the query's point stream: 1 or 2 batches
 #define GLENET_PIB_PF 1
 #endif
 constexpr int PIB_CHUNK = GLENET_PIB_CHUNK;     // points per work item of the query kernel
@@ -221,21 +209,12 @@ __device__ __forceinline__ void raster_fine_rows(const Footprint& f, float gx0, 
         if (!(xmax >= xmin)) continue;
         const int ix0 = max(0, min(PIB_FG - 1, (int)floorf((f.cx + xmin - eps_x - gx0) * finv_x)));
         const int ix1 = max(0, min(PIB_FG - 1, (int)floorf((f.cx + xmax + eps_x - gx0) * finv_x)));
-#if GLENET_PIB_ZSLABS > 0
-        constexpr int CPW = 32 / PIB_ZS;                    // cells per 32-bit word: OR the box's z slabs into the row's span
-        const unsigned int zrep = zmask * (PIB_ZS == 16 ? 0x00010001u : 0x01010101u);
-        for (int w = ix0 / CPW; w <= ix1 / CPW; ++w) {
-            const int lo = max(ix0 - w * CPW, 0) * PIB_ZS, hi = (min(ix1 - w * CPW, CPW - 1) + 1) * PIB_ZS;
-            const unsigned int mask = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-            atomicOr(&s_bits[iy * (PIB_FG / CPW) + w], zrep & mask);
+#if GLENET_PIB_ZSLABS
+        for (int w = ix0 >> 1; w <= (ix1 >> 1); ++w) {      // two 16-bit cells per word: OR the box's z slabs into the row's span
+            const unsigned int mask = (2 * w >= ix0 ? zmask : 0u) | (2 * w + 1 <= ix1 ? zmask << 16 : 0u);
+            atomicOr(&s_bits[iy * (PIB_FG / 2) + w], mask);
         }
 #else
-#if GLENET_PIB_HYBRID
-        for (int w = ix0 >> 3; w <= (ix1 >> 3); ++w) {     // z slabs of the 4 x 4 blocks the span touches (two 16-bit blocks per word)
-            const unsigned int mask = (8 * w + 3 >= ix0 ? zmask : 0u) | (8 * w + 4 <= ix1 ? zmask << 16 : 0u);
-            atomicOr(&s_bits[PIB_FBITWORDS + (iy >> 2) * (PIB_FG / 8) + w], mask);
-        }
-#endif
         (void)zmask;
         for (int w = ix0 >> 5; w <= (ix1 >> 5); ++w) {
             const int lo = max(ix0 - (w << 5), 0), hi = min(ix1 - (w << 5), 31);
@@ -390,9 +369,9 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
     if (!exhaustive && !empty) {
         // One box per thread (N <= 512 boxes is one round): with a few hundred boxes per frame, box-level
         // parallelism beats splitting one box's ~15 rows / ~15 cells over a warp (measured both ways).
-        //   pass 0: fine occupancy bitmap + coarse counts      pass 1: coarse fill (after the scan)
-        // With few boxes the CTA has threads to spare: `parts` threads share one box in pass 0 -- part 0 counts the
-        // coarse cells, the others rasterise interleaved fine rows -- laid out so that a warp holds one part only.
+        //   pass 0: fine map + coarse counts / inline candidates      pass 1 (only with crowded cells): their list slices
+        // With few boxes the CTA has threads to spare: `parts` threads share one box and take interleaved rows of both
+        // grids -- laid out so that a warp holds one part only.
         const int parts = N * 4 <= PIB_BUILD_THREADS ? 4 : (N * 2 <= PIB_BUILD_THREADS ? 2 : 1);
         for (int pass = 0; pass < 2; ++pass) {
             const int items = N * parts;
@@ -400,7 +379,6 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
                 const int part = it / N, k = it - part * N;
                 const Footprint fp = footprint(rec + (size_t)k * 8);
                 if (fp.never) continue;
-#if GLENET_PIB_BUILD_SPLIT
                 // the `parts` threads of a box take interleaved rows of BOTH grids, in both passes
                 const int row_phase = part, row_stride = parts;
                 if (!(GLENET_PIB_DBG & 1) && pass == 0) {
@@ -408,14 +386,6 @@ pib_build_kernel(const float* __restrict__ boxes_all, int N, PibWorkspace ws) {
                     if (zmask) raster_fine_rows(fp, bx0, by0, finv_x, finv_y, s_bits, zmask, row_phase, row_stride);
                 }
                 if (GLENET_PIB_DBG & 2) continue;
-#else
-                const int row_phase = 0, row_stride = 1;
-                if (!(GLENET_PIB_DBG & 1) && pass == 0 && (parts == 1 || part > 0)) {
-                    const unsigned int zmask = z_slab_mask(rec[(size_t)k * 8 + 2], rec[(size_t)k * 8 + 7], s_bounds[4], s_bounds[5]);
-                    if (zmask) raster_fine_rows(fp, bx0, by0, finv_x, finv_y, s_bits, zmask, parts == 1 ? 0 : part - 1, parts == 1 ? 1 : parts - 1);
-                }
-                if (part > 0 || (GLENET_PIB_DBG & 2)) continue;
-#endif
                 for_cells<PIB_G>(fp, bx0, by0, inv_x, inv_y, row_phase, row_stride, [&](int cell) {
                     if (pass == 0) {     // the first four candidates of a cell go inline; a fifth makes it a crowded cell
                         const unsigned int pos = atomicAdd(&cnt[cell], 1u);
@@ -487,44 +457,24 @@ __device__ __forceinline__ void load_pts4(const float* __restrict__ pts, int p0,
 }
 
 // Query kernel.  Persistent CTAs (GLENET_PIB_CTAS per SM) walk a contiguous range of (frame, chunk) work
-// items -- the chunks of one frame as ONE run of points -- and re-stage the frame tables (fine bitmap 8 KB,
+// items -- the chunks of one frame as ONE run of points -- and re-stage the frame tables (fine map 32 KB,
 // coarse cells 32 KB, box records) only when the frame changes.  Inside a run every WARP is autonomous -- no
 // CTA barrier on the streaming path:
-//   1. 4 consecutive points per lane (three float4 loads, two batches prefetched into registers and the
+//   1. 4 consecutive points per lane (three float4 loads, one batch prefetched into registers and the
 //      lines of the batch GLENET_PIB_L2PF further ahead prefetched into L2);
-//   2. fine-bitmap lookup in shared memory combined with the z window, provisional -1 for all four points
-//      with one int4 store;
-//   3. the ~9 % of points that stay hot go to the warp's private queue (ballot prefix, no atomics), and the
-//      warp drains it 32 entries at a time: coarse cell -> up to four inline candidates (a list through L2
-//      only for crowded cells) -> exact predicate -> minimum index over the provisional -1.
+//   2. fine-map lookup in shared memory (cell -> 16 z-slab bits -> the point's slab), provisional -1 for all
+//      four points with one int4 store;
+//   3. the ~10 % of points that stay hot go to the warp's private queue (ballot prefix, no atomics), and the
+//      warp drains it 32 entries at a time: coarse cell -> up to four inline candidates (a list slice through
+//      L2 only for crowded cells) -> exact predicate -> minimum index over the provisional -1.
+// The LSU data pipe (shared-memory wavefronts) is the busiest unit of this kernel, so the candidate records are
+// read as two LDS.128 from a 48-byte stride (a generic pointer here once made them eight scalar loads with
+// 8-way bank conflicts: 40 % of all wavefronts).
 template <bool REC_SMEM>   // box records staged in shared memory (N <= PIB_SMEM_BOXES) or read through L1 / L2
 __global__ void __launch_bounds__(PIB_THREADS, GLENET_PIB_CTAS)
 pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace ws, int* __restrict__ out_all,
                  int chunks_per_frame, int total_chunks) {
     extern __shared__ __align__(16) unsigned char pib_smem[];
-#if GLENET_PIB_PREFILL
-    // Provisional -1 for this CTA's whole range, written while the build kernel (which never touches `out`) still runs:
-    // that is HBM time nobody else is using, and the streaming loop below then only stores the hits.  Everything older
-    // than the build kernel has completed (only this grid is a programmatic dependent), and every later result store
-    // to these addresses comes from this CTA after at least one __syncthreads.
-    {
-        const int cb = (int)((long)blockIdx.x * total_chunks / gridDim.x), ce = (int)((long)(blockIdx.x + 1) * total_chunks / gridDim.x);
-        for (int c = cb; c < ce;) {
-            const int f = c / chunks_per_frame, chunk = c - f * chunks_per_frame;
-            const int chunk_last = min(ce - f * chunks_per_frame, chunks_per_frame);
-            c = f * chunks_per_frame + chunk_last;
-            int* o = out_all + (size_t)f * M;
-            const int pb = chunk * PIB_CHUNK, pe = (int)min((long)M, (long)chunk_last * PIB_CHUNK);
-            const int head = min(pe, pb + (int)((4 - (((uintptr_t)(o + pb) >> 2) & 3)) & 3));   // first 16-byte aligned element
-            if ((int)threadIdx.x < head - pb) o[pb + threadIdx.x] = -1;
-            const int nv = (pe - head) >> 2;
-            int4* o4 = reinterpret_cast<int4*>(o + head);
-            for (int i = threadIdx.x; i < nv; i += PIB_THREADS) o4[i] = make_int4(-1, -1, -1, -1);
-            const int tail = head + (nv << 2);
-            if ((int)threadIdx.x < pe - tail) o[tail + threadIdx.x] = -1;
-        }
-    }
-#endif
     asm volatile("griddepcontrol.wait;" ::: "memory");   // the build kernel (previous in the stream) has completed and flushed
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a programmatic dependent (e.g. the next call's build) may be scheduled as SMs free up
     float4* s_q = reinterpret_cast<float4*>(pib_smem);                                        // [warps][PIB_WQ] {x, y, z, index}
@@ -637,23 +587,14 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int ix = __float2int_rd(__fmaf_rn(cur.x[i], finv_x, foff_x)), iy = __float2int_rd(__fmaf_rn(cur.y[i], finv_y, foff_y));
-#if GLENET_PIB_ZSLABS > 0
-                // cell = z-slab bits; slabs outside [0, PIB_ZS) shift the bits out (PTX shr clamps the amount: negative slab
+#if GLENET_PIB_ZSLABS
+                // cell = 16 z-slab bits; slabs outside [0, 16) shift the bits out (PTX shr clamps the amount: negative slab
                 // numbers are huge unsigned amounts).  NaN z -> slab 0; corrected below.
                 const int zs = __float2int_rd(__fmaf_rn(cur.z[i], zc, zh));
-                const int ci = ((iy << 7) + ix) & (PIB_FG * PIB_FG - 1);
-                const unsigned int cell = PIB_ZS == 16 ? (unsigned int)reinterpret_cast<const unsigned short*>(s_bits)[ci]
-                                                       : (unsigned int)reinterpret_cast<const unsigned char*>(s_bits)[ci];
+                const unsigned int cell = reinterpret_cast<const unsigned short*>(s_bits)[((iy << 7) + ix) & (PIB_FG * PIB_FG - 1)];
                 unsigned int bit;
                 asm("shr.u32 %0, %1, %2;" : "=r"(bit) : "r"(cell), "r"(zs));
                 hot |= ((unsigned int)(ix | iy) < (unsigned int)PIB_FG) ? ((bit & 1u) << i) : 0u;
-#elif GLENET_PIB_HYBRID
-                const int zs = __float2int_rd(__fmaf_rn(cur.z[i], zc, zh));
-                const unsigned int word = s_bits[((iy << 3) + (ix >> 5)) & (PIB_FBITWORDS - 1)];
-                const unsigned int cell = reinterpret_cast<const unsigned short*>(s_bits + PIB_FBITWORDS)[(((iy >> 2) << 6) + (ix >> 2)) & 4095];
-                unsigned int bit;
-                asm("shr.u32 %0, %1, %2;" : "=r"(bit) : "r"(cell), "r"(zs));
-                hot |= ((unsigned int)(ix | iy) < (unsigned int)PIB_FG) ? ((bit & (word >> (ix & 31)) & 1u) << i) : 0u;
 #else
                 const unsigned int word = s_bits[((iy << 3) + (ix >> 5)) & (PIB_FWORDS - 1)];
 #if GLENET_PIB_ZWINDOW
@@ -678,25 +619,17 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
                     const float yi = i == 0 ? cur.y[0] : i == 1 ? cur.y[1] : i == 2 ? cur.y[2] : cur.y[3];
                     const int ix = __float2int_rd(__fmaf_rn(xi, finv_x, foff_x)), iy = __float2int_rd(__fmaf_rn(yi, finv_y, foff_y));
                     if ((unsigned int)(ix | iy) >= (unsigned int)PIB_FG) continue;
-#if GLENET_PIB_HYBRID
-                    const unsigned int any = (s_bits[((iy << 3) + (ix >> 5)) & (PIB_FBITWORDS - 1)] >> (ix & 31)) & 1u;
-#else
-                    const int ci = (iy << 7) + ix;
-                    const unsigned int any = PIB_ZS == 16 ? (unsigned int)reinterpret_cast<const unsigned short*>(s_bits)[ci]
-                                                          : (unsigned int)reinterpret_cast<const unsigned char*>(s_bits)[ci];
-#endif
+                    const unsigned int any = reinterpret_cast<const unsigned short*>(s_bits)[(iy << 7) + ix];
                     if (any) hot |= 1u << i;
                 }
             }
 #endif
             hot &= (1u << nvalid) - 1u;                        // never queue a point beyond the chunk
-#if !GLENET_PIB_PREFILL
             if (vec && nvalid == 4) *reinterpret_cast<int4*>(out + p0) = make_int4(-1, -1, -1, -1);
             else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) if (i < nvalid) out[p0 + i] = -1;
             }
-#endif
             if (__any_sync(0xffffffffu, hot != 0)) {
                 // append the hot points: one ballot per point slot gives every lane its queue position (the order of the
                 // queue is irrelevant) -- cheaper than a 5-step prefix sum followed by per-lane sequential writes
@@ -748,7 +681,7 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
 #if GLENET_PIB_PF >= 2
             Pts4 nxt2;
             if (j + 2 < NB) fetch(nxt2, j + 2);
-#elif GLENET_PIB_PF == 1
+#else
             if (j + 1 < NB) fetch(nxt, j + 1);
 #endif
 #if GLENET_PIB_L2PF
@@ -761,10 +694,8 @@ pib_query_kernel(const float* __restrict__ pts_all, int N, int M, PibWorkspace w
 #if GLENET_PIB_PF >= 2
             cur = nxt;
             nxt = nxt2;
-#elif GLENET_PIB_PF == 1
-            cur = nxt;
 #else
-            if (j + 1 < NB) fetch(cur, j + 1);
+            cur = nxt;
 #endif
         }
         if (qn) {                                              // leftovers of the run

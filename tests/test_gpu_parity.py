@@ -416,6 +416,18 @@ def test_points_in_boxes_properties_full_size(cuda):
     assert bool((R.points_in_boxes_gpu(pts_nan, boxes[None].to(cuda))[0, :7] == -1).all())
 
 
+def test_points_in_boxes_record_staging_boundary_vs_reference(cuda, ref_so):
+    """Up to 224 boxes the query keeps the records in shared memory (48-byte stride), beyond that it reads them through
+    L1 / L2: both kernels, and the frame tables re-staged between frames of one call, must agree with the reference."""
+    for n in (33, 223, 224, 225, 256, 700):
+        bx = torch.stack([synth.waymo_boxes(n, 60 + f) for f in range(3)])
+        pts = torch.stack([synth.points(40003, bx[f], synth.WAYMO_RANGE, 0.3, seed=70 + f) for f in range(3)]).contiguous().to(cuda)
+        bx = bx.to(cuda)
+        got, want = R.points_in_boxes_gpu(pts, bx), ref_so.points_in_boxes_gpu(pts, bx)
+        assert torch.equal(got, want), n
+        assert int((want >= 0).sum()) > 20000
+
+
 def test_points_in_boxes_z_window_and_crowded_cells_vs_reference(cuda, ref_so):
     """The z window of all boxes (points above / below every box skip the tables), cells with more than four candidates
     and degenerate heights must not change a single assignment: bit-equal to the reference kernel."""

@@ -1,0 +1,43 @@
+"""Per-SASS-instruction memory cost of a kernel from an .ncu-rep (source page): shared-memory wavefronts vs the ideal count,
+global sectors vs ideal, and the unit-level totals -- finds scalarised or bank-conflicting accesses that the stall samples
+do not point at.    python tools/ncu_hotmem.py <report.ncu-rep> [kernel-substring] [top]"""
+import csv, subprocess, sys
+
+def main():
+    path = sys.argv[1]; want = sys.argv[2] if len(sys.argv) > 2 else ""; top = int(sys.argv[3]) if len(sys.argv) > 3 else 14
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(raw.splitlines())); hdr = rows[0]
+    names = [r[hdr.index("Kernel Name")] for r in rows[2:]]
+    ids = [r[hdr.index("ID")] for r in rows[2:]]
+    for kid, name, r in zip(ids, names, rows[2:]):
+        if want not in name: continue
+        g = lambda k: r[hdr.index(k)] if k in hdr else "?"
+        print(f"== [{kid}] {name[:80]}  {g('gpu__time_duration.sum')} us  inst {g('smsp__inst_executed.sum')}  issue {g('smsp__issue_active.avg.pct_of_peak_sustained_active')}%  "
+              f"l1tex {g('l1tex__throughput.avg.pct_of_peak_sustained_active')}%  lsu-wavefronts {g('l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed')}%  "
+              f"shared-conflicts {g('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum')}  alu {g('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active')}%  fma {g('sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active')}%  xu {g('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active')}%")
+        src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass", "--kernel-id", f":::{int(kid)+1}" if False else "", ], stdout=subprocess.PIPE, text=True).stdout if False else None
+    # source page per kernel launch id
+    for kid, name in zip(ids, names):
+        if want not in name: continue
+        out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass", "--launch-skip", kid, "--launch-count", "1"], stdout=subprocess.PIPE, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        h = None
+        for i, r in enumerate(rows):
+            if r and r[0] == "Address": h = i; break
+        if h is None: continue
+        hd = rows[h]; ix = {k: j for j, k in enumerate(hd)}
+        sh, gl = [], []
+        f = lambda r, k: float(r[ix[k]] or 0) if k in ix and len(r) > ix[k] else 0.0
+        tot_sh = tot_ideal = 0
+        for r in rows[h + 1:]:
+            if len(r) < len(hd): continue
+            w, ideal = f(r, "L1 Wavefronts Shared"), f(r, "L1 Wavefronts Shared Ideal")
+            if w > 0: sh.append((w, ideal, f(r, "Instructions Executed"), f(r, "Avg. Predicated-On Threads Executed"), r[ix["Source"]].strip()[:70])); tot_sh += w; tot_ideal += ideal
+            s, si = f(r, "L2 Theoretical Sectors Global"), f(r, "L2 Theoretical Sectors Global Ideal")
+            if s > 0: gl.append((s, si, f(r, "Instructions Executed"), f(r, "Avg. Predicated-On Threads Executed"), r[ix["Source"]].strip()[:70]))
+        print(f"-- [{kid}] {name[:60]}: shared wavefronts {tot_sh:.0f} (ideal {tot_ideal:.0f})")
+        for x in sorted(sh, reverse=True)[:top]: print("   sh  %10.0f ideal %10.0f  inst %9.0f thr %4.1f  %s" % x)
+        for x in sorted(gl, reverse=True)[:max(4, top // 2)]: print("   gl  %10.0f ideal %10.0f  inst %9.0f thr %4.1f  %s" % x)
+
+if __name__ == "__main__":
+    main()
