@@ -42,7 +42,7 @@ namespace glenet {
 #define GLENET_IOU_THREADS 256
 #endif
 #ifndef GLENET_IOU_TR_MAX
-#define GLENET_IOU_TR_MAX 384
+#define GLENET_IOU_TR_MAX 448
 #endif
 #ifndef GLENET_IOU_CTAS
 #define GLENET_IOU_CTAS 3
@@ -51,7 +51,7 @@ namespace glenet {
 #define GLENET_IOU_CLIP_PAIRS (GLENET_IOU_THREADS - 32)
 #endif
 #ifndef GLENET_IOU_QCAP
-#define GLENET_IOU_QCAP 512
+#define GLENET_IOU_QCAP 768
 #endif
 #ifndef GLENET_IOU_ZBYTES
 #define GLENET_IOU_ZBYTES 4096
@@ -111,7 +111,7 @@ struct __align__(128) IouSmem {
     float rpre[IOU_TR_MAX * BPS];          // rows: raw box in the first 7 slots until a pair needs it, then the BoxPre record (same centre slots)
     float cpre[IOU_TC_MAX * BPS];
     float qres[IOU_Q2CAP];                 // clipped results, parked until the zero fill has landed
-    unsigned short queue[IOU_QCAP];        // (row << 7) | col  (row < 384, col < 128): survivors of the circle test
+    unsigned short queue[IOU_QCAP];        // (row << 7) | col  (row < 448, col < 128): survivors of the circle test
     unsigned short queue2[IOU_Q2CAP];      // survivors of the separating-axis test: the pairs that are clipped
     unsigned short plist[IOU_TR_MAX + IOU_TC_MAX];   // boxes to prepare in the current drain
     float red[IOU_THREADS / 32][5];
