@@ -727,13 +727,18 @@ static void pick_tiles(int na, int nb, int frames, int resident, int& TR, int& T
     }
     TC = ((nb + col_tiles - 1) / col_tiles + 3) / 4 * 4;   // multiple of 4 keeps every tile on the 16-byte store path
     col_tiles = (nb + TC - 1) / TC;
+    // Measured on the anchor sweep (tools/tile_rows_env_sweep.py, 128..448 rows): a wave of resident tiles takes
+    // 4.7 us + 20.3 ns per tile row (staging, cull and clip all grow with the rows), unless its zero fill takes longer.
+    // Few waves are quantised (the launch ends with its last, partly empty wave); many waves behave like a stream.
     const double slots = resident;
-    const double chain_us = 13.0, fill_bytes_per_us = 6.0e6;
+    const double fill_bytes_per_us = 6.0e6;
     double best = 0.0;
     TR = 32;
     for (int tr = 32; tr <= IOU_TR_MAX; tr += 32) {
         const double tiles = (double)((na + tr - 1) / tr) * col_tiles * frames;
-        const double waves = ceil(tiles / slots);
+        const double w = tiles / slots;
+        const double waves = w <= 4.0 ? ceil(w) : w + 0.5;
+        const double chain_us = 4.7 + 0.0203 * tr;
         const double fill_us = (double)tr * TC * 4.0 * (tiles < slots ? tiles : slots) / fill_bytes_per_us;
         const double cost = waves * (chain_us > fill_us ? chain_us : fill_us) + 0.002 * tr;   // ties go to the smaller tile
         if (tr == 32 || cost < best) { best = cost; TR = tr; }
