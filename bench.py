@@ -322,8 +322,9 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         try:
             win = sharded.ExchangeWindow(frames=FRAMES, nb=N_GT, list_cap=(FRAMES * sharded.slab_rows(N_ANCHORS, world) * N_GT) // 48)
-            exchange = ("in-kernel: row-sharded slabs stay resident; column max / first row over all ranks by system-scope atomic max into "
-                        "CUDA-IPC exchange windows from the IoU kernel's last CTA + flags (no NCCL on the data path)")
+            exchange = ("in-kernel: row-sharded slabs stay resident; every rank's column keys (max, first row) go into its slot of every "
+                        "peer's CUDA-IPC exchange window as plain 16-byte stores over NVLink + a step flag, the maximum over the slots is "
+                        "decoded locally (one PDL-chained exchange kernel behind the IoU kernel; no NCCL on the data path)")
         except Exception as e:   # IPC unavailable: the torch.distributed formulation carries the exchange
             win = None
             exchange = f"NCCL all_reduce of the column keys (CUDA IPC exchange windows unavailable: {type(e).__name__}: {e})"
