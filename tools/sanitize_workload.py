@@ -20,6 +20,8 @@ I1.boxes_aligned_iou3d_gpu(pr.to(dev), tg.to(dev), need_bev=True)
 bx = torch.stack([synth.waymo_boxes(40, 30 + f) for f in range(2)])
 pts = torch.stack([synth.points(9000, bx[f], synth.WAYMO_RANGE, 0.1, seed=f) for f in range(2)])
 R.points_in_boxes_gpu(pts.to(dev), bx.to(dev)); R.points_in_boxes_gpu(pts.to(dev), bx[:, :5].contiguous().to(dev))
+pk = synth.points(6000, p[:20].cpu(), synth.KITTI_RANGE, 0.5, seed=3)[None].to(dev)
+R.points_in_boxes_gpu(pk, p[None, :300].contiguous())           # > 224 boxes: records through L1 / L2; crowded cells: list slices
 R.points_in_boxes_cpu(pts[0], bx[0]); I.boxes_bev_iou_cpu(p[:50].cpu(), p[:40].cpu())
 # variance-voting / soft NMS (vnms.cu), the single-rank exchange window (assign + gather + scatter + decode kernels)
 v = (torch.rand((700, 7), generator=torch.Generator().manual_seed(5)) * 0.5 + 0.05).to(dev)
