@@ -48,8 +48,8 @@ PAIRS_PER_FRAME = N_ANCHORS * N_GT
 BYTES_PER_PAIR = 4.0           # the culled sweep is bound by the float32 result write
 WORKLOAD = "cfg4 anchor sweep: 16 frames x boxes_iou_bev(211200 KITTI anchors x 100 GT)"
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch from the ncu --set full capture in profiles/
-TRAFFIC_PER_LAUNCH = 1.309e9
-TRAFFIC_NOTE = ("profiles/r02_iou_frames_summary.txt: 1.301 GB written + 0.008 GB read per 16-frame launch on one GPU vs 1.352 GB "
+TRAFFIC_PER_LAUNCH = 1.314e9
+TRAFFIC_NOTE = ("profiles/r02_iou_frames_summary.txt: 1.305 GB written + 0.009 GB read per 16-frame launch on one GPU vs 1.352 GB "
                 "algorithmic (the bulk zero fill writes whole lines once; the box loads carry an L2 evict-last policy)")
 NVLINK_GBS = 770.0             # measured peer-copy bandwidth per direction (B200_PROFILING.md)
 PIB_B, PIB_M, PIB_N = 128, 180000, 200
