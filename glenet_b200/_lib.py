@@ -71,7 +71,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 
 def lib_path() -> str:

@@ -20,6 +20,8 @@
 #include "clip.cuh"
 #include "../../include/glenet_geom.h"
 #include <atomic>
+#include <float.h>
+#include <stdlib.h>
 
 #ifndef GLENET_NMS_DEFER      // 1: the exact clips of a tile are appended to a global list and run as one dense kernel
 #define GLENET_NMS_DEFER 1
@@ -51,8 +53,8 @@ struct NmsSmem {
     float rcx[NMS_TILE], rcy[NMS_TILE], rrad[NMS_TILE];
     float ccx[NMS_TILE], ccy[NMS_TILE], crad[NMS_TILE];
     float rpre[NMS_TILE * NBS];
-    float cpre[NMS_TILE * NBS];
-    unsigned long long bits[NMS_TILE];
+    float cpre[NMS_TILE * NBS];            // must follow rpre directly (nms_tile_clip<true> addresses it as records 64.. of rpre)
+    union { unsigned long long bits[NMS_TILE]; int idx[2 * NMS_TILE]; };   // mask words of the tile's rows | (spatial tiles) the boxes' score-order indices
     unsigned int wl[NMS_THREADS / 32][32 * CLIP_SLOTS];   // per-warp work lists of the clip's phase B
     unsigned short queue2[NMS_TILE * NMS_TILE];   // pairs whose IoU could exceed the threshold: the ones that are clipped
     unsigned char rflag[NMS_TILE], cflag[NMS_TILE];
@@ -87,28 +89,45 @@ __device__ __forceinline__ void tri_decode(int t, int nblk, int& rb, int& cb) {
 }
 
 // The in-tile exact clip over queue2 (all pairs when thresh < 0, or when the deferred-clip list is full), NMS_PASS pairs at a time.
-__device__ __noinline__ void nms_tile_clip(NmsSmem& sm, int nq2, float thresh) {
+// SP (spatial tiles): rows and columns are arbitrary boxes -- entry bit 12 says that the column box has the lower score index
+// (it is box_a then), and the bit goes straight to the global mask word of (lower index, higher index).
+template <bool SP>
+__device__ __noinline__ void nms_tile_clip(NmsSmem& sm, int nq2, float thresh, unsigned long long* __restrict__ mask = nullptr, int col_blocks = 0) {
     const int tid = threadIdx.x, warp = tid >> 5;
     auto set_bit = [&](int p, float ov, const float* a, const float* b) {
-        if (iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) > thresh)   // 32-bit halves: a native shared-memory atomic instead of a 64-bit CAS loop
-            atomicOr(reinterpret_cast<unsigned int*>(&sm.bits[p >> 6]) + ((p >> 5) & 1), 1u << (p & 31));
+        if (iou_from_overlap(a[BP_AREA], b[BP_AREA], ov) > thresh) {
+            if (SP) {
+                const int ri = sm.idx[(p >> 6) & 63], ci = sm.idx[NMS_TILE + (p & 63)];
+                const int i = min(ri, ci), j = max(ri, ci);
+                atomicOr(reinterpret_cast<unsigned int*>(mask + (size_t)i * col_blocks + (j >> 6)) + ((j >> 5) & 1), 1u << (j & 31));
+            } else {   // 32-bit halves: a native shared-memory atomic instead of a 64-bit CAS loop
+                atomicOr(reinterpret_cast<unsigned int*>(&sm.bits[p >> 6]) + ((p >> 5) & 1), 1u << (p & 31));
+            }
+        }
     };
     for (int base = 0; base < nq2; base += NMS_PASS) {
         // one pair per lane; A (result bits, corners), B (the warp's crossings pooled) and C (sort + fan) are warp-local
         const bool live = base + tid < nq2;
         const int p = live ? sm.queue2[base + tid] : 0;
-        const float* a = sm.rpre + (p >> 6) * NBS;
-        const float* b = sm.cpre + (p & 63) * NBS;
+        const bool swap = SP && ((p >> 12) & 1);
+        const int ra = (p >> 6) & 63, cb_ = p & 63;
+        const float* a = swap ? sm.cpre + cb_ * NBS : sm.rpre + ra * NBS;
+        const float* b = swap ? sm.rpre + ra * NBS : sm.cpre + cb_ * NBS;
         float2* slots = sm.verts + tid * CLIP_SLOTS;
         const unsigned int w = clip_pair_tests<true>(a, b, live);
         const unsigned int hits = clip_hits16(w);
         const int cnt = __popc(hits) + __popc(clip_corners8(w));
         const bool fast = cnt >= 3 && cnt <= CLIP_SLOTS;
         if (fast) clip_write_corners(a, b, w, slots);
-        clip_warp_points<true>(fast ? hits : 0u, (unsigned int)(p >> 6), (unsigned int)(p & 63), sm.wl[warp], sm.rpre, sm.cpre, NBS, sm.verts + (warp * 32) * CLIP_SLOTS);
+        // the pooled phases address the records as (array base, record number): cpre follows rpre in NmsSmem, so with
+        // rpre as the base of both operands a column record is number 64 + c and either box can be box_a
+        const unsigned int ia = SP ? (unsigned int)(swap ? NMS_TILE + cb_ : ra) : (unsigned int)ra;
+        const unsigned int ib = SP ? (unsigned int)(swap ? ra : NMS_TILE + cb_) : (unsigned int)cb_;
+        const float* brec = SP ? sm.rpre : sm.cpre;
+        clip_warp_points<true>(fast ? hits : 0u, ia, ib, sm.wl[warp], sm.rpre, brec, NBS, sm.verts + (warp * 32) * CLIP_SLOTS);
         // more than eight vertices (corners admitted by the margin next to a crossing): the whole warp, one pair at a time
         const bool slow = cnt > CLIP_SLOTS;
-        const float ov_slow = clip_warp_slow<true>(slow, w, (unsigned int)(p >> 6), (unsigned int)(p & 63), sm.rpre, sm.cpre, NBS, reinterpret_cast<float2*>(sm.wl[warp]));
+        const float ov_slow = clip_warp_slow<true>(slow, w, ia, ib, sm.rpre, brec, NBS, reinterpret_cast<float2*>(sm.wl[warp]));
         if (live) set_bit(p, slow ? ov_slow : (fast ? clip_area8<true>(slots, cnt) : 0.f), a, b);
     }
 }
@@ -295,9 +314,339 @@ nms_mask_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsign
 #endif
     // ---- phased clip (clip.cuh) over queue2: only when the pairs could not be deferred (out of line: it must not set the
     //      register budget of the phases every tile runs)
-    nms_tile_clip(sm, nq2, thresh);
+    nms_tile_clip<false>(sm, nq2, thresh);
     __syncthreads();
     if (tid < tr) mask[(size_t)(r0 + tid) * col_blocks + cb] = sm.bits[tid];
+}
+
+// ---------------------------------------------------------------- spatial tiles
+// Proposals arrive in score order, so every 64 x 64 tile of the (i, j) matrix mixes boxes from the whole scene: each of the
+// n^2 / 2 pairs costs a circle test, although a box only overlaps the few hundred boxes of its own object.  The mask does
+// not care in which order the pairs are examined -- only that every pair (i < j) whose circles meet is, with box i as
+// box_a -- so the pairs are enumerated over SPATIAL groups instead:
+//   nms_spatial_kernel (one CTA per frame; centre, cull radius and finiteness of every box cached in shared memory):
+//       counting sort of the boxes by the Morton code of their centre's cell (32 x 32 cells over the bounding box of the
+//       finite centres; boxes with a non-finite term go last); groups = runs of at most 64 consecutive boxes that never leave
+//       their 4 x 4 block of cells (a contiguous range of Morton codes), so a group's bounding box is an object-sized patch;
+//       the bounding box of every group's cull circles (infinite for a group with a non-finite box); and the list of work
+//       items (P <= Q, row quarter) whose group boxes meet -- the only pairs any circle test can pass for;
+//   nms_mask_spatial_kernel (persistent CTAs over that list): the tile phases of nms_mask_kernel on 16 rows of group P against
+//       group Q; a pair is oriented by its score indices (lower = row of the mask and box_a) and its bit goes straight to the
+//       global mask word, which the launcher zeroed.
+constexpr int NMS_SP_G = 32;                       // cells per axis of the sorting grid
+constexpr int NMS_SP_CELLS = NMS_SP_G * NMS_SP_G;
+constexpr int NMS_SP_SUPER = NMS_SP_CELLS / 16;    // 4 x 4 blocks of cells = 16 consecutive Morton codes
+constexpr int NMS_SP_THREADS = 1024;
+constexpr int NMS_SP_MAX_GROUPS = 255;             // group numbers travel in 8 bits
+constexpr int NMS_SP_MAX_N = (NMS_SP_MAX_GROUPS - NMS_SP_SUPER) * NMS_TILE;   // every block of cells can add one partial group
+constexpr int NMS_SP_QROWS = 16;                   // rows of a work item (a quarter of group P)
+
+__device__ __forceinline__ unsigned int morton5(unsigned int x, unsigned int y) {   // 5 + 5 bits interleaved
+    unsigned int r = 0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) r |= (((x >> b) & 1u) << (2 * b)) | (((y >> b) & 1u) << (2 * b + 1));
+    return r;
+}
+
+static size_t nms_spatial_smem(int n) { return (size_t)n * (sizeof(float4) + sizeof(unsigned short)); }
+
+__global__ void __launch_bounds__(NMS_SP_THREADS)
+nms_spatial_kernel(const float* __restrict__ boxes_all, int n, int* __restrict__ perm_all, int2* __restrict__ groups_all, int groups_cap,
+                   unsigned int* __restrict__ tiles, unsigned int* __restrict__ tile_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* s_box = reinterpret_cast<float4*>(smem_raw);                    // [n] {cx, cy, cull radius (+pad), 1 = all terms finite}
+    unsigned short* s_perm = reinterpret_cast<unsigned short*>(s_box + n);  // [n] sorted position -> box
+    __shared__ unsigned int cnt[NMS_SP_CELLS + 1];
+    __shared__ unsigned int wsum[NMS_SP_THREADS / 32];
+    __shared__ float red[4][NMS_SP_THREADS / 32];
+    __shared__ float s_b[4];
+    __shared__ float4 s_gbox[NMS_SP_MAX_GROUPS];
+    __shared__ int2 s_grp[NMS_SP_MAX_GROUPS];
+    __shared__ int s_gstart[NMS_SP_SUPER + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.x;
+    const float* boxes = boxes_all + (size_t)frame * n * 7;
+    int* perm = perm_all + (size_t)frame * n;
+    int2* groups = groups_all + (size_t)frame * groups_cap;
+    for (int i = tid; i <= NMS_SP_CELLS; i += NMS_SP_THREADS) cnt[i] = 0u;
+    // one pass over the boxes: cache what the rest needs, bounding box of the finite centres
+    float x0 = FLT_MAX, y0 = FLT_MAX, x1 = -FLT_MAX, y1 = -FLT_MAX;
+    for (int i = tid; i < n; i += NMS_SP_THREADS) {
+        const float* b = boxes + (size_t)i * 7;
+        const float cx = b[0], cy = b[1], rad = cull_radius(cx, cy, b[3], b[4]) + 1e-3f;   // the pad is far above the rounding of cx -+ rad
+        const bool fin = fabsf(cx) <= FLT_MAX && fabsf(cy) <= FLT_MAX && rad <= FLT_MAX;
+        s_box[i] = make_float4(cx, cy, rad, fin ? 1.f : 0.f);
+        if (fin) { x0 = fminf(x0, cx); x1 = fmaxf(x1, cx); y0 = fminf(y0, cy); y1 = fmaxf(y1, cy); }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if (lane == 0) { red[0][warp] = x0; red[1][warp] = y0; red[2][warp] = x1; red[3][warp] = y1; }
+    __syncthreads();
+    if (warp == 0) {
+        x0 = red[0][lane]; y0 = red[1][lane]; x1 = red[2][lane]; y1 = red[3][lane];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+            x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        }
+        if (lane == 0) {
+            // cell = floor((c - lo) * inv), clamped: any mapping will do (it only decides who shares a group)
+            const float ex = x1 - x0, ey = y1 - y0;
+            s_b[0] = x0; s_b[1] = y0;
+            s_b[2] = (ex > 0.f && ex <= FLT_MAX) ? (float)NMS_SP_G / ex : 0.f;
+            s_b[3] = (ey > 0.f && ey <= FLT_MAX) ? (float)NMS_SP_G / ey : 0.f;
+        }
+    }
+    __syncthreads();
+    const float lox = s_b[0], loy = s_b[1], invx = s_b[2], invy = s_b[3];
+    auto cell_of = [&](const float4 b) -> unsigned int {
+        if (b.w == 0.f) return NMS_SP_CELLS - 1;
+        const int ix = min(NMS_SP_G - 1, max(0, (int)((b.x - lox) * invx))), iy = min(NMS_SP_G - 1, max(0, (int)((b.y - loy) * invy)));
+        return morton5((unsigned int)ix, (unsigned int)iy);
+    };
+    for (int i = tid; i < n; i += NMS_SP_THREADS) atomicAdd(&cnt[cell_of(s_box[i])], 1u);
+    __syncthreads();
+    {   // exclusive scan of the 1024 cell counts (one per thread); cnt becomes the fill cursor
+        const unsigned int v = cnt[tid];
+        unsigned int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned int w = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const unsigned int excl = incl - v + (warp ? wsum[warp - 1] : 0u);
+        cnt[tid] = excl;
+        // groups: every block of 16 consecutive Morton codes cuts its run of boxes into pieces of at most 64
+        if ((tid & 15) == 0) s_gstart[tid >> 4] = (int)excl;      // first sorted position of the block (cursor values move below)
+        if (tid == 0) s_gstart[NMS_SP_SUPER] = n;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += NMS_SP_THREADS) {
+        const unsigned int pos = atomicAdd(&cnt[cell_of(s_box[i])], 1u);
+        s_perm[pos] = (unsigned short)i;
+        perm[pos] = i;
+    }
+    if (warp == 0) {   // group table: blocks 2 l and 2 l + 1 per lane, exclusive scan of their group counts
+        int start[2], len[2], ngr[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            start[h] = s_gstart[2 * lane + h];
+            len[h] = s_gstart[2 * lane + h + 1] - start[h];
+            ngr[h] = (len[h] + NMS_TILE - 1) / NMS_TILE;
+        }
+        int incl = ngr[0] + ngr[1];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        int g = incl - ngr[0] - ngr[1];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            for (int k = 0; k < ngr[h]; ++k, ++g)
+                if (g < NMS_SP_MAX_GROUPS) s_grp[g] = make_int2(start[h] + k * NMS_TILE, min(NMS_TILE, len[h] - k * NMS_TILE));
+        if (lane == 31) s_b[0] = __int_as_float(min(incl, NMS_SP_MAX_GROUPS));   // (n <= NMS_SP_MAX_N: never clipped)
+    }
+    __syncthreads();
+    const int ng = __float_as_int(s_b[0]);
+    // group bounding boxes: one warp per group, two boxes per lane
+    for (int g = warp; g < ng; g += NMS_SP_THREADS / 32) {
+        const int2 gr = s_grp[g];
+        float gx0 = FLT_MAX, gy0 = FLT_MAX, gx1 = -FLT_MAX, gy1 = -FLT_MAX;
+        bool bad = false;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = h * 32 + lane;
+            if (k < gr.y) {
+                const float4 b = s_box[s_perm[gr.x + k]];
+                if (b.w == 0.f) bad = true;
+                else { gx0 = fminf(gx0, b.x - b.z); gx1 = fmaxf(gx1, b.x + b.z); gy0 = fminf(gy0, b.y - b.z); gy1 = fmaxf(gy1, b.y + b.z); }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            gx0 = fminf(gx0, __shfl_xor_sync(0xffffffffu, gx0, o)); gy0 = fminf(gy0, __shfl_xor_sync(0xffffffffu, gy0, o));
+            gx1 = fmaxf(gx1, __shfl_xor_sync(0xffffffffu, gx1, o)); gy1 = fmaxf(gy1, __shfl_xor_sync(0xffffffffu, gy1, o));
+        }
+        if (__any_sync(0xffffffffu, bad)) { gx0 = gy0 = -CUDART_INF_F; gx1 = gy1 = CUDART_INF_F; }   // NaN anywhere: never culled
+        if (lane == 0) { s_gbox[g] = make_float4(gx0, gy0, gx1, gy1); groups[g] = gr; }
+    }
+    __syncthreads();
+    // work items: group pairs (P <= Q) whose bounding boxes meet, one item per quarter of P's rows
+    const int npairs = ng * (ng + 1) / 2;
+    for (int t = tid; t < npairs; t += NMS_SP_THREADS) {
+        int P, Q;
+        tri_decode(t, ng, P, Q);
+        const float4 a = s_gbox[P], b = s_gbox[Q];
+        if (a.x > b.z || b.x > a.z || a.y > b.w || b.y > a.w) continue;
+        const int nq = (s_grp[P].y + NMS_SP_QROWS - 1) / NMS_SP_QROWS;
+        const unsigned int at = atomicAdd(tile_count, (unsigned int)nq);
+        for (int q = 0; q < nq; ++q)
+            tiles[at + q] = ((unsigned int)frame << 18) | ((unsigned int)P << 10) | ((unsigned int)Q << 2) | (unsigned int)q;
+    }
+}
+
+__global__ void __launch_bounds__(NMS_THREADS, GLENET_NMS_CTAS)
+nms_mask_spatial_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsigned long long* __restrict__ mask_all, int col_blocks,
+                        const int* __restrict__ perm_all, const int2* __restrict__ groups_all, int groups_cap,
+                        const unsigned int* __restrict__ tiles, const unsigned int* __restrict__ tile_count,
+                        unsigned long long* __restrict__ list_count, unsigned long long* __restrict__ list, unsigned long long list_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NmsSmem& sm = *reinterpret_cast<NmsSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned int ntiles = tile_count[0];
+    unsigned int* next_item = const_cast<unsigned int*>(tile_count) + 1;     // zeroed by the launcher with the count
+    const float thr_lo = thresh * (1.f - 1e-3f) - 1e-5f, thr_hi = thresh * (1.f + 1e-3f) + 1e-5f;
+    // Work items differ by two orders of magnitude (an object's own groups vs. two groups whose boxes merely touch), so they are
+    // handed out dynamically: thread 0 claims the NEXT item when the current one starts (the atomic's latency hides behind the
+    // item) and publishes it at the end.
+    __shared__ unsigned int s_next;
+    unsigned int nxt = 0u;
+    auto fetch_next = [&]() -> unsigned int {
+        __syncthreads();                       // everybody is done with the item (and with s_next)
+        if (tid == 0) s_next = nxt;
+        __syncthreads();
+        return s_next;
+    };
+    for (unsigned int t = blockIdx.x; t < ntiles; t = fetch_next()) {
+        if (tid == 0) nxt = gridDim.x + atomicAdd(next_item, 1u);
+        const unsigned int tw = tiles[t];
+        const int frame = (int)(tw >> 18), P = (int)((tw >> 10) & 255u), Q = (int)((tw >> 2) & 255u), rbase = (int)(tw & 3u) * NMS_SP_QROWS;
+        const float* boxes = boxes_all + (size_t)frame * n * 7;
+        const int* perm = perm_all + (size_t)frame * n;
+        unsigned long long* mask = mask_all + (size_t)frame * n * col_blocks;
+        const int2 gp = groups_all[(size_t)frame * groups_cap + P], gq = groups_all[(size_t)frame * groups_cap + Q];
+        const int tr = gp.y, tc = gq.y;                                  // boxes in the two groups (<= 64)
+        const int rend = min(tr, rbase + NMS_SP_QROWS);                  // this item: rows [rbase, rend) of P against all of Q
+        for (int i = tid; i < (rend - rbase) + tc; i += NMS_THREADS) {
+            const bool is_row = i < rend - rbase;
+            const int k = is_row ? rbase + i : i - (rend - rbase);
+            const int id = perm[(is_row ? gp.x : gq.x) + k];
+            const float* box = boxes + (size_t)id * 7;
+            const float cx = box[0], cy = box[1], rad = cull_radius(box);
+            if (is_row) { sm.rcx[k] = cx; sm.rcy[k] = cy; sm.rrad[k] = rad; sm.rflag[k] = 0; sm.idx[k] = id; }
+            else        { sm.ccx[k] = cx; sm.ccy[k] = cy; sm.crad[k] = rad; sm.cflag[k] = 0; sm.idx[NMS_TILE + k] = id; }
+        }
+        if (tid == 0) { sm.qcount = 0; sm.q2count = 0; }
+        __syncthreads();
+        // cull pass: every unordered pair once (r < c inside a group); thread = one column and 4 of the item's 16 rows
+        const bool diag = P == Q;
+        constexpr int RPT = NMS_SP_QROWS * NMS_TILE / NMS_THREADS;       // 4
+        const int c = tid & (NMS_TILE - 1), rq = tid >> 6;
+        unsigned int hits = 0u;
+        if (c < tc) {
+            const float ccx = sm.ccx[c], ccy = sm.ccy[c], ccr = sm.crad[c];
+            const int lim = diag ? min(rend, c) : rend;
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const int r = rbase + k * (NMS_THREADS / NMS_TILE) + rq;
+                if (r < lim) {
+                    const float ddx = sm.rcx[r] - ccx, ddy = sm.rcy[r] - ccy, rr = sm.rrad[r] + ccr;
+                    hits |= (!(ddx * ddx + ddy * ddy > rr * rr) ? 1u : 0u) << k;     // NaN anywhere: not culled
+                }
+            }
+        }
+        {
+            const int cnt = __popc(hits);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+            const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
+            if (wtotal) {
+                int qb = 0;
+                if (lane == 31) qb = atomicAdd(&sm.qcount, wtotal);
+                qb = __shfl_sync(0xffffffffu, qb, 31) + incl - cnt;
+                if (hits && sm.cflag[c] == 0) sm.cflag[c] = 1;
+                while (hits) {
+                    const int k = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const int r = rbase + k * (NMS_THREADS / NMS_TILE) + rq;
+                    sm.queue[qb++] = (unsigned short)((r << 6) | c);
+                    if (sm.rflag[r] == 0) sm.rflag[r] = 1;
+                }
+            }
+        }
+        __syncthreads();
+        const int nq = sm.qcount;
+        if (nq == 0) continue;   // uniform
+        for (int i = tid; i < (rend - rbase) + tc; i += NMS_THREADS) {
+            const bool is_row = i < rend - rbase;
+            const int k = is_row ? rbase + i : i - (rend - rbase);
+            if ((is_row ? sm.rflag[k] : sm.cflag[k]) == 1) {
+                const float* box = boxes + (size_t)sm.idx[is_row ? k : NMS_TILE + k] * 7;
+                box_prepare<true, false>(box, device_trig(box[6]), (is_row ? sm.rpre : sm.cpre) + k * NBS);
+            }
+        }
+        __syncthreads();
+        // bound filter + approximate overlap, as in nms_mask_kernel; box_a = the box with the lower score index
+        for (int q0 = 0; q0 < nq; q0 += NMS_THREADS) {
+            const int q = q0 + tid;
+            int p = 0;
+            bool need = false;
+            if (q < nq) {
+                p = sm.queue[q];
+                const int ri = sm.idx[p >> 6], ci = sm.idx[NMS_TILE + (p & 63)];
+                const bool swap = ri > ci;
+                const float* a = swap ? sm.cpre + (p & 63) * NBS : sm.rpre + (p >> 6) * NBS;
+                const float* b = swap ? sm.rpre + (p >> 6) * NBS : sm.cpre + (p & 63) * NBS;
+                if (swap) p |= 1 << 12;
+                const float ub = overlap_upper_bound(a, b);
+                const float iou_ub = ub / fmaxf(a[BP_AREA] + b[BP_AREA] - ub, 1e-8f);
+                need = (!(ub <= 0.f) && !(iou_ub <= thr_lo)) || !(a[BP_AREA] + b[BP_AREA] > ub);
+#if GLENET_NMS_APPROX
+                if (need && overlap_approx_usable(a, b)) {
+                    const float ova = overlap_approx(a, b);
+                    float slack, band;
+                    overlap_approx_band(a, b, slack, band);
+                    const float s = a[BP_AREA] + b[BP_AREA];
+                    const float hi = ova + band + slack, lo = ova - slack;
+                    if (hi / fmaxf(s - hi, 1e-8f) <= thr_lo && s > hi) need = false;
+                    else if (lo > 0.f && s > lo && lo / fmaxf(s - lo, 1e-8f) > thr_hi) {
+                        need = false;
+                        const int i = min(ri, ci), j = max(ri, ci);
+                        atomicOr(reinterpret_cast<unsigned int*>(mask + (size_t)i * col_blocks + (j >> 6)) + ((j >> 5) & 1), 1u << (j & 31));
+                    }
+                }
+#endif
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, need);
+            if (m) {
+                int qb = 0;
+                if (lane == 0) qb = atomicAdd(&sm.q2count, __popc(m));
+                qb = __shfl_sync(0xffffffffu, qb, 0);
+                if (need) sm.queue2[qb + __popc(m & ((1u << lane) - 1))] = (unsigned short)p;
+            }
+        }
+        __syncthreads();
+        const int nq2 = sm.q2count;
+        if (nq2 == 0) continue;   // uniform
+        if (list) {
+            if (tid == 0) {
+                const unsigned long long base = atomicAdd(list_count, (unsigned long long)nq2);
+                sm.qcount = (base + (unsigned long long)nq2 <= list_cap) ? 1 : 0;
+                reinterpret_cast<unsigned long long*>(sm.wl[0])[0] = base;
+            }
+            __syncthreads();
+            const unsigned long long base = reinterpret_cast<unsigned long long*>(sm.wl[0])[0];
+            if (sm.qcount) {
+                for (int q = tid; q < nq2; q += NMS_THREADS) {
+                    const int p = sm.queue2[q];
+                    const int ri = sm.idx[(p >> 6) & 63], ci = sm.idx[NMS_TILE + (p & 63)];
+                    list[base + q] = ((unsigned long long)frame << 40) | ((unsigned long long)min(ri, ci) << 20) | (unsigned long long)max(ri, ci);
+                }
+                continue;   // uniform
+            }
+            for (int q = tid; q < nq2; q += NMS_THREADS) if (base + q < list_cap) list[base + q] = ~0ull;   // refused: void entries
+            __syncthreads();
+        }
+        nms_tile_clip<true>(sm, nq2, thresh, mask, col_blocks);
+    }
 }
 
 // Exact clip of the pairs the mask kernel could not decide (nms_mask_kernel, GLENET_NMS_DEFER): one pair per lane, both
@@ -472,6 +821,32 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask_all, int n, int col
     if (tid == 0) num_keep_all[frame] = num_keep;
 }
 
+// workspace: [mask][16-byte list counter][deferred-clip list][spatial: permutation | group table | work items | item counter]
+struct NmsWorkspace {
+    size_t mask_bytes, list_off, perm_off, groups_off, tiles_off, tcount_off, bytes;
+    unsigned long long list_cap;
+    size_t tiles_cap;
+    int groups_cap;
+};
+static NmsWorkspace nms_layout(int frames, int n) {
+    NmsWorkspace w;
+    const size_t col_blocks = ((size_t)n + NMS_TILE - 1) / NMS_TILE;
+    w.mask_bytes = align_up((size_t)frames * n * col_blocks * sizeof(unsigned long long), 16);
+    w.list_off = w.mask_bytes;                                  // 16-byte counter, then the entries
+    w.list_cap = nms_list_cap(frames, n);
+    size_t off = w.list_off + 16 + (size_t)w.list_cap * sizeof(unsigned long long);
+    off = align_up(off, 16);
+    const bool sp = n <= NMS_SP_MAX_N;                          // larger n never takes the spatial path
+    w.groups_cap = sp ? (int)(col_blocks + NMS_SP_SUPER < (size_t)NMS_SP_MAX_GROUPS ? col_blocks + NMS_SP_SUPER : (size_t)NMS_SP_MAX_GROUPS) : 0;
+    w.perm_off = off;   off += sp ? align_up((size_t)frames * n * sizeof(int), 16) : 0;
+    w.groups_off = off; off += align_up((size_t)frames * w.groups_cap * sizeof(int2), 16);
+    w.tiles_cap = (size_t)frames * ((size_t)w.groups_cap * (w.groups_cap + 1) / 2) * (NMS_TILE / NMS_SP_QROWS);
+    w.tiles_off = off;  off += align_up(w.tiles_cap * sizeof(unsigned int), 16);
+    w.tcount_off = off; off += 16;
+    w.bytes = off;
+    return w;
+}
+
 static int launch_nms(bool normal, const float* boxes, int frames, int n, float thresh, int64_t* keep,
                       int32_t* num_keep, void* ws, size_t ws_bytes, cudaStream_t stream, const char* what) {
     if (frames < 0 || n < 0) return fail(GLENET_EINVAL, "%s: negative size", what);
@@ -489,7 +864,7 @@ static int launch_nms(bool normal, const float* boxes, int frames, int n, float 
     if (tiles * frames > 0x7fffffffL) return fail(GLENET_EINVAL, "%s: too many tiles", what);
     unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws);
     // opt-in shared-memory sizes are per-device settings: remember where they have been set
-    static std::atomic<unsigned char> attr_done[GLENET_MAX_DEVICES];   // bit 0: mask kernels, bit 1 / 2: sweep kernel <false> / <true>
+    static std::atomic<unsigned char> attr_done[GLENET_MAX_DEVICES];   // bit 0: mask kernels, bit 1 / 2: sweep kernel <false> / <true>, bit 3: spatial mask kernel
     int dev = 0;
     cudaGetDevice(&dev);
     const bool cacheable = dev >= 0 && dev < GLENET_MAX_DEVICES;
@@ -502,17 +877,50 @@ static int launch_nms(bool normal, const float* boxes, int frames, int n, float 
         if (cacheable) attr_done[dev].fetch_or(1, std::memory_order_release);
     }
     const unsigned grid = (unsigned)(tiles * frames);
-    // deferred exact clips: [count][list] behind the mask (glenet_nms_workspace_bytes)
-    const size_t mask_bytes = align_up((size_t)frames * n * col_blocks * sizeof(unsigned long long), 16);
-    unsigned long long* list_count = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(ws) + mask_bytes);
+    const NmsWorkspace w = nms_layout(frames, n);
+    // deferred exact clips: [count][list] behind the mask
+    unsigned long long* list_count = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(ws) + w.list_off);
     unsigned long long* list = list_count + 2;
-    const unsigned long long list_cap = nms_list_cap(frames, n);
+    const unsigned long long list_cap = w.list_cap;
     const bool defer = GLENET_NMS_DEFER && !normal && n < (1 << 20) && frames < (1 << 23);
     if (defer) {
         cudaError_t e = cudaMemsetAsync(list_count, 0, 16, stream);
         if (e != cudaSuccess) return fail(-(int)e, "%s: memset failed", what);
     }
-    if (normal)
+    // spatial tiles (see nms_spatial_kernel): worth it once the n^2 / 2 circle tests dominate; a negative threshold keeps
+    // every pair (one global atomic each) and stays with the score-order tiles.  GLENET_NMS_SPATIAL=0 turns them off, =2 forces them.
+    static const int spatial_mode = [] { const char* e = getenv("GLENET_NMS_SPATIAL"); return e ? atoi(e) : 1; }();   // 0 off, 1 by size, 2 whenever legal (tests)
+    const bool spatial_on = spatial_mode != 0;
+    // (the binning kernel is a ~14 us serial prologue: the score-order tiles win for one or two frames of 4096 proposals)
+    const bool spatial = spatial_on && !normal && thresh >= 0.f && n <= NMS_SP_MAX_N && frames < (1 << 14) &&
+                         (spatial_mode == 2 || (n >= 1024 && (double)frames * n * n >= 2.5 * 4096.0 * 4096.0));
+    if (spatial) {
+        unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+        int* perm = reinterpret_cast<int*>(base + w.perm_off);
+        int2* groups = reinterpret_cast<int2*>(base + w.groups_off);
+        unsigned int* tile_list = reinterpret_cast<unsigned int*>(base + w.tiles_off);
+        unsigned int* tile_count = reinterpret_cast<unsigned int*>(base + w.tcount_off);
+        cudaError_t e = cudaMemsetAsync(tile_count, 0, 16, stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(mask, 0, (size_t)frames * n * col_blocks * sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return fail(-(int)e, "%s: memset failed", what);
+        int rc;
+        if (!(done & 8)) {
+            rc = set_smem(nms_mask_spatial_kernel, sizeof(NmsSmem), what);
+            if (rc) return rc;
+            rc = set_smem(nms_spatial_kernel, nms_spatial_smem(NMS_SP_MAX_N), what);
+            if (rc) return rc;
+            if (cacheable) attr_done[dev].fetch_or(8, std::memory_order_release);
+        }
+        nms_spatial_kernel<<<frames, NMS_SP_THREADS, nms_spatial_smem(n), stream>>>(boxes, n, perm, groups, w.groups_cap, tile_list, tile_count);
+        rc = check_launch(what);
+        if (rc) return rc;
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const size_t most = w.tiles_cap < (size_t)sms * GLENET_NMS_CTAS ? w.tiles_cap : (size_t)sms * GLENET_NMS_CTAS;
+        nms_mask_spatial_kernel<<<(unsigned)most, NMS_THREADS, sizeof(NmsSmem), stream>>>(boxes, n, thresh, mask, col_blocks, perm, groups, w.groups_cap,
+                                                                                         tile_list, tile_count,
+                                                                                         defer ? list_count : nullptr, defer ? list : nullptr, list_cap);
+    } else if (normal)
         nms_mask_kernel<true><<<grid, NMS_THREADS, sizeof(NmsSmem), stream>>>(boxes, n, thresh, mask, col_blocks, (int)tiles, nullptr, nullptr, 0ull);
     else
         nms_mask_kernel<false><<<grid, NMS_THREADS, sizeof(NmsSmem), stream>>>(boxes, n, thresh, mask, col_blocks, (int)tiles,
@@ -553,8 +961,8 @@ extern "C" {
 size_t glenet_nms_workspace_bytes(int frames, int n) {
     if (frames <= 0 || n <= 0) return 16;
     const size_t col_blocks = ((size_t)n + NMS_TILE - 1) / NMS_TILE;
-    // the suppression mask, then the list of pairs whose exact clip is deferred: a 16-byte counter + 32 n entries per frame
-    return align_up((size_t)frames * n * col_blocks * sizeof(unsigned long long), 16) + 16 + (size_t)nms_list_cap(frames, n) * sizeof(unsigned long long);
+    (void)col_blocks;
+    return nms_layout(frames, n).bytes;
 }
 
 #ifdef GLENET_PHASE_TIMING

@@ -881,7 +881,7 @@ int glenet_points_in_boxes_cpu_dialect(const float* boxes, const float* trig, in
     return check_launch(what);
 }
 
-int glenet_abi_version(void) { return 12; }
+int glenet_abi_version(void) { return 13; }
 const char* glenet_last_error(void) { return last_error_buf(); }
 
 }  // extern "C"

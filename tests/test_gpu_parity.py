@@ -829,3 +829,43 @@ def test_variance_voting_and_soft_nms_device_loops_vs_reference_loops(cuda, ref_
             assert k_got.is_cuda and sorted(k_got.tolist()) == sorted(k_ref.tolist()), (mode, variance is None)
             assert torch.allclose(b_got[k_ref], b_r[k_ref], rtol=0, atol=1e-4)
             assert k_ref.numel() > 5
+
+
+_SPATIAL_NMS_CHILD = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from glenet_b200 import iou3d_nms_utils as I, synth
+from oracle import ref
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(3)
+cases = []
+for n, k, seed in ((130, 3, 1), (1000, 8, 2), (2500, 20, 3), (4096, 20, 4), (64, 1, 5), (65, 2, 6)):
+    b, s = synth.proposals(n, k, seed)
+    cases.append((b, s))
+# a scene with far-apart objects, exact duplicates, boxes with NaN / inf terms and a zero-size box
+b, s = synth.proposals(1500, 12, 7)
+b[100] = b[7]; b[101] = b[7]; b[200, 0] = float("nan"); b[300, 3] = float("inf"); b[400, 6] = float("nan"); b[500, 3:5] = 0.0
+b[600:700, :2] += 5000.0
+cases.append((b, s))
+for b, s in cases:
+    b, s = b.to(dev), s.to(dev)
+    for thr in (0.7, 0.3, 0.01, 0.0):
+        got, want = I.nms_gpu(b, s, thr)[0], ref.nms_gpu(b, s, thr)[0]
+        assert torch.equal(got, want), (b.shape, thr, got.numel(), want.numel())
+fb = torch.stack([synth.proposals(2048, 10, 30 + f)[0] for f in range(3)]).to(dev)
+fs = torch.stack([synth.proposals(2048, 10, 30 + f)[1] for f in range(3)]).to(dev)
+keep, num = I.nms_gpu_batch(fb, fs, 0.5)
+for f in range(3):
+    assert torch.equal(keep[f, :int(num[f])], ref.nms_gpu(fb[f], fs[f], 0.5)[0]), f
+print("spatial nms ok")
+"""
+
+
+def test_nms_spatial_tiles_forced_vs_reference(cuda, ref_so):
+    """The spatial-tile mask kernels (taken by size in production) forced on for small, ragged and degenerate inputs
+    (GLENET_NMS_SPATIAL=2 is read once per process, hence the child): keep indices equal to the reference's."""
+    import os, subprocess, sys
+    env = dict(os.environ, GLENET_NMS_SPATIAL="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _SPATIAL_NMS_CHILD % root], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "spatial nms ok" in r.stdout, r.stdout[-3000:]

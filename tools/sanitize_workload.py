@@ -1,5 +1,6 @@
 """Small run of every kernel for compute-sanitizer (memcheck / racecheck):  compute-sanitizer --tool memcheck python tools/sanitize_workload.py"""
 import os, sys
+os.environ.setdefault("GLENET_NMS_SPATIAL", "2")   # the spatial-tile NMS kernels are taken by size in production: force them on the small inputs here
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from glenet_b200 import iou3d_nms_utils as I, iou3d_utils as I1, roiaware_pool3d_utils as R, synth
@@ -13,7 +14,8 @@ p, s = synth.proposals(700, 6, 1)
 p, s = p.to(dev), s.to(dev)
 I.boxes_iou_bev(p, p)                                           # dense tiles: queue overflow rounds, carried clip passes
 I.boxes_iou_frames_sparse(a, g4); I.iou_max_overlaps_frames(a, g4)
-I.nms_gpu(p, s, 0.7); I.nms_normal_gpu(p, s, 0.7); I.nms_gpu_batch(torch.stack([p, p]), torch.stack([s, s]), 0.5)
+I.nms_gpu(p, s, 0.7); I.nms_gpu(p[:300], s[:300], -1.0)         # spatial tiles (forced above); a negative threshold takes the score-order tiles and the in-tile clip
+I.nms_normal_gpu(p, s, 0.7); I.nms_gpu_batch(torch.stack([p, p]), torch.stack([s, s]), 0.5)
 I.boxes_iou3d_aligned(p[:600], p[:20], 30)
 pr, tg = synth.head_pairs(500, 0)
 I1.boxes_aligned_iou3d_gpu(pr.to(dev), tg.to(dev), need_bev=True)
