@@ -338,7 +338,8 @@ constexpr int NMS_SP_CELLS = NMS_SP_G * NMS_SP_G;
 constexpr int NMS_SP_SUPER = NMS_SP_CELLS / 16;    // 4 x 4 blocks of cells = 16 consecutive Morton codes
 constexpr int NMS_SP_THREADS = 1024;
 constexpr int NMS_SP_MAX_GROUPS = 255;             // group numbers travel in 8 bits
-constexpr int NMS_SP_MAX_N = (NMS_SP_MAX_GROUPS - NMS_SP_SUPER) * NMS_TILE;   // every block of cells can add one partial group
+constexpr int NMS_SP_MAX_N = 160 * NMS_TILE;      // 160 + 64 groups at most (every block of cells can add one partial group); 184 KB of cached boxes
+constexpr int NMS_SP_EDGES = 4096;                 // group pairs kept in shared memory for the component labelling
 constexpr int NMS_SP_QROWS = 16;                   // rows of a work item (a quarter of group P)
 
 __device__ __forceinline__ unsigned int morton5(unsigned int x, unsigned int y) {   // 5 + 5 bits interleaved
@@ -352,7 +353,8 @@ static size_t nms_spatial_smem(int n) { return (size_t)n * (sizeof(float4) + siz
 
 __global__ void __launch_bounds__(NMS_SP_THREADS)
 nms_spatial_kernel(const float* __restrict__ boxes_all, int n, int* __restrict__ perm_all, int2* __restrict__ groups_all, int groups_cap,
-                   unsigned int* __restrict__ tiles, unsigned int* __restrict__ tile_count) {
+                   unsigned int* __restrict__ tiles, unsigned int* __restrict__ tile_count,
+                   int* __restrict__ labels_all, unsigned long long* __restrict__ members_all, int col_blocks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* s_box = reinterpret_cast<float4*>(smem_raw);                    // [n] {cx, cy, cull radius (+pad), 1 = all terms finite}
     unsigned short* s_perm = reinterpret_cast<unsigned short*>(s_box + n);  // [n] sorted position -> box
@@ -363,6 +365,10 @@ nms_spatial_kernel(const float* __restrict__ boxes_all, int n, int* __restrict__
     __shared__ float4 s_gbox[NMS_SP_MAX_GROUPS];
     __shared__ int2 s_grp[NMS_SP_MAX_GROUPS];
     __shared__ int s_gstart[NMS_SP_SUPER + 1];
+    __shared__ int s_lab[NMS_SP_MAX_GROUPS + 1];
+    __shared__ int s_changed;
+    __shared__ unsigned int s_edge[NMS_SP_EDGES];      // (P << 8) | Q of the meeting pairs, P < Q
+    __shared__ unsigned int s_nedge;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.x;
     const float* boxes = boxes_all + (size_t)frame * n * 7;
@@ -477,19 +483,193 @@ nms_spatial_kernel(const float* __restrict__ boxes_all, int n, int* __restrict__
         if (__any_sync(0xffffffffu, bad)) { gx0 = gy0 = -CUDART_INF_F; gx1 = gy1 = CUDART_INF_F; }   // NaN anywhere: never culled
         if (lane == 0) { s_gbox[g] = make_float4(gx0, gy0, gx1, gy1); groups[g] = gr; }
     }
+    for (int g = tid; g < ng; g += NMS_SP_THREADS) s_lab[g] = g;
+    if (tid == 0) s_nedge = 0u;
     __syncthreads();
     // work items: group pairs (P <= Q) whose bounding boxes meet, one item per quarter of P's rows
     const int npairs = ng * (ng + 1) / 2;
+    auto meet = [&](int P, int Q) -> bool {
+        const float4 a = s_gbox[P], b = s_gbox[Q];
+        return !(a.x > b.z || b.x > a.z || a.y > b.w || b.y > a.w);
+    };
     for (int t = tid; t < npairs; t += NMS_SP_THREADS) {
         int P, Q;
         tri_decode(t, ng, P, Q);
-        const float4 a = s_gbox[P], b = s_gbox[Q];
-        if (a.x > b.z || b.x > a.z || a.y > b.w || b.y > a.w) continue;
+        if (!meet(P, Q)) continue;
         const int nq = (s_grp[P].y + NMS_SP_QROWS - 1) / NMS_SP_QROWS;
         const unsigned int at = atomicAdd(tile_count, (unsigned int)nq);
         for (int q = 0; q < nq; ++q)
             tiles[at + q] = ((unsigned int)frame << 18) | ((unsigned int)P << 10) | ((unsigned int)Q << 2) | (unsigned int)q;
+        if (P != Q) {
+            atomicMin(&s_lab[Q], P);
+            const unsigned int e = atomicAdd(&s_nedge, 1u);
+            if (e < (unsigned int)NMS_SP_EDGES) s_edge[e] = ((unsigned int)P << 8) | (unsigned int)Q;
+        }
     }
+    // Connected components of the "group boxes meet" graph: a mask bit can only join boxes of one component, so the greedy
+    // sweep runs per component, all components in parallel (nms_component_sweep_kernel).  Minimum-label propagation over the
+    // edges + pointer jumping until no edge joins two labels; the label of a component is its lowest group number.
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_changed = 0;
+        for (int g = tid; g < ng; g += NMS_SP_THREADS) { const int l = s_lab[g]; const int ll = s_lab[l]; if (ll < l) s_lab[g] = ll; }
+        __syncthreads();
+        auto join = [&](int P, int Q) {
+            const int a = s_lab[P], b = s_lab[Q];
+            if (a != b) { const int m = min(a, b); atomicMin(&s_lab[P], m); atomicMin(&s_lab[Q], m); s_changed = 1; }
+        };
+        const unsigned int ne = s_nedge;       // (final: written before the barrier above)
+        if (ne <= (unsigned int)NMS_SP_EDGES) {
+            for (unsigned int e = tid; e < ne; e += NMS_SP_THREADS) join((int)(s_edge[e] >> 8), (int)(s_edge[e] & 255u));
+        } else {                               // more meeting pairs than the list holds: walk all pairs again
+            for (int t = tid; t < npairs; t += NMS_SP_THREADS) {
+                int P, Q;
+                tri_decode(t, ng, P, Q);
+                if (P != Q && meet(P, Q)) join(P, Q);
+            }
+        }
+        __syncthreads();
+        if (!s_changed) break;   // uniform
+    }
+    // labels (-1 beyond the frame's groups) and one membership bitmap per component, indexed by score position
+    int* labels = labels_all + (size_t)frame * (groups_cap + 1);
+    unsigned long long* members = members_all + (size_t)frame * groups_cap * col_blocks;   // zeroed by the launcher
+    int roots = 0;
+    for (int g = tid; g < groups_cap; g += NMS_SP_THREADS) {
+        const int l = g < ng ? s_lab[g] : -1;
+        labels[g] = l;
+        roots += (l == g) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) roots += __shfl_xor_sync(0xffffffffu, roots, o);
+    if (lane == 0 && roots) atomicAdd(&labels[groups_cap], roots);          // number of components (slot zeroed by the launcher)
+    for (int g = warp; g < ng; g += NMS_SP_THREADS / 32) {
+        const int2 gr = s_grp[g];
+        unsigned long long* m = members + (size_t)s_lab[g] * col_blocks;
+        for (int k = lane; k < gr.y; k += 32) {
+            const int box = s_perm[gr.x + k];
+            atomicOr(&m[box >> 6], 1ull << (box & 63));
+        }
+    }
+}
+
+// Greedy sweep per component: one warp per component label.  The warp holds the component's membership bits, the suppression
+// bits and the kept bits in registers (up to 6 words of 64 boxes per lane); each iteration finds the lowest member that is not
+// yet suppressed -- it is kept --, ORs its mask row into the suppression bits, and repeats: one iteration (one L2 round trip)
+// per KEPT box of the component.  The last warp of a frame to finish turns the kept bits into the ascending index list.
+constexpr int NMS_CS_WARPS = 8;
+constexpr int NMS_CS_KMAX = (NMS_SP_MAX_N / NMS_TILE + 31) / 32;   // words per lane: at most 5
+template <int NMS_CS_K>   // words of 64 boxes per lane: ceil(n / 2048) -- the loop is one dependent instruction chain per warp, so dead words cost
+__global__ void __launch_bounds__(NMS_CS_WARPS * 32)
+nms_component_sweep_kernel(const unsigned long long* __restrict__ mask_all, int n, int col_blocks, int frames, int groups_cap,
+                           const int* __restrict__ labels_all, const unsigned long long* __restrict__ members_all,
+                           unsigned long long* __restrict__ kept_all, unsigned int* __restrict__ done_all,
+                           long long* __restrict__ keep_all, int* __restrict__ num_keep_all) {
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * NMS_CS_WARPS + (threadIdx.x >> 5);
+    if (wid >= frames * groups_cap) return;
+    const int frame = wid / groups_cap, g = wid - frame * groups_cap;
+    const int* labels = labels_all + (size_t)frame * (groups_cap + 1);
+    if (labels[g] != g) return;                                   // not the label of a component
+    const unsigned long long* mask = mask_all + (size_t)frame * n * col_blocks;
+    const unsigned long long* members = members_all + ((size_t)frame * groups_cap + g) * col_blocks;
+    unsigned long long* keptw = kept_all + (size_t)frame * col_blocks;
+    unsigned long long mem[NMS_CS_K], remv[NMS_CS_K], kept[NMS_CS_K];
+#pragma unroll
+    for (int k = 0; k < NMS_CS_K; ++k) {
+        const int w = k * 32 + lane;
+        mem[k] = w < col_blocks ? members[w] : 0ull;
+        remv[k] = 0ull; kept[k] = 0ull;
+    }
+    constexpr int NB = 4;   // candidates whose rows travel together: one L2 round trip confirms up to four kept boxes
+    for (;;) {
+        // the NB lowest members not yet suppressed or kept (words ascend with k, then with the lane); the lowest one is kept for
+        // sure, each further one unless a row ORed in before it suppresses it
+        unsigned long long tmp[NMS_CS_K];
+#pragma unroll
+        for (int k = 0; k < NMS_CS_K; ++k) tmp[k] = mem[k] & ~remv[k];
+        int ck[NB], cs[NB], cb[NB];
+        int nc = 0;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            int fk = -1;
+            unsigned long long cw = 0ull;
+            unsigned int bal = 0u;
+#pragma unroll
+            for (int k = 0; k < NMS_CS_K; ++k) {
+                if (fk < 0) {
+                    const unsigned int b = __ballot_sync(0xffffffffu, tmp[k] != 0ull);
+                    if (b) { fk = k; cw = tmp[k]; bal = b; }
+                }
+            }
+            ck[c] = fk; cs[c] = 0; cb[c] = 0;
+            if (fk >= 0) {
+                cs[c] = __ffs((int)bal) - 1;
+                cb[c] = __ffsll((long long)__shfl_sync(0xffffffffu, cw, cs[c])) - 1;
+                nc = c + 1;
+#pragma unroll
+                for (int k = 0; k < NMS_CS_K; ++k) if (k == fk && lane == cs[c]) tmp[k] &= ~(1ull << cb[c]);
+            }
+        }
+        if (nc == 0) break;
+        unsigned long long rows[NB][NMS_CS_K];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            const int i = ((ck[c] * 32 + cs[c]) << 6) + cb[c];
+            const unsigned long long* row = mask + (size_t)(c < nc ? i : 0) * col_blocks;
+#pragma unroll
+            for (int k = 0; k < NMS_CS_K; ++k) {
+                const int w = k * 32 + lane;
+                rows[c][k] = (c < nc && w < col_blocks) ? __ldcg(row + w) : 0ull;     // written by the mask kernels' atomics: read through L2
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            if (c < nc) {
+                // still unsuppressed?  (the owner lane's word, broadcast; candidate 0 always is)
+                unsigned long long ow = 0ull;
+#pragma unroll
+                for (int k = 0; k < NMS_CS_K; ++k) if (k == ck[c]) ow = remv[k];
+                ow = __shfl_sync(0xffffffffu, ow, cs[c]);
+                if (!((ow >> cb[c]) & 1ull)) {
+#pragma unroll
+                    for (int k = 0; k < NMS_CS_K; ++k) {
+                        unsigned long long r = rows[c][k];
+                        if (k == ck[c] && lane == cs[c]) { r |= 1ull << cb[c]; kept[k] |= 1ull << cb[c]; }
+                        remv[k] |= r;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NMS_CS_K; ++k) {
+        const int w = k * 32 + lane;
+        if (w < col_blocks && kept[k]) atomicOr(&keptw[w], kept[k]);
+    }
+    __threadfence();
+    __syncwarp();
+    unsigned int last = 0u;
+    if (lane == 0) last = (atomicAdd(&done_all[frame], 1u) == (unsigned int)labels[groups_cap] - 1u) ? 1u : 0u;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    // kept bits -> ascending indices
+    long long* keep = keep_all + (size_t)frame * n;
+    int base = 0;
+#pragma unroll
+    for (int k = 0; k < NMS_CS_K; ++k) {
+        const int w = k * 32 + lane;
+        unsigned long long kw = w < col_blocks ? __ldcg(keptw + w) : 0ull;
+        const int c = __popcll(kw);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        int pos = base + incl - c;
+        while (kw) { const int b = __ffsll((long long)kw) - 1; kw &= kw - 1; keep[pos++] = (long long)(w * 64 + b); }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) num_keep_all[frame] = base;
 }
 
 __global__ void __launch_bounds__(NMS_THREADS, GLENET_NMS_CTAS)
@@ -823,7 +1003,7 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask_all, int n, int col
 
 // workspace: [mask][16-byte list counter][deferred-clip list][spatial: permutation | group table | work items | item counter]
 struct NmsWorkspace {
-    size_t mask_bytes, list_off, perm_off, groups_off, tiles_off, tcount_off, bytes;
+    size_t mask_bytes, list_off, perm_off, groups_off, tiles_off, tcount_off, zero_off, zero_bytes, labels_off, done_off, kept_off, members_off, bytes;
     unsigned long long list_cap;
     size_t tiles_cap;
     int groups_cap;
@@ -843,6 +1023,13 @@ static NmsWorkspace nms_layout(int frames, int n) {
     w.tiles_cap = (size_t)frames * ((size_t)w.groups_cap * (w.groups_cap + 1) / 2) * (NMS_TILE / NMS_SP_QROWS);
     w.tiles_off = off;  off += align_up(w.tiles_cap * sizeof(unsigned int), 16);
     w.tcount_off = off; off += 16;
+    // zeroed per call: component labels (+ count), per-frame done counters, kept bits, membership bitmaps
+    w.zero_off = off;
+    w.labels_off = off;  off += align_up((size_t)frames * (w.groups_cap + 1) * sizeof(int), 16);
+    w.done_off = off;    off += align_up((size_t)frames * sizeof(unsigned int), 16);
+    w.kept_off = off;    off += sp ? align_up((size_t)frames * col_blocks * sizeof(unsigned long long), 16) : 0;
+    w.members_off = off; off += align_up((size_t)frames * w.groups_cap * col_blocks * sizeof(unsigned long long), 16);
+    w.zero_bytes = off - w.zero_off;
     w.bytes = off;
     return w;
 }
@@ -891,16 +1078,18 @@ static int launch_nms(bool normal, const float* boxes, int frames, int n, float 
     // every pair (one global atomic each) and stays with the score-order tiles.  GLENET_NMS_SPATIAL=0 turns them off, =2 forces them.
     static const int spatial_mode = [] { const char* e = getenv("GLENET_NMS_SPATIAL"); return e ? atoi(e) : 1; }();   // 0 off, 1 by size, 2 whenever legal (tests)
     const bool spatial_on = spatial_mode != 0;
-    // (the binning kernel is a ~14 us serial prologue: the score-order tiles win for one or two frames of 4096 proposals)
-    const bool spatial = spatial_on && !normal && thresh >= 0.f && n <= NMS_SP_MAX_N && frames < (1 << 14) &&
-                         (spatial_mode == 2 || (n >= 1024 && (double)frames * n * n >= 2.5 * 4096.0 * 4096.0));
+    const bool spatial = spatial_on && !normal && thresh >= 0.f && n <= NMS_SP_MAX_N && frames < (1 << 14) && (spatial_mode == 2 || n >= 1024);
     if (spatial) {
         unsigned char* base = reinterpret_cast<unsigned char*>(ws);
         int* perm = reinterpret_cast<int*>(base + w.perm_off);
         int2* groups = reinterpret_cast<int2*>(base + w.groups_off);
         unsigned int* tile_list = reinterpret_cast<unsigned int*>(base + w.tiles_off);
         unsigned int* tile_count = reinterpret_cast<unsigned int*>(base + w.tcount_off);
-        cudaError_t e = cudaMemsetAsync(tile_count, 0, 16, stream);
+        int* labels = reinterpret_cast<int*>(base + w.labels_off);
+        unsigned int* done_cnt = reinterpret_cast<unsigned int*>(base + w.done_off);
+        unsigned long long* kept_bits = reinterpret_cast<unsigned long long*>(base + w.kept_off);
+        unsigned long long* members = reinterpret_cast<unsigned long long*>(base + w.members_off);
+        cudaError_t e = cudaMemsetAsync(tile_count, 0, 16 + w.zero_bytes, stream);      // the zeroed block follows the counter
         if (e == cudaSuccess) e = cudaMemsetAsync(mask, 0, (size_t)frames * n * col_blocks * sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return fail(-(int)e, "%s: memset failed", what);
         int rc;
@@ -911,7 +1100,8 @@ static int launch_nms(bool normal, const float* boxes, int frames, int n, float 
             if (rc) return rc;
             if (cacheable) attr_done[dev].fetch_or(8, std::memory_order_release);
         }
-        nms_spatial_kernel<<<frames, NMS_SP_THREADS, nms_spatial_smem(n), stream>>>(boxes, n, perm, groups, w.groups_cap, tile_list, tile_count);
+        nms_spatial_kernel<<<frames, NMS_SP_THREADS, nms_spatial_smem(n), stream>>>(boxes, n, perm, groups, w.groups_cap, tile_list, tile_count,
+                                                                                    labels, members, col_blocks);
         rc = check_launch(what);
         if (rc) return rc;
         int sms = 148;
@@ -933,6 +1123,28 @@ static int launch_nms(bool normal, const float* boxes, int frames, int n, float 
         nms_clip_list_kernel<<<sms * 4, NCL_THREADS, 0, stream>>>(boxes, n, thresh, mask, col_blocks, list_count, list, list_cap);
         rc = check_launch(what);
         if (rc) return rc;
+    }
+    if (spatial) {
+        const NmsWorkspace w2 = nms_layout(frames, n);
+        unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+        const long warps = (long)frames * w2.groups_cap;
+        const unsigned cs_grid = (unsigned)((warps + NMS_CS_WARPS - 1) / NMS_CS_WARPS);
+        const int* labels = reinterpret_cast<const int*>(base + w2.labels_off);
+        const unsigned long long* members = reinterpret_cast<const unsigned long long*>(base + w2.members_off);
+        unsigned long long* kept_bits = reinterpret_cast<unsigned long long*>(base + w2.kept_off);
+        unsigned int* done_cnt = reinterpret_cast<unsigned int*>(base + w2.done_off);
+        long long* keep_ll = reinterpret_cast<long long*>(keep);
+        static_assert(NMS_CS_KMAX == 5, "instantiations below");
+#define GLENET_CS_LAUNCH(K) nms_component_sweep_kernel<K><<<cs_grid, NMS_CS_WARPS * 32, 0, stream>>>(mask, n, col_blocks, frames, w2.groups_cap, labels, members, kept_bits, done_cnt, keep_ll, num_keep)
+        switch ((col_blocks + 31) / 32) {
+            case 1: GLENET_CS_LAUNCH(1); break;
+            case 2: GLENET_CS_LAUNCH(2); break;
+            case 3: GLENET_CS_LAUNCH(3); break;
+            case 4: GLENET_CS_LAUNCH(4); break;
+            default: GLENET_CS_LAUNCH(5); break;
+        }
+#undef GLENET_CS_LAUNCH
+        return check_launch(what);
     }
     const size_t remv_bytes = sizeof(unsigned long long) * col_blocks;
     const size_t pre_bytes = remv_bytes + 2 * sizeof(unsigned long long) * (size_t)n;

@@ -34,8 +34,9 @@ def test_library_builds_loads_and_exports_everything():
     assert sorted(glenet_b200.EXPORTS) == declared_symbols()
     assert lib.glenet_abi_version() == 13
     # mask + deferred-clip list (16-byte counter + 32 n entries) + spatial tiles (permutation, table of up to 64 + 64 groups,
-    # 4 work items per group pair, counter)
-    assert lib.glenet_nms_workspace_bytes(1, 4096) == 4096 * 64 * 8 + 16 + 32 * 4096 * 8 + 4096 * 4 + 128 * 8 + 128 * 129 // 2 * 4 * 4 + 16
+    # 4 work items per group pair, counter) + component sweep (labels + count, done counter, kept bits, membership bitmaps)
+    assert lib.glenet_nms_workspace_bytes(1, 4096) == (4096 * 64 * 8 + 16 + 32 * 4096 * 8 + 4096 * 4 + 128 * 8 + 128 * 129 // 2 * 4 * 4 + 16
+                                                       + 528 + 16 + 64 * 8 + 128 * 64 * 8)
     assert lib.glenet_points_in_boxes_workspace_bytes(2, 200) > 2 * 200 * 32
     # workspace layout of csrc/pib.cu (pib_layout): per frame a 48-byte header, 8 floats per box, 32 N + 8192 list slots
     # (slices of crowded coarse cells), a 128 x 128 fine map of 16 z-slab bits and 4096 packed 8-byte coarse cells; every
