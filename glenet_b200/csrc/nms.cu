@@ -15,6 +15,10 @@
 //                 super-diagonal words; the other warps OR the kept rows' remaining mask words
 //                 into the running suppression words one step later.  keep[] and the count stay
 //                 on the device.
+//   spatial path (1024 <= n <= 10240, thresh >= 0; "spatial tiles" below): the pairs are enumerated over
+//                 groups of neighbouring boxes instead of score-order tiles -- only groups whose bounding
+//                 boxes meet are paired -- and the greedy sweep runs per connected component of that
+//                 group graph, one warp per component.  Same mask bits, same keep list.
 #include "common.cuh"
 #include "geom.cuh"
 #include "clip.cuh"
