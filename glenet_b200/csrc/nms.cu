@@ -679,13 +679,13 @@ nms_component_sweep_kernel(const unsigned long long* __restrict__ mask_all, int 
 __global__ void __launch_bounds__(NMS_THREADS, GLENET_NMS_CTAS)
 nms_mask_spatial_kernel(const float* __restrict__ boxes_all, int n, float thresh, unsigned long long* __restrict__ mask_all, int col_blocks,
                         const int* __restrict__ perm_all, const int2* __restrict__ groups_all, int groups_cap,
-                        const unsigned int* __restrict__ tiles, const unsigned int* __restrict__ tile_count,
+                        const unsigned int* __restrict__ tiles, unsigned int* tile_count,   // [0] number of items, [1] next item to hand out
                         unsigned long long* __restrict__ list_count, unsigned long long* __restrict__ list, unsigned long long list_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem& sm = *reinterpret_cast<NmsSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned int ntiles = tile_count[0];
-    unsigned int* next_item = const_cast<unsigned int*>(tile_count) + 1;     // zeroed by the launcher with the count
+    unsigned int* next_item = tile_count + 1;                                // zeroed by the launcher with the count
     const float thr_lo = thresh * (1.f - 1e-3f) - 1e-5f, thr_hi = thresh * (1.f + 1e-3f) + 1e-5f;
     // Work items differ by two orders of magnitude (an object's own groups vs. two groups whose boxes merely touch), so they are
     // handed out dynamically: thread 0 claims the NEXT item when the current one starts (the atomic's latency hides behind the
