@@ -45,6 +45,7 @@ vnms_kernel(float* __restrict__ boxes_all, float* __restrict__ scores_all, const
     float* s_w = reinterpret_cast<float*>(s_undone + (n + 31) / 32);     // [VN_STAGE] exp(-(1 - iou)^2 / 0.05)
     float* s_var = s_w + VN_STAGE;                                       // [VN_STAGE][7]
     float* s_box = s_var + VN_STAGE * 7;                                 // [VN_STAGE][7]
+    float* s_term = s_box + VN_STAGE * 7;                                // [VN_STAGE][7] the addends of the current pass
     __shared__ VnmsBest s_best[VN_THREADS / 32];
     __shared__ int s_cnt[VN_THREADS / 32];
     __shared__ int s_top, s_left, s_nsel;
@@ -119,11 +120,16 @@ vnms_kernel(float* __restrict__ boxes_all, float* __restrict__ scores_all, const
 
         // ---- 2. + 3a. IoU column, and the voters in index order
         int nsel = 0;
+        // (a column of the row-major matrix: one sector per element -- all rounds' loads are issued before anything waits on them)
+#pragma unroll 4
+        for (int k = 0; k < rounds; ++k) {
+            const int j = k * VN_THREADS + tid;
+            if (j < n && ((s_undone[j >> 5] >> (j & 31)) & 1u)) s_iou[j] = __ldg(iou + (size_t)j * n + top);
+        }
         for (int k = 0; k < rounds; ++k) {
             const int j = k * VN_THREADS + tid;
             const bool in_play = j < n && ((s_undone[j >> 5] >> (j & 31)) & 1u);
-            float v = 0.f;
-            if (in_play) { v = iou[(size_t)j * n + top]; s_iou[j] = v; }
+            const float v = in_play ? s_iou[j] : 0.f;      // (written by this thread above)
             if (var) {
                 const bool sel = in_play && v > thr;
                 const unsigned int m = __ballot_sync(0xffffffffu, sel);
@@ -145,12 +151,15 @@ vnms_kernel(float* __restrict__ boxes_all, float* __restrict__ scores_all, const
                 for (int c0 = 0; c0 < nvote; c0 += VN_STAGE) {
                     const int cn = min(VN_STAGE, nvote - c0);
                     __syncthreads();
+                    const bool staged = pass == 1 && nvote <= VN_STAGE;     // one chunk: weights, boxes and variances are still there from pass 0
+                    if (!staged)
                     for (int t = tid; t < cn; t += VN_THREADS) {
                         const bool is_top = SOFT && c0 + t == nsel;
                         const int j = is_top ? top : s_sel[c0 + t];
                         const float d = 1.f - s_iou[j];
                         s_w[t] = is_top ? 1.f : expf(__fdiv_rn(-1.f * (d * d), 0.05f));   // std_iou_sigma = 0.05 (:257 / :339)
                     }
+                    if (!staged)
                     for (int t = tid; t < cn * 7; t += VN_THREADS) {
                         const int r = t / 7, c = t - r * 7;
                         const int j = (SOFT && c0 + r == nsel) ? top : s_sel[c0 + r];
@@ -158,20 +167,27 @@ vnms_kernel(float* __restrict__ boxes_all, float* __restrict__ scores_all, const
                         s_var[t] = c < var_cols ? var[(size_t)j * var_cols + c] : 1.f;
                     }
                     __syncthreads();
-                    if (tid < DIMS) {
+                    // the terms in parallel (weight / variance, heading rules, normalised product -- each rounded as numpy rounds
+                    // it); only the additions have to run in index order
+                    {
                         const float top_h = s_toph;
-                        const float norm = pass ? s_sum[tid] : 1.f;
-                        for (int t = 0; t < cn; ++t) {
-                            float x = s_box[t * 7 + tid];
-                            float w = __fdiv_rn(s_w[t], s_var[t * 7 + tid]);
-                            if (!SOFT && tid == 6) {
+                        for (int t = tid; t < cn * 7; t += VN_THREADS) {
+                            const int r = t / 7, c = t - r * 7;
+                            if (c >= DIMS) continue;
+                            float x = s_box[t];
+                            float w = __fdiv_rn(s_w[r], s_var[t]);
+                            if (!SOFT && c == 6) {
                                 // headings on the far side of the +-pi cut are moved next to the top box (:250-253), and
                                 // boxes turned by pi/4 or more do not vote for the heading (:261)
                                 if (fabsf(x - top_h) >= 4.712388980384690f) x = top_h > 0.f ? x + 6.283185307179586f : x - 6.283185307179586f;
                                 if (fabsf(x - top_h) >= 0.7853981633974483f) w = 0.f;
                             }
-                            acc = pass ? acc + __fdiv_rn(w, norm) * x : acc + w;
+                            s_term[t] = pass ? __fmul_rn(__fdiv_rn(w, s_sum[c]), x) : w;
                         }
+                    }
+                    __syncthreads();
+                    if (tid < DIMS) {
+                        for (int t = 0; t < cn; ++t) acc = __fadd_rn(acc, s_term[t * 7 + tid]);
                     }
                 }
                 __syncthreads();
@@ -206,7 +222,7 @@ vnms_kernel(float* __restrict__ boxes_all, float* __restrict__ scores_all, const
 }
 
 static size_t vnms_smem_bytes(int n) {
-    return sizeof(float) * 2 * (size_t)n + sizeof(int) * (size_t)n + sizeof(unsigned int) * (((size_t)n + 31) / 32) + sizeof(float) * VN_STAGE * 15 + 64;
+    return sizeof(float) * 2 * (size_t)n + sizeof(int) * (size_t)n + sizeof(unsigned int) * (((size_t)n + 31) / 32) + sizeof(float) * VN_STAGE * 22 + 64;
 }
 
 }  // namespace glenet
