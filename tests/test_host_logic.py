@@ -193,3 +193,88 @@ def test_rotate_iou_and_crop_wrappers_host_side():
     assert o.tolist() == [0] and c.shape == (0, 4)
     o, c = G.crop_gt_objects(np.zeros((0, 5), dtype=np.float32), np.zeros((3, 7)), "waymo")
     assert o.tolist() == [0, 0, 0, 0] and c.shape == (0, 5)
+
+
+def _spatial_groups_model(boxes):
+    """numpy model of nms_spatial_kernel's grouping (csrc/nms.cu): counting sort by the Morton code of the centre's cell
+    (32 x 32 cells over the finite centres), groups of <= 64 consecutive boxes confined to a 4 x 4 block of cells, the
+    bounding box of each group's cull circles (infinite with a non-finite member), components of the "boxes meet" graph."""
+    import numpy as np
+    b = boxes.astype(np.float32)
+    n = len(b)
+    cx, cy = b[:, 0], b[:, 1]
+    rad = (np.float32(0.5) * np.sqrt(b[:, 3] * b[:, 3] + b[:, 4] * b[:, 4])) * np.float32(1.0001) + np.float32(0.03) \
+        + np.float32(2e-6) * (np.abs(cx) + np.abs(cy)) + np.float32(1e-3)
+    with np.errstate(invalid="ignore", over="ignore"):
+        fin = np.isfinite(cx) & np.isfinite(cy) & np.isfinite(rad)
+    G = 32
+    cell = np.full(n, G * G - 1, dtype=np.int64)
+    if fin.any():
+        x0, x1, y0, y1 = cx[fin].min(), cx[fin].max(), cy[fin].min(), cy[fin].max()
+        invx = np.float32(G) / (x1 - x0) if x1 > x0 else np.float32(0)
+        invy = np.float32(G) / (y1 - y0) if y1 > y0 else np.float32(0)
+        ix = np.clip(((cx[fin] - x0) * invx).astype(np.int64), 0, G - 1)
+        iy = np.clip(((cy[fin] - y0) * invy).astype(np.int64), 0, G - 1)
+        m = np.zeros_like(ix)
+        for bit in range(5):
+            m |= ((ix >> bit) & 1) << (2 * bit) | ((iy >> bit) & 1) << (2 * bit + 1)
+        cell[fin] = m
+    perm = np.argsort(cell, kind="stable")          # (the kernel's order inside a cell is arbitrary; any order is a valid model)
+    block = cell[perm] >> 4
+    groups = []
+    for s in range(G * G // 16):
+        idx = perm[block == s]
+        for k in range(0, len(idx), 64):
+            groups.append(idx[k:k + 64])
+    boxes_g = []
+    for g in groups:
+        if not fin[g].all():
+            boxes_g.append((-np.inf, -np.inf, np.inf, np.inf))
+        else:
+            boxes_g.append(((cx[g] - rad[g]).min(), (cy[g] - rad[g]).min(), (cx[g] + rad[g]).max(), (cy[g] + rad[g]).max()))
+    ng = len(groups)
+    meet = np.zeros((ng, ng), dtype=bool)
+    for p in range(ng):
+        for q in range(ng):
+            a, c = boxes_g[p], boxes_g[q]
+            meet[p, q] = not (a[0] > c[2] or c[0] > a[2] or a[1] > c[3] or c[1] > a[3])
+    lab = np.arange(ng)
+    changed = True
+    while changed:
+        changed = False
+        for p in range(ng):
+            for q in range(ng):
+                if meet[p, q] and lab[p] != lab[q]:
+                    lab[p] = lab[q] = min(lab[p], lab[q]); changed = True
+    return groups, meet, lab, rad - np.float32(1e-3)
+
+
+def test_nms_spatial_grouping_never_separates_a_pair_the_circle_test_keeps():
+    """Design invariant behind the spatial-tile NMS: the groups partition the boxes, hold at most 64 each, there are at most
+    n / 64 + 64 of them, and every pair the mask kernel's circle test would keep -- including every pair with a NaN / inf
+    term, which is never culled -- lies in two groups whose bounding boxes meet, hence in one component of the sweep."""
+    import numpy as np
+    from glenet_b200 import synth
+    rng = np.random.default_rng(5)
+    cases = [synth.proposals(1500, 12, 1)[0].numpy(), synth.proposals(4096, 20, 2)[0].numpy(), synth.kitti_boxes(700, 3).numpy()]
+    odd = synth.proposals(900, 6, 4)[0].numpy().copy()
+    odd[10, 0] = np.nan; odd[20, 3] = np.inf; odd[30:60, :2] += 4000.0; odd[100] = odd[7]; odd[200:260, :2] = odd[200, :2]
+    cases.append(odd)
+    cases.append(np.tile(synth.kitti_boxes(1, 9).numpy(), (300, 1)))          # every box on one spot: a single cell
+    for b in cases:
+        n = len(b)
+        groups, meet, lab, rad = _spatial_groups_model(b)
+        assert sorted(np.concatenate(groups).tolist()) == list(range(n))
+        assert max(len(g) for g in groups) <= 64 and len(groups) <= (n + 63) // 64 + 64
+        gid = np.empty(n, dtype=np.int64)
+        for k, g in enumerate(groups):
+            gid[g] = k
+        sample = rng.integers(0, n, (200000, 2))
+        i, j = sample[:, 0], sample[:, 1]
+        cx, cy = b[:, 0].astype(np.float32), b[:, 1].astype(np.float32)
+        with np.errstate(invalid="ignore", over="ignore"):
+            dx, dy, rr = cx[i] - cx[j], cy[i] - cy[j], rad[i] + rad[j]
+            kept = ~(dx * dx + dy * dy > rr * rr)                               # the kernel's test: NaN anywhere => not culled
+        assert kept.sum() > 1000
+        assert meet[gid[i[kept]], gid[j[kept]]].all()
+        assert (lab[gid[i[kept]]] == lab[gid[j[kept]]]).all()
