@@ -656,8 +656,9 @@ def side_runs(torch, I, R, synth, dev, hbm_gbs, fp32, cpu_pib, cfg0_cpu):
                   "frames_per_s_dropin_loop": 8 / (ms_l * 1e-3), "ms_batched": ms_b, "ms_dropin_loop": ms_l}
     if "cfg1_nms_8x4096_upper_triangle" in fm:
         out["nms"]["roofline"] = fp32_roof(fm["cfg1_nms_8x4096_upper_triangle"]["flops"], ms_b,
-                                           "whole batched call (sort + mask kernel + sweep); the mask kernel is ~80 % of it (profiles/); FLOPs = SURVEY 8d model over the "
-                                           "8 x 8.39e6 upper-triangle pairs of the seeded input (profiles/flop_model.json)")
+                                           "whole batched call (sort + spatial binning + mask kernel + deferred exact clips + per-component sweep; the mask kernel is ~40 % of it, "
+                                           "profiles/r02_nms_summary.txt); FLOPs = SURVEY 8d model over the 8 x 8.39e6 upper-triangle pairs of the seeded input "
+                                           "(profiles/flop_model.json) -- the work the reference does, not the pairs this path still examines")
     # GLENet's NMS_TYPE: variance-voting NMS on 4096 proposals (N x N CPU-dialect IoU + the voting loop, all on the device)
     vb, vs = synth.proposals(4096, 20, 31)
     vv = (torch.rand((4096, 7), generator=torch.Generator().manual_seed(5)) * 0.5 + 0.05)
@@ -674,7 +675,7 @@ def side_runs(torch, I, R, synth, dev, hbm_gbs, fp32, cpu_pib, cfg0_cpu):
     out["iou3d_cvae"] = {"workload": "cfg3: 600000 aligned pairs (30 samples x 20000 GT), all overlapping", "value": 600000 / (ms * 1e-3),
                          "unit": "pairs/s", "ms": ms,
                          "roofline": fp32_roof(flops3, ms, "FLOPs = SURVEY 8d model summed over the seeded 600000 pairs (675 per pair, profiles/flop_model.json); "
-                                               "executed FP32 instructions and pipe utilisation: profiles/r02_iou_aligned_summary.txt")}
+                                               "executed FP32 instructions and pipe utilisation: profiles/r02_iou_dense_summary.txt")}
     # cfg2: boxes_iou3d_gpu 4096 x 200
     g2 = synth.waymo_boxes(200, 2)
     pr, _ = synth.proposals(4096, seed=3, base=g2)
