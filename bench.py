@@ -538,6 +538,31 @@ def run_ours(args, rank, world, local_rank):
                           "h2d_bytes_per_step": (N_ANCHORS + FRAMES * N_GT) * 28, "d2h_bytes_per_step": FRAMES * rows * 12 + FRAMES * N_GT * 12,
                           "api": "anchor_assign_sharded(dense=False): row / column max + argmax only (axis_aligned_target_assigner.py:141-165), host buffers both ways"}
 
+    # ---- the per-frame operations of the metric at N > 1: replicas only (frames are independent, no collective): every rank runs
+    #      its own batch, time = max over ranks, throughput = all ranks' units / that time
+    if world > 1 and not args.no_extra:
+        try:
+            rb = torch.stack([synth.waymo_boxes(PIB_N, 100 + PIB_B * rank + f) for f in range(PIB_B)])
+            rp = torch.stack([synth.points(PIB_M, rb[f], synth.WAYMO_RANGE, 0.05, seed=500 + PIB_B * rank + f) for f in range(PIB_B)])
+            rb, rp = rb.to(dev), rp.to(dev)
+            ms_r = timed(lambda: R.points_in_boxes_gpu(rp, rb), 10, 3) / 10
+            shard["points_in_boxes_replicas"] = {
+                "workload": f"cfg2 on every GPU: {PIB_B} frames x {PIB_M} points x {PIB_N} boxes per rank (per-frame boxes and points, own seeds per rank)",
+                "ms": ms_r, "value": world * PIB_B * PIB_M / (ms_r * 1e-3), "unit": "points/s", "scaling": "weak (replicas only: no data-path collective)",
+                "frac_of_hbm_per_gpu": PIB_B * PIB_M * 16 / (ms_r * 1e-3) / 1e9 / hbm_gbs}
+            del rb, rp
+            nb_, ns_ = [], []
+            for f in range(8):
+                b_, s_ = synth.proposals(4096, 20, 20 + 8 * rank + f)
+                nb_.append(b_); ns_.append(s_)
+            nb_, ns_ = torch.stack(nb_).to(dev), torch.stack(ns_).to(dev)
+            ms_n = timed(lambda: I.nms_gpu_batch(nb_, ns_, 0.7), 10, 3) / 10
+            shard["nms_replicas"] = {"workload": "cfg1 on every GPU: 8 frames x nms_gpu(4096 proposals, thresh 0.7) per rank", "ms": ms_n,
+                                     "value": world * 8 / (ms_n * 1e-3), "unit": "frames/s", "scaling": "weak (replicas only: no data-path collective)"}
+            del nb_, ns_
+        except Exception as e:   # a side measurement must not take the headline down
+            shard["replicas_error"] = f"{type(e).__name__}: {e}"
+
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra:
         extra = side_runs(torch, I, R, synth, dev, hbm_gbs, fp32, cpu_pib, cfg0_cpu)
