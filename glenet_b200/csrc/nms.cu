@@ -1090,10 +1090,8 @@ static int launch_nms(bool normal, const float* boxes, int frames, int n, float 
         unsigned int* tile_list = reinterpret_cast<unsigned int*>(base + w.tiles_off);
         unsigned int* tile_count = reinterpret_cast<unsigned int*>(base + w.tcount_off);
         int* labels = reinterpret_cast<int*>(base + w.labels_off);
-        unsigned int* done_cnt = reinterpret_cast<unsigned int*>(base + w.done_off);
-        unsigned long long* kept_bits = reinterpret_cast<unsigned long long*>(base + w.kept_off);
         unsigned long long* members = reinterpret_cast<unsigned long long*>(base + w.members_off);
-        cudaError_t e = cudaMemsetAsync(tile_count, 0, 16 + w.zero_bytes, stream);      // the zeroed block follows the counter
+        cudaError_t e = cudaMemsetAsync(tile_count, 0, 16 + w.zero_bytes, stream);      // counter + labels, done counters, kept bits, membership bitmaps
         if (e == cudaSuccess) e = cudaMemsetAsync(mask, 0, (size_t)frames * n * col_blocks * sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return fail(-(int)e, "%s: memset failed", what);
         int rc;
